@@ -1,0 +1,132 @@
+/*
+ * oracle.h -- CPU restatement of RMCL's ray-casting-correspondence hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under rmcl_b200/ (the product) may include,
+ * link or call this.  Allowed users: tests/, __graft_entry__.smoke(), and the
+ * cpu_baseline / --impl reference legs of bench.py.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in rmagine (+Embree), which
+ * is not vendored under /root/reference (source_dependencies.yaml:4-7, unpinned
+ * `main`; rmcl/CMakeLists.txt:62-73 asks for rmagine >= 2.4.0) and cannot be built
+ * here; the reference ships no tests or golden vectors.
+ * Every function below cites the in-tree reference call site it follows; rmagine
+ * semantics are restated from its published behaviour and
+ * pinned only against analytic cases (tests/test_oracle_*.py).
+ */
+#ifndef RMCL_ORACLE_H
+#define RMCL_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- POD layouts at the boundary ---- */
+typedef struct { float x, y, z; } orc_vec3;                       /* rm::Vector3f, 12 B   */
+typedef struct { float x, y, z, w; } orc_quat;                    /* rm::Quaternion, 16 B */
+typedef struct { orc_quat R; orc_vec3 t; uint32_t stamp; } orc_transform; /* rm::Transform 32 B */
+typedef struct { float m[9]; } orc_mat3;                          /* rm::Matrix3x3, column-major m[c*3+r] */
+typedef struct {
+    orc_vec3 dataset_mean; orc_vec3 model_mean; orc_mat3 covariance; uint32_t n_meas;
+} orc_cross_stats;                                                /* rm::CrossStatistics 64 B */
+typedef struct { float mean, sigma; uint32_t n_meas; } orc_gaussian1d;  /* rm::Gaussian1D 12 B */
+/* rmcl_ros/include/rmcl_ros/rmcl/ParticleAttributes.hpp:18-32 */
+typedef struct { orc_gaussian1d likelihood; float state_sigma[6]; } orc_particle_attr; /* 36 B */
+/* rmcl_ros/include/rmcl_ros/rmcl/RangeMeasurement.hpp:10-21 */
+typedef struct { orc_vec3 orig, dir; float range; orc_mat3 cov; } orc_range_meas;       /* 64 B */
+
+/* rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:122-134 (defaults there) */
+typedef struct {
+    float dist_sigma;                 /* 2.0   */
+    float real_hit_sim_miss_error;    /* 100.0 */
+    float real_miss_sim_hit_error;    /* 100.0 */
+    float real_miss_sim_miss_error;   /* 0.0   */
+    float range_min, range_max;       /* 0.05, 80.0 */
+    int   ng_mode;                    /* 0 = raw (un-normalised) Ng like the Embree path (quirk D1), 1 = unit normal like the OptiX path */
+} orc_pf_params;
+
+typedef struct orc_scene orc_scene;
+
+/* ---- scene (stands in for rm::EmbreeMap: closest-hit over a triangle mesh) ---- */
+orc_scene* orc_scene_create(const float* verts_xyz, uint32_t nv, const uint32_t* faces_ijk, uint32_t nf);
+void       orc_scene_destroy(orc_scene* s);
+uint32_t   orc_scene_num_faces(const orc_scene* s);
+
+/* closest hit, t in (0, tfar]; tie -> smaller face id.  brute != 0: test every triangle (no BVH).
+ * Restates rtcIntersect1 as used at PCDSensorUpdaterEmbree.cpp:30-47. ng = raw geometric normal (v1-v0)x(v2-v0). */
+int  orc_intersect(const orc_scene* s, const float o[3], const float d[3], float tfar, int brute,
+                   float* t_out, uint32_t* face_out, float ng_out[3]);
+void orc_intersect_batch(const orc_scene* s, uint32_t n, const float* origs, const float* dirs, float tfar, int brute,
+                         float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out);
+
+/* ---- sensor models (rmagine SphericalModel / PinholeModel::getDirection; witness rmcl_ros/src/util/conversions.cpp:174-188) ---- */
+void orc_spherical_dirs(float phi_min, float phi_inc, uint32_t phi_n, float theta_min, float theta_inc, uint32_t theta_n, float* dirs_out);
+void orc_pinhole_dirs(uint32_t width, uint32_t height, float fx, float fy, float cx, float cy, float* dirs_out);
+
+/* ---- math ---- */
+void orc_transform_mul(const orc_transform* a, const orc_transform* b, orc_transform* out);
+void orc_transform_inv(const orc_transform* a, orc_transform* out);
+void orc_transform_point(const orc_transform* T, const float p[3], float out[3]);
+void orc_quat_rotate(const orc_quat* q, const float v[3], float out[3]);
+
+/* ---- RCCEmbree*::find == X SimulatorEmbree::simulate (rmcl/src/rmcl/registration/RCCEmbree.cpp:26-36,58-68,89-99,121-131) ----
+ * rays given as sensor-frame tables: dirs[n], origs[n_origs] with n_origs in {1 (shared origin: spherical/pinhole/O1Dn), n (OnDn)}.
+ * Outputs in the SENSOR frame; misses: hits=0, points/normals NaN, face id 0xFFFFFFFF, range = range_max + 1. Any out pointer may be NULL. */
+void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb,
+                  uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_max,
+                  float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges);
+
+/* MICP*Sensor*::unpackMessage (rmcl_ros/src/micpl/MICPSphericalSensorCPU.cpp:181-233): dataset point = dir*range (+orig), mask = range in [min,max] */
+void orc_dataset_from_ranges(uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, const float* ranges,
+                             float range_min, float range_max, float* points, uint8_t* mask, uint32_t* n_valid);
+
+/* ---- rm::statistics_p2l as called at rmcl/src/rmcl/registration/CorrespondencesCPU.cpp:26-30 (formula witness rmcl_ros/src/micpl/MICPSensorCPU.cpp:71-98) ----
+ * orc_statistics_p2l:     FP32, sequential `stats += CrossStatistics(Di,Mi)` merges (restates the reference arithmetic, one thread).
+ * orc_statistics_p2l_f64: identical FP32 per-element math and gating (=> identical n_meas), accumulation in double sum form (precision reference). */
+void orc_statistics_p2l(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
+                        const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out);
+void orc_statistics_p2l_f64(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
+                            const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out);
+/* max_dist interpolation of CorrespondencesCPU.cpp:21-23 */
+float orc_adaptive_max_dist(float max_dist, float adaptive_max_dist_min, double convergence_progress);
+
+void orc_cross_stats_identity(orc_cross_stats* s);
+void orc_cross_stats_merge(const orc_cross_stats* a, const orc_cross_stats* b, orc_cross_stats* out);            /* rm::CrossStatistics::operator+= */
+void orc_cross_stats_transform(const orc_transform* T, const orc_cross_stats* s, orc_cross_stats* out);            /* Transform * CrossStatistics */
+
+/* rm::umeyama_transform(CrossStatistics) as called at rmcl_ros/src/nodes/micp_localization.cpp:952-953 */
+void orc_umeyama(const orc_cross_stats* s, orc_transform* out);
+
+/* One MICPLocalizationNode::correctOnce for ONE sensor (micp_localization.cpp:899-984 + MICPSensor.hpp:146-184).
+ * Returns Tom_new; optional outputs: T_onew_oold, last merged stats. */
+void orc_micp_correct_once(const orc_scene* s,
+                           uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_max,
+                           const float* dataset_pts, const uint8_t* dataset_mask,
+                           const orc_transform* Tom, const orc_transform* Tbo, const orc_transform* Tsb,
+                           uint32_t optimization_iterations, float max_dist, float adaptive_max_dist_min,
+                           double convergence_progress, int f64_accum,
+                           orc_transform* Tom_new, orc_transform* T_onew_oold, orc_cross_stats* Cmerged_o);
+
+/* v1 SphereCorrectorEmbree::correct(Tbm[N]) shape (rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:117-133):
+ * per pose: simulate at Tbm[p], P2L against the dataset built from `ranges`, one Umeyama step; Tdelta is in the BASE frame. */
+void orc_correct_batch(const orc_scene* s, uint32_t n_poses, const orc_transform* Tbm, const orc_transform* Tsb,
+                       uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max,
+                       const float* ranges, float max_dist, int f64_accum,
+                       orc_transform* Tdelta, uint32_t* ncorr, orc_cross_stats* stats_b);
+
+/* ---- particle filter: PCDSensorUpdaterEmbree::update hot loop (PCDSensorUpdaterEmbree.cpp:290-342) with beams as input ---- */
+float orc_pf_evaluate_rcc(const orc_scene* s, const orc_range_meas* meas_m, const orc_pf_params* p);               /* :18-86 */
+void  orc_pf_sensor_update_one(const orc_scene* s, const orc_transform* Tsm, const orc_range_meas* meas_s,
+                               const orc_pf_params* p, orc_particle_attr* attr_inout);                              /* :197-241 */
+void  orc_pf_update(const orc_scene* s, uint32_t n_particles, const orc_transform* poses, orc_particle_attr* attrs,
+                    const orc_transform* Tsb, uint32_t n_beams, const orc_range_meas* beams_s, const orc_pf_params* p);
+void  orc_gaussian1d_add(orc_gaussian1d* a, const orc_gaussian1d* b);                                               /* rm::Gaussian1D::operator+= */
+
+int orc_num_threads(void);
+void orc_set_num_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
