@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- ray-correspondences/s (and MICP-L iters/s) of the ray-casting-correspondence path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): MICP-L SphereCorrector, 1 pose x 128x1024 spherical scan on the 1 000 000-triangle
+building mesh.  One step = one MICPLocalizationNode::correctOnce for that sensor: 1 find (131 072 rays traced) + 5 x (P2L cross
+statistics -> Umeyama -> compose), rmcl_ros/src/nodes/micp_localization.cpp:899-984.
+  value : device-resident step (dataset already in HBM), timed with CUDA events on the launching stream, L2 flushed between steps.
+  e2e   : the same step through the C-ABI entry b2_rcc_correct_once_ranges with the scan in pinned HOST memory: H2D of the ranges and
+          D2H of the result inside the timed region (host wall clock around the synchronous call).
+N > 1 (torchrun): poses are sharded, one pose (one sensor) per GPU, map replicated, no data-path collective ("weak" scaling).
+
+  python bench.py --gpus 1 --steps 200 --warmup 20
+  python bench.py --impl reference ...      # the reference's CPU path (oracle port: Embree/rmagine are not buildable here) on the host cores
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FACES = 1_000_000
+ITERATIONS = 5
+MAX_DIST, ADAPTIVE_MIN = 1.0, 0.15
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C3 particle filter, v1 batched correct)")
+    ap.add_argument("--faces", type=int, default=N_FACES)
+    return ap.parse_args()
+
+
+def rank_pose(synth, rank):
+    """pose guess of this rank's sensor: T_gt o (0.1,-0.05,0.2 m, yaw 3 deg) o a small rank-dependent shift"""
+    T = synth.compose(synth.building_gt_pose(), synth.scenario_pose_offset())
+    if rank:
+        T = synth.compose(T, synth.make_transform((0.01 * rank, -0.007 * rank, 0.0), (0, 0, 0.002 * rank)))
+    return T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(2)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.f.name):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(args, steps, warmup):
+    """The reference's CPU path restated (oracle port) on the host cores: same step, same inputs."""
+    from oracle import pyoracle as po
+    from rmcl_b200 import synth
+    V, F = synth.building(args.faces)
+    sc = po.Scene(V, F)
+    m = synth.c2_sensor()
+    o, d = po.model_rays(m)
+    Tsb, Tgt, I = synth.scenario_tsb(), synth.building_gt_pose(), synth.make_transform()
+    ranges = synth.noisy_ranges(sc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max)
+    dp, dm, _ = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
+    Tom = rank_pose(synth, 0)
+    for _ in range(warmup):
+        sc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
+    dt = (time.perf_counter() - t0) / steps
+    return m.size / dt, dt, po.num_threads(), m.size
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "C2: MICP-L correctOnce, 1 pose x 128x1024 spherical scan, building mesh", "n_faces": args.faces, "rays_per_step_per_gpu": 131072,
+              "inner_iterations": ITERATIONS, "poses_per_gpu": 1, "parallelism": f"pose-shard x{world} (map replicated, no collective)",
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+        val, dt, cores, n = cpu_reference_leg(args, steps, warmup)
+        line = {"impl": "reference", "metric": "ray-correspondences/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "micp_iters_per_s": 1.0 / dt,
+                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} full C2 correctOnce steps (131072 rays + 5 reductions each) on the CPU oracle, OpenMP over rays and over reduction chunks; Embree/rmagine not buildable here"},
+                "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import rmcl_b200
+    from rmcl_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+
+    # ---- set-up (untimed): map build (host SAH -> HBM), model, synthetic scan produced by the library itself at T_gt ----
+    V, F = synth.building(args.faces)
+    gmap = rmcl_b200.Map(V, F, device=local_rank)
+    info = gmap.info()
+    m = synth.c2_sensor()
+    Tsb, Tgt, I = synth.scenario_tsb(), synth.building_gt_pose(), synth.make_transform()
+    h = rmcl_b200.RCCB200Spherical(gmap)
+    h.setStream(stream.cuda_stream)
+    h.setTsb(Tsb)
+    h.setModel(m)
+    h.setParams(MAX_DIST, ADAPTIVE_MIN)
+    h.find(Tgt)
+    ranges = synth.noisy_ranges(h.modelView()["ranges"], m.range_max)
+    ranges_pinned = torch.from_numpy(ranges.copy()).pin_memory()
+    h.setRanges(ranges)
+    Tom = rank_pose(synth, rank)
+    h.enableTiming(True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps ----
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        h.correctOnce(Tom, I, ITERATIONS, 0.0)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    find_ms, red_ms = [], []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = rmcl_b200.kernel_launch_count()
+    for a, b in ev:
+        flush.fill_(2)                      # untimed L2 flush
+        a.record(stream)
+        Tn, Td, Cm = h.correctOnce(Tom, I, ITERATIONS, 0.0)
+        b.record(stream)
+        f_ms, r_ms = h.lastTiming()
+        find_ms.append(f_ms)
+        red_ms.append(r_ms)
+    launches = rmcl_b200.kernel_launch_count() - launches0
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end-to-end steps: host ranges in, host result out ----
+    for _ in range(max(3, args.warmup // 4)):
+        h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.fill_(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Tn2, Td2, Cm2 = h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    rays_total = float(m.size) * args.steps * world
+    value = rays_total / (dev_ms_max * 1e-3)
+    e2e_value = rays_total / (e2e_ms_max * 1e-3)
+
+    # ---- secondary workloads (reported under "extra"; same timing rules) ----
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank)
+        except Exception as e:                     # never lose the headline because a secondary workload failed
+            extra = {"error": repr(e)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_rcc_find): algorithmic bytes per launch / CUDA-event duration ----
+    q = np.asarray(synth.compose(Tom, Tsb)["R"], np.float64)
+    tsm = np.asarray(synth.compose(Tom, Tsb)["t"], np.float32)
+    from rmcl_b200.api import _SphericalModel  # noqa: F401
+    dirs_s = spherical_dirs_np(m)
+    dirs_m = synth._qrot(q[None, :], dirs_s.astype(np.float64)).astype(np.float32)
+    vn, vt = gmap.traversal_stats(np.tile(tsm, (len(dirs_m), 1)), dirs_m, m.range_max)
+    b_io = 12 + 33                                   # direction table in, point+normal+hit+face+range out
+    bytes_per_ray = vn * 80.0 + vt * 48.0 + b_io
+    find_s = float(np.mean(find_ms)) * 1e-3
+    achieved = bytes_per_ray * m.size / find_s / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_rcc_find_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_rcc_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 80, "tri_bytes": 48, "io_bytes_per_ray": b_io,
+                "kernel_ms": find_s * 1e3, "kernel_share_of_step": float(np.mean(find_ms)) / (dev_ms / args.steps),
+                "kernel_rays_per_s": m.size / find_s}
+
+    # ---- CPU baseline (oracle port) on this box's host cores, bounded sample ----
+    cpu = None
+    if world == 1 or rank == 0:
+        try:
+            val, dt, cores, _ = cpu_reference_leg(args, 10, 1)
+            cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                   "sample": "10 full C2 correctOnce steps on the CPU oracle (FP32 merges, OpenMP over rays and reduction chunks); Embree/rmagine unavailable",
+                   "ms_per_step": dt * 1e3}
+        except Exception as e:
+            cpu = {"error": repr(e)}
+
+    line = {"metric": "ray-correspondences/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "micp_iters_per_s": args.steps * world / (dev_ms_max * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(ranges.nbytes + 416), "d2h_bytes_per_step": 416,
+                    "ms_per_step": e2e_ms_max / args.steps, "timer": "host wall clock around the synchronous C-ABI call"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms": {"find": float(np.mean(find_ms)), "reduce_x5_umeyama": float(np.mean(red_ms))},
+            "map": {"n_nodes": info["n_nodes"], "bvh_mb": info["bvh_bytes"] / 1e6, "build_ms": info["build_ms"], "max_depth": info["max_depth"]},
+            "result_check": {"n_meas": int(Cm["n_meas"]), "dt_norm": float(np.linalg.norm(Td["t"]))},
+            "extra": extra}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def spherical_dirs_np(m):
+    phi = (np.float32(m.phi_min) + np.arange(m.phi_size, dtype=np.float32) * np.float32(m.phi_inc))
+    th = (np.float32(m.theta_min) + np.arange(m.theta_size, dtype=np.float32) * np.float32(m.theta_inc))
+    cp, sp = np.cos(phi)[:, None], np.sin(phi)[:, None]
+    d = np.stack([cp * np.cos(th)[None, :], cp * np.sin(th)[None, :], np.repeat(sp, len(th), 1)], -1)
+    return d.reshape(-1, 3).astype(np.float32)
+
+
+def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank):
+    """C3: particle filter 100k particles x 180 beams per GPU (particles sharded across ranks); v1: batched correct(), 1000 poses x vlp16_900."""
+    out = {}
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- C3 ----
+    pts = h.modelView()["points"]                       # last find was at the guess pose; any finite scan works as beam source
+    beams = synth.pf_beams(pts, 180)
+    n_part = 100_000
+    P, A = synth.pf_particles(n_part * world)
+    from rmcl_b200.shard import shard_range
+    b, e = shard_range(len(P), rank, world)
+    Pd = torch.from_numpy(P[b:e].view(np.float32).reshape(-1, 8).copy()).cuda()
+    A0 = torch.from_numpy(A[b:e].view(np.float32).reshape(-1, 9).copy()).cuda()
+    up = rmcl_b200.PCDSensorUpdaterB200(gmap)
+    up.setStream(stream.cuda_stream)
+    prm = rmcl_b200.PFParams.defaults()
+    steps, warm = 10, 3
+    tot = 0.0
+    for i in range(warm + steps):
+        Ad = A0.clone()
+        flush.fill_(4)
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        up.update(Pd, Ad, Tsb, beams, prm)
+        bb.record(stream)
+        torch.cuda.synchronize()
+        if i >= warm:
+            tot += a.elapsed_time(bb)
+    ms = maxr(tot) / steps
+    # end to end with host particles
+    Ph, Ah = P[b:e].copy(), A[b:e].copy()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        up.update(Ph, Ah, Tsb, beams, prm)
+    e2e = maxr((time.perf_counter() - t0) / 3)
+    out["c3_pf"] = {"workload": f"C3: particle-filter sensor update, {n_part} particles x 180 beams per GPU, 1M-triangle mesh", "rays_per_s": n_part * world * 180 / (ms * 1e-3),
+                    "ms_per_step": ms, "e2e_rays_per_s": n_part * world * 180 / e2e, "e2e_ms_per_step": e2e * 1e3,
+                    "h2d_bytes_per_step": n_part * (32 + 36) + 180 * 32, "d2h_bytes_per_step": n_part * 36}
+    # ---- v1 batched correct ----
+    hv = rmcl_b200.SphereCorrectorB200(gmap)
+    hv.setStream(stream.cuda_stream)
+    hv.setTsb(Tsb)
+    mv = synth.vlp16_900()
+    mv.range_min = 0.0
+    hv.setModel(mv)
+    hv.setParams(1.0, 0.15)
+    hv.find(Tgt)
+    hv.setInputData(hv.modelView()["ranges"])
+    n_poses = 1000
+    T = synth.transforms(n_poses)
+    T[:] = synth.compose(Tgt, synth.scenario_pose_offset())
+    rng = np.random.default_rng(rank)
+    T["t"] += rng.uniform(-0.05, 0.05, (n_poses, 3)).astype(np.float32)
+    Td_ = torch.from_numpy(T.view(np.float32).reshape(-1, 8).copy()).cuda()
+    tot = 0.0
+    for i in range(warm + steps):
+        flush.fill_(5)
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        hv.correct(Td_)
+        bb.record(stream)
+        torch.cuda.synchronize()
+        if i >= warm:
+            tot += a.elapsed_time(bb)
+    ms = maxr(tot) / steps
+    out["v1_batch"] = {"workload": "v1 correct(): 1000 poses x vlp16_900 (14400 rays) per GPU, fused trace+P2L+Umeyama", "rays_per_s": n_poses * world * mv.size / (ms * 1e-3),
+                       "ms_per_step": ms, "reference_numbers": "Embree 0.201 s, OptiX 0.0169 s per correct() on a 1M-face sphere (BASELINE.md)"}
+    return out
+
+
+if __name__ == "__main__":
+    main()

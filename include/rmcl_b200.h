@@ -1,0 +1,172 @@
+/*
+ * rmcl_b200.h -- C ABI of the B200-native ray-casting-correspondence library (librmcl_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of uos/rmcl: plain pointers and sizes, no C++
+ * or torch types.  Every entry point cites the reference interface it replaces (paths relative to the rmcl repo).
+ * The reference-side bindings a maintainer would add are shown in INTEGRATION.md; the C++ shim classes with the
+ * reference's names live in include/rmcl_b200/ (C++ headers).
+ *
+ * Conventions
+ *  - every function returns B2_OK (0) or a negative B2_ERR_*; b2_last_error() gives the thread-local message.
+ *  - nothing here falls back to the CPU: if no CUDA device / kernel image is usable the call fails with B2_ERR_CUDA.
+ *  - "device pointer" arguments are CUDA device addresses on the mesh's device; all work is enqueued on the handle's
+ *    stream (b2_*_set_stream, default: the legacy default stream).  Calls that return data to HOST memory synchronise
+ *    that stream; calls that take/return only device pointers do not.
+ *  - layouts are byte-compatible with rmagine / rmcl.
+ */
+#ifndef RMCL_B200_H
+#define RMCL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2_API
+#else
+#define B2_API __attribute__((visibility("default")))
+#endif
+
+/* ---------------------------------------------------------------- POD types ---------------------------------- */
+typedef struct { float x, y, z; } b2_vec3;                                   /* rmagine::Vector3f   (12 B) */
+typedef struct { float x, y, z, w; } b2_quat;                                /* rmagine::Quaternion (16 B) */
+typedef struct { b2_quat R; b2_vec3 t; uint32_t stamp; } b2_transform;       /* rmagine::Transform  (32 B) */
+typedef struct { float m[9]; } b2_mat3;                                      /* rmagine::Matrix3x3, column-major */
+typedef struct { b2_vec3 dataset_mean, model_mean; b2_mat3 covariance; uint32_t n_meas; } b2_cross_stats; /* rmagine::CrossStatistics (64 B) */
+typedef struct { float mean, sigma; uint32_t n_meas; } b2_gaussian1d;        /* rmagine::Gaussian1D (12 B) */
+typedef struct { b2_gaussian1d likelihood; float state_sigma[6]; } b2_particle_attr;  /* rmcl::ParticleAttributes, rmcl_ros/include/rmcl_ros/rmcl/ParticleAttributes.hpp:18-32 (36 B) */
+typedef struct { b2_vec3 orig, dir; float range; b2_mat3 cov; } b2_range_meas;         /* rmcl::RangeMeasurement,  rmcl_ros/include/rmcl_ros/rmcl/RangeMeasurement.hpp:10-21 (64 B) */
+
+/* rmagine::SphericalModel as filled at rmcl_ros/src/util/conversions.cpp:22-34 */
+typedef struct { float phi_min, phi_inc; uint32_t phi_size; float theta_min, theta_inc; uint32_t theta_size; float range_min, range_max; } b2_spherical_model;
+/* rmagine::PinholeModel as filled at rmcl_ros/src/util/conversions.cpp:48-60 */
+typedef struct { uint32_t width, height; float fx, fy, cx, cy; float range_min, range_max; } b2_pinhole_model;
+
+/* PCDSensorUpdaterEmbree config, rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:122-134 (defaults in comments) */
+typedef struct {
+    float dist_sigma;                 /* 2.0   */
+    float real_hit_sim_miss_error;    /* 100.0 */
+    float real_miss_sim_hit_error;    /* 100.0 */
+    float real_miss_sim_miss_error;   /* 0.0   */
+    float range_min, range_max;       /* sensor_range 0.05 .. 80.0 */
+    int   ng_mode;                    /* 0: raw un-normalised geometric normal (Embree path, :57-68); 1: unit normal (OptiX path, BeamEvaluateProgram.cu:104-113) */
+} b2_pf_params;
+
+typedef struct {
+    uint32_t n_faces, n_vertices, n_nodes, n_leaf_tris, max_depth;
+    uint64_t bvh_bytes;               /* nodes + leaf triangle records resident in HBM */
+    float    build_ms;                /* wall time of b2_mesh_create (host build + upload, or device build) */
+    int      device;
+    int      build_mode;
+    float    sah_cost;
+} b2_mesh_info;
+
+typedef struct b2_mesh b2_mesh;       /* immutable map: triangle mesh + in-HBM BVH.  Stands in for rmagine::EmbreeMap / OptixMap */
+typedef struct b2_rcc  b2_rcc;        /* one ray-casting-correspondence set == one rmcl::RCC..{Spherical,Pinhole,O1Dn,OnDn} object */
+typedef struct b2_pf   b2_pf;         /* one particle-filter sensor updater == rmcl::PCDSensorUpdater{Embree,Optix} */
+
+enum {
+    B2_OK = 0,
+    B2_ERR_INVALID = -1,      /* bad argument / call order (e.g. find before set_model) */
+    B2_ERR_CUDA = -2,         /* CUDA runtime error (message in b2_last_error) */
+    B2_ERR_NO_MAP = -3,       /* empty mesh: mirrors "NO MAP"/"EMPTY MAP" of PCDSensorUpdaterOptix.cpp:179-192 */
+    B2_ERR_OOM = -4,
+    B2_ERR_UNSUPPORTED = -5
+};
+enum { B2_BUILD_HOST_SAH = 0, B2_BUILD_DEVICE_LBVH = 1 };
+
+B2_API const char* b2_last_error(void);
+B2_API int         b2_version(void);
+B2_API int         b2_device_count(int* n);
+
+/* ---------------------------------------------------------------- map ---------------------------------------- */
+/* replaces rm::import_embree_map + Embree scene commit (rmcl_ros/src/nodes/micp_localization.cpp:188,
+ * rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:158): vertices/faces in HOST memory -> BVH resident in HBM of `device`. */
+B2_API int b2_mesh_create(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces,
+                          int device, int build_mode, b2_mesh** out);
+B2_API int b2_mesh_destroy(b2_mesh* m);
+B2_API int b2_mesh_get_info(const b2_mesh* m, b2_mesh_info* info);
+/* closest hit for arbitrary rays (host arrays in, host arrays out): t in (0,tfar], tie -> smaller face id.
+ * Replaces rtcIntersect1 as used at rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:30-47. Any output may be NULL. */
+B2_API int b2_mesh_intersect(const b2_mesh* m, const float* origs_xyz, const float* dirs_xyz, uint32_t n, float tfar,
+                             float* t_out, uint32_t* face_out, float* ng_out_xyz, uint8_t* hit_out);
+/* traversal counters of the same rays (instrumented build of the same kernel): mean nodes visited / triangles tested per ray */
+B2_API int b2_mesh_intersect_stats(const b2_mesh* m, const float* origs_xyz, const float* dirs_xyz, uint32_t n, float tfar,
+                                   double* mean_nodes, double* mean_tris);
+
+/* ---------------------------------------------------------------- MICP-L: RCC ------------------------------ */
+/* ctor(map): rmcl/include/rmcl/registration/RCCEmbree.hpp:25-26 */
+B2_API int b2_rcc_create(b2_mesh* map, b2_rcc** out);
+B2_API int b2_rcc_destroy(b2_rcc* h);
+B2_API int b2_rcc_set_stream(b2_rcc* h, void* cuda_stream);
+/* Correspondences_::setTsb, rmcl/include/rmcl/registration/Correspondences.hpp:33-36 */
+B2_API int b2_rcc_set_tsb(b2_rcc* h, const b2_transform* Tsb);
+/* ModelSetter<ModelT>::setModel, rmcl/src/rmcl/registration/RCCEmbree.cpp:21-24,53-56,84-87,116-119 */
+B2_API int b2_rcc_set_model_spherical(b2_rcc* h, const b2_spherical_model* model);
+B2_API int b2_rcc_set_model_pinhole(b2_rcc* h, const b2_pinhole_model* model);
+B2_API int b2_rcc_set_model_o1dn(b2_rcc* h, uint32_t width, uint32_t height, const float orig_xyz[3], const float* dirs_xyz, float range_min, float range_max);
+B2_API int b2_rcc_set_model_ondn(b2_rcc* h, uint32_t width, uint32_t height, const float* origs_xyz, const float* dirs_xyz, float range_min, float range_max);
+/* public fields params.max_dist / adaptive_max_dist_min, Correspondences.hpp:22-23 */
+B2_API int b2_rcc_set_params(b2_rcc* h, float max_dist, float adaptive_max_dist_min);
+/* public field dataset (points + mask), Correspondences.hpp:24; src_is_device != 0: pointers are device addresses */
+B2_API int b2_rcc_set_dataset(b2_rcc* h, const float* points_xyz, const uint8_t* mask, uint32_t n, int src_is_device);
+/* MICP..Sensor..::unpackMessage (rmcl_ros/src/micpl/MICPSphericalSensorCPU.cpp:181-233) on the device: dataset = dir*range (+orig),
+ * mask = range in [range.min, range.max].  Also the v1 setInputData(ranges) (lidar_corrector_embree_benchmark.cpp:118). */
+B2_API int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device);
+/* RCC..::find(Tbm_est), rmcl/src/rmcl/registration/RCCEmbree.cpp:26-36,58-68,89-99,121-131 */
+B2_API int b2_rcc_find(b2_rcc* h, const b2_transform* Tbm_est);
+/* Correspondences{CPU,CUDA}::computeCrossStatistics, rmcl/src/rmcl/registration/CorrespondencesCPU.cpp:10-39 (CUDA twin CorrespondencesCUDA.cpp:9-30) */
+B2_API int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T_snew_sold, double convergence_progress, b2_cross_stats* out_host);
+/* modelView()/datasetView(), Correspondences.hpp:47-62: device pointers (points/normals packed xyz, hits/mask u8) + our extra face ids / ranges */
+B2_API int b2_rcc_model_view(b2_rcc* h, float** points, float** normals, uint8_t** hits, uint32_t** face_ids, float** ranges, uint32_t* n);
+B2_API int b2_rcc_dataset_view(b2_rcc* h, float** points, uint8_t** mask, uint32_t* n);
+/* host copies of the model buffers (synchronises); any pointer may be NULL */
+B2_API int b2_rcc_download_model(b2_rcc* h, float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges);
+B2_API int b2_rcc_download_dataset(b2_rcc* h, float* points, uint8_t* mask);
+
+/* One MICPLocalizationNode::correctOnce for this sensor, entirely on the device
+ * (rmcl_ros/src/nodes/micp_localization.cpp:899-984 + rmcl_ros/include/rmcl_ros/micpl/MICPSensor.hpp:146-184):
+ * find(Tom*Tbo), then `iterations` x { P2L cross statistics -> frame changes -> Umeyama -> compose }.  Outputs to HOST (may be NULL). */
+B2_API int b2_rcc_correct_once(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations,
+                               double convergence_progress, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
+/* same, but the scan arrives as HOST ranges and is uploaded inside the call (end-to-end entry point used by bench.py "e2e") */
+B2_API int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges_host, uint32_t n, const b2_transform* Tom, const b2_transform* Tbo,
+                                      uint32_t iterations, double convergence_progress, b2_transform* Tom_new, b2_transform* T_onew_oold,
+                                      b2_cross_stats* Cmerged_o);
+
+/* v1 {Sphere,Pinhole,O1Dn}Corrector{Embree,Optix}::correct(Tbm[N]) -> {Tdelta[N], Ncorr[N]}
+ * (shape: rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:86-133, ..._optix_benchmark.cpp:85-155):
+ * fused trace -> P2L gate -> per-pose cross statistics -> batched Umeyama, one launch sequence for all poses.
+ * poses_on_device / out_on_device select HOST or DEVICE pointers. Outputs may be NULL. */
+B2_API int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t n_poses, int poses_on_device,
+                                b2_transform* Tdelta, uint32_t* ncorr, b2_cross_stats* stats_b, int out_on_device);
+/* rm::umeyama_transform for n statistics (rmcl_ros/src/nodes/micp_localization.cpp:952-953) */
+B2_API int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_transform* out, int on_device, int device, void* cuda_stream);
+
+/* ---------------------------------------------------------------- particle filter ---------------------------- */
+B2_API int b2_pf_create(b2_mesh* map, b2_pf** out);
+B2_API int b2_pf_destroy(b2_pf* h);
+B2_API int b2_pf_set_stream(b2_pf* h, void* cuda_stream);
+/* ParticleUpdater<VRAM_CUDA>::update (rmcl_ros/include/rmcl_ros/rmcl/ParticleUpdater.hpp:39-43) with the hot loop of
+ * PCDSensorUpdaterEmbree::update (rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:290-342): all beams x all particles in ONE launch,
+ * per-particle likelihood merged in beam order, attrs read-modified-written once.  poses/attrs: DEVICE pointers; beams: HOST. */
+B2_API int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n_particles,
+                               const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
+/* ParticleUpdater<RAM>::update: HOST poses/attrs; copies in, updates, copies attrs back (end-to-end entry point) */
+B2_API int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses_host, b2_particle_attr* attrs_host, uint32_t n_particles,
+                                    const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
+
+/* ---------------------------------------------------------------- introspection ------------------------------ */
+/* CUDA-event timing of the kernels inside b2_rcc_correct_once*(): when enabled, events are recorded on the handle's stream around the
+ * find kernel and around the reduction/Umeyama kernels; b2_rcc_last_timing returns the two durations of the most recent call (ms). */
+B2_API int b2_rcc_enable_timing(b2_rcc* h, int enable);
+B2_API int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+B2_API uint64_t b2_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMCL_B200_H */

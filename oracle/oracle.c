@@ -571,6 +571,32 @@ void orc_statistics_p2l(const orc_transform* Tpre, uint32_t n, const float* dpts
     *out = acc;
 }
 
+/* Parallel variant used for TIMING the CPU baseline: rmagine reduces with TBB/OpenMP, i.e. per-thread partial CrossStatistics merged
+ * at the end.  Fixed chunks of 1024 elements, FP32 merges inside a chunk, chunks merged in index order (deterministic). */
+void orc_statistics_p2l_par(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
+                            const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out)
+{
+    const uint32_t chunk = 1024, nchunks = (n + chunk - 1) / chunk;
+    orc_cross_stats* part = (orc_cross_stats*)malloc(sizeof(orc_cross_stats) * (nchunks ? nchunks : 1));
+    #pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (int64_t)nchunks; c++) {
+        orc_cross_stats acc; orc_cross_stats_identity(&acc);
+        const uint32_t b = (uint32_t)c * chunk, e = b + chunk < n ? b + chunk : n;
+        for (uint32_t i = b; i < e; i++) {
+            orc_vec3 Di, Mi;
+            if (!p2l_elem(Tpre, i, dpts, dmask, mpts, mnrm, mmask, max_dist, &Di, &Mi)) continue;
+            orc_cross_stats one; orc_cross_stats_identity(&one);
+            one.dataset_mean = Di; one.model_mean = Mi; one.n_meas = 1;
+            orc_cross_stats merged; orc_cross_stats_merge(&acc, &one, &merged); acc = merged;
+        }
+        part[c] = acc;
+    }
+    orc_cross_stats acc; orc_cross_stats_identity(&acc);
+    for (uint32_t c = 0; c < nchunks; c++) { orc_cross_stats merged; orc_cross_stats_merge(&acc, &part[c], &merged); acc = merged; }
+    free(part);
+    *out = acc;
+}
+
 void orc_statistics_p2l_f64(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
                             const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out)
 {
@@ -723,8 +749,9 @@ void orc_micp_correct_once(const orc_scene* s,
         /* MICPSensor.hpp:178 */
         const orc_transform T_snew_sold = T_mul(T_mul(T_inv(*Tsb), T_bnew_bold), *Tsb);
         orc_cross_stats stats_s, stats_b, Cs_o, ident;
-        if (f64_accum) orc_statistics_p2l_f64(&T_snew_sold, n, dataset_pts, dataset_mask, mp, mn, mh, md, &stats_s);
-        else           orc_statistics_p2l(&T_snew_sold, n, dataset_pts, dataset_mask, mp, mn, mh, md, &stats_s);
+        if (f64_accum == 1)      orc_statistics_p2l_f64(&T_snew_sold, n, dataset_pts, dataset_mask, mp, mn, mh, md, &stats_s);
+        else if (f64_accum == 2) orc_statistics_p2l_par(&T_snew_sold, n, dataset_pts, dataset_mask, mp, mn, mh, md, &stats_s);
+        else                     orc_statistics_p2l(&T_snew_sold, n, dataset_pts, dataset_mask, mp, mn, mh, md, &stats_s);
         orc_cross_stats_transform(Tsb, &stats_s, &stats_b);      /* MICPSensor.hpp:182 */
         orc_cross_stats_transform(Tbo, &stats_b, &Cs_o);         /* micp_localization.cpp:931 */
         orc_cross_stats_identity(&ident);

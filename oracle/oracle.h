@@ -86,6 +86,8 @@ void orc_dataset_from_ranges(uint32_t n, const float* origs_s, uint32_t n_origs,
  * orc_statistics_p2l_f64: identical FP32 per-element math and gating (=> identical n_meas), accumulation in double sum form (precision reference). */
 void orc_statistics_p2l(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
                         const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out);
+void orc_statistics_p2l_par(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
+                            const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out);   /* OpenMP chunks, FP32: timing baseline */
 void orc_statistics_p2l_f64(const orc_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask,
                             const float* mpts, const float* mnrm, const uint8_t* mmask, float max_dist, orc_cross_stats* out);
 /* max_dist interpolation of CorrespondencesCPU.cpp:21-23 */
@@ -105,7 +107,7 @@ void orc_micp_correct_once(const orc_scene* s,
                            const float* dataset_pts, const uint8_t* dataset_mask,
                            const orc_transform* Tom, const orc_transform* Tbo, const orc_transform* Tsb,
                            uint32_t optimization_iterations, float max_dist, float adaptive_max_dist_min,
-                           double convergence_progress, int f64_accum,
+                           double convergence_progress, int f64_accum /* 0: FP32 sequential, 1: FP64 sums, 2: FP32 OpenMP chunks */,
                            orc_transform* Tom_new, orc_transform* T_onew_oold, orc_cross_stats* Cmerged_o);
 
 /* v1 SphereCorrectorEmbree::correct(Tbm[N]) shape (rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:117-133):

@@ -131,7 +131,7 @@ class Scene:
         Tom, Tbo, Tsb = _tf(Tom), _tf(Tbo), _tf(Tsb)
         lib().orc_micp_correct_once(self._h, C.c_uint32(n), _p(origs_s), C.c_uint32(origs_s.shape[0]), _p(dirs_s), C.c_float(range_max),
                                     _p(dp), _p(dm), _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist),
-                                    C.c_float(adaptive_max_dist_min), C.c_double(convergence_progress), C.c_int(int(f64_accum)),
+                                    C.c_float(adaptive_max_dist_min), C.c_double(convergence_progress), C.c_int(int(f64_accum)),   # 0 seq f32, 1 f64, 2 parallel f32
                                     _p(Tn), _p(Td), _p(Cm))
         return Tn, Td, Cm
 

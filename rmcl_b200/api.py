@@ -1,0 +1,382 @@
+"""Host-side mirror of the reference's interface for the ray-casting-correspondence path, over the C ABI (ctypes).
+
+Class / method names follow the reference (file:line cited per method); all arithmetic happens in librmcl_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .synth import CROSS_STATS_DTYPE, PARTICLE_ATTR_DTYPE, RANGE_MEAS_DTYPE, TRANSFORM_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "librmcl_b200.so")
+_lib = None
+
+B2_BUILD_HOST_SAH = 0
+B2_BUILD_DEVICE_LBVH = 1
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rmcl_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+class _SphericalModel(C.Structure):
+    _fields_ = [("phi_min", C.c_float), ("phi_inc", C.c_float), ("phi_size", C.c_uint32), ("theta_min", C.c_float), ("theta_inc", C.c_float),
+                ("theta_size", C.c_uint32), ("range_min", C.c_float), ("range_max", C.c_float)]
+
+
+class _PinholeModel(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float)]
+
+
+class PFParams(C.Structure):
+    """PCDSensorUpdaterEmbree config (rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:122-134)."""
+    _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
+                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int)]
+
+    @staticmethod
+    def defaults(ng_mode=0):
+        return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode)
+
+
+class _MeshInfo(C.Structure):
+    _fields_ = [("n_faces", C.c_uint32), ("n_vertices", C.c_uint32), ("n_nodes", C.c_uint32), ("n_leaf_tris", C.c_uint32), ("max_depth", C.c_uint32),
+                ("bvh_bytes", C.c_uint64), ("build_ms", C.c_float), ("device", C.c_int), ("build_mode", C.c_int), ("sah_cost", C.c_float)]
+
+
+EXPORTS = [
+    "b2_last_error", "b2_version", "b2_device_count", "b2_mesh_create", "b2_mesh_destroy", "b2_mesh_get_info", "b2_mesh_intersect",
+    "b2_mesh_intersect_stats", "b2_rcc_create", "b2_rcc_destroy", "b2_rcc_set_stream", "b2_rcc_set_tsb", "b2_rcc_set_model_spherical",
+    "b2_rcc_set_model_pinhole", "b2_rcc_set_model_o1dn", "b2_rcc_set_model_ondn", "b2_rcc_set_params", "b2_rcc_set_dataset", "b2_rcc_set_ranges",
+    "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
+    "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
+    "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing",
+]
+
+
+def load_library():
+    """Load librmcl_b200.so.  Fails loudly when it is missing: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise B2Error(-2, f"CUDA library not built: {_LIB_PATH} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    lib = C.CDLL(_LIB_PATH)
+    for name in EXPORTS:
+        getattr(lib, name)            # AttributeError if the ABI is incomplete
+    lib.b2_last_error.restype = C.c_char_p
+    lib.b2_kernel_launch_count.restype = C.c_uint64
+    for name in EXPORTS:
+        if name not in ("b2_last_error", "b2_kernel_launch_count"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise B2Error(rc, load_library().b2_last_error().decode("utf-8", "replace"))
+
+
+def kernel_launch_count():
+    return int(load_library().b2_kernel_launch_count())
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _tf(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype.itemsize != 32:
+        raise TypeError("expected 32-byte Transform records (synth.TRANSFORM_DTYPE)")
+    return a
+
+
+def _devptr(x):
+    """Device address of a torch CUDA tensor (or a raw int)."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        if not x.is_cuda or not x.is_contiguous():
+            raise TypeError("expected a contiguous CUDA tensor")
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+class Map:
+    """Triangle mesh + in-HBM BVH; stands in for rm::EmbreeMap / rm::OptixMap (rm::import_embree_map, micp_localization.cpp:188)."""
+
+    def __init__(self, verts, faces, device=0, build_mode=B2_BUILD_HOST_SAH):
+        lib = load_library()
+        verts = _f32(verts).reshape(-1, 3)
+        faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        h = C.c_void_p()
+        _chk(lib.b2_mesh_create(_p(verts), C.c_uint32(len(verts)), _p(faces), C.c_uint32(len(faces)), C.c_int(device), C.c_int(build_mode), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().b2_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        inf = _MeshInfo()
+        _chk(load_library().b2_mesh_get_info(self._h, C.byref(inf)))
+        return {k: getattr(inf, k) for k, _ in _MeshInfo._fields_}
+
+    def intersect(self, origs, dirs, tfar=np.inf):
+        """Closest hit for arbitrary rays (replaces rtcIntersect1, PCDSensorUpdaterEmbree.cpp:30-47)."""
+        origs, dirs = _f32(origs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        n = len(origs)
+        t, f, ng, h = np.empty(n, np.float32), np.empty(n, np.uint32), np.empty((n, 3), np.float32), np.empty(n, np.uint8)
+        _chk(load_library().b2_mesh_intersect(self._h, _p(origs), _p(dirs), C.c_uint32(n), C.c_float(tfar), _p(t), _p(f), _p(ng), _p(h)))
+        return t, f, ng, h
+
+    def traversal_stats(self, origs, dirs, tfar=np.inf):
+        origs, dirs = _f32(origs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        a, b = C.c_double(), C.c_double()
+        _chk(load_library().b2_mesh_intersect_stats(self._h, _p(origs), _p(dirs), C.c_uint32(len(origs)), C.c_float(tfar), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class RCCB200:
+    """Ray-casting correspondences on the B200: the Correspondences_<VRAM_CUDA> interface
+    (rmcl/include/rmcl/registration/Correspondences.hpp:16-88) + the fused drivers."""
+
+    def __init__(self, map_: Map):
+        self.map = map_
+        h = C.c_void_p()
+        _chk(load_library().b2_rcc_create(map_._h, C.byref(h)))
+        self._h = h
+        self.n = 0
+        self.outdated = True                       # Correspondences.hpp:31
+        self.max_dist = 1.0                        # params.max_dist, :22
+        self.adaptive_max_dist_min = 0.15          # :23
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().b2_rcc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setStream(self, cuda_stream):
+        _chk(load_library().b2_rcc_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def enableTiming(self, on=True):
+        _chk(load_library().b2_rcc_enable_timing(self._h, C.c_int(int(on))))
+
+    def lastTiming(self):
+        """(find_ms, reduce_ms) of the most recent correctOnce, from CUDA events recorded on the handle's stream."""
+        a, b = C.c_float(), C.c_float()
+        _chk(load_library().b2_rcc_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def setTsb(self, Tsb):                         # Correspondences.hpp:33-36
+        _chk(load_library().b2_rcc_set_tsb(self._h, _p(_tf(Tsb))))
+
+    def setParams(self, max_dist, adaptive_max_dist_min):
+        self.max_dist, self.adaptive_max_dist_min = float(max_dist), float(adaptive_max_dist_min)
+        _chk(load_library().b2_rcc_set_params(self._h, C.c_float(max_dist), C.c_float(adaptive_max_dist_min)))
+
+    def setModel(self, m):                         # ModelSetter<ModelT>::setModel (RCCEmbree.cpp:21-24 ...)
+        lib = load_library()
+        name = type(m).__name__
+        if name == "SphericalModel":
+            sm = _SphericalModel(m.phi_min, m.phi_inc, m.phi_size, m.theta_min, m.theta_inc, m.theta_size, m.range_min, m.range_max)
+            _chk(lib.b2_rcc_set_model_spherical(self._h, C.byref(sm)))
+        elif name == "PinholeModel":
+            pm = _PinholeModel(m.width, m.height, m.fx, m.fy, m.cx, m.cy, m.range_min, m.range_max)
+            _chk(lib.b2_rcc_set_model_pinhole(self._h, C.byref(pm)))
+        elif name == "O1DnModel":
+            o, d = _f32(m.orig).reshape(3), _f32(m.dirs).reshape(-1, 3)
+            _chk(lib.b2_rcc_set_model_o1dn(self._h, C.c_uint32(m.width), C.c_uint32(m.height), _p(o), _p(d), C.c_float(m.range_min), C.c_float(m.range_max)))
+        elif name == "OnDnModel":
+            o, d = _f32(m.origs).reshape(-1, 3), _f32(m.dirs).reshape(-1, 3)
+            _chk(lib.b2_rcc_set_model_ondn(self._h, C.c_uint32(m.width), C.c_uint32(m.height), _p(o), _p(d), C.c_float(m.range_min), C.c_float(m.range_max)))
+        else:
+            raise TypeError(name)
+        self.model = m
+        self.n = m.size
+
+    def setDataset(self, points, mask=None):       # public field `dataset`, Correspondences.hpp:24
+        if hasattr(points, "data_ptr"):
+            n = points.numel() // 3
+            _chk(load_library().b2_rcc_set_dataset(self._h, _devptr(points), _devptr(mask), C.c_uint32(n), C.c_int(1)))
+        else:
+            points = _f32(points).reshape(-1, 3)
+            mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+            _chk(load_library().b2_rcc_set_dataset(self._h, _p(points), _p(mask), C.c_uint32(len(points)), C.c_int(0)))
+        self.outdated = True
+
+    def setRanges(self, ranges):                   # MICP..Sensor..::unpackMessage / v1 setInputData
+        if hasattr(ranges, "data_ptr"):
+            _chk(load_library().b2_rcc_set_ranges(self._h, _devptr(ranges), C.c_uint32(ranges.numel()), C.c_int(1)))
+        else:
+            ranges = _f32(ranges).reshape(-1)
+            _chk(load_library().b2_rcc_set_ranges(self._h, _p(ranges), C.c_uint32(len(ranges)), C.c_int(0)))
+        self.outdated = True
+
+    setInputData = setRanges
+
+    def find(self, Tbm_est):                       # RCCEmbree.cpp:26-36
+        _chk(load_library().b2_rcc_find(self._h, _p(_tf(Tbm_est))))
+        self.outdated = False
+
+    def computeCrossStatistics(self, T_snew_sold, convergence_progress=0.0):   # CorrespondencesCPU.cpp:10-39
+        out = np.zeros((), CROSS_STATS_DTYPE)
+        _chk(load_library().b2_rcc_cross_statistics(self._h, _p(_tf(T_snew_sold)), C.c_double(convergence_progress), _p(out)))
+        return out
+
+    def modelView(self):                           # Correspondences.hpp:47-54 (host copies)
+        n = self.n
+        out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
+                   face_ids=np.empty(n, np.uint32), ranges=np.empty(n, np.float32))
+        _chk(load_library().b2_rcc_download_model(self._h, _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"])))
+        return out
+
+    def datasetView(self):                         # Correspondences.hpp:56-62 (host copies)
+        p, m, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        _chk(load_library().b2_rcc_dataset_view(self._h, C.byref(p), C.byref(m), C.byref(n)))
+        out = dict(points=np.empty((n.value, 3), np.float32), mask=np.empty(n.value, np.uint8))
+        _chk(load_library().b2_rcc_download_dataset(self._h, _p(out["points"]), _p(out["mask"])))
+        return out
+
+    def correctOnce(self, Tom, Tbo, iterations=5, convergence_progress=0.0, ranges=None):
+        """MICPLocalizationNode::correctOnce for this sensor (micp_localization.cpp:899-984), fully on the device.
+        With `ranges` (host array) the scan upload is part of the call (end-to-end entry point)."""
+        Tn, Td, Cm = np.zeros((), TRANSFORM_DTYPE), np.zeros((), TRANSFORM_DTYPE), np.zeros((), CROSS_STATS_DTYPE)
+        lib = load_library()
+        if ranges is None:
+            _chk(lib.b2_rcc_correct_once(self._h, _p(_tf(Tom)), _p(_tf(Tbo)), C.c_uint32(iterations), C.c_double(convergence_progress), _p(Tn), _p(Td), _p(Cm)))
+        else:
+            if hasattr(ranges, "data_ptr"):       # pinned / pageable HOST torch tensor
+                rp, rn = C.c_void_p(ranges.data_ptr()), ranges.numel()
+            else:
+                ranges = _f32(ranges).reshape(-1)
+                rp, rn = _p(ranges), len(ranges)
+            _chk(lib.b2_rcc_correct_once_ranges(self._h, rp, C.c_uint32(rn), _p(_tf(Tom)), _p(_tf(Tbo)), C.c_uint32(iterations),
+                                                C.c_double(convergence_progress), _p(Tn), _p(Td), _p(Cm)))
+        self.outdated = False
+        return Tn, Td, Cm
+
+    def correct(self, Tbm):
+        """v1 {Sphere,Pinhole,O1Dn}Corrector::correct(Tbm[N]) -> (Tdelta[N], Ncorr[N], stats_b[N])
+        (rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:127-133)."""
+        lib = load_library()
+        if hasattr(Tbm, "data_ptr"):
+            import torch
+            n = Tbm.numel() * Tbm.element_size() // 32
+            Td = torch.empty((n, 8), dtype=torch.float32, device=Tbm.device)
+            nc = torch.empty((n,), dtype=torch.int32, device=Tbm.device)
+            st = torch.empty((n, 16), dtype=torch.float32, device=Tbm.device)
+            _chk(lib.b2_rcc_correct_batch(self._h, _devptr(Tbm), C.c_uint32(n), C.c_int(1), _devptr(Td), _devptr(nc), _devptr(st), C.c_int(1)))
+            return Td, nc, st
+        Tbm = _tf(Tbm).reshape(-1)
+        n = len(Tbm)
+        Td, nc, st = np.zeros(n, TRANSFORM_DTYPE), np.zeros(n, np.uint32), np.zeros(n, CROSS_STATS_DTYPE)
+        _chk(lib.b2_rcc_correct_batch(self._h, _p(Tbm), C.c_uint32(n), C.c_int(0), _p(Td), _p(nc), _p(st), C.c_int(0)))
+        return Td, nc, st
+
+
+class RCCB200Spherical(RCCB200):
+    """rmcl::RCCEmbreeSpherical / RCCOptixSpherical twin (rmcl/include/rmcl/registration/RCCEmbree.hpp:18-33)."""
+
+
+class RCCB200Pinhole(RCCB200):
+    """rmcl::RCCEmbreePinhole twin (RCCEmbree.hpp:35-49)."""
+
+
+class RCCB200O1Dn(RCCB200):
+    """rmcl::RCCEmbreeO1Dn twin (RCCEmbree.hpp:51-66)."""
+
+
+class RCCB200OnDn(RCCB200):
+    """rmcl::RCCEmbreeOnDn twin (RCCEmbree.hpp:68-83)."""
+
+
+# v1 names used by the legacy benchmarks (lidar_corrector_{embree,optix}_benchmark.cpp:86)
+SphereCorrectorB200 = RCCB200Spherical
+PinholeCorrectorB200 = RCCB200Pinhole
+O1DnCorrectorB200 = RCCB200O1Dn
+OnDnCorrectorB200 = RCCB200OnDn
+
+
+def umeyama_transform(stats, device=0):
+    """rm::umeyama_transform for an array of CrossStatistics (micp_localization.cpp:952-953)."""
+    stats = np.ascontiguousarray(stats).reshape(-1)
+    out = np.zeros(len(stats), TRANSFORM_DTYPE)
+    _chk(load_library().b2_umeyama_batch(_p(stats), C.c_uint32(len(stats)), _p(out), C.c_int(0), C.c_int(device), None))
+    return out
+
+
+class PCDSensorUpdaterB200:
+    """Particle-filter sensor update: ParticleUpdater<MemT>::update (rmcl_ros/include/rmcl_ros/rmcl/ParticleUpdater.hpp:39-43) with the
+    hot loop of PCDSensorUpdaterEmbree::update (PCDSensorUpdaterEmbree.cpp:290-342).  Beams are an input (quirk D5)."""
+
+    def __init__(self, map_: Map):
+        self.map = map_
+        h = C.c_void_p()
+        _chk(load_library().b2_pf_create(map_._h, C.byref(h)))
+        self._h = h
+        self.config = PFParams.defaults()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().b2_pf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setStream(self, cuda_stream):
+        _chk(load_library().b2_pf_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def update(self, particle_poses, particle_attrs, Tsb, beams, params: PFParams | None = None):
+        """RAM variant: numpy arrays in, updated attrs array out.  VRAM variant: torch CUDA tensors, attrs updated in place."""
+        prm = params or self.config
+        beams = np.ascontiguousarray(beams)
+        assert beams.dtype.itemsize == 64
+        Tsb = _tf(Tsb)
+        lib = load_library()
+        if hasattr(particle_poses, "data_ptr"):
+            n = particle_poses.numel() * particle_poses.element_size() // 32
+            _chk(lib.b2_pf_sensor_update(self._h, _devptr(particle_poses), _devptr(particle_attrs), C.c_uint32(n), _p(Tsb), _p(beams),
+                                         C.c_uint32(len(beams)), C.byref(prm)))
+            return particle_attrs
+        poses = _tf(particle_poses).reshape(-1)
+        attrs = np.ascontiguousarray(particle_attrs).copy()
+        assert attrs.dtype.itemsize == 36
+        _chk(lib.b2_pf_sensor_update_host(self._h, _p(poses), _p(attrs), C.c_uint32(len(poses)), _p(Tsb), _p(beams), C.c_uint32(len(beams)), C.byref(prm)))
+        return attrs

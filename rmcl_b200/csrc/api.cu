@@ -1,0 +1,648 @@
+// api.cu -- C ABI (include/rmcl_b200.h) over the sm_100a kernels.  No CPU fallback anywhere: every entry point either runs
+// the CUDA path or fails with B2_ERR_CUDA.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(B2_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NOTNULL(p) do { if (!(p)) return fail(B2_ERR_INVALID, "%s: null argument '%s'", __func__, #p); } while (0)
+
+extern "C" const char* b2_last_error(void) { return g_err; }
+extern "C" int b2_version(void) { return 100; }
+extern "C" uint64_t b2_kernel_launch_count(void) { return g_launches.load(); }
+extern "C" int b2_device_count(int* n) { NOTNULL(n); CU(cudaGetDeviceCount(n)); return B2_OK; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct b2_mesh {
+    int device = 0; int build_mode = 0;
+    B2Node8* d_nodes = nullptr; B2Tri* d_tris = nullptr;
+    uint32_t n_nodes = 0, n_tris = 0, n_faces = 0, n_verts = 0, max_depth = 0;
+    float build_ms = 0.f, sah = 0.f;
+    BvhView view() const { BvhView v; v.nodes = reinterpret_cast<const uint4*>(d_nodes); v.tris = reinterpret_cast<const float4*>(d_tris); return v; }
+};
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return B2_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, sizeof(T) * n);
+        if (e != cudaSuccess) return fail(B2_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", sizeof(T) * n, cudaGetErrorString(e));
+        cap = n; return B2_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+#define RES(call) do { int r_ = (call); if (r_ != B2_OK) return r_; } while (0)
+
+extern "C" int b2_mesh_create(const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf, int device, int build_mode, b2_mesh** out)
+{
+    NOTNULL(out); *out = nullptr;
+    if (nf == 0 || nv == 0) return fail(B2_ERR_NO_MAP, "EMPTY MAP: %u vertices, %u faces", nv, nf);
+    NOTNULL(verts); NOTNULL(faces);
+    if (build_mode != B2_BUILD_HOST_SAH) return fail(B2_ERR_UNSUPPORTED, "build_mode %d not available in this build", build_mode);
+    int ndev = 0; CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    const auto t0 = std::chrono::steady_clock::now();
+    B2BvhHost hb; const char* err = "";
+    const int rc = b2_build_bvh8_host(verts, nv, faces, nf, &hb, &err);
+    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : (rc == -4 ? B2_ERR_OOM : B2_ERR_INVALID), "BVH build failed: %s", err);
+    b2_mesh* m = new (std::nothrow) b2_mesh();
+    if (!m) { b2_free_bvh8_host(&hb); return fail(B2_ERR_OOM, "out of host memory"); }
+    m->device = device; m->build_mode = build_mode; m->n_nodes = hb.n_nodes; m->n_tris = hb.n_tris; m->n_faces = nf; m->n_verts = nv;
+    m->max_depth = hb.max_depth; m->sah = hb.sah_cost;
+    cudaError_t e = cudaMalloc((void**)&m->d_nodes, sizeof(B2Node8) * (size_t)hb.n_nodes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_tris, sizeof(B2Tri) * (size_t)std::max(hb.n_tris, 1u));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_nodes, hb.nodes, sizeof(B2Node8) * (size_t)hb.n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_tris, hb.tris, sizeof(B2Tri) * (size_t)hb.n_tris, cudaMemcpyHostToDevice);
+    b2_free_bvh8_host(&hb);
+    if (e != cudaSuccess) { if (m->d_nodes) cudaFree(m->d_nodes); if (m->d_tris) cudaFree(m->d_tris); delete m; return fail(B2_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e)); }
+    m->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = m;
+    return B2_OK;
+}
+
+extern "C" int b2_mesh_destroy(b2_mesh* m)
+{
+    if (!m) return B2_OK;
+    cudaSetDevice(m->device);
+    if (m->d_nodes) cudaFree(m->d_nodes);
+    if (m->d_tris) cudaFree(m->d_tris);
+    delete m;
+    return B2_OK;
+}
+
+extern "C" int b2_mesh_get_info(const b2_mesh* m, b2_mesh_info* info)
+{
+    NOTNULL(m); NOTNULL(info);
+    info->n_faces = m->n_faces; info->n_vertices = m->n_verts; info->n_nodes = m->n_nodes; info->n_leaf_tris = m->n_tris; info->max_depth = m->max_depth;
+    info->bvh_bytes = (uint64_t)m->n_nodes * sizeof(B2Node8) + (uint64_t)m->n_tris * sizeof(B2Tri);
+    info->build_ms = m->build_ms; info->device = m->device; info->build_mode = m->build_mode; info->sah_cost = m->sah;
+    return B2_OK;
+}
+
+static int intersect_impl(const b2_mesh* m, const float* origs, const float* dirs, uint32_t n, float tfar,
+                          float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out, double* mean_nodes, double* mean_tris)
+{
+    NOTNULL(m);
+    if (n == 0) return B2_OK;
+    NOTNULL(origs); NOTNULL(dirs);
+    CU(cudaSetDevice(m->device));
+    DevBuf<float> d_o, d_d, d_t, d_ng; DevBuf<uint32_t> d_f; DevBuf<uint8_t> d_h; DevBuf<unsigned long long> d_c;
+    int rc = B2_OK;
+    auto cleanup = [&]() { d_o.release(); d_d.release(); d_t.release(); d_ng.release(); d_f.release(); d_h.release(); d_c.release(); };
+    if ((rc = d_o.reserve(3 * (size_t)n)) || (rc = d_d.reserve(3 * (size_t)n)) || (rc = d_t.reserve(n)) || (rc = d_ng.reserve(3 * (size_t)n)) ||
+        (rc = d_f.reserve(n)) || (rc = d_h.reserve(n)) || (rc = d_c.reserve(2))) { cleanup(); return rc; }
+    cudaError_t e = cudaMemcpy(d_o.p, origs, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_d.p, dirs, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_c.p, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        const uint32_t grid = (n + 127) / 128;
+        if (mean_nodes || mean_tris) k_intersect<true><<<grid, 128>>>(m->view(), d_o.p, d_d.p, n, tfar, d_t.p, d_f.p, d_ng.p, d_h.p, d_c.p);
+        else k_intersect<false><<<grid, 128>>>(m->view(), d_o.p, d_d.p, n, tfar, d_t.p, d_f.p, d_ng.p, d_h.p, d_c.p);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && t_out) e = cudaMemcpy(t_out, d_t.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && face_out) e = cudaMemcpy(face_out, d_f.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ng_out) e = cudaMemcpy(ng_out, d_ng.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && hit_out) e = cudaMemcpy(hit_out, d_h.p, n, cudaMemcpyDeviceToHost);
+    unsigned long long c[2] = {0, 0};
+    if (e == cudaSuccess && (mean_nodes || mean_tris)) e = cudaMemcpy(c, d_c.p, sizeof(c), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(B2_ERR_CUDA, "b2_mesh_intersect: %s", cudaGetErrorString(e));
+    if (mean_nodes) *mean_nodes = (double)c[0] / (double)n;
+    if (mean_tris) *mean_tris = (double)c[1] / (double)n;
+    return B2_OK;
+}
+
+extern "C" int b2_mesh_intersect(const b2_mesh* m, const float* origs, const float* dirs, uint32_t n, float tfar,
+                                 float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out)
+{
+    return intersect_impl(m, origs, dirs, n, tfar, t_out, face_out, ng_out, hit_out, nullptr, nullptr);
+}
+extern "C" int b2_mesh_intersect_stats(const b2_mesh* m, const float* origs, const float* dirs, uint32_t n, float tfar, double* mean_nodes, double* mean_tris)
+{
+    double a = 0, b = 0;
+    int rc = intersect_impl(m, origs, dirs, n, tfar, nullptr, nullptr, nullptr, nullptr, &a, &b);
+    if (rc == B2_OK) { if (mean_nodes) *mean_nodes = a; if (mean_tris) *mean_tris = b; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RCC handle
+// ---------------------------------------------------------------------------------------------------------------------
+struct HostPin {            // pinned staging for small results
+    b2_transform T[3]; b2_cross_stats S[2]; IcpState icp;
+};
+
+struct b2_rcc {
+    b2_mesh* map = nullptr; cudaStream_t stream = 0;
+    b2_transform Tsb{};
+    bool has_model = false; uint32_t n = 0, width = 0, height = 0, n_origs = 1; float range_min = 0.f, range_max = 0.f;
+    float max_dist = 1.0f, adaptive_max_dist_min = 0.15f;
+    DevBuf<float> d_dirs, d_origs;
+    DevBuf<float> d_dpts; DevBuf<uint8_t> d_dmask; uint32_t n_dataset = 0; DevBuf<float> d_ranges_in;
+    DevBuf<float> d_mpts, d_mnrm, d_mranges; DevBuf<uint8_t> d_mhits; DevBuf<uint32_t> d_mfaces; uint32_t n_model = 0; bool found = false;
+    DevBuf<double> d_partials; DevBuf<unsigned int> d_ticket; DevBuf<b2_cross_stats> d_stats; DevBuf<IcpState> d_icp;
+    DevBuf<b2_transform> d_poses, d_tdelta; DevBuf<uint32_t> d_ncorr; DevBuf<b2_cross_stats> d_bstats;
+    HostPin* pin = nullptr;
+    int red_grid = 0;
+    bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
+};
+
+static b2_transform tf_identity_pod() { b2_transform T; memset(&T, 0, sizeof(T)); T.R.w = 1.0f; return T; }
+
+extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
+{
+    NOTNULL(out); *out = nullptr;
+    if (!map) return fail(B2_ERR_NO_MAP, "NO MAP");
+    CU(cudaSetDevice(map->device));
+    b2_rcc* h = new (std::nothrow) b2_rcc();
+    if (!h) return fail(B2_ERR_OOM, "out of host memory");
+    h->map = map; h->Tsb = tf_identity_pod();
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, map->device));
+    h->red_grid = prop.multiProcessorCount;
+    int rc;
+    if ((rc = h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)) || (rc = h->d_ticket.reserve(1)) || (rc = h->d_stats.reserve(1)) || (rc = h->d_icp.reserve(1))) { delete h; return rc; }
+    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
+    CU(cudaMallocHost((void**)&h->pin, sizeof(HostPin)));
+    *out = h;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_destroy(b2_rcc* h)
+{
+    if (!h) return B2_OK;
+    cudaSetDevice(h->map->device);
+    cudaStreamSynchronize(h->stream);
+    h->d_dirs.release(); h->d_origs.release(); h->d_dpts.release(); h->d_dmask.release(); h->d_ranges_in.release();
+    h->d_mpts.release(); h->d_mnrm.release(); h->d_mranges.release(); h->d_mhits.release(); h->d_mfaces.release();
+    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release();
+    h->d_poses.release(); h->d_tdelta.release(); h->d_ncorr.release(); h->d_bstats.release();
+    if (h->pin) cudaFreeHost(h->pin);
+    for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_enable_timing(b2_rcc* h, int enable)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    if (enable) for (int i = 0; i < 3; i++) if (!h->ev[i]) CU(cudaEventCreate(&h->ev[i]));
+    h->timing = enable != 0; h->timing_valid = false;
+    return B2_OK;
+}
+extern "C" int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms)
+{
+    NOTNULL(h);
+    if (!h->timing || !h->timing_valid) return fail(B2_ERR_INVALID, "no timing recorded (b2_rcc_enable_timing + a correct_once call first)");
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaEventSynchronize(h->ev[2]));
+    float a = 0.f, b = 0.f;
+    CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1])); CU(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    if (find_ms) *find_ms = a; if (reduce_ms) *reduce_ms = b;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_stream(b2_rcc* h, void* s) { NOTNULL(h); h->stream = (cudaStream_t)s; return B2_OK; }
+extern "C" int b2_rcc_set_tsb(b2_rcc* h, const b2_transform* Tsb) { NOTNULL(h); NOTNULL(Tsb); h->Tsb = *Tsb; return B2_OK; }
+extern "C" int b2_rcc_set_params(b2_rcc* h, float max_dist, float amin) { NOTNULL(h); h->max_dist = max_dist; h->adaptive_max_dist_min = amin; return B2_OK; }
+
+// upload sensor-frame ray tables.  Direction tables are evaluated on the host with libm cosf/sinf exactly like
+// rmagine's SphericalModel::getDirection does on the CPU path (witness rmcl_ros/src/util/conversions.cpp:174-188), so the
+// rays are bit-identical to the reference's; this runs once per setModel, not per scan.
+static int set_model_tables(b2_rcc* h, uint32_t w, uint32_t hgt, const float* origs, uint32_t n_origs, const float* dirs, float rmin, float rmax)
+{
+    CU(cudaSetDevice(h->map->device));
+    const size_t n = (size_t)w * hgt;
+    if (n == 0) { h->has_model = true; h->n = 0; h->width = w; h->height = hgt; return B2_OK; }   // zero-size model: find() silently returns (RCCOptix.cpp:30-34)
+    if (n > 0xffffffffu / 4) return fail(B2_ERR_INVALID, "model too large");
+    RES(h->d_dirs.reserve(3 * n)); RES(h->d_origs.reserve(3 * (size_t)n_origs));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(h->d_dirs.p, dirs, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_origs.p, origs, sizeof(float) * 3 * (size_t)n_origs, cudaMemcpyHostToDevice));
+    h->has_model = true; h->n = (uint32_t)n; h->width = w; h->height = hgt; h->n_origs = n_origs; h->range_min = rmin; h->range_max = rmax;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_model_spherical(b2_rcc* h, const b2_spherical_model* m)
+{
+    NOTNULL(h); NOTNULL(m);
+    const size_t n = (size_t)m->phi_size * m->theta_size;
+    std::vector<float> dirs(3 * n);
+    for (uint32_t vid = 0; vid < m->phi_size; vid++) {
+        const float phi = m->phi_min + (float)vid * m->phi_inc;
+        const float cp = cosf(phi), sp = sinf(phi);
+        for (uint32_t hid = 0; hid < m->theta_size; hid++) {
+            const float theta = m->theta_min + (float)hid * m->theta_inc;
+            float* d = &dirs[3 * ((size_t)vid * m->theta_size + hid)];
+            d[0] = cp * cosf(theta); d[1] = cp * sinf(theta); d[2] = sp;
+        }
+    }
+    const float o[3] = {0.f, 0.f, 0.f};
+    return set_model_tables(h, m->theta_size, m->phi_size, o, 1, dirs.data(), m->range_min, m->range_max);
+}
+
+extern "C" int b2_rcc_set_model_pinhole(b2_rcc* h, const b2_pinhole_model* m)
+{
+    NOTNULL(h); NOTNULL(m);
+    const size_t n = (size_t)m->width * m->height;
+    std::vector<float> dirs(3 * n);
+    for (uint32_t vid = 0; vid < m->height; vid++)
+        for (uint32_t hid = 0; hid < m->width; hid++) {
+            const float px = ((float)hid - m->cx) / m->fx, py = ((float)vid - m->cy) / m->fy;
+            const float nrm = sqrtf(px * px + py * py + 1.0f * 1.0f);
+            const float ox = px / nrm, oy = py / nrm, oz = 1.0f / nrm;            // optical frame, normalised
+            float* d = &dirs[3 * ((size_t)vid * m->width + hid)];
+            d[0] = oz; d[1] = -ox; d[2] = -oy;                                     // x forward, y left, z up
+        }
+    const float o[3] = {0.f, 0.f, 0.f};
+    return set_model_tables(h, m->width, m->height, o, 1, dirs.data(), m->range_min, m->range_max);
+}
+
+extern "C" int b2_rcc_set_model_o1dn(b2_rcc* h, uint32_t w, uint32_t hgt, const float orig[3], const float* dirs, float rmin, float rmax)
+{
+    NOTNULL(h); if ((size_t)w * hgt) { NOTNULL(orig); NOTNULL(dirs); }
+    return set_model_tables(h, w, hgt, orig, 1, dirs, rmin, rmax);
+}
+extern "C" int b2_rcc_set_model_ondn(b2_rcc* h, uint32_t w, uint32_t hgt, const float* origs, const float* dirs, float rmin, float rmax)
+{
+    NOTNULL(h); if ((size_t)w * hgt) { NOTNULL(origs); NOTNULL(dirs); }
+    return set_model_tables(h, w, hgt, origs, (uint32_t)((size_t)w * hgt), dirs, rmin, rmax);
+}
+
+extern "C" int b2_rcc_set_dataset(b2_rcc* h, const float* pts, const uint8_t* mask, uint32_t n, int src_is_device)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    if (n) { NOTNULL(pts); }
+    RES(h->d_dpts.reserve(3 * (size_t)std::max(n, 1u))); RES(h->d_dmask.reserve(std::max(n, 1u)));
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n) {
+        CU(cudaMemcpyAsync(h->d_dpts.p, pts, sizeof(float) * 3 * (size_t)n, kind, h->stream));
+        if (mask) CU(cudaMemcpyAsync(h->d_dmask.p, mask, n, kind, h->stream));
+        else CU(cudaMemsetAsync(h->d_dmask.p, 1, n, h->stream));                  // empty mask == all valid (statistics_p2l semantics)
+        if (!src_is_device) CU(cudaStreamSynchronize(h->stream));                 // caller may reuse its buffers
+    }
+    h->n_dataset = n;
+    return B2_OK;
+}
+
+static int ranges_to_dataset(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device)
+{
+    if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
+    if (n != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n, h->n);
+    if (n == 0) { h->n_dataset = 0; return B2_OK; }
+    NOTNULL(ranges);
+    RES(h->d_dpts.reserve(3 * (size_t)n)); RES(h->d_dmask.reserve(n)); RES(h->d_ranges_in.reserve(n));
+    CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges, sizeof(float) * n, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    k_dataset_from_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, n, h->range_min, h->range_max, h->d_dpts.p, h->d_dmask.p);
+    LAUNCHED();
+    h->n_dataset = n;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    RES(ranges_to_dataset(h, ranges, n, src_is_device));
+    if (!src_is_device) CU(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+static int reserve_model(b2_rcc* h, size_t n)
+{
+    // buffers only ever grow (RCCEmbree.cpp:28-33)
+    RES(h->d_mpts.reserve(3 * n)); RES(h->d_mnrm.reserve(3 * n)); RES(h->d_mranges.reserve(n)); RES(h->d_mhits.reserve(n)); RES(h->d_mfaces.reserve(n));
+    return B2_OK;
+}
+
+static RayModel ray_model(const b2_rcc* h)
+{
+    RayModel m; m.dirs = h->d_dirs.p; m.origs = h->d_origs.p; m.n_origs = h->n_origs; m.n = h->n; m.range_min = h->range_min; m.range_max = h->range_max; return m;
+}
+static ModelBuffers model_buffers(const b2_rcc* h)
+{
+    ModelBuffers b; b.pts = h->d_mpts.p; b.nrm = h->d_mnrm.p; b.hits = h->d_mhits.p; b.faces = h->d_mfaces.p; b.ranges = h->d_mranges.p; return b;
+}
+
+static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* icp_dev)
+{
+    if (!h->has_model) return fail(B2_ERR_INVALID, "find before setModel");
+    if (h->n == 0) return B2_OK;
+    RES(reserve_model(h, h->n));
+    const uint32_t grid = (h->n + 127) / 128;
+    k_rcc_find<<<grid, 128, 0, h->stream>>>(h->map->view(), nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h));
+    LAUNCHED();
+    h->n_model = h->n; h->found = true;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_find(b2_rcc* h, const b2_transform* Tbm)
+{
+    NOTNULL(h); NOTNULL(Tbm);
+    CU(cudaSetDevice(h->map->device));
+    return launch_find(h, Tbm, nullptr);
+}
+
+static int launch_reduce(b2_rcc* h, const b2_transform* Tpre_host, float max_dist, IcpState* icp_dev, b2_cross_stats* out_dev)
+{
+    const uint32_t n = std::min(h->n_dataset, h->n_model);
+    int grid = (int)std::min<uint32_t>((uint32_t)h->red_grid, (n + B2_RED_BLOCK - 1) / B2_RED_BLOCK);
+    if (grid < 1) grid = 1;
+    k_p2l_reduce<<<grid, B2_RED_BLOCK, 0, h->stream>>>(h->d_dpts.p, h->d_dmask.p, h->d_mpts.p, h->d_mnrm.p, h->d_mhits.p, n,
+                                                       Tpre_host ? *Tpre_host : tf_identity_pod(), max_dist, icp_dev, h->d_partials.p, h->d_ticket.p, out_dev);
+    LAUNCHED();
+    return B2_OK;
+}
+
+static float adaptive_max_dist(const b2_rcc* h, double cp)
+{
+    // CorrespondencesCPU.cpp:21-23
+    return (float)(h->max_dist * (1.0 - cp) + h->adaptive_max_dist_min * cp);
+}
+
+extern "C" int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T, double cp, b2_cross_stats* out)
+{
+    NOTNULL(h); NOTNULL(T); NOTNULL(out);
+    CU(cudaSetDevice(h->map->device));
+    if (!h->found) return fail(B2_ERR_INVALID, "computeCrossStatistics before find");
+    if (h->n_dataset == 0) return fail(B2_ERR_INVALID, "computeCrossStatistics without a dataset");
+    RES(launch_reduce(h, T, adaptive_max_dist(h, cp), nullptr, h->d_stats.p));
+    CU(cudaMemcpyAsync(&h->pin->S[0], h->d_stats.p, sizeof(b2_cross_stats), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = h->pin->S[0];
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_model_view(b2_rcc* h, float** p, float** nr, uint8_t** hi, uint32_t** f, float** r, uint32_t* n)
+{
+    NOTNULL(h);
+    if (p) *p = h->d_mpts.p; if (nr) *nr = h->d_mnrm.p; if (hi) *hi = h->d_mhits.p; if (f) *f = h->d_mfaces.p; if (r) *r = h->d_mranges.p; if (n) *n = h->n_model;
+    return B2_OK;
+}
+extern "C" int b2_rcc_dataset_view(b2_rcc* h, float** p, uint8_t** m, uint32_t* n)
+{
+    NOTNULL(h);
+    if (p) *p = h->d_dpts.p; if (m) *m = h->d_dmask.p; if (n) *n = h->n_dataset;
+    return B2_OK;
+}
+extern "C" int b2_rcc_download_model(b2_rcc* h, float* p, float* nr, uint8_t* hi, uint32_t* f, float* r)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    const size_t n = h->n_model;
+    CU(cudaStreamSynchronize(h->stream));
+    if (n == 0) return B2_OK;
+    if (p) CU(cudaMemcpy(p, h->d_mpts.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (nr) CU(cudaMemcpy(nr, h->d_mnrm.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (hi) CU(cudaMemcpy(hi, h->d_mhits.p, n, cudaMemcpyDeviceToHost));
+    if (f) CU(cudaMemcpy(f, h->d_mfaces.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    if (r) CU(cudaMemcpy(r, h->d_mranges.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_rcc_download_dataset(b2_rcc* h, float* p, uint8_t* m)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    const size_t n = h->n_dataset;
+    CU(cudaStreamSynchronize(h->stream));
+    if (n == 0) return B2_OK;
+    if (p) CU(cudaMemcpy(p, h->d_dpts.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (m) CU(cudaMemcpy(m, h->d_dmask.p, n, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double cp,
+                             b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    if (!h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
+    if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
+    IcpState& st = h->pin->icp;
+    memset(&st, 0, sizeof(st));
+    st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = h->Tsb; st.max_dist = adaptive_max_dist(h, cp);
+    st.T_onew_oold = tf_identity_pod(); st.Tom_new = *Tom;
+    CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
+    k_icp_init<<<1, 32, 0, h->stream>>>(h->d_icp.p);
+    LAUNCHED();
+    if (h->n > 0) {
+        if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
+        RES(launch_find(h, nullptr, h->d_icp.p));
+        if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+        for (uint32_t it = 0; it < iterations; it++) RES(launch_reduce(h, nullptr, 0.f, h->d_icp.p, nullptr));
+        if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
+    }
+    CU(cudaMemcpyAsync(&st, h->d_icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (Tom_new) *Tom_new = st.Tom_new;
+    if (T_onew_oold) *T_onew_oold = st.T_onew_oold;
+    if (Cmerged) *Cmerged = st.Cmerged_o;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_correct_once(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double cp,
+                                   b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
+    CU(cudaSetDevice(h->map->device));
+    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged);
+}
+
+extern "C" int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges, uint32_t n, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations,
+                                          double cp, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
+    CU(cudaSetDevice(h->map->device));
+    RES(ranges_to_dataset(h, ranges, n, 0));
+    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged);
+}
+
+extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t n_poses, int poses_on_device,
+                                    b2_transform* Tdelta, uint32_t* ncorr, b2_cross_stats* stats_b, int out_on_device)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    if (!h->has_model) return fail(B2_ERR_INVALID, "correct before setModel");
+    if (n_poses == 0 || h->n == 0) return B2_OK;
+    NOTNULL(Tbm);
+    if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "correct before setInputData (dataset %u != model %u)", h->n_dataset, h->n);
+    const b2_transform* poses_dev = Tbm;
+    if (!poses_on_device) {
+        RES(h->d_poses.reserve(n_poses));
+        CU(cudaMemcpyAsync(h->d_poses.p, Tbm, sizeof(b2_transform) * (size_t)n_poses, cudaMemcpyHostToDevice, h->stream));
+        poses_dev = h->d_poses.p;
+    }
+    const uint32_t rays_per_block = B2_FUSED_BLOCK * 8;
+    const uint32_t bpp = (h->n + rays_per_block - 1) / rays_per_block;
+    const uint64_t grid = (uint64_t)bpp * n_poses;
+    if (grid > 0x7fffffffull) return fail(B2_ERR_INVALID, "too many poses");
+    RES(h->d_partials.reserve((size_t)std::max<uint64_t>(grid, (uint64_t)h->red_grid) * (B2_NACC + 1)));
+    k_rcc_fused_batch<<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
+                                                                       bpp, rays_per_block, h->d_partials.p);
+    LAUNCHED();
+    b2_transform* td = Tdelta; uint32_t* nc = ncorr; b2_cross_stats* sb = stats_b;
+    if (!out_on_device) {
+        RES(h->d_tdelta.reserve(n_poses)); RES(h->d_ncorr.reserve(n_poses)); RES(h->d_bstats.reserve(n_poses));
+        td = h->d_tdelta.p; nc = h->d_ncorr.p; sb = h->d_bstats.p;
+    }
+    k_umeyama_from_partials<<<(n_poses + 63) / 64, 64, 0, h->stream>>>(h->d_partials.p, bpp, n_poses, h->Tsb, td, nc, sb);
+    LAUNCHED();
+    if (!out_on_device) {
+        if (Tdelta) CU(cudaMemcpyAsync(Tdelta, td, sizeof(b2_transform) * (size_t)n_poses, cudaMemcpyDeviceToHost, h->stream));
+        if (ncorr) CU(cudaMemcpyAsync(ncorr, nc, sizeof(uint32_t) * (size_t)n_poses, cudaMemcpyDeviceToHost, h->stream));
+        if (stats_b) CU(cudaMemcpyAsync(stats_b, sb, sizeof(b2_cross_stats) * (size_t)n_poses, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return B2_OK;
+}
+
+extern "C" int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_transform* out, int on_device, int device, void* stream_)
+{
+    if (n == 0) return B2_OK;
+    NOTNULL(stats); NOTNULL(out);
+    CU(cudaSetDevice(device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (on_device) {
+        k_umeyama_batch<<<(n + 63) / 64, 64, 0, stream>>>(stats, n, out);
+        LAUNCHED();
+        return B2_OK;
+    }
+    DevBuf<b2_cross_stats> ds; DevBuf<b2_transform> dt;
+    int rc;
+    if ((rc = ds.reserve(n)) || (rc = dt.reserve(n))) { ds.release(); dt.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(ds.p, stats, sizeof(b2_cross_stats) * (size_t)n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) { k_umeyama_batch<<<(n + 63) / 64, 64, 0, stream>>>(ds.p, n, dt.p); g_launches.fetch_add(1); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dt.p, sizeof(b2_transform) * (size_t)n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    ds.release(); dt.release();
+    if (e != cudaSuccess) return fail(B2_ERR_CUDA, "b2_umeyama_batch: %s", cudaGetErrorString(e));
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// particle filter
+// ---------------------------------------------------------------------------------------------------------------------
+struct b2_pf {
+    b2_mesh* map = nullptr; cudaStream_t stream = 0;
+    DevBuf<PfBeam> d_beams; PfBeam* h_beams = nullptr; size_t h_beams_cap = 0;
+    DevBuf<b2_transform> d_poses; DevBuf<b2_particle_attr> d_attrs;
+    int smem_optin = 0;
+};
+
+extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
+{
+    NOTNULL(out); *out = nullptr;
+    if (!map) return fail(B2_ERR_NO_MAP, "NO MAP");
+    CU(cudaSetDevice(map->device));
+    b2_pf* h = new (std::nothrow) b2_pf();
+    if (!h) return fail(B2_ERR_OOM, "out of host memory");
+    h->map = map;
+    CU(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device));
+    CU(cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    *out = h;
+    return B2_OK;
+}
+extern "C" int b2_pf_destroy(b2_pf* h)
+{
+    if (!h) return B2_OK;
+    cudaSetDevice(h->map->device);
+    cudaStreamSynchronize(h->stream);
+    h->d_beams.release(); h->d_poses.release(); h->d_attrs.release();
+    if (h->h_beams) cudaFreeHost(h->h_beams);
+    delete h;
+    return B2_OK;
+}
+extern "C" int b2_pf_set_stream(b2_pf* h, void* s) { NOTNULL(h); h->stream = (cudaStream_t)s; return B2_OK; }
+
+static uint32_t dir_sort_key(const b2_range_meas& m)
+{
+    // Morton code of the direction on a 1024^3 lattice: neighbouring beams end up in the same warp (coherent traversal)
+    auto q = [](float v) { int i = (int)((v * 0.5f + 0.5f) * 1023.0f); return (uint32_t)std::min(std::max(i, 0), 1023); };
+    auto spread = [](uint32_t x) { x &= 0x3ff; x = (x | (x << 16)) & 0x30000ff; x = (x | (x << 8)) & 0x300f00f; x = (x | (x << 4)) & 0x30c30c3; x = (x | (x << 2)) & 0x9249249; return x; };
+    return spread(q(m.dir.x)) | (spread(q(m.dir.y)) << 1) | (spread(q(m.dir.z)) << 2);
+}
+
+static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,
+                          const b2_range_meas* beams, uint32_t n_beams, const b2_pf_params* prm)
+{
+    if (n == 0 || n_beams == 0) return B2_OK;
+    // beams: host -> compact, direction-sorted device table (merge order preserved through PfBeam::slot)
+    if (h->h_beams_cap < n_beams) {
+        if (h->h_beams) cudaFreeHost(h->h_beams);
+        h->h_beams = nullptr; h->h_beams_cap = 0;
+        CU(cudaMallocHost((void**)&h->h_beams, sizeof(PfBeam) * (size_t)n_beams));
+        h->h_beams_cap = n_beams;
+    }
+    RES(h->d_beams.reserve(n_beams));
+    CU(cudaStreamSynchronize(h->stream));                 // previous launch may still read the staging buffer's device copy
+    std::vector<std::pair<uint32_t, uint32_t>> order(n_beams);
+    for (uint32_t i = 0; i < n_beams; i++) order[i] = {dir_sort_key(beams[i]), i};
+    std::sort(order.begin(), order.end());
+    for (uint32_t j = 0; j < n_beams; j++) {
+        const b2_range_meas& m = beams[order[j].second];
+        PfBeam& b = h->h_beams[j];
+        b.ox = m.orig.x; b.oy = m.orig.y; b.oz = m.orig.z; b.dx = m.dir.x; b.dy = m.dir.y; b.dz = m.dir.z; b.range = m.range; b.slot = order[j].second;
+    }
+    CU(cudaMemcpyAsync(h->d_beams.p, h->h_beams, sizeof(PfBeam) * (size_t)n_beams, cudaMemcpyHostToDevice, h->stream));
+    // particles per block: as many as fit the shared-memory evaluation tile, capped so that a block still has enough rays
+    const size_t bytes_per_particle = sizeof(float) * (size_t)n_beams;
+    if (bytes_per_particle > (size_t)h->smem_optin) return fail(B2_ERR_UNSUPPORTED, "too many beams per update (%u)", n_beams);
+    uint32_t ppb = (uint32_t)std::min<size_t>((size_t)h->smem_optin / bytes_per_particle, 64);
+    const uint32_t want = std::max(1u, (B2_PF_BLOCK * 8 + n_beams - 1) / n_beams);       // ~8 rays per thread
+    ppb = std::max(1u, std::min(ppb, want));
+    ppb = std::min(ppb, (uint32_t)B2_PF_BLOCK);
+    const uint32_t grid = (n + ppb - 1) / ppb;
+    k_pf_update<<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    LAUNCHED();
+    return B2_OK;
+}
+
+extern "C" int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,
+                                   const b2_range_meas* beams, uint32_t n_beams, const b2_pf_params* prm)
+{
+    NOTNULL(h); NOTNULL(Tsb); NOTNULL(prm);
+    if (n) { NOTNULL(poses_dev); NOTNULL(attrs_dev); }
+    if (n_beams) NOTNULL(beams);
+    CU(cudaSetDevice(h->map->device));
+    return pf_update_impl(h, poses_dev, attrs_dev, n, Tsb, beams, n_beams, prm);
+}
+
+extern "C" int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses, b2_particle_attr* attrs, uint32_t n, const b2_transform* Tsb,
+                                        const b2_range_meas* beams, uint32_t n_beams, const b2_pf_params* prm)
+{
+    NOTNULL(h); NOTNULL(Tsb); NOTNULL(prm);
+    if (n == 0) return B2_OK;
+    NOTNULL(poses); NOTNULL(attrs);
+    if (n_beams) NOTNULL(beams);
+    CU(cudaSetDevice(h->map->device));
+    RES(h->d_poses.reserve(n)); RES(h->d_attrs.reserve(n));
+    CU(cudaMemcpyAsync(h->d_poses.p, poses, sizeof(b2_transform) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_attrs.p, attrs, sizeof(b2_particle_attr) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    RES(pf_update_impl(h, h->d_poses.p, h->d_attrs.p, n, Tsb, beams, n_beams, prm));
+    CU(cudaMemcpyAsync(attrs, h->d_attrs.p, sizeof(b2_particle_attr) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}

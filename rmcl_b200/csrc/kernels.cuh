@@ -1,0 +1,584 @@
+// kernels.cuh -- CUDA kernels of the ray-casting-correspondence path (sm_100a).  Compiled with -fmad=false: every FMA is explicit.
+#pragma once
+#include "trace.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device-side CrossStatistics helpers (mirror oracle/oracle.c op for op; tolerance-level parity is all that is required,
+// but identical order keeps whole ICP chains bit-identical in practice)
+// ---------------------------------------------------------------------------------------------------------------------
+struct CStats { V3 dm, mm; float C[9]; uint32_t n; };     // C column-major [c*3+r]
+
+B2_DEV CStats cs_identity() { CStats s; s.dm = mk3(0, 0, 0); s.mm = mk3(0, 0, 0); for (int i = 0; i < 9; i++) s.C[i] = 0.f; s.n = 0; return s; }
+B2_DEV CStats cs_load(const b2_cross_stats* p)
+{
+    CStats s; s.dm = mk3(p->dataset_mean.x, p->dataset_mean.y, p->dataset_mean.z); s.mm = mk3(p->model_mean.x, p->model_mean.y, p->model_mean.z);
+    for (int i = 0; i < 9; i++) s.C[i] = p->covariance.m[i]; s.n = p->n_meas; return s;
+}
+B2_DEV void cs_store(b2_cross_stats* p, const CStats& s)
+{
+    p->dataset_mean.x = s.dm.x; p->dataset_mean.y = s.dm.y; p->dataset_mean.z = s.dm.z;
+    p->model_mean.x = s.mm.x; p->model_mean.y = s.mm.y; p->model_mean.z = s.mm.z;
+    for (int i = 0; i < 9; i++) p->covariance.m[i] = s.C[i]; p->n_meas = s.n;
+}
+// rm::CrossStatistics::operator+= (oracle: orc_cross_stats_merge)
+B2_DEV CStats cs_merge(const CStats& a, const CStats& b)
+{
+    CStats r;
+    const uint32_t n = a.n + b.n;
+    if (n == 0) return cs_identity();
+    const float w1 = dvd((float)a.n, (float)n), w2 = dvd((float)b.n, (float)n);
+    r.n = n;
+    r.dm = v_add(v_scale(a.dm, w1), v_scale(b.dm, w2));
+    r.mm = v_add(v_scale(a.mm, w1), v_scale(b.mm, w2));
+    const V3 ma = v_sub(a.mm, r.mm), da = v_sub(a.dm, r.dm), mb = v_sub(b.mm, r.mm), db = v_sub(b.dm, r.dm);
+    const float mav[3] = {ma.x, ma.y, ma.z}, dav[3] = {da.x, da.y, da.z}, mbv[3] = {mb.x, mb.y, mb.z}, dbv[3] = {db.x, db.y, db.z};
+    #pragma unroll
+    for (int c = 0; c < 3; c++)
+        #pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            const float p1 = add(mul(a.C[c * 3 + rr], w1), mul(b.C[c * 3 + rr], w2));
+            const float p2 = add(mul(mul(mav[rr], dav[c]), w1), mul(mul(mbv[rr], dbv[c]), w2));
+            r.C[c * 3 + rr] = add(p1, p2);
+        }
+    return r;
+}
+// Transform * CrossStatistics (oracle: orc_cross_stats_transform)
+B2_DEV CStats cs_transform(Tf T, const CStats& s)
+{
+    CStats r; r.n = s.n; r.dm = tf_apply(T, s.dm); r.mm = tf_apply(T, s.mm);
+    const float x = T.R.x, y = T.R.y, z = T.R.z, w = T.R.w;
+    float R[3][3];
+    R[0][0] = sub(1.0f, mul(2.0f, add(mul(y, y), mul(z, z)))); R[0][1] = mul(2.0f, sub(mul(x, y), mul(z, w))); R[0][2] = mul(2.0f, add(mul(x, z), mul(y, w)));
+    R[1][0] = mul(2.0f, add(mul(x, y), mul(z, w))); R[1][1] = sub(1.0f, mul(2.0f, add(mul(x, x), mul(z, z)))); R[1][2] = mul(2.0f, sub(mul(y, z), mul(x, w)));
+    R[2][0] = mul(2.0f, sub(mul(x, z), mul(y, w))); R[2][1] = mul(2.0f, add(mul(y, z), mul(x, w))); R[2][2] = sub(1.0f, mul(2.0f, add(mul(x, x), mul(y, y))));
+    float RC[3][3];
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) { float acc = 0.0f; for (int k = 0; k < 3; k++) acc = add(acc, mul(R[i][k], s.C[j * 3 + k])); RC[i][j] = acc; }
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) { float acc = 0.0f; for (int k = 0; k < 3; k++) acc = add(acc, mul(RC[i][k], R[j][k])); r.C[j * 3 + i] = acc; }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rm::umeyama_transform (micp_localization.cpp:952-953): 3x3 SVD in double, same algorithm / order as oracle svd3()
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV double det3d(const double A[3][3])
+{
+    return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0])
+         + A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+}
+
+__host__ __device__ __noinline__ void svd3_dev(const double A[3][3], double U[3][3], double w[3], double V[3][3])
+{
+    double B[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { B[i][j] = A[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0;
+        for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+            double alpha = 0, beta = 0, gamma = 0;
+            for (int i = 0; i < 3; i++) { alpha += B[i][p] * B[i][p]; beta += B[i][q] * B[i][q]; gamma += B[i][p] * B[i][q]; }
+            if (gamma == 0.0) continue;
+            const double lim = 1e-30 + 1e-16 * sqrt(alpha * beta);
+            if (fabs(gamma) <= lim) continue;
+            off += fabs(gamma);
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            for (int i = 0; i < 3; i++) {
+                const double bp = B[i][p], bq = B[i][q]; B[i][p] = c * bp - sn * bq; B[i][q] = sn * bp + c * bq;
+                const double vp = V[i][p], vq = V[i][q]; V[i][p] = c * vp - sn * vq; V[i][q] = sn * vp + c * vq;
+            }
+        }
+        if (off == 0.0) break;
+    }
+    int idx[3] = {0, 1, 2}; double nrm[3];
+    for (int j = 0; j < 3; j++) nrm[j] = sqrt(B[0][j] * B[0][j] + B[1][j] * B[1][j] + B[2][j] * B[2][j]);
+    for (int a = 0; a < 2; a++) for (int b = a + 1; b < 3; b++) if (nrm[idx[b]] > nrm[idx[a]]) { int t = idx[a]; idx[a] = idx[b]; idx[b] = t; }
+    double Vs[3][3], Bs[3][3];
+    for (int j = 0; j < 3; j++) { w[j] = nrm[idx[j]]; for (int i = 0; i < 3; i++) { Vs[i][j] = V[i][idx[j]]; Bs[i][j] = B[i][idx[j]]; } }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = Vs[i][j];
+    const double tiny = 1e-12 * (w[0] > 0 ? w[0] : 1.0);
+    bool good[3];
+    for (int j = 0; j < 3; j++) {
+        good[j] = w[j] > tiny;
+        if (good[j]) for (int i = 0; i < 3; i++) U[i][j] = Bs[i][j] / w[j];
+    }
+    if (!good[0]) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) U[i][j] = (i == j) ? 1.0 : 0.0; return; }
+    if (!good[1]) {
+        const double a[3] = {U[0][0], U[1][0], U[2][0]};
+        const int k = fabs(a[0]) < fabs(a[1]) ? (fabs(a[0]) < fabs(a[2]) ? 0 : 2) : (fabs(a[1]) < fabs(a[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[k] = 1.0;
+        const double b[3] = {a[1] * e[2] - a[2] * e[1], a[2] * e[0] - a[0] * e[2], a[0] * e[1] - a[1] * e[0]};
+        const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+        for (int i = 0; i < 3; i++) U[i][1] = b[i] / nb;
+    }
+    if (!good[2] || !good[1]) {
+        const double c[3] = {U[1][0] * U[2][1] - U[2][0] * U[1][1], U[2][0] * U[0][1] - U[0][0] * U[2][1], U[0][0] * U[1][1] - U[1][0] * U[0][1]};
+        const double sgn = det3d(V) < 0 ? -1.0 : 1.0;
+        for (int i = 0; i < 3; i++) U[i][2] = sgn * c[i];
+    }
+}
+
+__host__ __device__ __noinline__ Tf umeyama_dev(const CStats& s)
+{
+    Tf out = tf_identity();
+    if (s.n == 0) return out;
+    double C[3][3], U[3][3], V[3][3], w[3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r][c] = (double)s.C[c * 3 + r];
+    svd3_dev(C, U, w, V);
+    const double sgn = (det3d(U) * det3d(V) < 0.0) ? -1.0 : 1.0;
+    double R[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
+    double q[4];
+    const double tr = R[0][0] + R[1][1] + R[2][2];
+    if (tr > 0.0) {
+        const double sc = sqrt(tr + 1.0) * 2.0; q[3] = 0.25 * sc;
+        q[0] = (R[2][1] - R[1][2]) / sc; q[1] = (R[0][2] - R[2][0]) / sc; q[2] = (R[1][0] - R[0][1]) / sc;
+    } else if (R[0][0] > R[1][1] && R[0][0] > R[2][2]) {
+        const double sc = sqrt(1.0 + R[0][0] - R[1][1] - R[2][2]) * 2.0; q[3] = (R[2][1] - R[1][2]) / sc;
+        q[0] = 0.25 * sc; q[1] = (R[0][1] + R[1][0]) / sc; q[2] = (R[0][2] + R[2][0]) / sc;
+    } else if (R[1][1] > R[2][2]) {
+        const double sc = sqrt(1.0 + R[1][1] - R[0][0] - R[2][2]) * 2.0; q[3] = (R[0][2] - R[2][0]) / sc;
+        q[0] = (R[0][1] + R[1][0]) / sc; q[1] = 0.25 * sc; q[2] = (R[1][2] + R[2][1]) / sc;
+    } else {
+        const double sc = sqrt(1.0 + R[2][2] - R[0][0] - R[1][1]) * 2.0; q[3] = (R[1][0] - R[0][1]) / sc;
+        q[0] = (R[0][2] + R[2][0]) / sc; q[1] = (R[1][2] + R[2][1]) / sc; q[2] = 0.25 * sc;
+    }
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    out.R.x = (float)(q[0] / n); out.R.y = (float)(q[1] / n); out.R.z = (float)(q[2] / n); out.R.w = (float)(q[3] / n);
+    out.t = v_sub(s.mm, q_rot(out.R, s.dm));
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// P2L accumulation (rm::statistics_p2l, called at CorrespondencesCPU.cpp:26-30): FP32 per-element math identical to the oracle
+// (=> identical gating, identical n_meas), sums in FP64 "sum form": n, S_d, S_m, S_{m d^T}
+// ---------------------------------------------------------------------------------------------------------------------
+#define B2_NACC 15
+struct P2LAcc { double v[B2_NACC]; uint32_t n; };
+
+B2_DEV void acc_zero(P2LAcc& a) { for (int i = 0; i < B2_NACC; i++) a.v[i] = 0.0; a.n = 0; }
+B2_DEV void acc_add_pair(P2LAcc& a, V3 D, V3 M)
+{
+    const double d[3] = {(double)D.x, (double)D.y, (double)D.z}, m[3] = {(double)M.x, (double)M.y, (double)M.z};
+    a.v[0] += d[0]; a.v[1] += d[1]; a.v[2] += d[2];
+    a.v[3] += m[0]; a.v[4] += m[1]; a.v[5] += m[2];
+    #pragma unroll
+    for (int c = 0; c < 3; c++)
+        #pragma unroll
+        for (int r = 0; r < 3; r++) a.v[6 + c * 3 + r] += m[r] * d[c];
+    a.n++;
+}
+// P2L gate for one pair; returns true and (D, M) if accepted
+B2_DEV bool p2l_pair(Tf Tpre, V3 d, V3 I, V3 N, float max_dist, V3& D, V3& M)
+{
+    D = tf_apply(Tpre, d);
+    const float sd = v_dot(v_sub(I, D), N);
+    if (!(fabsf(sd) < max_dist)) return false;
+    M = v_add(D, v_scale(N, sd));
+    return true;
+}
+B2_DEV CStats acc_finalize(const double* v, uint32_t n)
+{
+    CStats s = cs_identity();
+    if (n == 0) return s;
+    const double inv = 1.0 / (double)n;
+    double dm[3], mm[3];
+    for (int k = 0; k < 3; k++) { dm[k] = v[k] * inv; mm[k] = v[3 + k] * inv; }
+    s.dm = mk3((float)dm[0], (float)dm[1], (float)dm[2]);
+    s.mm = mk3((float)mm[0], (float)mm[1], (float)mm[2]);
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) s.C[c * 3 + r] = (float)(v[6 + c * 3 + r] * inv - mm[r] * dm[c]);
+    s.n = n;
+    return s;
+}
+
+// block-level sum of the accumulators; result valid in thread 0.  smem: double[(B2_NACC+1) * 32]
+template <int BLOCK>
+__device__ __forceinline__ void block_reduce_acc(P2LAcc& a, double* smem)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = BLOCK / 32;
+    #pragma unroll
+    for (int i = 0; i < B2_NACC; i++) a.v[i] = warp_sum(a.v[i]);
+    a.n = warp_sum_u32(a.n);
+    if (lane == 0) {
+        #pragma unroll
+        for (int i = 0; i < B2_NACC; i++) smem[i * NW + warp] = a.v[i];
+        smem[B2_NACC * NW + warp] = (double)a.n;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        #pragma unroll
+        for (int i = 0; i <= B2_NACC; i++) {
+            double x = lane < NW ? smem[i * NW + lane] : 0.0;
+            x = warp_sum(x);
+            if (i < B2_NACC) a.v[i] = x; else a.n = (uint32_t)(x + 0.5);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ICP state kept on the device between the kernels of one correctOnce (micp_localization.cpp:899-984)
+// ---------------------------------------------------------------------------------------------------------------------
+struct IcpState {
+    b2_transform Tom, Tbo, Tsb;          // inputs
+    b2_transform T_onew_oold;            // :910, :963
+    b2_transform T_snew_sold;            // pre-transform of the NEXT reduction (MICPSensor.hpp:178)
+    b2_transform Tom_new;                // :972-984
+    b2_cross_stats Cmerged_o;            // :918-937 (single sensor)
+    b2_cross_stats stats_s;              // last sensor-frame statistics
+    float max_dist;
+    uint32_t iter;
+};
+
+B2_DEV Tf icp_pretransform(Tf Tbo, Tf Tsb, Tf T_onew_oold)
+{
+    const Tf T_bnew_bold = tf_mul(tf_mul(tf_inv(Tbo), T_onew_oold), Tbo);      // micp_localization.cpp:926
+    return tf_mul(tf_mul(tf_inv(Tsb), T_bnew_bold), Tsb);                      // MICPSensor.hpp:178
+}
+
+// one inner iteration after the reduction delivered stats_s (thread 0 only)
+B2_DEV void icp_step(IcpState* st, const CStats& stats_s)
+{
+    const Tf Tbo = tf_load(&st->Tbo), Tsb = tf_load(&st->Tsb), Tom = tf_load(&st->Tom);
+    Tf T_onew_oold = tf_load(&st->T_onew_oold);
+    const CStats stats_b = cs_transform(Tsb, stats_s);                        // MICPSensor.hpp:182
+    const CStats Cs_o = cs_transform(Tbo, stats_b);                           // micp_localization.cpp:931
+    const CStats Cmerged = cs_merge(cs_identity(), Cs_o);                     // :918,:936
+    const Tf T_inner = umeyama_dev(Cmerged);                                  // :952-953
+    T_onew_oold = tf_mul(T_onew_oold, T_inner);                               // :963
+    tf_store(&st->T_onew_oold, T_onew_oold);
+    tf_store(&st->T_snew_sold, icp_pretransform(Tbo, Tsb, T_onew_oold));
+    Tf Tn = tf_mul(Tom, T_onew_oold);                                         // :972
+    if (Cmerged.n > 0) Tn.R = q_normalize(Tn.R); else Tn = Tom;               // :974-984
+    tf_store(&st->Tom_new, Tn);
+    cs_store(&st->Cmerged_o, Cmerged);
+    cs_store(&st->stats_s, stats_s);
+    st->iter++;
+}
+
+__global__ void k_icp_init(IcpState* st)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const Tf I = tf_identity();
+        tf_store(&st->T_onew_oold, I);
+        tf_store(&st->T_snew_sold, icp_pretransform(tf_load(&st->Tbo), tf_load(&st->Tsb), I));
+        tf_store(&st->Tom_new, tf_load(&st->Tom));
+        st->iter = 0;
+        // Tbm for the find: MICPSensor.hpp:148  Tbm = Tom * Tbo  (stored in Tom_new's neighbour? no: computed by the find kernel itself)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// generic closest hit for arbitrary rays (b2_mesh_intersect)
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_intersect(BvhView bvh, const float* __restrict__ origs, const float* __restrict__ dirs, uint32_t n, float tfar,
+                                                   float* __restrict__ t_out, uint32_t* __restrict__ face_out, float* __restrict__ ng_out, uint8_t* __restrict__ hit_out,
+                                                   unsigned long long* __restrict__ counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nn = 0, nt = 0;
+    if (i < n) {
+        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        HitRec h = trace_init(tfar);
+        trace_closest<STATS>(bvh, r, h, nn, nt);
+        const bool hit = h.face != B2_NOFACE;
+        if (t_out) t_out[i] = hit ? h.t : u2f(0x7f800000u);
+        if (face_out) face_out[i] = h.face;
+        if (hit_out) hit_out[i] = hit ? 1 : 0;
+        if (ng_out) {
+            V3 ng = mk3(0.f, 0.f, 0.f);
+            if (hit) ng = tri_ng(bvh, h.tri);
+            ng_out[3 * i] = ng.x; ng_out[3 * i + 1] = ng.y; ng_out[3 * i + 2] = ng.z;
+        }
+    }
+    if (STATS) {
+        const uint32_t sn = warp_sum_u32(nn), stt = warp_sum_u32(nt);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(counters, (unsigned long long)sn); atomicAdd(counters + 1, (unsigned long long)stt); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MICP*Sensor*::unpackMessage on the device (MICPSphericalSensorCPU.cpp:181-233)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_dataset_from_ranges(const float* __restrict__ ranges, const float* __restrict__ dirs, const float* __restrict__ origs, uint32_t n_origs,
+                                      uint32_t n, float range_min, float range_max, float* __restrict__ pts, uint8_t* __restrict__ mask)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float r = ranges[i];
+    const uint32_t oi = n_origs == 1 ? 0 : i;
+    pts[3 * i + 0] = add(mul(dirs[3 * i + 0], r), origs[3 * oi + 0]);
+    pts[3 * i + 1] = add(mul(dirs[3 * i + 1], r), origs[3 * oi + 1]);
+    pts[3 * i + 2] = add(mul(dirs[3 * i + 2], r), origs[3 * oi + 2]);
+    mask[i] = (r < range_min || r > range_max) ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RCC*::find (RCCEmbree.cpp:26-36 ...): one thread per (pose, ray); writes the model buffers in the SENSOR frame
+// ---------------------------------------------------------------------------------------------------------------------
+struct RayModel {
+    const float* dirs;      // n x 3 (sensor frame)
+    const float* origs;     // n_origs x 3
+    uint32_t n_origs;       // 1 or n
+    uint32_t n;             // rays per pose
+    float range_min, range_max;
+};
+
+struct ModelBuffers {
+    float* pts; float* nrm; uint8_t* hits; uint32_t* faces; float* ranges;
+};
+
+// shared epilogue: hit record -> sensor-frame point / normal exactly like the oracle's orc_simulate
+B2_DEV void hit_to_sensor(const BvhView& bvh, const HitRec& h, Q4 Rms, V3 dir_s, V3 orig_s, V3& p, V3& ns)
+{
+    const V3 ng = tri_ng(bvh, h.tri);
+    p = v_add(v_scale(dir_s, h.t), orig_s);
+    const V3 nm = v_normalize(ng);
+    ns = q_rot(Rms, nm);
+    if (v_dot(dir_s, ns) > 0.0f) ns = v_neg(ns);
+    ns = v_normalize(ns);
+}
+
+// one ray of find(): trace + write the model buffers at index o
+B2_DEV void find_one(const BvhView& bvh, Tf Tsm, const RayModel& model, uint32_t i, uint64_t o, const ModelBuffers& out)
+{
+    const Q4 Rms = q_conj(Tsm.R);
+    const uint32_t oi = model.n_origs == 1 ? 0 : i;
+    const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
+    const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
+    const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s));
+    HitRec h = trace_init(model.range_max);
+    uint32_t nn = 0, nt = 0;
+    trace_closest<false>(bvh, r, h, nn, nt);
+    if (h.face != B2_NOFACE) {
+        V3 p, ns; hit_to_sensor(bvh, h, Rms, dir_s, orig_s, p, ns);
+        out.pts[3 * o] = p.x; out.pts[3 * o + 1] = p.y; out.pts[3 * o + 2] = p.z;
+        out.nrm[3 * o] = ns.x; out.nrm[3 * o + 1] = ns.y; out.nrm[3 * o + 2] = ns.z;
+        out.hits[o] = 1; out.faces[o] = h.face; out.ranges[o] = h.t;
+    } else {
+        const float qnan = u2f(0x7fc00000u);
+        out.pts[3 * o] = qnan; out.pts[3 * o + 1] = qnan; out.pts[3 * o + 2] = qnan;
+        out.nrm[3 * o] = qnan; out.nrm[3 * o + 1] = qnan; out.nrm[3 * o + 2] = qnan;
+        out.hits[o] = 0; out.faces[o] = B2_NOFACE; out.ranges[o] = add(model.range_max, 1.0f);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_rcc_find(BvhView bvh, const b2_transform* __restrict__ Tbm_dev, const IcpState* __restrict__ icp, b2_transform Tbm_val,
+                                                  b2_transform Tsb_val, RayModel model, uint32_t n_poses, ModelBuffers out)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)model.n * n_poses;
+    if (gid >= total) return;
+    const uint32_t pose = (uint32_t)(gid / model.n), i = (uint32_t)(gid % model.n);
+    Tf Tbm;
+    if (icp) Tbm = tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo));           // MICPSensor.hpp:148
+    else if (Tbm_dev) Tbm = tf_load(Tbm_dev + pose);
+    else Tbm = tf_from_pod(Tbm_val);
+    find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, gid, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Correspondences*::computeCrossStatistics (CorrespondencesCPU.cpp:10-39): N-element masked reduction -> CrossStatistics.
+// Deterministic: per-block partials, the last block to finish sums them in block order.  With `icp` set, the last block also
+// performs the rest of the inner iteration (frame changes, Umeyama, compose) so one correctOnce needs 1 + iterations launches.
+// ---------------------------------------------------------------------------------------------------------------------
+#define B2_RED_BLOCK 256
+__global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask,
+                                                             const float* __restrict__ mpts, const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask,
+                                                             uint32_t n, b2_transform Tpre_val, float max_dist_val, IcpState* icp,
+                                                             double* __restrict__ partials, unsigned int* __restrict__ ticket, b2_cross_stats* __restrict__ out)
+{
+    __shared__ double smem[(B2_NACC + 1) * (B2_RED_BLOCK / 32)];
+    __shared__ bool is_last;
+    const Tf Tpre = icp ? tf_load(&icp->T_snew_sold) : tf_from_pod(Tpre_val);
+    const float max_dist = icp ? icp->max_dist : max_dist_val;
+    P2LAcc acc; acc_zero(acc);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!(dmask[i] > 0) || !(mmask[i] > 0)) continue;
+        V3 D, M;
+        if (p2l_pair(Tpre, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), mk3(mpts[3 * i], mpts[3 * i + 1], mpts[3 * i + 2]),
+                     mk3(mnrm[3 * i], mnrm[3 * i + 1], mnrm[3 * i + 2]), max_dist, D, M))
+            acc_add_pair(acc, D, M);
+    }
+    block_reduce_acc<B2_RED_BLOCK>(acc, smem);
+    if (threadIdx.x == 0) {
+        double* p = partials + (size_t)blockIdx.x * (B2_NACC + 1);
+        for (int i = 0; i < B2_NACC; i++) p[i] = acc.v[i];
+        p[B2_NACC] = (double)acc.n;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        double v[B2_NACC]; for (int i = 0; i < B2_NACC; i++) v[i] = 0.0;
+        double cnt = 0.0;
+        for (uint32_t b = 0; b < gridDim.x; b++) {
+            const volatile double* p = partials + (size_t)b * (B2_NACC + 1);
+            for (int i = 0; i < B2_NACC; i++) v[i] += p[i];
+            cnt += p[B2_NACC];
+        }
+        const CStats s = acc_finalize(v, (uint32_t)(cnt + 0.5));
+        if (out) cs_store(out, s);
+        if (icp) icp_step(icp, s);
+        *ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v1 batched correct(): fused trace -> P2L gate -> per-block partial statistics (no model buffers written)
+// grid = n_poses * blocks_per_pose; each block handles `rays_per_block` consecutive rays of one pose
+// ---------------------------------------------------------------------------------------------------------------------
+#define B2_FUSED_BLOCK 128
+__global__ void __launch_bounds__(B2_FUSED_BLOCK) k_rcc_fused_batch(BvhView bvh, const b2_transform* __restrict__ Tbm_dev, b2_transform Tsb_val, RayModel model,
+                                                                    const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, float max_dist,
+                                                                    uint32_t blocks_per_pose, uint32_t rays_per_block, double* __restrict__ partials)
+{
+    __shared__ double smem[(B2_NACC + 1) * (B2_FUSED_BLOCK / 32)];
+    const uint32_t pose = blockIdx.x / blocks_per_pose, chunk = blockIdx.x % blocks_per_pose;
+    const Tf Tsm = tf_mul(tf_load(Tbm_dev + pose), tf_from_pod(Tsb_val));
+    const Q4 Rms = q_conj(Tsm.R);
+    const Tf I = tf_identity();
+    P2LAcc acc; acc_zero(acc);
+    const uint32_t begin = chunk * rays_per_block;
+    const uint32_t end = min(begin + rays_per_block, model.n);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        if (!(dmask[i] > 0)) continue;
+        const uint32_t oi = model.n_origs == 1 ? 0 : i;
+        const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
+        const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
+        const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s));
+        HitRec h = trace_init(model.range_max);
+        uint32_t nn = 0, nt = 0;
+        trace_closest<false>(bvh, r, h, nn, nt);
+        if (h.face == B2_NOFACE) continue;
+        V3 p, ns; hit_to_sensor(bvh, h, Rms, dir_s, orig_s, p, ns);
+        V3 D, M;
+        if (p2l_pair(I, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), p, ns, max_dist, D, M)) acc_add_pair(acc, D, M);
+    }
+    block_reduce_acc<B2_FUSED_BLOCK>(acc, smem);
+    if (threadIdx.x == 0) {
+        double* p = partials + (size_t)blockIdx.x * (B2_NACC + 1);
+        for (int i = 0; i < B2_NACC; i++) p[i] = acc.v[i];
+        p[B2_NACC] = (double)acc.n;
+    }
+}
+
+// per pose: sum the block partials in order -> stats_s -> stats_b = Tsb * stats_s -> Umeyama
+__global__ void k_umeyama_from_partials(const double* __restrict__ partials, uint32_t blocks_per_pose, uint32_t n_poses, b2_transform Tsb_val,
+                                        b2_transform* __restrict__ Tdelta, uint32_t* __restrict__ ncorr, b2_cross_stats* __restrict__ stats_b_out)
+{
+    const uint32_t pose = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pose >= n_poses) return;
+    double v[B2_NACC]; for (int i = 0; i < B2_NACC; i++) v[i] = 0.0;
+    double cnt = 0.0;
+    for (uint32_t b = 0; b < blocks_per_pose; b++) {
+        const double* p = partials + ((size_t)pose * blocks_per_pose + b) * (B2_NACC + 1);
+        for (int i = 0; i < B2_NACC; i++) v[i] += p[i];
+        cnt += p[B2_NACC];
+    }
+    const CStats ss = acc_finalize(v, (uint32_t)(cnt + 0.5));
+    const CStats sb = cs_transform(tf_from_pod(Tsb_val), ss);
+    const Tf T = umeyama_dev(sb);
+    if (Tdelta) tf_store(Tdelta + pose, T);
+    if (ncorr) ncorr[pose] = sb.n;
+    if (stats_b_out) cs_store(stats_b_out + pose, sb);
+}
+
+__global__ void k_umeyama_batch(const b2_cross_stats* __restrict__ stats, uint32_t n, b2_transform* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tf_store(out + i, umeyama_dev(cs_load(stats + i)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// particle filter: PCDSensorUpdaterEmbree::update hot loop (PCDSensorUpdaterEmbree.cpp:290-342) in ONE launch.
+// A block owns PPB particles x all beams.  Phase 1: every (particle, beam) ray is traced by some thread, its Gaussian
+// evaluation stored in shared memory.  Phase 2: one thread per particle merges the evaluations IN BEAM ORDER
+// (the reference's sequential FP32 Gaussian1D += order, quirk D6) and read-modify-writes the 36-byte attrs once.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PfBeam { float ox, oy, oz, dx, dy, dz, range; uint32_t slot; };   // slot = original beam index (merge order)
+
+B2_DEV void gaussian1d_add(b2_gaussian1d& a, float b_mean, float b_sigma, uint32_t b_n)
+{
+    const uint32_t n = a.n_meas + b_n;
+    if (n == 0) return;
+    const float w1 = dvd((float)a.n_meas, (float)n), w2 = dvd((float)b_n, (float)n);
+    const float mean = add(mul(a.mean, w1), mul(b_mean, w2));
+    const float d1 = sub(a.mean, mean), d2 = sub(b_mean, mean);
+    const float sigma = add(add(mul(a.sigma, w1), mul(b_sigma, w2)), add(mul(mul(d1, d1), w1), mul(mul(d2, d2), w2)));
+    a.mean = mean; a.sigma = sigma; a.n_meas = n;
+}
+
+// Gaussian evaluation of one (particle, beam) pair: sensorUpdate() up to `eval` (PCDSensorUpdaterEmbree.cpp:197-224)
+B2_DEV float pf_eval_one(const BvhView& bvh, Tf Tsm, const PfBeam& b, const b2_pf_params& prm, float sigma_quad, double denom)
+{
+    const V3 orig_m = tf_apply(Tsm, mk3(b.ox, b.oy, b.oz));                                // RangeMeasurement.hpp:29-42
+    const V3 dir_m = q_rot(Tsm.R, mk3(b.dx, b.dy, b.dz));
+    const bool real_hit = (prm.range_min <= b.range) && (b.range <= prm.range_max);        // :27
+    const RaySetup r = ray_setup(orig_m, dir_m);
+    HitRec h = trace_init(u2f(0x7f800000u));                                               // tfar = +inf (:38)
+    uint32_t nn = 0, nt = 0;
+    trace_closest<false>(bvh, r, h, nn, nt);
+    const bool sim_hit = (h.face != B2_NOFACE) && (h.t > prm.range_min);                   // :47
+    float error;
+    if (sim_hit) {
+        if (real_hit) {
+            V3 n = tri_ng(bvh, h.tri);
+            if (prm.ng_mode == 1) n = v_normalize(n);
+            const V3 preal = v_add(orig_m, v_scale(dir_m, b.range));
+            const V3 pint = v_add(orig_m, v_scale(dir_m, h.t));
+            error = fabsf(v_dot(v_sub(pint, preal), n));                                   // :54-68
+        } else error = prm.real_miss_sim_hit_error;
+    } else error = real_hit ? prm.real_hit_sim_miss_error : prm.real_miss_sim_miss_error;
+    const float arg = dvd(dvd(-mul(error, error), sigma_quad), 2.0f);                      // :224
+    return (float)(exp((double)arg) / denom);
+}
+B2_DEV void pf_constants(const b2_pf_params& prm, float& sigma_quad, double& denom)
+{
+    sigma_quad = mul(prm.dist_sigma, prm.dist_sigma);
+    denom = sqrt((double)mul(2.0f, sigma_quad) * 3.14159265358979323846);                  // sqrt(2*sq*M_PI)
+}
+// merge the evaluations of one particle in beam order (:232-238)
+B2_DEV void pf_merge(b2_gaussian1d& lk, const float* e, uint32_t n_beams)
+{
+    for (uint32_t b = 0; b < n_beams; b++) {
+        gaussian1d_add(lk, e[b], 0.0f, 1u);
+        lk.n_meas = lk.n_meas < 10000u ? lk.n_meas : 10000u;                               // MAX_N_MEAS
+    }
+}
+
+#define B2_PF_BLOCK 128
+__global__ void __launch_bounds__(B2_PF_BLOCK) k_pf_update(BvhView bvh, const b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n_particles,
+                                                           b2_transform Tsb_val, const PfBeam* __restrict__ beams, uint32_t n_beams, b2_pf_params prm, uint32_t ppb)
+{
+    extern __shared__ float s_eval[];            // [ppb][n_beams]
+    const uint32_t p0 = blockIdx.x * ppb;
+    const uint32_t np = min(ppb, n_particles - p0);
+    float sigma_quad; double denom; pf_constants(prm, sigma_quad, denom);
+    const Tf Tsb = tf_from_pod(Tsb_val);
+    const uint32_t total = np * n_beams;
+    for (uint32_t w = threadIdx.x; w < total; w += blockDim.x) {
+        const uint32_t pl = w / n_beams, bi = w % n_beams;
+        const Tf Tsm = tf_mul(tf_load(poses + p0 + pl), Tsb);                              // :337-338
+        const PfBeam b = beams[bi];
+        s_eval[pl * n_beams + b.slot] = pf_eval_one(bvh, Tsm, b, prm, sigma_quad, denom);
+    }
+    __syncthreads();
+    if (threadIdx.x < np) {
+        b2_particle_attr* ap = attrs + p0 + threadIdx.x;
+        b2_gaussian1d lk = ap->likelihood;
+        pf_merge(lk, s_eval + threadIdx.x * n_beams, n_beams);
+        ap->likelihood = lk;
+    }
+}

@@ -1,0 +1,125 @@
+// emul.cu -- TEST HARNESS ONLY: runs the product's host+device traversal / math functions (rmcl_b200/csrc/*.cuh) on the CPU so
+// that the BVH builder, the traversal logic and the op-for-op parity with the oracle can be checked in a container without a GPU.
+// Not part of librmcl_b200.so and never shipped; built into tests/emul/_build/libb2emul.so by tests/emul/Makefile.
+// Host code is compiled with -ffp-contract=off -mfma, so plain float ops are individually rounded exactly like the device's
+// __fmul_rn/__fadd_rn and fmaf() is a true FMA.
+#include "../../rmcl_b200/csrc/kernels.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+
+struct EmulScene { B2BvhHost bvh; };
+
+__attribute__((visibility("default"))) void* emul_scene_create(const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf)
+{
+    EmulScene* s = new EmulScene();
+    const char* err = "";
+    if (b2_build_bvh8_host(verts, nv, faces, nf, &s->bvh, &err) != 0) { delete s; return nullptr; }
+    return s;
+}
+__attribute__((visibility("default"))) void emul_scene_destroy(void* p) { if (p) { b2_free_bvh8_host(&((EmulScene*)p)->bvh); delete (EmulScene*)p; } }
+__attribute__((visibility("default"))) void emul_scene_info(void* p, uint32_t* n_nodes, uint32_t* n_tris, uint32_t* depth, float* sah)
+{
+    EmulScene* s = (EmulScene*)p; *n_nodes = s->bvh.n_nodes; *n_tris = s->bvh.n_tris; *depth = s->bvh.max_depth; *sah = s->bvh.sah_cost;
+}
+static BvhView view(void* p) { EmulScene* s = (EmulScene*)p; BvhView v; v.nodes = (const uint4*)s->bvh.nodes; v.tris = (const float4*)s->bvh.tris; return v; }
+
+__attribute__((visibility("default"))) void emul_intersect(void* sc, const float* origs, const float* dirs, uint32_t n, float tfar,
+                                                           float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out, double* mean_nodes, double* mean_tris)
+{
+    const BvhView bvh = view(sc);
+    unsigned long long tn = 0, tt = 0;
+    #pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn, tt)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        HitRec h = trace_init(tfar);
+        uint32_t nn = 0, nt = 0;
+        trace_closest<true>(bvh, r, h, nn, nt);
+        tn += nn; tt += nt;
+        const bool hit = h.face != B2_NOFACE;
+        if (t_out) t_out[i] = hit ? h.t : u2f(0x7f800000u);
+        if (face_out) face_out[i] = h.face;
+        if (hit_out) hit_out[i] = hit;
+        if (ng_out) { V3 ng = mk3(0, 0, 0); if (hit) ng = tri_ng(bvh, h.tri); ng_out[3 * i] = ng.x; ng_out[3 * i + 1] = ng.y; ng_out[3 * i + 2] = ng.z; }
+    }
+    if (mean_nodes) *mean_nodes = (double)tn / (double)(n ? n : 1);
+    if (mean_tris) *mean_tris = (double)tt / (double)(n ? n : 1);
+}
+
+__attribute__((visibility("default"))) void emul_find(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* origs, uint32_t n_origs,
+                                                      const float* dirs, float range_max, float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* ranges)
+{
+    const BvhView bvh = view(sc);
+    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = 0.f; m.range_max = range_max;
+    ModelBuffers out; out.pts = pts; out.nrm = nrm; out.hits = hits; out.faces = faces; out.ranges = ranges;
+    const Tf Tsm = tf_mul(tf_from_pod(*Tbm), tf_from_pod(*Tsb));
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) find_one(bvh, Tsm, m, (uint32_t)i, (uint64_t)i, out);
+}
+
+// sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
+__attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
+                                                                  const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)
+{
+    P2LAcc acc; acc_zero(acc);
+    const Tf T = tf_from_pod(*Tpre);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!(dmask[i] > 0) || !(mmask[i] > 0)) continue;
+        V3 D, M;
+        if (p2l_pair(T, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), mk3(mpts[3 * i], mpts[3 * i + 1], mpts[3 * i + 2]),
+                     mk3(mnrm[3 * i], mnrm[3 * i + 1], mnrm[3 * i + 2]), max_dist, D, M)) acc_add_pair(acc, D, M);
+    }
+    cs_store(out, acc_finalize(acc.v, acc.n));
+}
+
+__attribute__((visibility("default"))) void emul_umeyama(const b2_cross_stats* s, b2_transform* out) { memset(out, 0, sizeof(*out)); tf_store(out, umeyama_dev(cs_load(s))); }
+__attribute__((visibility("default"))) void emul_cs_merge(const b2_cross_stats* a, const b2_cross_stats* b, b2_cross_stats* out) { cs_store(out, cs_merge(cs_load(a), cs_load(b))); }
+__attribute__((visibility("default"))) void emul_cs_transform(const b2_transform* T, const b2_cross_stats* s, b2_cross_stats* out) { cs_store(out, cs_transform(tf_from_pod(*T), cs_load(s))); }
+
+// whole correctOnce with the device functions (find_one + sequential reduce + icp_step)
+__attribute__((visibility("default"))) void emul_correct_once(void* sc, uint32_t n, const float* origs, uint32_t n_origs, const float* dirs, float range_max,
+                                                              const float* dpts, const uint8_t* dmask, const b2_transform* Tom, const b2_transform* Tbo, const b2_transform* Tsb,
+                                                              uint32_t iterations, float max_dist, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    std::vector<float> mp(3 * (size_t)n), mn(3 * (size_t)n), mr(n); std::vector<uint8_t> mh(n); std::vector<uint32_t> mf(n);
+    IcpState st; memset(&st, 0, sizeof(st));
+    st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = *Tsb; st.max_dist = max_dist;
+    const Tf I = tf_identity();
+    tf_store(&st.T_onew_oold, I);
+    tf_store(&st.T_snew_sold, icp_pretransform(tf_load(&st.Tbo), tf_load(&st.Tsb), I));
+    tf_store(&st.Tom_new, tf_load(&st.Tom));
+    b2_transform Tbm; memset(&Tbm, 0, sizeof(Tbm)); tf_store(&Tbm, tf_mul(tf_load(&st.Tom), tf_load(&st.Tbo)));
+    emul_find(sc, &Tbm, Tsb, n, origs, n_origs, dirs, range_max, mp.data(), mn.data(), mh.data(), mf.data(), mr.data());
+    for (uint32_t it = 0; it < iterations; it++) {
+        b2_cross_stats ss;
+        emul_cross_statistics(&st.T_snew_sold, n, dpts, dmask, mp.data(), mn.data(), mh.data(), max_dist, &ss);
+        icp_step(&st, cs_load(&ss));
+    }
+    *Tom_new = st.Tom_new; *T_onew_oold = st.T_onew_oold; *Cmerged = st.Cmerged_o;
+}
+
+__attribute__((visibility("default"))) void emul_pf_update(void* sc, uint32_t n_particles, const b2_transform* poses, b2_particle_attr* attrs, const b2_transform* Tsb,
+                                                           uint32_t n_beams, const b2_range_meas* beams, const b2_pf_params* prm)
+{
+    const BvhView bvh = view(sc);
+    float sigma_quad; double denom; pf_constants(*prm, sigma_quad, denom);
+    std::vector<PfBeam> pb(n_beams);
+    for (uint32_t j = 0; j < n_beams; j++) {
+        const b2_range_meas& m = beams[j];
+        pb[j].ox = m.orig.x; pb[j].oy = m.orig.y; pb[j].oz = m.orig.z; pb[j].dx = m.dir.x; pb[j].dy = m.dir.y; pb[j].dz = m.dir.z; pb[j].range = m.range; pb[j].slot = j;
+    }
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)n_particles; p++) {
+        std::vector<float> e(n_beams);
+        const Tf Tsm = tf_mul(tf_load(poses + p), tf_from_pod(*Tsb));
+        for (uint32_t j = 0; j < n_beams; j++) e[pb[j].slot] = pf_eval_one(bvh, Tsm, pb[j], *prm, sigma_quad, denom);
+        b2_gaussian1d lk = attrs[p].likelihood;
+        pf_merge(lk, e.data(), n_beams);
+        attrs[p].likelihood = lk;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""ctypes binding of tests/emul/libb2emul.so -- TEST HARNESS ONLY (CPU run of the product's host+device traversal code)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libb2emul.so")
+
+TRANSFORM = np.dtype([("R", np.float32, 4), ("t", np.float32, 3), ("stamp", np.uint32)])
+CROSS_STATS = np.dtype([("dataset_mean", np.float32, 3), ("model_mean", np.float32, 3), ("covariance", np.float32, 9), ("n_meas", np.uint32)])
+
+
+class PFParams(C.Structure):
+    _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
+                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int)]
+
+
+def build(force=False):
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+        _lib.emul_scene_create.restype = C.c_void_p
+    return _lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+class Scene:
+    def __init__(self, verts, faces):
+        self.verts = _f32(verts).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        h = lib().emul_scene_create(_p(self.verts), C.c_uint32(len(self.verts)), _p(self.faces), C.c_uint32(len(self.faces)))
+        if not h:
+            raise RuntimeError("emul BVH build failed")
+        self._h = C.c_void_p(h)
+
+    def __del__(self):
+        try:
+            lib().emul_scene_destroy(self._h)
+        except Exception:
+            pass
+
+    def info(self):
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_float()
+        lib().emul_scene_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return dict(n_nodes=a.value, n_tris=b.value, max_depth=c.value, sah=d.value)
+
+    def intersect(self, origs, dirs, tfar=np.inf):
+        origs, dirs = _f32(origs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        n = len(origs)
+        t, f, ng, h = np.empty(n, np.float32), np.empty(n, np.uint32), np.empty((n, 3), np.float32), np.empty(n, np.uint8)
+        mn, mt = C.c_double(), C.c_double()
+        lib().emul_intersect(self._h, _p(origs), _p(dirs), C.c_uint32(n), C.c_float(tfar), _p(t), _p(f), _p(ng), _p(h), C.byref(mn), C.byref(mt))
+        return t, f, ng, h, (mn.value, mt.value)
+
+    def find(self, Tbm, Tsb, origs_s, dirs_s, range_max):
+        origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
+        n = len(dirs_s)
+        out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
+                   face_ids=np.empty(n, np.uint32), ranges=np.empty(n, np.float32))
+        Tbm, Tsb = np.ascontiguousarray(Tbm), np.ascontiguousarray(Tsb)
+        lib().emul_find(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_max),
+                        _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
+        return out
+
+    def correct_once(self, origs_s, dirs_s, range_max, dpts, dmask, Tom, Tbo, Tsb, iterations, max_dist):
+        origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
+        dpts, dmask = _f32(dpts), np.ascontiguousarray(dmask, np.uint8)
+        Tn, Td, Cm = np.zeros((), TRANSFORM), np.zeros((), TRANSFORM), np.zeros((), CROSS_STATS)
+        Tom, Tbo, Tsb = np.ascontiguousarray(Tom), np.ascontiguousarray(Tbo), np.ascontiguousarray(Tsb)
+        lib().emul_correct_once(self._h, C.c_uint32(len(dirs_s)), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_max), _p(dpts), _p(dmask),
+                                _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm))
+        return Tn, Td, Cm
+
+    def pf_update(self, poses, attrs, Tsb, beams, params):
+        poses = np.ascontiguousarray(poses)
+        attrs = np.ascontiguousarray(attrs).copy()
+        beams = np.ascontiguousarray(beams)
+        Tsb = np.ascontiguousarray(Tsb)
+        prm = PFParams(params.dist_sigma, params.real_hit_sim_miss_error, params.real_miss_sim_hit_error, params.real_miss_sim_miss_error,
+                       params.range_min, params.range_max, params.ng_mode)
+        lib().emul_pf_update(self._h, C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(Tsb), C.c_uint32(len(beams)), _p(beams), C.byref(prm))
+        return attrs
+
+
+def cross_statistics(Tpre, dpts, dmask, mpts, mnrm, mmask, max_dist):
+    out = np.zeros((), CROSS_STATS)
+    dpts, mpts, mnrm = _f32(dpts), _f32(mpts), _f32(mnrm)
+    dmask, mmask = np.ascontiguousarray(dmask, np.uint8), np.ascontiguousarray(mmask, np.uint8)
+    Tpre = np.ascontiguousarray(Tpre)
+    lib().emul_cross_statistics(_p(Tpre), C.c_uint32(len(dmask)), _p(dpts), _p(dmask), _p(mpts), _p(mnrm), _p(mmask), C.c_float(max_dist), _p(out))
+    return out
+
+
+def umeyama(stats):
+    stats = np.ascontiguousarray(stats)
+    out = np.zeros((), TRANSFORM)
+    lib().emul_umeyama(_p(stats), _p(out))
+    return out

@@ -1,0 +1,92 @@
+"""CPU tests: the product's host+device traversal / math code (rmcl_b200/csrc/*.cuh), run on the CPU through the test-only harness
+tests/emul, against the oracle.  Covers the host BVH8 builder, the quantised-box traversal (conservative culling) and the op-for-op
+arithmetic of find / P2L / Umeyama / ICP step / PF evaluation -- everything except the CUDA launch plumbing, which the -m gpu tests cover."""
+import numpy as np
+import pytest
+
+from conftest import mesh, oracle_scene, random_rays
+
+_EMUL = {}
+
+
+def emul_scene(name):
+    import pyemul
+    if name not in _EMUL:
+        V, F = mesh(name)
+        _EMUL[name] = pyemul.Scene(V, F)
+    return _EMUL[name]
+
+
+@pytest.fixture(scope="module")
+def pe():
+    import pyemul
+    pyemul.build()
+    return pyemul
+
+
+@pytest.mark.parametrize("name,lo,hi", [("cube29", -9.5, 9.5), ("uvsphere:40:60", -6.0, 6.0), ("building:60000", 1.0, 2.9), ("indoor:20000", 0.2, 2.8)])
+def test_traversal_bit_exact(pe, po, name, lo, hi):
+    osc, esc = oracle_scene(name), emul_scene(name)
+    inf = esc.info()
+    assert inf["n_tris"] == len(mesh(name)[1]) and inf["max_depth"] < 30
+    o, d = random_rays(20000, lo, hi, seed=2)
+    t1, f1, n1, h1 = osc.intersect(o, d, brute=False)
+    t2, f2, n2, h2, st = esc.intersect(o, d)
+    assert np.array_equal(f1, f2) and np.array_equal(t1, t2) and np.array_equal(n1, n2) and np.array_equal(h1, h2)
+    assert 1.0 < st[0] < 60.0
+    # axis-aligned rays (idir clamp path) and finite tfar
+    rng = np.random.default_rng(5)
+    ax = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 3000)] * rng.choice([-1.0, 1.0], (3000, 1)).astype(np.float32)
+    a = osc.intersect(o[:3000], ax, tfar=3.0)
+    b = esc.intersect(o[:3000], ax, tfar=3.0)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+def test_find_all_models_bit_exact(pe, po, synth):
+    osc, esc = oracle_scene("indoor:20000"), emul_scene("indoor:20000")
+    Tbm, Tsb = synth.indoor_gt_pose(), synth.scenario_tsb()
+    sph = synth.SphericalModel(-0.5, 1.0 / 31, 32, -np.pi, 2 * np.pi / 64, 64, 0.1, 30.0)
+    pin = synth.PinholeModel(80, 60, 65.0, 65.0, 39.5, 29.5, 0.3, 10.0)
+    rng = np.random.default_rng(1)
+    dirs = rng.normal(size=(500, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    o1 = synth.O1DnModel(50, 10, np.array([0.1, 0.0, 0.05], np.float32), dirs, 0.1, 20.0)
+    on = synth.OnDnModel(50, 10, rng.uniform(-0.2, 0.2, (500, 3)).astype(np.float32), dirs, 0.1, 20.0)
+    for m in (sph, pin, o1, on):
+        o, d = po.model_rays(m)
+        r1 = osc.simulate(Tbm, Tsb, o, d, m.range_max)
+        r2 = esc.find(Tbm, Tsb, o, d, m.range_max)
+        for k in r1:
+            assert np.array_equal(r1[k], r2[k], equal_nan=True), (type(m).__name__, k)
+        assert 0.3 < r1["hits"].mean() <= 1.0
+
+
+def test_icp_chain_bit_exact(pe, po, synth):
+    osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
+    m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 31, 32, -np.pi, 2 * np.pi / 256, 256, 0.5, 120.0)
+    o, d = po.model_rays(m)
+    Tgt, Tsb = synth.building_gt_pose(), synth.scenario_tsb()
+    ranges = synth.noisy_ranges(osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max)
+    dp, dm, _ = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
+    Tbo = synth.make_transform((0.05, 0.02, 0.0), (0, 0, 0.1))
+    Tom = synth.compose(synth.compose(Tgt, synth.scenario_pose_offset()), synth.inverse(Tbo))
+    a = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, iterations=5, max_dist=1.0, adaptive_max_dist_min=0.15, f64_accum=True)
+    b = esc.correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0)
+    assert a[2]["n_meas"] == b[2]["n_meas"] and a[2]["n_meas"] > 5000
+    assert np.abs(a[0]["t"] - b[0]["t"]).max() <= 1e-6 and np.abs(a[0]["R"] - b[0]["R"]).max() <= 1e-6
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()      # same algorithm, same order -> same bits
+
+
+def test_pf_bit_exact(pe, po, synth):
+    osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    Tsb = synth.scenario_tsb()
+    pts = osc.simulate(synth.building_gt_pose(), Tsb, o, d, 80.0)["points"]
+    beams = synth.pf_beams(pts, 40)
+    P, A = synth.pf_particles(300)
+    for ng in (0, 1):
+        prm = po.PFParams.defaults(ng)
+        a = osc.pf_update(P, A, Tsb, beams, prm)
+        b = esc.pf_update(P, A, Tsb, beams, prm)
+        assert a.tobytes() == b.tobytes()

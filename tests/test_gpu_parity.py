@@ -1,0 +1,307 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI (librmcl_b200.so) via rmcl_b200.api;
+the oracle (oracle/) is only the checker.  Bar: bit-exact for hit flags / face ids / n_meas (and, by construction of the shared
+hit definition, for ranges / points / normals); stated float tolerances for reduced quantities."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import gpu_map, mesh, oracle_scene, quat_close, random_rays
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+TOL_DT = 1e-5          # north-star tolerance on the pose update (metres / quaternion components)
+TOL_STATS = 2e-6       # CrossStatistics means (FP64 sum form on both sides, different summation order)
+TOL_LIK = 2e-6         # PF likelihood (device exp() vs glibc exp() can differ in the last double bit before rounding to float)
+
+
+def _rcc(synth, name, model, Tsb=None, cls=None):
+    import rmcl_b200
+    h = (cls or rmcl_b200.RCCB200Spherical)(gpu_map(name))
+    h.setTsb(synth.scenario_tsb() if Tsb is None else Tsb)
+    h.setModel(model)
+    h.setParams(1.0, 0.15)
+    return h
+
+
+def test_library_is_the_cuda_one():
+    import rmcl_b200
+    lib = rmcl_b200.load_library()
+    assert lib.b2_version() >= 100
+    before = rmcl_b200.kernel_launch_count()
+    gpu_map("cube29").intersect([[0, 0, 0]], [[1, 0, 0]])
+    assert rmcl_b200.kernel_launch_count() > before
+
+
+@pytest.mark.parametrize("name,lo,hi,n", [("cube29", -9.5, 9.5, 50000), ("uvsphere:40:60", -6.0, 6.0, 50000),
+                                          ("building:200000", 1.0, 2.9, 200000), ("indoor:20000", 0.2, 2.8, 50000)])
+def test_closest_hit_bit_exact(po, name, lo, hi, n):
+    o, d = random_rays(n, lo, hi, seed=4)
+    t1, f1, n1, h1 = oracle_scene(name).intersect(o, d)
+    t2, f2, n2, h2 = gpu_map(name).intersect(o, d)
+    assert np.array_equal(h1, h2) and np.array_equal(f1, f2)
+    assert np.array_equal(t1, t2) and np.array_equal(n1, n2)
+    # axis-aligned rays and finite tfar
+    rng = np.random.default_rng(5)
+    ax = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 5000)] * rng.choice([-1.0, 1.0], (5000, 1)).astype(np.float32)
+    a = oracle_scene(name).intersect(o[:5000], ax, tfar=3.0)
+    b = gpu_map(name).intersect(o[:5000], ax, tfar=3.0)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+def test_c1_find_golden(po, synth):
+    """C1: 32x32 spherical on the 10 092-triangle cube, against the committed golden vectors."""
+    g = np.load(os.path.join(GOLD, "c1_cube.npz"))
+    h = _rcc(synth, "cube29", synth.c1_sensor(), Tsb=g["Tsb"])
+    h.find(g["Tgt"])
+    mv = h.modelView()
+    for k in ("ranges", "hits", "face_ids", "points", "normals"):
+        assert np.array_equal(mv[k], g[k], equal_nan=True), k
+    hit = mv["hits"] > 0
+    assert np.abs(mv["ranges"][hit] - g["analytic_ranges"][hit]).max() < 2e-5
+    # P2L + Umeyama against golden statistics
+    h.setDataset(g["dataset_points"], g["dataset_mask"])
+    h.find(g["Tguess"])
+    st = h.computeCrossStatistics(synth.make_transform())
+    assert st["n_meas"] == g["stats_f64"]["n_meas"]
+    assert np.abs(st["dataset_mean"] - g["stats_f64"]["dataset_mean"]).max() <= TOL_STATS
+    assert np.abs(st["model_mean"] - g["stats_f64"]["model_mean"]).max() <= TOL_STATS
+    assert np.abs(st["covariance"] - g["stats_f64"]["covariance"]).max() <= 2e-5
+    import rmcl_b200
+    T = rmcl_b200.umeyama_transform(g["stats_f64"][None])[0]
+    assert np.abs(T["t"] - g["umeyama_f64"]["t"]).max() <= 1e-6 and quat_close(T["R"], g["umeyama_f64"]["R"], 1e-6)
+    # whole correctOnce
+    Tn, Td, Cm = h.correctOnce(g["Tguess"], synth.make_transform(), 5, 0.0)
+    assert Cm["n_meas"] == g["Cmerged"]["n_meas"]
+    assert np.abs(Tn["t"] - g["Tom_new"]["t"]).max() <= TOL_DT and quat_close(Tn["R"], g["Tom_new"]["R"], TOL_DT)
+
+
+def test_umeyama_golden(synth):
+    import rmcl_b200
+    g = np.load(os.path.join(GOLD, "umeyama.npz"))
+    T = rmcl_b200.umeyama_transform(g["stats"])
+    for out, ref, truth in zip(T, g["T"], g["truth"]):
+        assert quat_close(out["R"], ref["R"], 1e-6) and np.abs(out["t"] - ref["t"]).max() <= 1e-6
+        assert quat_close(out["R"], truth[:4], 2e-6)
+    z = np.zeros(1, synth.CROSS_STATS_DTYPE)
+    I = rmcl_b200.umeyama_transform(z)[0]
+    assert np.allclose(I["R"], [0, 0, 0, 1]) and np.allclose(I["t"], 0)
+
+
+@pytest.mark.parametrize("case", ["C2", "C4", "o1dn", "ondn"])
+def test_find_all_models(po, synth, case):
+    import rmcl_b200
+    rng = np.random.default_rng(1)
+    if case == "C2":       # 128 x 1024 spherical on the 1M-triangle building
+        name, m, Tbm, cls = "building:1000000", synth.c2_sensor(), synth.building_gt_pose(), rmcl_b200.RCCB200Spherical
+    elif case == "C4":     # 640 x 480 pinhole on the 500k-triangle indoor scene
+        name, m, Tbm, cls = "indoor:500000", synth.c4_sensor(), synth.indoor_gt_pose(), rmcl_b200.RCCB200Pinhole
+    else:
+        dirs = rng.normal(size=(4000, 3)).astype(np.float32)
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        name, Tbm = "indoor:20000", synth.indoor_gt_pose()
+        if case == "o1dn":
+            m, cls = synth.O1DnModel(400, 10, np.array([0.1, 0.0, 0.05], np.float32), dirs, 0.1, 20.0), rmcl_b200.RCCB200O1Dn
+        else:
+            m, cls = synth.OnDnModel(400, 10, rng.uniform(-0.2, 0.2, (4000, 3)).astype(np.float32), dirs, 0.1, 20.0), rmcl_b200.RCCB200OnDn
+    o, d = po.model_rays(m)
+    ref = oracle_scene(name).simulate(Tbm, synth.scenario_tsb(), o, d, m.range_max)
+    h = _rcc(synth, name, m, cls=cls)
+    h.find(Tbm)
+    mv = h.modelView()
+    assert np.array_equal(mv["hits"], ref["hits"]) and np.array_equal(mv["face_ids"], ref["face_ids"])       # bit-exact
+    for k in ("ranges", "points", "normals"):
+        assert np.array_equal(mv[k], ref[k], equal_nan=True), k
+    assert ref["hits"].mean() > 0.3
+    # idempotence: a second find at the same pose rewrites identical buffers
+    h.find(Tbm)
+    mv2 = h.modelView()
+    assert all(np.array_equal(mv[k], mv2[k], equal_nan=True) for k in mv)
+
+
+def test_c2_micp_correct_once(po, synth):
+    """C2 end to end: scan at T_gt (+noise, 2 % dropped), pose guess offset, one correctOnce (5 inner iterations)."""
+    name, m = "building:1000000", synth.c2_sensor()
+    osc = oracle_scene(name)
+    o, d = po.model_rays(m)
+    Tgt, Tsb = synth.building_gt_pose(), synth.scenario_tsb()
+    ranges = synth.noisy_ranges(osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max)
+    dp, dm, nvalid = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
+    Tbo = synth.make_transform((0.05, 0.02, 0.0), (0, 0, 0.1))
+    Tom = synth.compose(synth.compose(Tgt, synth.scenario_pose_offset()), synth.inverse(Tbo))
+    h = _rcc(synth, name, m)
+    h.setRanges(ranges)                                           # unpackMessage on the device
+    ds = h.datasetView()
+    assert np.array_equal(ds["points"], dp) and np.array_equal(ds["mask"], dm) and int(dm.sum()) == nvalid
+    for cp in (0.0, 0.6):
+        ref64 = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, cp, f64_accum=True)
+        ref32 = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, cp, f64_accum=False)
+        for via_ranges in (False, True):
+            Tn, Td, Cm = h.correctOnce(Tom, Tbo, 5, cp, ranges=ranges if via_ranges else None)
+            assert abs(int(Cm["n_meas"]) - int(ref64[2]["n_meas"])) <= 2                      # gate decisions (exact unless an ulp flips one)
+            assert np.abs(Tn["t"] - ref64[0]["t"]).max() <= TOL_DT and quat_close(Tn["R"], ref64[0]["R"], TOL_DT)
+            assert np.abs(Td["t"] - ref64[1]["t"]).max() <= TOL_DT and quat_close(Td["R"], ref64[1]["R"], TOL_DT)
+            # against the reference's own FP32 sequential accumulation the gap is that arithmetic's noise floor (documented in DESIGN.md)
+            assert np.abs(Tn["t"] - ref32[0]["t"]).max() <= 2e-4 and quat_close(Tn["R"], ref32[0]["R"], 5e-5)
+    # single reduction: n_meas exact
+    h.find(synth.compose(Tom, Tbo))
+    I = synth.make_transform()
+    st = h.computeCrossStatistics(I, 0.0)
+    mv = h.modelView()
+    ref = po.statistics_p2l(I, dp, dm, mv["points"], mv["normals"], mv["hits"], 1.0, f64=True)
+    assert st["n_meas"] == ref["n_meas"]
+    assert np.abs(st["dataset_mean"] - ref["dataset_mean"]).max() <= TOL_STATS and np.abs(st["covariance"] - ref["covariance"]).max() <= 5e-5
+    # round trip: noise-free scan taken at the pose itself -> identity update
+    clean = osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"]
+    h.setRanges(clean)
+    Tn, Td, Cm = h.correctOnce(Tgt, I, 5, 0.0)
+    assert np.abs(Td["t"]).max() < 1e-5 and quat_close(Td["R"], [0, 0, 0, 1], 1e-6) and Cm["n_meas"] > 100000
+
+
+def test_correct_batch_v1(po, synth):
+    """v1 correct(Tbm[N]) (lidar_corrector_embree_benchmark.cpp:86-133) on the sphere map with vlp16_900, range.min = 0."""
+    name = "uvsphere:40:60"
+    osc = oracle_scene(name)
+    m = synth.vlp16_900()
+    m.range_min = 0.0
+    o, d = po.model_rays(m)
+    I = synth.make_transform()
+    ranges = osc.simulate(I, I, o, d, m.range_max)["ranges"]
+    rng = np.random.default_rng(2)
+    T = synth.transforms(48)
+    T["t"] = rng.uniform(-0.3, 0.3, (48, 3)).astype(np.float32)
+    T["t"][0] = (0, 0, 0.2)
+    yaw = rng.uniform(-0.1, 0.1, 48)
+    T["R"][:, 2], T["R"][:, 3] = np.sin(yaw / 2), np.cos(yaw / 2)
+    Tsb = synth.make_transform((0.01, 0, 0.02), (0, 0, 0.05))
+    ref = osc.correct_batch(T, Tsb, o, d, m.range_min, m.range_max, ranges, 1.0, f64_accum=True)
+    h = _rcc(synth, name, m, Tsb=Tsb)
+    h.setInputData(ranges)
+    Td, nc, st = h.correct(T)
+    assert np.array_equal(nc, ref[1])                                       # Ncorr bit-exact
+    assert np.abs(Td["t"] - ref[0]["t"]).max() <= TOL_DT
+    assert all(quat_close(a, b, TOL_DT) for a, b in zip(Td["R"], ref[0]["R"]))
+    assert np.abs(st["dataset_mean"] - ref[2]["dataset_mean"]).max() <= 5e-6
+    # ten benchmark-style iterations move pose 0 back towards the origin
+    Tc = T.copy()
+    for _ in range(10):
+        Td, nc, _ = h.correct(Tc)
+        Tc = synth.compose(Tc, Td)
+    assert abs(Tc["t"][0, 2]) < 0.2
+
+
+@pytest.mark.parametrize("ng_mode", [0, 1])
+def test_pf_sensor_update(po, synth, ng_mode):
+    import rmcl_b200
+    name = "building:200000"
+    osc = oracle_scene(name)
+    m = synth.c2_sensor()
+    o, d = po.model_rays(m)
+    Tsb = synth.scenario_tsb()
+    pts = osc.simulate(synth.building_gt_pose(), Tsb, o, d, 80.0)["points"]
+    beams = synth.pf_beams(pts, 180)
+    beams["range"][:3] = (0.01, 200.0, 90.0)                     # real misses (out of sensor range) exercise the penalty branches
+    P, A = synth.pf_particles(5000)
+    A["likelihood"]["n_meas"][:10] = 9990                        # clamp at MAX_N_MEAS
+    prm = po.PFParams.defaults(ng_mode)
+    ref = osc.pf_update(P, A, Tsb, beams, prm)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map(name))
+    out = up.update(P, A, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    assert np.array_equal(out["likelihood"]["n_meas"], ref["likelihood"]["n_meas"])
+    assert np.array_equal(out["state_sigma"], ref["state_sigma"])
+    assert np.abs(out["likelihood"]["mean"] - ref["likelihood"]["mean"]).max() <= TOL_LIK
+    assert np.abs(out["likelihood"]["sigma"] - ref["likelihood"]["sigma"]).max() <= TOL_LIK
+    frac_exact = np.mean(out["likelihood"]["mean"] == ref["likelihood"]["mean"])
+    assert frac_exact > 0.99
+    # sharding invariance: the two halves computed separately equal the whole, bit for bit
+    a = up.update(P[:2500], A[:2500], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    b = up.update(P[2500:], A[2500:], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    assert np.concatenate([a, b]).tobytes() == out.tobytes()
+    # device-resident variant (ParticleUpdater<VRAM_CUDA>)
+    import torch
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+    up.update(Pd, Ad, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    torch.cuda.synchronize()
+    assert Ad.cpu().numpy().view(synth.PARTICLE_ATTR_DTYPE).reshape(-1).tobytes() == out.tobytes()
+
+
+def test_pf_golden(po, synth):
+    import rmcl_b200
+    g = np.load(os.path.join(GOLD, "pf_cube.npz"))
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map("cube29"))
+    for ng in (0, 1):
+        out = up.update(g["poses"], g["attrs0"], g["Tsb"], g["beams"], rmcl_b200.PFParams.defaults(ng))
+        ref = g[f"attrs_ng{ng}"]
+        assert np.array_equal(out["likelihood"]["n_meas"], ref["likelihood"]["n_meas"])
+        assert np.abs(out["likelihood"]["mean"] - ref["likelihood"]["mean"]).max() <= TOL_LIK
+
+
+def test_edge_cases(po, synth):
+    import rmcl_b200
+    # empty map -> B2_ERR_NO_MAP ("EMPTY MAP", PCDSensorUpdaterOptix.cpp:187-192)
+    with pytest.raises(rmcl_b200.B2Error) as e:
+        rmcl_b200.Map(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    assert e.value.code == -3
+    # face index out of range
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map(np.zeros((3, 3), np.float32), np.array([[0, 1, 7]], np.uint32))
+    # single-triangle map; rays that miss everything are NaN-encoded
+    one = rmcl_b200.Map(np.array([[5, -1, -1], [5, 1, -1], [5, 0, 1]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    t, f, ng, hit = one.intersect([[0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 1, 0]])
+    assert hit.tolist() == [1, 0] and f[0] == 0 and f[1] == 0xFFFFFFFF and abs(t[0] - 5) < 1e-6
+    h = rmcl_b200.RCCB200Spherical(one)
+    m = synth.SphericalModel(0.0, 0.0, 1, -np.pi, 2 * np.pi / 8, 8, 0.1, 50.0)
+    h.setTsb(synth.make_transform())
+    h.setModel(m)
+    h.find(synth.make_transform())
+    mv = h.modelView()
+    assert mv["hits"].sum() == 1 and np.isnan(mv["points"][mv["hits"] == 0]).all()
+    # dataset size mismatch / call order errors
+    with pytest.raises(rmcl_b200.B2Error):
+        h.setRanges(np.ones(5, np.float32))
+    h2 = rmcl_b200.RCCB200Spherical(one)
+    with pytest.raises(rmcl_b200.B2Error):
+        h2.find(synth.make_transform())                              # find before setModel
+    # zero-size model: find silently returns (RCCOptix.cpp:30-34)
+    h2.setModel(synth.SphericalModel(0, 0, 0, 0, 0, 0, 0.1, 1.0))
+    h2.find(synth.make_transform())
+    # fully masked dataset -> n_meas = 0 -> identity update, Tom unchanged (micp_localization.cpp:974)
+    h.setDataset(np.zeros((8, 3), np.float32), np.zeros(8, np.uint8))
+    Tom = synth.make_transform((0.1, 0.2, 0.3), (0, 0, 0.4))
+    Tn, Td, Cm = h.correctOnce(Tom, synth.make_transform(), 5, 0.0)
+    assert Cm["n_meas"] == 0 and np.array_equal(Tn["t"], Tom["t"]) and np.array_equal(Tn["R"], Tom["R"])
+    # PF with zero particles / zero beams is a no-op
+    up = rmcl_b200.PCDSensorUpdaterB200(one)
+    P, A = synth.pf_particles(4)
+    out = up.update(P, A, synth.make_transform(), np.zeros(0, synth.RANGE_MEAS_DTYPE))
+    assert out.tobytes() == A.tobytes()
+
+
+def test_full_size_properties_c3(po, synth):
+    """BASELINE sizes where the oracle is too slow for a full compare: C3 (100k particles x 180 beams, 1M triangles) checked through
+    size-independent properties: oracle parity on a sample, sharding invariance, merge-count, bounded likelihood."""
+    import rmcl_b200
+    name = "building:1000000"
+    osc = oracle_scene(name)
+    m = synth.c2_sensor()
+    o, d = po.model_rays(m)
+    Tsb = synth.scenario_tsb()
+    pts = osc.simulate(synth.building_gt_pose(), Tsb, o, d, 80.0)["points"]
+    beams = synth.pf_beams(pts, 180)
+    P, A = synth.pf_particles(100_000)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map(name))
+    prm = rmcl_b200.PFParams.defaults()
+    out = up.update(P, A, Tsb, beams, prm)
+    assert (out["likelihood"]["n_meas"] == 180).all()
+    assert (out["likelihood"]["mean"] >= 0).all() and (out["likelihood"]["mean"] <= 0.19947115).all()
+    idx = np.random.default_rng(0).choice(100_000, 3000, replace=False)
+    ref = osc.pf_update(P[idx], A[idx], Tsb, beams, po.PFParams.defaults())
+    assert np.abs(out["likelihood"]["mean"][idx] - ref["likelihood"]["mean"]).max() <= TOL_LIK
+    parts = [up.update(P[a:b], A[a:b], Tsb, beams, prm) for a, b in ((0, 12500), (12500, 50000), (50000, 100000))]
+    assert np.concatenate(parts).tobytes() == out.tobytes()
+    # second update accumulates: n_meas 360, and equals updating with the beams concatenated twice
+    out2 = up.update(P[:2000], out[:2000], Tsb, beams, prm)
+    both = up.update(P[:2000], A[:2000], Tsb, np.concatenate([beams, beams]), prm)
+    assert (out2["likelihood"]["n_meas"] == 360).all() and out2.tobytes() == both.tobytes()

@@ -1,0 +1,240 @@
+"""CPU tests: the oracle against closed-form geometry, numpy restatements and the committed golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import mesh, oracle_scene, quat_close, random_rays
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_layouts(po, synth):
+    assert po.TRANSFORM.itemsize == 32 and po.CROSS_STATS.itemsize == 64 and po.PARTICLE_ATTR.itemsize == 36 and po.RANGE_MEAS.itemsize == 64
+    assert synth.TRANSFORM_DTYPE == po.TRANSFORM and synth.CROSS_STATS_DTYPE == po.CROSS_STATS
+
+
+def test_spherical_dirs_formula(po, synth):
+    m = synth.c1_sensor()
+    d = po.spherical_dirs(m)
+    phi = (np.float32(m.phi_min) + np.arange(m.phi_size, dtype=np.float32) * np.float32(m.phi_inc)).astype(np.float64)
+    th = (np.float32(m.theta_min) + np.arange(m.theta_size, dtype=np.float32) * np.float32(m.theta_inc)).astype(np.float64)
+    ref = np.stack([np.cos(phi)[:, None] * np.cos(th)[None, :], np.cos(phi)[:, None] * np.sin(th)[None, :], np.repeat(np.sin(phi)[:, None], len(th), 1)], -1)
+    assert np.abs(d.reshape(m.phi_size, m.theta_size, 3) - ref).max() < 2e-7          # buffer id = vid*W + hid
+    assert np.abs(np.linalg.norm(d, axis=1) - 1).max() < 1e-6
+
+
+def test_pinhole_dirs_formula(po, synth):
+    m = synth.PinholeModel(64, 48, 52.5, 52.5, 31.5, 23.5, 0.3, 10.0)
+    d = po.pinhole_dirs(m).reshape(48, 64, 3)
+    v, h = np.meshgrid(np.arange(48), np.arange(64), indexing="ij")
+    opt = np.stack([(h - m.cx) / m.fx, (v - m.cy) / m.fy, np.ones_like(h, float)], -1)
+    opt /= np.linalg.norm(opt, axis=-1, keepdims=True)
+    ref = np.stack([opt[..., 2], -opt[..., 0], -opt[..., 1]], -1)
+    assert np.abs(d - ref).max() < 2e-7
+
+
+def test_cube_closed_form_and_golden(po, synth):
+    g = np.load(os.path.join(GOLD, "c1_cube.npz"))
+    sc = oracle_scene("cube29")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    assert np.array_equal(d, g["dirs"])
+    sim = sc.simulate(g["Tgt"], g["Tsb"], o, d, m.range_max)
+    # regression against the committed vectors: bit-exact
+    for k in ("ranges", "hits", "face_ids", "points", "normals"):
+        assert np.array_equal(sim[k], g[k], equal_nan=True), k
+    hit = sim["hits"] > 0
+    assert hit.mean() > 0.99
+    # closed form
+    assert np.abs(sim["ranges"][hit] - g["analytic_ranges"][hit]).max() < 2e-5
+    assert np.abs(sim["normals"][hit] - g["analytic_normals"][hit]).max() < 1e-6
+    assert np.abs(sim["points"][hit] - d[hit] * sim["ranges"][hit, None]).max() == 0.0      # point = dir*t (+0)
+    # misses are NaN-encoded
+    if (~hit).any():
+        assert np.isnan(sim["points"][~hit]).all() and np.isnan(sim["normals"][~hit]).all()
+        assert (sim["face_ids"][~hit] == 0xFFFFFFFF).all()
+
+
+@pytest.mark.parametrize("name,lo,hi", [("cube29", -9.5, 9.5), ("uvsphere:40:60", -6.0, 6.0)])
+def test_bvh_equals_brute_force(po, name, lo, hi):
+    sc = oracle_scene(name)
+    o, d = random_rays(4000, lo, hi, seed=1)
+    t1, f1, n1, h1 = sc.intersect(o, d, brute=False)
+    t2, f2, n2, h2 = sc.intersect(o, d, brute=True)
+    assert np.array_equal(t1, t2) and np.array_equal(f1, f2) and np.array_equal(h1, h2) and np.array_equal(n1, n2)
+    # axis-aligned and grid-vertex-aimed rays (ties on shared edges / vertices)
+    V, _ = mesh(name)
+    rng = np.random.default_rng(3)
+    gv = V[rng.integers(0, len(V), 1500)]
+    o0 = np.zeros_like(gv)
+    dv = gv / np.linalg.norm(gv, axis=1, keepdims=True)
+    ax = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 500)] * rng.choice([-1.0, 1.0], (500, 1)).astype(np.float32)
+    o1 = rng.uniform(lo, hi, (500, 3)).astype(np.float32)
+    for oo, dd in ((o0, dv), (o1, ax)):
+        a = sc.intersect(oo, dd, brute=False)
+        b = sc.intersect(oo, dd, brute=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_tfar_and_tie_rule(po):
+    # two coincident triangles: the smaller face id wins; tfar cuts hits
+    V = np.array([[0, -1, -1], [0, 1, -1], [0, 0, 1]], np.float32) + np.array([5, 0, 0], np.float32)
+    V2 = np.concatenate([V, V])
+    F = np.array([[3, 4, 5], [0, 1, 2]], np.uint32)
+    sc = po.Scene(V2, F)
+    t, f, ng, h = sc.intersect([[0, 0, 0]], [[1, 0, 0]])
+    assert h[0] == 1 and f[0] == 0 and abs(t[0] - 5.0) < 1e-6
+    assert np.allclose(ng[0], [4.0, 0, 0])                       # raw Ng = (v1-v0)x(v2-v0), |Ng| = 2*area
+    t, f, ng, h = sc.intersect([[0, 0, 0]], [[1, 0, 0]], tfar=4.9)
+    assert h[0] == 0
+    t, f, ng, h = sc.intersect([[0, 0, 0]], [[-1, 0, 0]])
+    assert h[0] == 0                                             # t > 0 only
+
+
+def test_p2l_matches_numpy_and_golden(po, synth):
+    g = np.load(os.path.join(GOLD, "c1_cube.npz"))
+    sc = oracle_scene("cube29")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    model = sc.simulate(g["Tguess"], g["Tsb"], o, d, m.range_max)
+    I = synth.make_transform()
+    s32 = po.statistics_p2l(I, g["dataset_points"], g["dataset_mask"], model["points"], model["normals"], model["hits"], 1.0)
+    s64 = po.statistics_p2l(I, g["dataset_points"], g["dataset_mask"], model["points"], model["normals"], model["hits"], 1.0, f64=True)
+    assert s32.tobytes() == g["stats_f32"].tobytes() and s64.tobytes() == g["stats_f64"].tobytes()
+    # numpy restatement of the formula witnessed at rmcl_ros/src/micpl/MICPSensorCPU.cpp:71-98
+    D = g["dataset_points"].astype(np.float64)
+    Ii, Ni = model["points"].astype(np.float64), model["normals"].astype(np.float64)
+    ok = (g["dataset_mask"] > 0) & (model["hits"] > 0)
+    sd = np.where(ok, ((Ii - D) * Ni).sum(1), np.inf)
+    acc = np.abs(sd) < 1.0
+    M = D[acc] + Ni[acc] * sd[acc, None]
+    Dm, Mm = D[acc].mean(0), M.mean(0)
+    Cov = (M - Mm).T @ (D[acc] - Dm) / acc.sum()
+    assert int(s64["n_meas"]) == int(acc.sum()) == int(s32["n_meas"])
+    assert np.abs(s64["dataset_mean"] - Dm).max() < 1e-6 and np.abs(s64["model_mean"] - Mm).max() < 1e-6
+    assert np.abs(s64["covariance"].reshape(3, 3).T - Cov).max() < 2e-5
+    # FP32 sequential merges (reference arithmetic) agree with the FP64 sum form to FP32 noise
+    assert np.abs(s32["dataset_mean"] - s64["dataset_mean"]).max() < 1e-4
+    assert np.abs(s32["covariance"] - s64["covariance"]).max() < 2e-3
+
+
+def test_cross_stats_merge_and_transform(po, synth):
+    rng = np.random.default_rng(0)
+    P = rng.normal(size=(300, 3)) * 3
+    Q = P + rng.normal(size=(300, 3)) * 0.1
+
+    def stats(p, q):
+        s = np.zeros((), po.CROSS_STATS)
+        s["dataset_mean"], s["model_mean"], s["n_meas"] = p.mean(0), q.mean(0), len(p)
+        s["covariance"] = ((q - q.mean(0)).T @ (p - p.mean(0)) / len(p)).T.reshape(-1)
+        return s
+    a, b, full = stats(P[:100], Q[:100]), stats(P[100:], Q[100:]), stats(P, Q)
+    mrg = po.cross_stats_merge(a, b)
+    assert mrg["n_meas"] == 300
+    assert np.abs(mrg["dataset_mean"] - full["dataset_mean"]).max() < 1e-5
+    assert np.abs(mrg["covariance"] - full["covariance"]).max() < 1e-4
+    ident = np.zeros((), po.CROSS_STATS)
+    assert po.cross_stats_merge(ident, a).tobytes() == a.tobytes()          # Identity is neutral (micp_localization.cpp:918)
+    T = synth.make_transform((1, 2, 3), (0.1, -0.2, 0.7))
+    tr = po.cross_stats_transform(T, full)
+    q = np.asarray(T["R"], np.float64)
+    Pt, Qt = synth._qrot(q[None], P) + T["t"], synth._qrot(q[None], Q) + T["t"]
+    ref = stats(Pt, Qt)
+    assert np.abs(tr["dataset_mean"] - ref["dataset_mean"]).max() < 1e-5 and np.abs(tr["covariance"] - ref["covariance"]).max() < 1e-4
+
+
+def test_umeyama_known_answers(po):
+    g = np.load(os.path.join(GOLD, "umeyama.npz"))
+    for s, T, truth in zip(g["stats"], g["T"], g["truth"]):
+        out = po.umeyama(s)
+        assert out.tobytes() == T.tobytes()                                   # regression
+        assert quat_close(out["R"], truth[:4], 2e-6) and np.abs(out["t"] - truth[4:]).max() < 2e-5   # exact rigid motion recovered
+    z = np.zeros((), po.CROSS_STATS)
+    I = po.umeyama(z)
+    assert np.allclose(I["R"], [0, 0, 0, 1]) and np.allclose(I["t"], 0)       # n_meas == 0 -> identity
+
+
+def test_umeyama_reflection_case(po):
+    # covariance with det < 0 (noise-dominated planar set): result must still be a proper rotation
+    s = np.zeros((), po.CROSS_STATS)
+    C = np.diag([2.0, 1.0, -0.01])
+    s["covariance"] = C.T.reshape(-1)
+    s["n_meas"] = 10
+    T = po.umeyama(s)
+    q = np.asarray(T["R"], np.float64)
+    assert abs(np.linalg.norm(q) - 1) < 1e-6
+    assert quat_close(q, [0, 0, 0, 1], 1e-6)
+
+
+def test_adaptive_max_dist(po):
+    assert po.adaptive_max_dist(1.0, 0.15, 0.0) == pytest.approx(1.0)
+    assert po.adaptive_max_dist(1.0, 0.15, 1.0) == pytest.approx(0.15)
+    assert po.adaptive_max_dist(1.0, 0.15, 0.5) == pytest.approx(0.575)
+
+
+def test_micp_correct_once_converges_and_golden(po, synth):
+    g = np.load(os.path.join(GOLD, "c1_cube.npz"))
+    sc = oracle_scene("cube29")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    I = synth.make_transform()
+    Tn, Td, Cm = sc.micp_correct_once(o, d, m.range_max, g["dataset_points"], g["dataset_mask"], g["Tguess"], I, g["Tsb"], f64_accum=True)
+    assert Tn.tobytes() == g["Tom_new"].tobytes() and Cm.tobytes() == g["Cmerged"].tobytes()
+    Tom = g["Tguess"]
+    for _ in range(25):
+        Tom, _, _ = sc.micp_correct_once(o, d, m.range_max, g["dataset_points"], g["dataset_mask"], Tom, I, g["Tsb"], f64_accum=True)
+    assert np.abs(Tom["t"] - g["Tgt"]["t"]).max() < 0.01 and quat_close(Tom["R"], g["Tgt"]["R"], 2e-3)
+
+
+def test_legacy_benchmark_scenario(po, synth):
+    """lidar_corrector_embree_benchmark.cpp:84-135: sphere map, vlp16_900 with range.min=0, T_curr = I with z+0.2, 10 x correct()."""
+    V, F = mesh("uvsphere:40:60")
+    sc = po.Scene(V, F)
+    m = synth.vlp16_900()
+    m.range_min = 0.0
+    o, d = po.model_rays(m)
+    I = synth.make_transform()
+    ranges = sc.simulate(I, I, o, d, m.range_max)["ranges"]
+    T = synth.transforms(3)
+    T["t"][:, 2] = 0.2
+    z_prev = 0.2
+    for _ in range(10):
+        Td, nc, _ = sc.correct_batch(T, I, o, d, m.range_min, m.range_max, ranges, max_dist=1.0, f64_accum=True)
+        assert (nc > 14000).all()
+        T = np.array([po.transform_mul(T[i], Td[i]) for i in range(len(T))])
+        z = float(np.abs(T["t"][:, 2]).max())
+        assert z < z_prev                                            # point-to-plane slides along the equator band: slow but monotone
+        z_prev = z
+    assert z_prev < 0.17 and np.abs(T["t"][:, :2]).max() < 1e-3
+
+
+def test_gaussian_and_pf_penalties(po, synth):
+    g = np.load(os.path.join(GOLD, "pf_cube.npz"))
+    sc = oracle_scene("cube29")
+    for ng_mode in (0, 1):
+        out = sc.pf_update(g["poses"], g["attrs0"], g["Tsb"], g["beams"], po.PFParams.defaults(ng_mode))
+        assert out.tobytes() == g[f"attrs_ng{ng_mode}"].tobytes()
+        assert (out["likelihood"]["n_meas"] == 24).all()
+        assert (out["likelihood"]["mean"] <= 1.0 / math.sqrt(2 * 4.0 * math.pi) + 1e-7).all()
+    # a beam that is out of sensor range in reality but hits in simulation -> penalty 100 m -> eval underflows to 0
+    b = g["beams"][:1].copy()
+    b["range"] = 500.0
+    out = sc.pf_update(g["poses"][:4], g["attrs0"][:4], g["Tsb"], b, po.PFParams.defaults())
+    assert (out["likelihood"]["mean"] == 0.0).all() and (out["likelihood"]["n_meas"] == 1).all()
+    # n_meas clamps at MAX_N_MEAS = 10000 (ParticleAttributes.hpp:34)
+    a = g["attrs0"][:2].copy()
+    a["likelihood"]["n_meas"] = 9999
+    out = sc.pf_update(g["poses"][:2], a, g["Tsb"], g["beams"][:5], po.PFParams.defaults())
+    assert (out["likelihood"]["n_meas"] == 10000).all()
+
+
+def test_dataset_from_ranges_mask(po, synth):
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    r = np.full(m.size, 5.0, np.float32)
+    r[0], r[1], r[2] = 0.01, 1000.0, m.range_max
+    pts, mask, nv = po.dataset_from_ranges(o, d, r, m.range_min, m.range_max)
+    assert mask[0] == 0 and mask[1] == 0 and mask[2] == 1 and nv == m.size - 2
+    assert np.array_equal(pts[5], d[5] * np.float32(5.0))
