@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -342,7 +343,8 @@ static int reserve_model(b2_rcc* h, size_t n)
 
 static RayModel ray_model(const b2_rcc* h)
 {
-    RayModel m; m.dirs = h->d_dirs.p; m.origs = h->d_origs.p; m.n_origs = h->n_origs; m.n = h->n; m.range_min = h->range_min; m.range_max = h->range_max; return m;
+    RayModel m; m.dirs = h->d_dirs.p; m.origs = h->d_origs.p; m.n_origs = h->n_origs; m.n = h->n; m.range_min = h->range_min; m.range_max = h->range_max;
+    m.width = h->width; m.height = h->height; return m;
 }
 static ModelBuffers model_buffers(const b2_rcc* h)
 {
@@ -354,8 +356,9 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     if (!h->has_model) return fail(B2_ERR_INVALID, "find before setModel");
     if (h->n == 0) return B2_OK;
     RES(reserve_model(h, h->n));
-    const uint32_t grid = (h->n + 127) / 128;
-    k_rcc_find<<<grid, 128, 0, h->stream>>>(h->map->view(), nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h));
+    const uint32_t grid = (h->n + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK;
+    static const int prefetch_mode = [] { const char* e = getenv("B2_FIND_PREFETCH"); return e ? atoi(e) : 1; }();
+    k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h));
     LAUNCHED();
     h->n_model = h->n; h->found = true;
     return B2_OK;
@@ -445,9 +448,10 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
     memset(&st, 0, sizeof(st));
     st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = h->Tsb; st.max_dist = adaptive_max_dist(h, cp);
     st.T_onew_oold = tf_identity_pod(); st.Tom_new = *Tom;
+    // pre-transform of the first reduction, evaluated on the host with the same inline functions the kernels use (individually
+    // rounded ops on both sides -> identical bits); saves a launch
+    tf_store(&st.T_snew_sold, icp_pretransform(tf_from_pod(*Tbo), tf_from_pod(h->Tsb), tf_identity()));
     CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
-    k_icp_init<<<1, 32, 0, h->stream>>>(h->d_icp.p);
-    LAUNCHED();
     if (h->n > 0) {
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         RES(launch_find(h, nullptr, h->d_icp.p));

@@ -36,6 +36,14 @@ B2_DEV float u2f(uint32_t a) { return __uint_as_float(a); }
 B2_DEV int clz32(uint32_t a) { return __clz((int)a); }
 B2_DEV int popc32(uint32_t a) { return __popc(a); }
 template <typename T> B2_DEV T ldg(const T* p) { return __ldg(p); }
+B2_DEV uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
+// PRMT with an IMMEDIATE selector and the second operand in a register (nvcc otherwise folds the constant operand into the
+// immediate slot and materialises every selector with a MOV)
+template <int SEL> __device__ __forceinline__ uint32_t prmt_imm(uint32_t x, uint32_t y)
+{
+    uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(y), "n"(SEL)); return d;
+}
+__device__ __forceinline__ uint32_t opaque_const(uint32_t v) { uint32_t d; asm("mov.b32 %0, %1;" : "=r"(d) : "r"(v)); return d; }
 #else   // host emulation: compiled with -ffp-contract=off, so plain ops are individually rounded
 B2_DEV float mul(float a, float b) { return a * b; }
 B2_DEV float add(float a, float b) { return a + b; }
@@ -48,6 +56,15 @@ B2_DEV float u2f(uint32_t a) { float f; memcpy(&f, &a, 4); return f; }
 B2_DEV int clz32(uint32_t a) { return a ? __builtin_clz(a) : 32; }
 B2_DEV int popc32(uint32_t a) { return __builtin_popcount(a); }
 template <typename T> B2_DEV T ldg(const T* p) { return *p; }
+template <int SEL> inline uint32_t prmt_imm(uint32_t x, uint32_t y);
+inline uint32_t opaque_const(uint32_t v) { return v; }
+B2_DEV uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t v = ((uint64_t)y << 32) | x; uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+template <int SEL> inline uint32_t prmt_imm(uint32_t x, uint32_t y) { return byte_perm(x, y, (uint32_t)SEL); }
 #endif
 
 B2_DEV V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }

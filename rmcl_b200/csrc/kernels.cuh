@@ -123,16 +123,59 @@ __host__ __device__ __noinline__ void svd3_dev(const double A[3][3], double U[3]
     }
 }
 
+// orthogonal polar factor of a 3x3 matrix with positive determinant; false if not applicable / not converged
+__host__ __device__ __noinline__ bool polar_newton3(const double A[3][3], double Q[3][3])
+{
+    double X[3][3];
+    double fro = 0.0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) fro += A[i][j] * A[i][j];
+    if (!(fro > 0.0)) return false;
+    const double inv_n = 1.0 / sqrt(fro);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) X[i][j] = A[i][j] * inv_n;
+    for (int it = 0; it < 40; it++) {
+        // cofactor matrix = det * X^-T
+        double Cf[3][3];
+        Cf[0][0] = X[1][1] * X[2][2] - X[1][2] * X[2][1]; Cf[0][1] = X[1][2] * X[2][0] - X[1][0] * X[2][2]; Cf[0][2] = X[1][0] * X[2][1] - X[1][1] * X[2][0];
+        Cf[1][0] = X[0][2] * X[2][1] - X[0][1] * X[2][2]; Cf[1][1] = X[0][0] * X[2][2] - X[0][2] * X[2][0]; Cf[1][2] = X[0][1] * X[2][0] - X[0][0] * X[2][1];
+        Cf[2][0] = X[0][1] * X[1][2] - X[0][2] * X[1][1]; Cf[2][1] = X[0][2] * X[1][0] - X[0][0] * X[1][2]; Cf[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+        const double det = X[0][0] * Cf[0][0] + X[0][1] * Cf[0][1] + X[0][2] * Cf[0][2];
+        if (!(det > 1e-14)) return false;                         // reflection, singular or NaN: let the SVD decide
+        double nx = 0.0, nc = 0.0;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { nx += X[i][j] * X[i][j]; nc += Cf[i][j] * Cf[i][j]; }
+        // Frobenius scaling g^2 = |X^-T|_F / |X|_F  with X^-T = Cf / det
+        const double g2 = sqrt(nc / nx) / det;
+        const double g = sqrt(g2);
+        const double a = 0.5 * g, b = 0.5 / (g * det);
+        double diff = 0.0;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+            const double y = a * X[i][j] + b * Cf[i][j];
+            const double d = y - X[i][j]; diff += d * d;
+            X[i][j] = y;
+        }
+        if (diff < 1e-30) {
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] = X[i][j];
+            return true;
+        }
+    }
+    return false;
+}
+
 __host__ __device__ __noinline__ Tf umeyama_dev(const CStats& s)
 {
     Tf out = tf_identity();
     if (s.n == 0) return out;
-    double C[3][3], U[3][3], V[3][3], w[3];
+    double C[3][3], R[3][3];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r][c] = (double)s.C[c * 3 + r];
-    svd3_dev(C, U, w, V);
-    const double sgn = (det3d(U) * det3d(V) < 0.0) ? -1.0 : 1.0;
-    double R[3][3];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
+    // Fast path: for det(C) > 0 the Umeyama rotation U S V^T (S = I) is the orthogonal polar factor of C, obtained with the scaled
+    // Newton iteration X <- (g X + X^-T / g) / 2 (quadratically convergent, ~100 serial FP64 instructions per step instead of the
+    // ~4000 of a Jacobi SVD -- this code runs on ONE thread between two reductions of the ICP loop, so its latency is the step's).
+    // det(C) <= 0 (reflection case), a singular C or no convergence fall back to the SVD.
+    if (!polar_newton3(C, R)) {
+        double U[3][3], V[3][3], w[3];
+        svd3_dev(C, U, w, V);
+        const double sgn = (det3d(U) * det3d(V) < 0.0) ? -1.0 : 1.0;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
+    }
     double q[4];
     const double tr = R[0][0] + R[1][1] + R[2][2];
     if (tr > 0.0) {
@@ -262,18 +305,6 @@ B2_DEV void icp_step(IcpState* st, const CStats& stats_s)
     st->iter++;
 }
 
-__global__ void k_icp_init(IcpState* st)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const Tf I = tf_identity();
-        tf_store(&st->T_onew_oold, I);
-        tf_store(&st->T_snew_sold, icp_pretransform(tf_load(&st->Tbo), tf_load(&st->Tsb), I));
-        tf_store(&st->Tom_new, tf_load(&st->Tom));
-        st->iter = 0;
-        // Tbm for the find: MICPSensor.hpp:148  Tbm = Tom * Tbo  (stored in Tom_new's neighbour? no: computed by the find kernel itself)
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // generic closest hit for arbitrary rays (b2_mesh_intersect)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -329,7 +360,20 @@ struct RayModel {
     uint32_t n_origs;       // 1 or n
     uint32_t n;             // rays per pose
     float range_min, range_max;
+    uint32_t width, height; // scan raster (buffer id = vid*width + hid); used for the coherent tile order
 };
+
+// Rays are traced in 8x4 raster tiles (one tile per warp) instead of 32-long row segments: neighbouring rows/columns of a
+// LiDAR / depth raster stay inside the same BVH subtrees, which shortens the warp's union of traversal paths.  Results are
+// written at the original buffer id, so the order is invisible outside.
+B2_DEV uint32_t tile_order(uint32_t k, uint32_t width, uint32_t height)
+{
+    if ((width & 7u) || (height & 3u)) return k;
+    const uint32_t tile = k >> 5, within = k & 31u, tiles_per_row = width >> 3;
+    const uint32_t hid = (tile % tiles_per_row) * 8u + (within & 7u);
+    const uint32_t vid = (tile / tiles_per_row) * 4u + (within >> 3);
+    return vid * width + hid;
+}
 
 struct ModelBuffers {
     float* pts; float* nrm; uint8_t* hits; uint32_t* faces; float* ranges;
@@ -370,18 +414,40 @@ B2_DEV void find_one(const BvhView& bvh, Tf Tsm, const RayModel& model, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(128) k_rcc_find(BvhView bvh, const b2_transform* __restrict__ Tbm_dev, const IcpState* __restrict__ icp, b2_transform Tbm_val,
-                                                  b2_transform Tsb_val, RayModel model, uint32_t n_poses, ModelBuffers out)
+// bulk prefetch of this block's slice of the node array into L2 (UBLKPF): after a cold start the top of the tree then comes from
+// L2 instead of one DRAM round trip per level.  16-byte granularity, fire and forget.
+__device__ __forceinline__ void bulk_prefetch_slice(const void* base, uint64_t total)
 {
+    const uint64_t per = ((total + gridDim.x - 1) / gridDim.x + 15ull) & ~15ull;
+    const uint64_t beg = (uint64_t)blockIdx.x * per;
+    if (beg < total) {
+        const uint32_t bytes = (uint32_t)min(per, total - beg) & ~15u;
+        const char* ptr = reinterpret_cast<const char*>(base) + beg;
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+    }
+}
+// mode 1: node array; mode 2: node array + leaf triangle records (the whole map, 56 MB for 1M triangles, fits the 126 MB L2)
+__device__ __forceinline__ void prefetch_map_l2(const BvhView& bvh, uint32_t n_nodes, uint32_t n_tris, int mode)
+{
+    if (threadIdx.x == 0 && mode >= 1) bulk_prefetch_slice(bvh.nodes, (uint64_t)n_nodes * 80ull);
+    if (threadIdx.x == 32 % blockDim.x && mode >= 2) bulk_prefetch_slice(bvh.tris, (uint64_t)n_tris * 48ull);
+}
+
+#define B2_FIND_BLOCK 64
+__global__ void __launch_bounds__(B2_FIND_BLOCK) k_rcc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const b2_transform* __restrict__ Tbm_dev,
+                                                            const IcpState* __restrict__ icp, b2_transform Tbm_val, b2_transform Tsb_val, RayModel model, uint32_t n_poses,
+                                                            ModelBuffers out)
+{
+    prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)model.n * n_poses;
     if (gid >= total) return;
-    const uint32_t pose = (uint32_t)(gid / model.n), i = (uint32_t)(gid % model.n);
+    const uint32_t pose = (uint32_t)(gid / model.n), i = tile_order((uint32_t)(gid % model.n), model.width, model.height);
     Tf Tbm;
     if (icp) Tbm = tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo));           // MICPSensor.hpp:148
     else if (Tbm_dev) Tbm = tf_load(Tbm_dev + pose);
     else Tbm = tf_from_pod(Tbm_val);
-    find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, gid, out);
+    find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, (uint64_t)pose * model.n + i, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -401,11 +467,13 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
     const float max_dist = icp ? icp->max_dist : max_dist_val;
     P2LAcc acc; acc_zero(acc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (!(dmask[i] > 0) || !(mmask[i] > 0)) continue;
+        // all eleven loads are issued before the first use (no mask-dependent early-out): one memory round trip per element
+        const uint8_t dm = dmask[i], mm = mmask[i];
+        const V3 d = mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]);
+        const V3 I = mk3(mpts[3 * i], mpts[3 * i + 1], mpts[3 * i + 2]);
+        const V3 N = mk3(mnrm[3 * i], mnrm[3 * i + 1], mnrm[3 * i + 2]);
         V3 D, M;
-        if (p2l_pair(Tpre, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), mk3(mpts[3 * i], mpts[3 * i + 1], mpts[3 * i + 2]),
-                     mk3(mnrm[3 * i], mnrm[3 * i + 1], mnrm[3 * i + 2]), max_dist, D, M))
-            acc_add_pair(acc, D, M);
+        if ((dm > 0) && (mm > 0) && p2l_pair(Tpre, d, I, N, max_dist, D, M)) acc_add_pair(acc, D, M);
     }
     block_reduce_acc<B2_RED_BLOCK>(acc, smem);
     if (threadIdx.x == 0) {
@@ -419,17 +487,26 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // deterministic parallel sum of the block partials: thread (g, i) adds value i of blocks g, g+16, ...; then the 16 group sums in order
+    __shared__ double s_part[16][B2_NACC + 1];
+    {
+        const uint32_t i = threadIdx.x & 15u, g = threadIdx.x >> 4;           // 256 threads = 16 groups x 16 values
+        double a = 0.0;
+        for (uint32_t b = g; b < gridDim.x; b += 16u) a += __ldcg(partials + (size_t)b * (B2_NACC + 1) + i);
+        s_part[g][i] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < B2_NACC + 1) {
+        double a = 0.0;
+        #pragma unroll
+        for (int g = 0; g < 16; g++) a += s_part[g][threadIdx.x];
+        s_part[0][threadIdx.x] = a;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        double v[B2_NACC]; for (int i = 0; i < B2_NACC; i++) v[i] = 0.0;
-        double cnt = 0.0;
-        for (uint32_t b = 0; b < gridDim.x; b++) {
-            const volatile double* p = partials + (size_t)b * (B2_NACC + 1);
-            for (int i = 0; i < B2_NACC; i++) v[i] += p[i];
-            cnt += p[B2_NACC];
-        }
-        const CStats s = acc_finalize(v, (uint32_t)(cnt + 0.5));
-        if (out) cs_store(out, s);
-        if (icp) icp_step(icp, s);
+        const CStats st = acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5));
+        if (out) cs_store(out, st);
+        if (icp) icp_step(icp, st);
         *ticket = 0u;
     }
 }
@@ -451,7 +528,8 @@ __global__ void __launch_bounds__(B2_FUSED_BLOCK) k_rcc_fused_batch(BvhView bvh,
     P2LAcc acc; acc_zero(acc);
     const uint32_t begin = chunk * rays_per_block;
     const uint32_t end = min(begin + rays_per_block, model.n);
-    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    for (uint32_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        const uint32_t i = tile_order(k, model.width, model.height);
         if (!(dmask[i] > 0)) continue;
         const uint32_t oi = model.n_origs == 1 ? 0 : i;
         const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);

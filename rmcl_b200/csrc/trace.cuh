@@ -102,9 +102,21 @@ B2_DEV V3 tri_ng(const BvhView& bvh, uint32_t tri_idx)
     return cross_fma(v_sub(mk3(b.x, b.y, b.z), v0), v_sub(mk3(c.x, c.y, c.z), v0));
 }
 
-B2_DEV float byte_f(uint32_t w, int sh) { return (float)((w >> sh) & 0xffu); }
+// byte s of w as an exact float 2^23 + b: one PRMT, no I2F (the XU pipe was the busiest pipe with cvt, profiles/r01)
+template <int S> B2_DEV float byte_magic(uint32_t w, uint32_t k4b) { return u2f(prmt_imm<0x7540 + S>(w, k4b)); }
+
+#define B2_C3P 0.99951171875f          // 1 - 2^-11 : C3 folded into the near planes (see below)
 
 // Intersect the 8 children of one node; returns the hit mask: bits 31..24 inner children by priority (slot ^ oct), bits 23..0 leaf triangles.
+//
+// Per axis k (ad = scale*idir, ao = (p - o)*idir) the real-valued child planes are t = q*ad + ao, q in 0..255.  Computed form:
+//     far :  tf_k = fma(q', ad,       cf),  cf = (ao + dl) - 2^23*ad                q' = 2^23 + q (exact float, byte_magic)
+//     near:  tn_k = fma(q', ad*C3',   cn),  cn = (ao - dl)*C3' - 2^23*(ad*C3')      C3' = 1 - 2^-11
+//     dl = |ao|*2^-20 + |ad|*(1 + 2^-12)
+// The 2^23 offset of q' cancels exactly against the constant (same rounded ad); rounding the constant costs at most |ad|/2 and is
+// covered by the |ad| term of dl; the remaining dl >= 2^-20(|ao| + 256|ad|) dominates the FMA-path error and F's relative error
+// (trace.cuh header).  Scaling the near side by C3' makes  max(tn_x,tn_y,tn_z,0) <= min(tf_x,tf_y,tf_z,tbest*C1)  at least as
+// permissive as the oracle's visit rule V (tn <= tbest*C1 && tf >= max(0, tn*C3)) on the float box inside the quantised one.
 B2_DEV uint32_t node_test(const uint4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& imask)
 {
     const uint4 n0 = ldg(np + 0), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
@@ -115,10 +127,11 @@ B2_DEV uint32_t node_test(const uint4* __restrict__ np, const RaySetup& r, float
 
     const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
     const float aox = (px - r.o.x) * r.idir.x, aoy = (py - r.o.y) * r.idir.y, aoz = (pz - r.o.z) * r.idir.z;
-    const float k = 9.5367431640625e-07f;   // 2^-20
-    const float dlx = fmaf(256.0f, fabsf(adx), fabsf(aox)) * k, dly = fmaf(256.0f, fabsf(ady), fabsf(aoy)) * k, dlz = fmaf(256.0f, fabsf(adz), fabsf(aoz)) * k;
-    const float onx = aox - dlx, ony = aoy - dly, onz = aoz - dlz;     // near-plane offsets (widened)
-    const float ofx = aox + dlx, ofy = aoy + dly, ofz = aoz + dlz;     // far-plane offsets (widened)
+    const float k20 = 9.5367431640625e-07f, k1 = 1.000244140625f, two23 = 8388608.0f;
+    const float dlx = fmaf(fabsf(adx), k1, fabsf(aox) * k20), dly = fmaf(fabsf(ady), k1, fabsf(aoy) * k20), dlz = fmaf(fabsf(adz), k1, fabsf(aoz) * k20);
+    const float anx = adx * B2_C3P, any_ = ady * B2_C3P, anz = adz * B2_C3P;
+    const float cnx = fmaf(-two23, anx, (aox - dlx) * B2_C3P), cny = fmaf(-two23, any_, (aoy - dly) * B2_C3P), cnz = fmaf(-two23, anz, (aoz - dlz) * B2_C3P);
+    const float cfx = fmaf(-two23, adx, aox + dlx), cfy = fmaf(-two23, ady, aoy + dly), cfz = fmaf(-two23, adz, aoz + dlz);
 
     // near/far byte planes by ray direction sign
     const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
@@ -126,27 +139,36 @@ B2_DEV uint32_t node_test(const uint4* __restrict__ np, const RaySetup& r, float
     const uint32_t qny0 = ny ? n4.x : n2.z, qny1 = ny ? n4.y : n2.w, qfy0 = ny ? n2.z : n4.x, qfy1 = ny ? n2.w : n4.y;
     const uint32_t qnz0 = nz ? n4.z : n3.x, qnz1 = nz ? n4.w : n3.y, qfz0 = nz ? n3.x : n4.z, qfz1 = nz ? n3.y : n4.w;
 
+    // octant permutation of the priority bits of all inner children at once: meta ^= oct where (meta & 0x18) == 0x18
+    const uint32_t m0 = n1.z ^ ((((n1.z >> 3) & (n1.z >> 4)) & 0x01010101u) * r.oct);
+    const uint32_t m1 = n1.w ^ ((((n1.w >> 3) & (n1.w >> 4)) & 0x01010101u) * r.oct);
+
     const float tlim = tbest * B2_C1;
+    const uint32_t k4b = opaque_const(0x4B000000u);
     uint32_t hitmask = 0;
-    #pragma unroll
-    for (int s = 0; s < 8; s++) {
-        const int sh = 8 * (s & 3);
-        const uint32_t meta = ((s < 4 ? n1.z : n1.w) >> sh) & 0xffu;
-        const float tnx = fmaf(byte_f(s < 4 ? qnx0 : qnx1, sh), adx, onx);
-        const float tny = fmaf(byte_f(s < 4 ? qny0 : qny1, sh), ady, ony);
-        const float tnz = fmaf(byte_f(s < 4 ? qnz0 : qnz1, sh), adz, onz);
-        const float tfx = fmaf(byte_f(s < 4 ? qfx0 : qfx1, sh), adx, ofx);
-        const float tfy = fmaf(byte_f(s < 4 ? qfy0 : qfy1, sh), ady, ofy);
-        const float tfz = fmaf(byte_f(s < 4 ? qfz0 : qfz1, sh), adz, ofz);
-        const float tn = fmaxf(fmaxf(tnx, tny), tnz);
-        const float tf = fminf(fminf(tfx, tfy), tfz);
-        const bool hit = (tn <= tlim) && (tf >= fmaxf(0.0f, tn * B2_C3));
-        if (hit) {
-            const bool inner = (meta & 0x18u) == 0x18u;
-            const uint32_t bit = (meta & 0x1fu) ^ (inner ? r.oct : 0u);
-            hitmask |= (meta >> 5) << bit;
-        }
+#define B2_CHILD(S, QNX, QNY, QNZ, QFX, QFY, QFZ, M)                                                    \
+    {                                                                                                    \
+        const float tnx = fmaf(byte_magic<(S) & 3>(QNX, k4b), anx, cnx);                                 \
+        const float tny = fmaf(byte_magic<(S) & 3>(QNY, k4b), any_, cny);                                \
+        const float tnz = fmaf(byte_magic<(S) & 3>(QNZ, k4b), anz, cnz);                                 \
+        const float tfx = fmaf(byte_magic<(S) & 3>(QFX, k4b), adx, cfx);                                 \
+        const float tfy = fmaf(byte_magic<(S) & 3>(QFY, k4b), ady, cfy);                                 \
+        const float tfz = fmaf(byte_magic<(S) & 3>(QFZ, k4b), adz, cfz);                                 \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                       \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlim));                                       \
+        const uint32_t meta = ((M) >> (8 * ((S) & 3))) & 0xffu;                                          \
+        const uint32_t bits = (meta >> 5) << (meta & 0x1fu);                                             \
+        hitmask |= (tn <= tf) ? bits : 0u;                                                               \
     }
+    B2_CHILD(0, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
+    B2_CHILD(1, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
+    B2_CHILD(2, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
+    B2_CHILD(3, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
+    B2_CHILD(4, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
+    B2_CHILD(5, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
+    B2_CHILD(6, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
+    B2_CHILD(7, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
+#undef B2_CHILD
     return hitmask;
 }
 

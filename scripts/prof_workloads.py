@@ -1,0 +1,45 @@
+"""Short run of every kernel for ncu (few launches each).  python scripts/prof_workloads.py [faces]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rmcl_b200
+from rmcl_b200 import synth
+
+faces = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+V, F = synth.building(faces)
+gmap = rmcl_b200.Map(V, F)
+m = synth.c2_sensor()
+Tsb, Tgt, I = synth.scenario_tsb(), synth.building_gt_pose(), synth.make_transform()
+h = rmcl_b200.RCCB200Spherical(gmap)
+h.setTsb(Tsb); h.setModel(m); h.setParams(1.0, 0.15)
+h.find(Tgt)
+ranges = synth.noisy_ranges(h.modelView()["ranges"], m.range_max)
+h.setRanges(ranges)
+Tom = synth.compose(Tgt, synth.scenario_pose_offset())
+for _ in range(steps):
+    h.correctOnce(Tom, I, 5, 0.0)
+pts = h.modelView()["points"]
+beams = synth.pf_beams(pts, 180)
+P, A = synth.pf_particles(100_000)
+up = rmcl_b200.PCDSensorUpdaterB200(gmap)
+Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+for _ in range(2):
+    up.update(Pd, Ad, Tsb, beams)
+torch.cuda.synchronize()
+hv = rmcl_b200.SphereCorrectorB200(gmap)
+hv.setTsb(Tsb)
+mv = synth.vlp16_900(); mv.range_min = 0.0
+hv.setModel(mv); hv.find(Tgt); hv.setInputData(hv.modelView()["ranges"])
+T = synth.transforms(1000); T[:] = Tom
+T["t"] += np.random.default_rng(0).uniform(-0.05, 0.05, (1000, 3)).astype(np.float32)
+Td = torch.from_numpy(T.view(np.float32).reshape(-1, 8).copy()).cuda()
+for _ in range(2):
+    hv.correct(Td)
+torch.cuda.synchronize()
+print("done", rmcl_b200.kernel_launch_count())

@@ -28,7 +28,7 @@ __attribute__((visibility("default"))) void emul_scene_info(void* p, uint32_t* n
 static BvhView view(void* p) { EmulScene* s = (EmulScene*)p; BvhView v; v.nodes = (const uint4*)s->bvh.nodes; v.tris = (const float4*)s->bvh.tris; return v; }
 
 __attribute__((visibility("default"))) void emul_intersect(void* sc, const float* origs, const float* dirs, uint32_t n, float tfar,
-                                                           float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out, double* mean_nodes, double* mean_tris)
+                                                           float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out, double* mean_nodes, double* mean_tris, uint32_t* per_ray_nodes, uint32_t* per_ray_tris)
 {
     const BvhView bvh = view(sc);
     unsigned long long tn = 0, tt = 0;
@@ -39,6 +39,8 @@ __attribute__((visibility("default"))) void emul_intersect(void* sc, const float
         uint32_t nn = 0, nt = 0;
         trace_closest<true>(bvh, r, h, nn, nt);
         tn += nn; tt += nt;
+        if (per_ray_nodes) per_ray_nodes[i] = nn;
+        if (per_ray_tris) per_ray_tris[i] = nt;
         const bool hit = h.face != B2_NOFACE;
         if (t_out) t_out[i] = hit ? h.t : u2f(0x7f800000u);
         if (face_out) face_out[i] = h.face;

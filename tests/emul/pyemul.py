@@ -65,12 +65,16 @@ class Scene:
         lib().emul_scene_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return dict(n_nodes=a.value, n_tris=b.value, max_depth=c.value, sah=d.value)
 
-    def intersect(self, origs, dirs, tfar=np.inf):
+    def intersect(self, origs, dirs, tfar=np.inf, per_ray=False):
         origs, dirs = _f32(origs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
         n = len(origs)
         t, f, ng, h = np.empty(n, np.float32), np.empty(n, np.uint32), np.empty((n, 3), np.float32), np.empty(n, np.uint8)
         mn, mt = C.c_double(), C.c_double()
-        lib().emul_intersect(self._h, _p(origs), _p(dirs), C.c_uint32(n), C.c_float(tfar), _p(t), _p(f), _p(ng), _p(h), C.byref(mn), C.byref(mt))
+        pn = np.zeros(n, np.uint32) if per_ray else None
+        pt = np.zeros(n, np.uint32) if per_ray else None
+        lib().emul_intersect(self._h, _p(origs), _p(dirs), C.c_uint32(n), C.c_float(tfar), _p(t), _p(f), _p(ng), _p(h), C.byref(mn), C.byref(mt), _p(pn), _p(pt))
+        if per_ray:
+            return t, f, ng, h, (mn.value, mt.value), pn, pt
         return t, f, ng, h, (mn.value, mt.value)
 
     def find(self, Tbm, Tsb, origs_s, dirs_s, range_max):

@@ -90,3 +90,34 @@ def test_pf_bit_exact(pe, po, synth):
         a = osc.pf_update(P, A, Tsb, beams, prm)
         b = esc.pf_update(P, A, Tsb, beams, prm)
         assert a.tobytes() == b.tobytes()
+
+
+def test_umeyama_fast_path_and_fallback(pe, po):
+    """Device Umeyama (Newton polar iteration, SVD fallback) against the oracle's Jacobi SVD: goldens, reflection, rank-deficient, zero."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "umeyama.npz"))
+    for s, T in zip(g["stats"], g["T"]):
+        out = pe.umeyama(s)
+        assert np.abs(out["t"] - T["t"]).max() <= 1e-6 and min(np.abs(out["R"] - T["R"]).max(), np.abs(out["R"] + T["R"]).max()) <= 1e-6
+    rng = np.random.default_rng(3)
+    for k in range(200):
+        s = np.zeros((), po.CROSS_STATS)
+        A = rng.normal(size=(3, 3))
+        if k % 4 == 1:
+            A[:, 2] *= -1e-3                      # det < 0: reflection branch
+        if k % 4 == 2:
+            A[2, :] = 0.0                         # rank 2
+        if k % 4 == 3:
+            A = np.diag(rng.uniform(0.5, 2.0, 3)) + 1e-3 * A      # near-SPD (the ICP case)
+        s["covariance"] = A.T.reshape(-1).astype(np.float32)
+        s["dataset_mean"], s["model_mean"], s["n_meas"] = rng.normal(size=3), rng.normal(size=3), 100
+        a, b = po.umeyama(s), pe.umeyama(s)
+        sv = np.linalg.svd(s["covariance"].reshape(3, 3).T.astype(np.float64), compute_uv=False)
+        if sv[1] < 1e-3 * sv[0] or sv[2] < 1e-6 * sv[0]:
+            continue                              # rotation not unique: nothing to compare
+        q1, q2 = np.asarray(a["R"], np.float64), np.asarray(b["R"], np.float64)
+        tol = 2e-6 if sv[2] > 1e-3 * sv[0] else 1e-3
+        assert min(np.abs(q1 - q2).max(), np.abs(q1 + q2).max()) <= tol, (k, sv)
+    z = np.zeros((), po.CROSS_STATS)
+    I = pe.umeyama(z)
+    assert np.allclose(I["R"], [0, 0, 0, 1]) and np.allclose(I["t"], 0)
