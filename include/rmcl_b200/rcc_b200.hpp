@@ -1,0 +1,212 @@
+// rcc_b200.hpp -- C++ host classes with the reference's names and signatures for the ray-casting-correspondence path, implemented over
+// the C ABI (include/rmcl_b200.h).  These are what rmcl_ros' loadSensor / RmclNode would instantiate for a "b200" backend string
+// (INTEGRATION.md).  Header-only; link with -lrmcl_b200.
+//
+//   rmcl::Correspondences_<MemT>            rmcl/include/rmcl/registration/Correspondences.hpp:16-88
+//   rmcl::RCCB200{Spherical,Pinhole,O1Dn,OnDn}  twins of rmcl::RCCEmbree* / RCCOptix*  (RCCEmbree.hpp:18-83, RCCOptix.hpp:18-93)
+//   rmcl::{Sphere,Pinhole,O1Dn,OnDn}CorrectorB200  v1 API used by rmcl_ros/src/benchmarks/lidar_corrector_{embree,optix}_benchmark.cpp:86-155
+//   rmcl::PCDSensorUpdaterB200              rmcl_ros/include/rmcl_ros/rmcl/ParticleUpdater.hpp:39-43 + PCDSensorUpdaterEmbree.cpp:244-352
+#pragma once
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rmcl_b200.h"
+#include "rmagine_compat.hpp"
+
+namespace rmcl {
+
+namespace rm = rmagine;
+
+inline void b2_check(int rc, const char* what)
+{
+    // error convention of the reference: std::runtime_error for map / configuration failures (micp_localization.cpp:124, PCDSensorUpdaterEmbree.cpp:165)
+    if (rc != B2_OK) throw std::runtime_error(std::string(what) + ": " + b2_last_error());
+}
+
+// stands in for rm::EmbreeMap / rm::OptixMap; shared between sensors and plugins like the reference's map container (micp_localization.cpp:545)
+class B200Map {
+public:
+    B200Map(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces, int device = 0, int build_mode = B2_BUILD_HOST_SAH)
+    { b2_check(b2_mesh_create(verts_xyz, n_vertices, faces_ijk, n_faces, device, build_mode, &m_), "B200Map"); }
+    ~B200Map() { b2_mesh_destroy(m_); }
+    B200Map(const B200Map&) = delete; B200Map& operator=(const B200Map&) = delete;
+    b2_mesh* handle() const { return m_; }
+    b2_mesh_info info() const { b2_mesh_info i; b2_check(b2_mesh_get_info(m_, &i), "B200Map::info"); return i; }
+private:
+    b2_mesh* m_ = nullptr;
+};
+using B200MapPtr = std::shared_ptr<B200Map>;
+
+// device-resident point cloud views (rm::PointCloudView_<VRAM_CUDA>)
+struct PointCloudViewB200 { rm::MemoryView<rm::Vector3f, rm::VRAM_CUDA> points; rm::MemoryView<uint8_t, rm::VRAM_CUDA> mask; rm::MemoryView<rm::Vector3f, rm::VRAM_CUDA> normals; };
+
+struct ParticleAttributes { rm::Gaussian1D likelihood; float state_sigma[6]; };                // ParticleAttributes.hpp:18-32
+struct RangeMeasurement { rm::Vector3f orig, dir; float range; rm::Matrix3x3 cov; };            // RangeMeasurement.hpp:10-21
+static_assert(sizeof(ParticleAttributes) == 36 && sizeof(RangeMeasurement) == 64, "rmcl layouts");
+struct ParticleUpdateResults {};
+struct ParticleUpdateConfig {};
+
+// --- Correspondences_ interface, device flavour --------------------------------------------------------------------------------
+class CorrespondencesB200 {
+public:
+    rm::UmeyamaReductionConstraints params{1.0f};      // Correspondences.hpp:22
+    float adaptive_max_dist_min = 0.15f;               // :23
+    bool outdated = true;                              // :31
+
+    explicit CorrespondencesB200(B200MapPtr map) : map_(std::move(map))
+    {
+        if (!map_) throw std::runtime_error("NO MAP");                                           // PCDSensorUpdaterOptix.cpp:179-185
+        b2_check(b2_rcc_create(map_->handle(), &h_), "RCCB200");
+    }
+    virtual ~CorrespondencesB200() { b2_rcc_destroy(h_); }
+    CorrespondencesB200(const CorrespondencesB200&) = delete; CorrespondencesB200& operator=(const CorrespondencesB200&) = delete;
+
+    virtual void setTsb(const rm::Transform& Tsb) { Tsb_ = Tsb; b2_check(b2_rcc_set_tsb(h_, tf(&Tsb)), "setTsb"); }     // :33-36
+    // the public `dataset` field of the reference becomes two setters (the buffers live in HBM, owned by the handle)
+    void setDataset(const rm::Vector3f* points, const uint8_t* mask, size_t n, bool on_device = false)
+    { b2_check(b2_rcc_set_dataset(h_, reinterpret_cast<const float*>(points), mask, (uint32_t)n, on_device ? 1 : 0), "setDataset"); outdated = true; }
+    void setRanges(const float* ranges, size_t n, bool on_device = false)                          // MICPSphericalSensorCPU.cpp:181-233 on the device
+    { b2_check(b2_rcc_set_ranges(h_, ranges, (uint32_t)n, on_device ? 1 : 0), "setRanges"); outdated = true; }
+
+    virtual void find(const rm::Transform& Tbm_est)                                                // :42-44
+    { sync_params(); b2_check(b2_rcc_find(h_, tf(&Tbm_est)), "find"); outdated = false; }
+
+    virtual rm::CrossStatistics computeCrossStatistics(const rm::Transform& T_snew_sold, double convergence_progress = 0.0) const   // :75-77
+    {
+        sync_params();
+        rm::CrossStatistics out;
+        b2_check(b2_rcc_cross_statistics(h_, tf(&T_snew_sold), convergence_progress, reinterpret_cast<b2_cross_stats*>(&out)), "computeCrossStatistics");
+        return out;
+    }
+    PointCloudViewB200 modelView()                                                                 // :47-54
+    {
+        float *p = nullptr, *nr = nullptr; uint8_t* hi = nullptr; uint32_t n = 0;
+        b2_check(b2_rcc_model_view(h_, &p, &nr, &hi, nullptr, nullptr, &n), "modelView");
+        return PointCloudViewB200{{reinterpret_cast<rm::Vector3f*>(p), n}, {hi, n}, {reinterpret_cast<rm::Vector3f*>(nr), n}};
+    }
+    PointCloudViewB200 datasetView()                                                               // :56-62
+    {
+        float* p = nullptr; uint8_t* m = nullptr; uint32_t n = 0;
+        b2_check(b2_rcc_dataset_view(h_, &p, &m, &n), "datasetView");
+        return PointCloudViewB200{{reinterpret_cast<rm::Vector3f*>(p), n}, {m, n}, {nullptr, 0}};
+    }
+    // one MICPLocalizationNode::correctOnce for this sensor on the device (micp_localization.cpp:899-984)
+    rm::Transform correctOnce(const rm::Transform& Tom, const rm::Transform& Tbo, unsigned iterations = 5, double convergence_progress = 0.0,
+                              rm::Transform* T_onew_oold = nullptr, rm::CrossStatistics* Cmerged_o = nullptr)
+    {
+        sync_params();
+        rm::Transform out;
+        b2_check(b2_rcc_correct_once(h_, tf(&Tom), tf(&Tbo), iterations, convergence_progress, reinterpret_cast<b2_transform*>(&out),
+                                     reinterpret_cast<b2_transform*>(T_onew_oold), reinterpret_cast<b2_cross_stats*>(Cmerged_o)), "correctOnce");
+        outdated = false;
+        return out;
+    }
+    void setStream(void* cuda_stream) { b2_check(b2_rcc_set_stream(h_, cuda_stream), "setStream"); }
+    b2_rcc* handle() const { return h_; }
+
+protected:
+    static const b2_transform* tf(const rm::Transform* T) { return reinterpret_cast<const b2_transform*>(T); }
+    void sync_params() const { b2_rcc_set_params(h_, params.max_dist, adaptive_max_dist_min); }
+    B200MapPtr map_;
+    b2_rcc* h_ = nullptr;
+    rm::Transform Tsb_ = rm::Transform::Identity();
+};
+
+class RCCB200Spherical : public CorrespondencesB200, public rm::ModelSetter<rm::SphericalModel> {
+public:
+    explicit RCCB200Spherical(B200MapPtr map) : CorrespondencesB200(std::move(map)) {}
+    void setModel(const rm::SphericalModel& m) override                                           // RCCEmbree.cpp:21-24
+    {
+        b2_spherical_model s{m.phi.min, m.phi.inc, m.phi.size, m.theta.min, m.theta.inc, m.theta.size, m.range.min, m.range.max};
+        b2_check(b2_rcc_set_model_spherical(h_, &s), "setModel");
+    }
+};
+class RCCB200Pinhole : public CorrespondencesB200, public rm::ModelSetter<rm::PinholeModel> {
+public:
+    explicit RCCB200Pinhole(B200MapPtr map) : CorrespondencesB200(std::move(map)) {}
+    void setModel(const rm::PinholeModel& m) override                                             // RCCEmbree.cpp:53-56
+    {
+        b2_pinhole_model p{m.width, m.height, m.f[0], m.f[1], m.c[0], m.c[1], m.range.min, m.range.max};
+        b2_check(b2_rcc_set_model_pinhole(h_, &p), "setModel");
+    }
+};
+class RCCB200O1Dn : public CorrespondencesB200, public rm::ModelSetter<rm::O1DnModel> {
+public:
+    explicit RCCB200O1Dn(B200MapPtr map) : CorrespondencesB200(std::move(map)) {}
+    void setModel(const rm::O1DnModel& m) override                                                // RCCEmbree.cpp:84-87
+    { b2_check(b2_rcc_set_model_o1dn(h_, m.width, m.height, &m.orig.x, reinterpret_cast<const float*>(m.dirs.data()), m.range.min, m.range.max), "setModel"); }
+};
+class RCCB200OnDn : public CorrespondencesB200, public rm::ModelSetter<rm::OnDnModel> {
+public:
+    explicit RCCB200OnDn(B200MapPtr map) : CorrespondencesB200(std::move(map)) {}
+    void setModel(const rm::OnDnModel& m) override                                                // RCCEmbree.cpp:116-119
+    {
+        b2_check(b2_rcc_set_model_ondn(h_, m.width, m.height, reinterpret_cast<const float*>(m.origs.data()), reinterpret_cast<const float*>(m.dirs.data()),
+                                       m.range.min, m.range.max), "setModel");
+    }
+};
+
+// --- v1 batched corrector API (lidar_corrector_embree_benchmark.cpp:86-133) -------------------------------------------------------
+struct CorrectionResultsB200 { std::vector<rm::Transform> Tdelta; std::vector<uint32_t> Ncorr; };
+template <typename RCC> class CorrectorB200 : public RCC {
+public:
+    using RCC::RCC;
+    void setInputData(const float* ranges, size_t n, bool on_device = false) { this->setRanges(ranges, n, on_device); }       // :118
+    CorrectionResultsB200 correct(const std::vector<rm::Transform>& Tbm)                                                       // :127-133
+    {
+        this->sync_params();
+        CorrectionResultsB200 r; r.Tdelta.resize(Tbm.size()); r.Ncorr.resize(Tbm.size());
+        b2_check(b2_rcc_correct_batch(this->h_, reinterpret_cast<const b2_transform*>(Tbm.data()), (uint32_t)Tbm.size(), 0,
+                                      reinterpret_cast<b2_transform*>(r.Tdelta.data()), r.Ncorr.data(), nullptr, 0), "correct");
+        return r;
+    }
+};
+using SphereCorrectorB200 = CorrectorB200<RCCB200Spherical>;
+using PinholeCorrectorB200 = CorrectorB200<RCCB200Pinhole>;
+using O1DnCorrectorB200 = CorrectorB200<RCCB200O1Dn>;
+using OnDnCorrectorB200 = CorrectorB200<RCCB200OnDn>;
+
+inline rm::Transform umeyama_transform(const rm::CrossStatistics& s, int device = 0)              // micp_localization.cpp:952-953
+{
+    rm::Transform T;
+    b2_check(b2_umeyama_batch(reinterpret_cast<const b2_cross_stats*>(&s), 1, reinterpret_cast<b2_transform*>(&T), 0, device, nullptr), "umeyama_transform");
+    return T;
+}
+
+// --- particle filter sensor update ------------------------------------------------------------------------------------------------
+class PCDSensorUpdaterB200 {
+public:
+    b2_pf_params config{2.0f, 100.0f, 100.0f, 0.0f, 0.05f, 80.0f, 0};                           // PCDSensorUpdaterEmbree.cpp:122-134
+    explicit PCDSensorUpdaterB200(B200MapPtr map) : map_(std::move(map))
+    {
+        if (!map_) throw std::runtime_error("NO MAP");
+        b2_check(b2_pf_create(map_->handle(), &h_), "PCDSensorUpdaterB200");
+    }
+    ~PCDSensorUpdaterB200() { b2_pf_destroy(h_); }
+    void setTsb(const rm::Transform& Tsb) { Tsb_ = Tsb; }
+    // beams replace the random_device sampling of :276-327 (quirk D5): the caller samples the cloud and passes RangeMeasurements
+    void setBeams(const std::vector<RangeMeasurement>& beams) { beams_ = beams; }
+    // ParticleUpdater<RAM>::update
+    ParticleUpdateResults update(rm::MemoryView<rm::Transform, rm::RAM> poses, rm::MemoryView<ParticleAttributes, rm::RAM> attrs, const ParticleUpdateConfig& = {})
+    {
+        b2_check(b2_pf_sensor_update_host(h_, reinterpret_cast<const b2_transform*>(poses.raw()), reinterpret_cast<b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
+                                          reinterpret_cast<const b2_transform*>(&Tsb_), reinterpret_cast<const b2_range_meas*>(beams_.data()), (uint32_t)beams_.size(), &config), "update");
+        return {};
+    }
+    // ParticleUpdater<VRAM_CUDA>::update
+    ParticleUpdateResults update(rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs, const ParticleUpdateConfig& = {})
+    {
+        b2_check(b2_pf_sensor_update(h_, reinterpret_cast<const b2_transform*>(poses.raw()), reinterpret_cast<b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
+                                     reinterpret_cast<const b2_transform*>(&Tsb_), reinterpret_cast<const b2_range_meas*>(beams_.data()), (uint32_t)beams_.size(), &config), "update");
+        return {};
+    }
+private:
+    B200MapPtr map_;
+    b2_pf* h_ = nullptr;
+    rm::Transform Tsb_ = rm::Transform::Identity();
+    std::vector<RangeMeasurement> beams_;
+};
+
+}  // namespace rmcl
