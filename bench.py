@@ -94,10 +94,32 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU leg may really use: min(affinity mask, cgroup CPU quota) -- oversubscribing a quota-limited container
+    makes OpenMP crawl."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    env = os.environ.get("B2_CPU_THREADS")
+    return max(1, int(env)) if env else n
+
+
 def cpu_reference_leg(args, steps, warmup):
     """The reference's CPU path restated (oracle port) on the host cores: same step, same inputs."""
     from oracle import pyoracle as po
     from rmcl_b200 import synth
+    po.set_num_threads(host_threads())
     V, F = synth.building(args.faces)
     sc = po.Scene(V, F)
     m = synth.c2_sensor()
@@ -112,7 +134,7 @@ def cpu_reference_leg(args, steps, warmup):
     for _ in range(steps):
         sc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
     dt = (time.perf_counter() - t0) / steps
-    return m.size / dt, dt, po.num_threads(), m.size
+    return m.size / dt, dt, host_threads(), m.size
 
 
 def main():
@@ -133,7 +155,8 @@ def main():
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "micp_iters_per_s": 1.0 / dt,
                 "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                                 "sample": f"{steps} full C2 correctOnce steps (131072 rays + 5 reductions each) on the CPU oracle, OpenMP over rays and over reduction chunks; Embree/rmagine not buildable here"},
+                                 "sample": f"{steps} full C2 correctOnce steps (131072 rays + 5 reductions each) on the CPU oracle, OpenMP over rays and over reduction chunks, threads = min(CPU affinity, cgroup CPU quota); Embree/rmagine not buildable here",
+                                 "host_logical_cpus": os.cpu_count()},
                 "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -240,7 +263,7 @@ def main():
     dirs_m = synth._qrot(q[None, :], dirs_s.astype(np.float64)).astype(np.float32)
     vn, vt = gmap.traversal_stats(np.tile(tsm, (len(dirs_m), 1)), dirs_m, m.range_max)
     b_io = 12 + 33                                   # direction table in, point+normal+hit+face+range out
-    bytes_per_ray = vn * 80.0 + vt * 48.0 + b_io
+    bytes_per_ray = vn * 224.0 + vt * 48.0 + b_io
     find_s = float(np.mean(find_ms)) * 1e-3
     achieved = bytes_per_ray * m.size / find_s / 1e9
     peaks = {}
@@ -256,7 +279,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": "k_rcc_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 80, "tri_bytes": 48, "io_bytes_per_ray": b_io,
+                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 224, "tri_bytes": 48, "io_bytes_per_ray": b_io,
                 "kernel_ms": find_s * 1e3, "kernel_share_of_step": float(np.mean(find_ms)) / (dev_ms / args.steps),
                 "kernel_rays_per_s": m.size / find_s}
 

@@ -36,8 +36,12 @@ struct b2_mesh {
     int device = 0; int build_mode = 0;
     B2Node8* d_nodes = nullptr; B2Tri* d_tris = nullptr;
     uint32_t n_nodes = 0, n_tris = 0, n_faces = 0, n_verts = 0, max_depth = 0;
-    float build_ms = 0.f, sah = 0.f;
-    BvhView view() const { BvhView v; v.nodes = reinterpret_cast<const uint4*>(d_nodes); v.tris = reinterpret_cast<const float4*>(d_tris); return v; }
+    float build_ms = 0.f, sah = 0.f, abs_max[3] = {0.f, 0.f, 0.f};
+    BvhView view() const
+    {
+        BvhView v; v.nodes = reinterpret_cast<const float4*>(d_nodes); v.tris = reinterpret_cast<const float4*>(d_tris);
+        v.bx = abs_max[0]; v.by = abs_max[1]; v.bz = abs_max[2]; return v;
+    }
 };
 
 template <typename T> struct DevBuf {
@@ -71,6 +75,7 @@ extern "C" int b2_mesh_create(const float* verts, uint32_t nv, const uint32_t* f
     if (!m) { b2_free_bvh8_host(&hb); return fail(B2_ERR_OOM, "out of host memory"); }
     m->device = device; m->build_mode = build_mode; m->n_nodes = hb.n_nodes; m->n_tris = hb.n_tris; m->n_faces = nf; m->n_verts = nv;
     m->max_depth = hb.max_depth; m->sah = hb.sah_cost;
+    for (int k = 0; k < 3; k++) m->abs_max[k] = hb.abs_max[k];
     cudaError_t e = cudaMalloc((void**)&m->d_nodes, sizeof(B2Node8) * (size_t)hb.n_nodes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_tris, sizeof(B2Tri) * (size_t)std::max(hb.n_tris, 1u));
     if (e == cudaSuccess) e = cudaMemcpy(m->d_nodes, hb.nodes, sizeof(B2Node8) * (size_t)hb.n_nodes, cudaMemcpyHostToDevice);

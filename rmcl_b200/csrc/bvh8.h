@@ -1,20 +1,23 @@
-// bvh8.h -- in-HBM layout of the map: 8-wide BVH with 8-bit quantised child boxes (80-byte nodes) + 48-byte leaf
-// triangle records.  Shared by the host builder, the device builder and the traversal kernels.
+// bvh8.h -- in-HBM layout of the map: 8-wide BVH with FLOAT child boxes (224-byte nodes) + 48-byte leaf triangle records.
+// Shared by the host builder and the traversal kernels.
 //
-// The layout idea (8 children, per-node quantisation frame, octant-ordered child slots, triangle ranges per node) is the
-// published "compressed wide BVH" of Ylitie, Karras, Laine, HPG 2017; this is an independent implementation.
+// Why uncompressed: on B200 the whole map (1M triangles: 22 MB nodes + 48 MB triangles) sits in the 126 MB L2 and the traversal is
+// bound by instruction issue, not by bytes (profiles/r01: warm vs cold L2 differ by 10 %, DRAM traffic 6.5 MB per 131k-ray launch).
+// Round 1 started with 80-byte nodes with 8-bit quantised planes (the published "compressed wide BVH" idea, Ylitie et al. 2017): every
+// visit paid ~70 instructions of per-node frame math and 48 byte->float conversions.  Float planes need neither: a child plane is one
+// FMA with per-RAY constants.  The wide-node organisation kept from that design: 8 children in octant-ordered slots (traversal order =
+// slot ^ ray octant, no sorting at run time), one contiguous run of inner children and of leaf triangles per node, <= 3 triangles per
+// leaf child encoded in a meta byte.
 //
-// Node (80 B = 5 x 16 B, loaded as 5 x LDG.128):
-//   q0: float px, py, pz;  u8 ex, ey, ez (IEEE exponent bytes: scale_k = 2^(e_k-127)), u8 imask (bit s: slot s is an inner node)
-//   q1: u32 child_base (index of first inner child), u32 tri_base (index of first leaf triangle record),
-//       u8 meta[8]  (slot s: 0 = empty; inner: 0x20 | (24 + s); leaf: (unary tri count 1|3|7) << 5 | offset of first tri from tri_base)
-//   q2: u8 qlo_x[8], u8 qlo_y[8]
-//   q3: u8 qlo_z[8], u8 qhi_x[8]
-//   q4: u8 qhi_y[8], u8 qhi_z[8]
-//   child box (real numbers): lo_k = p_k + qlo_k[s] * scale_k, hi_k = p_k + qhi_k[s] * scale_k  -- always CONTAINS the float AABB of
-//   every triangle below it (the builder checks this in double precision).
-//   Slot s "points" along D_s = (s&1 ? + : -, s&2 ? + : -, s&4 ? + : -); a ray with octant code r (bit k set iff d_k >= 0) visits
-//   inner children in order of descending (s ^ r).
+// Node (224 B = 14 x 16 B), planes SoA so that a ray picks "near" and "far" arrays by its direction signs with an address offset:
+//   +0    float lo_x[8]   +32  float lo_y[8]   +64  float lo_z[8]
+//   +96   float hi_x[8]   +128 float hi_y[8]   +160 float hi_z[8]
+//   +192  u32 child_base (index of first inner child), u32 tri_base (index of first leaf triangle record), u8 meta[8]
+//   +208  u32 imask (bit s: slot s is an inner node), 12 B pad
+//   meta[s]: 0 = empty; inner: 0x20 | (24 + s); leaf: (unary triangle count 1|3|7) << 5 | offset of its first triangle from tri_base
+//   empty slots have lo = +inf, hi = -inf (never hit).  Child boxes are the exact float AABBs (min/max of vertices) of the triangles below.
+//   Slot s "points" along D_s = (s&1 ? + : -, s&2 ? + : -, s&4 ? + : -); a ray with octant code r (bit k set iff d_k >= 0) visits inner
+//   children in order of descending (s ^ r).
 //
 // Leaf triangle record (48 B = 3 x 16 B): (v0.xyz, face_id as bits), (v1.xyz, 0), (v2.xyz, 0); records of one node are contiguous,
 // in slot order; at most 3 triangles per leaf child, at most 24 per node.
@@ -22,16 +25,17 @@
 #include <stdint.h>
 
 struct alignas(16) B2Node8 {
-    float    p[3];
-    uint8_t  e[3];
-    uint8_t  imask;
+    float    lo[3][8];
+    float    hi[3][8];
     uint32_t child_base;
     uint32_t tri_base;
     uint8_t  meta[8];
-    uint8_t  qlo[3][8];
-    uint8_t  qhi[3][8];
+    uint32_t imask;
+    uint32_t pad[3];
 };
-static_assert(sizeof(B2Node8) == 80, "node must be 80 bytes");
+static_assert(sizeof(B2Node8) == 224, "node must be 224 bytes");
+#define B2_NODE_BYTES 224
+#define B2_NODE_QUADS 14
 
 struct alignas(16) B2Tri {
     float    v0[3]; uint32_t face_id;
@@ -43,13 +47,13 @@ static_assert(sizeof(B2Tri) == 48, "triangle record must be 48 bytes");
 #define B2_TRAVERSAL_STACK 40          // uint2 entries per ray; builder refuses trees deeper than B2_TRAVERSAL_STACK - 4
 #define B2_MAX_LEAF_TRIS 3
 
-// host-side result of a build (either builder)
+// host-side result of a build
 struct B2BvhHost {
     B2Node8* nodes = nullptr; uint32_t n_nodes = 0;
     B2Tri*   tris = nullptr;  uint32_t n_tris = 0;
     uint32_t max_depth = 0;
     float    sah_cost = 0.f;
-    float    scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
+    float    abs_max[3] = {0, 0, 0};   // max |coordinate| per axis over all vertices (slack constant of the box test)
 };
 
 // host SAH builder (bvh_build.cpp). Returns 0 on success, negative on failure (message via *err).

@@ -1,5 +1,5 @@
 // bvh_build.cpp -- host builder of the in-HBM map: binned-SAH binary BVH -> cost-optimal 8-wide collapse -> octant slot
-// assignment -> 8-bit quantisation (layout: bvh8.h).  Runs once per map at b2_mesh_create (replaces the Embree scene commit
+// assignment -> float child boxes (layout: bvh8.h).  Runs once per map at b2_mesh_create (replaces the Embree scene commit
 // behind rm::import_embree_map, rmcl_ros/src/nodes/micp_localization.cpp:188); it is NOT on the per-scan path.
 #include "bvh8.h"
 
@@ -253,34 +253,15 @@ int b2_build_bvh8_host(const float* verts, uint32_t nv, const uint32_t* faces, u
         }
 
         B2Node8 nd8; memset(&nd8, 0, sizeof(nd8));
-        // quantisation frame
-        double scale[3];
-        for (int k = 0; k < 3; k++) {
-            nd8.p[k] = nd.box.lo[k];
-            const double ext = (double)nd.box.hi[k] - (double)nd.box.lo[k];
-            int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 255.0)) : -100;
-            e = std::max(e, -100);
-            while (std::ldexp(255.0, e) < ext) e++;
-            e = std::min(e, 120);
-            nd8.e[k] = (uint8_t)(e + 127);
-            scale[k] = std::ldexp(1.0, e);
-        }
+        for (int k = 0; k < 3; k++) for (int s8 = 0; s8 < 8; s8++) { nd8.lo[k][s8] = INFINITY; nd8.hi[k][s8] = -INFINITY; }
         nd8.child_base = (uint32_t)nodes8.size();
         nd8.tri_base = (uint32_t)tris8.size();
         uint32_t tri_off = 0;
         for (int s = 0; s < 8; s++) {
             const int c = child_in_slot[s];
-            if (c < 0) continue;                      // meta 0, boxes 0: never hit (qlo 0 / qhi 0 is a valid box -> mask by meta)
+            if (c < 0) continue;                      // empty slot: meta 0, box (+inf, -inf)
             const Node2& cn = n2[ch[c].node2];
-            for (int k = 0; k < 3; k++) {
-                double ql = std::floor(((double)cn.box.lo[k] - (double)nd8.p[k]) / scale[k]);
-                double qh = std::ceil(((double)cn.box.hi[k] - (double)nd8.p[k]) / scale[k]);
-                ql = std::min(std::max(ql, 0.0), 255.0); qh = std::min(std::max(qh, 0.0), 255.0);
-                // containment check in double (real-valued planes)
-                while (ql > 0.0 && (double)nd8.p[k] + ql * scale[k] > (double)cn.box.lo[k]) ql -= 1.0;
-                while (qh < 255.0 && (double)nd8.p[k] + qh * scale[k] < (double)cn.box.hi[k]) qh += 1.0;
-                nd8.qlo[k][s] = (uint8_t)ql; nd8.qhi[k][s] = (uint8_t)qh;
-            }
+            for (int k = 0; k < 3; k++) { nd8.lo[k][s] = cn.box.lo[k]; nd8.hi[k][s] = cn.box.hi[k]; }
             if (ch[c].leaf) {
                 tl.clear(); collect_tris(n2, ch[c].node2, tl);
                 std::sort(tl.begin(), tl.end());
@@ -321,5 +302,7 @@ int b2_build_bvh8_host(const float* verts, uint32_t nv, const uint32_t* faces, u
     memcpy(out->tris, tris8.data(), sizeof(B2Tri) * tris8.size());
     out->max_depth = max_depth;
     out->sah_cost = (float)sah;
+    for (int k = 0; k < 3; k++) out->abs_max[k] = 0.f;
+    for (size_t i = 0; i < (size_t)nv; i++) for (int k = 0; k < 3; k++) out->abs_max[k] = std::max(out->abs_max[k], std::fabs(verts[3 * i + k]));
     return 0;
 }

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128) k_intersect(BvhView bvh, const float* __r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nn = 0, nt = 0;
     if (i < n) {
-        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), bvh);
         HitRec h = trace_init(tfar);
         trace_closest<STATS>(bvh, r, h, nn, nt);
         const bool hit = h.face != B2_NOFACE;
@@ -397,7 +397,7 @@ B2_DEV void find_one(const BvhView& bvh, Tf Tsm, const RayModel& model, uint32_t
     const uint32_t oi = model.n_origs == 1 ? 0 : i;
     const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
     const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
-    const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s));
+    const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s), bvh);
     HitRec h = trace_init(model.range_max);
     uint32_t nn = 0, nt = 0;
     trace_closest<false>(bvh, r, h, nn, nt);
@@ -429,7 +429,7 @@ __device__ __forceinline__ void bulk_prefetch_slice(const void* base, uint64_t t
 // mode 1: node array; mode 2: node array + leaf triangle records (the whole map, 56 MB for 1M triangles, fits the 126 MB L2)
 __device__ __forceinline__ void prefetch_map_l2(const BvhView& bvh, uint32_t n_nodes, uint32_t n_tris, int mode)
 {
-    if (threadIdx.x == 0 && mode >= 1) bulk_prefetch_slice(bvh.nodes, (uint64_t)n_nodes * 80ull);
+    if (threadIdx.x == 0 && mode >= 1) bulk_prefetch_slice(bvh.nodes, (uint64_t)n_nodes * (uint64_t)B2_NODE_BYTES);
     if (threadIdx.x == 32 % blockDim.x && mode >= 2) bulk_prefetch_slice(bvh.tris, (uint64_t)n_tris * 48ull);
 }
 
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(B2_FUSED_BLOCK) k_rcc_fused_batch(BvhView bvh,
         const uint32_t oi = model.n_origs == 1 ? 0 : i;
         const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
         const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
-        const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s));
+        const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s), bvh);
         HitRec h = trace_init(model.range_max);
         uint32_t nn = 0, nt = 0;
         trace_closest<false>(bvh, r, h, nn, nt);
@@ -604,7 +604,7 @@ B2_DEV float pf_eval_one(const BvhView& bvh, Tf Tsm, const PfBeam& b, const b2_p
     const V3 orig_m = tf_apply(Tsm, mk3(b.ox, b.oy, b.oz));                                // RangeMeasurement.hpp:29-42
     const V3 dir_m = q_rot(Tsm.R, mk3(b.dx, b.dy, b.dz));
     const bool real_hit = (prm.range_min <= b.range) && (b.range <= prm.range_max);        // :27
-    const RaySetup r = ray_setup(orig_m, dir_m);
+    const RaySetup r = ray_setup(orig_m, dir_m, bvh);
     HitRec h = trace_init(u2f(0x7f800000u));                                               // tfar = +inf (:38)
     uint32_t nn = 0, nt = 0;
     trace_closest<false>(bvh, r, h, nn, nt);

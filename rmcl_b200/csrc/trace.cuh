@@ -9,11 +9,16 @@
 //   candidate t (Moeller-Trumbore, scaled form, explicit FMA chains) is a HIT iff t > 0 and, for the triangle's own AABB,
 //       tn <= fl(t*C1)  and  tf >= fl(t*C2)                       C1 = 1+2^-14, C2 = 1-2^-14
 //   result = argmin (t, face id) over HITs with t <= tfar.
-// CULLING: a child box is skipped only if NOT (tn' <= fl(tbest*C1) && tf' >= max(0, fl(tn'*C3))), C3 = 1-2^-12, where tn'/tf' are
-//   computed from the QUANTISED planes with FMAs and widened by a per-node, per-axis slack
-//       delta_k = 2^-20 * (|(p_k - o_k) * idir_k| + 256 * |scale_k * idir_k|)
-//   which dominates both the FMA-path rounding error and F's own relative error, so tn' <= tn_F(box) and tf' >= tf_F(box) for the
-//   float box the quantised one contains.  Hence every HIT's leaf is visited and the result equals the brute-force answer.
+// CULLING: a child box (exact float AABB of the triangles below it) is skipped only if NOT
+//       max(tn'_x, tn'_y, tn'_z, 0) <= min(tf'_x, tf'_y, tf'_z, fl(tbest*C1))
+//   with  tf'_k = fma(far_plane_k,  idir_k,      -cf_k),  cf_k = oi_k - dl_k                 oi_k = fl(o_k * idir_k)
+//         tn'_k = fma(near_plane_k, idir_k*C3',  -cn_k),  cn_k = (oi_k + dl_k) * C3'         C3' = 1 - 2^-11
+//         dl_k  = 2^-20 * (|oi_k| + B_k * |idir_k|)        B_k = max |vertex coordinate| on axis k
+//   All constants are per RAY (RaySetup); a node visit is 48 FMAs + min/max, no per-node setup.  dl_k bounds the FMA-path error
+//   (<= 2^-23 (|plane*idir| + |oi|)) plus F's own error, so tn' <= C3' * tn_F and tf' >= tf_F for the same float box; with the C3' scale
+//   this test is at least as permissive as the oracle's visit rule V (tn <= tbest*C1 && tf >= max(0, tn*C3), C3 = 1-2^-12): if tn_F > 0,
+//   tn' <= tn_F*C3' <= fl(tn_F*C3) <= tf_F <= tf'; if tn_F <= 0, tn' <= 0 <= tf_F.  Hence every HIT's leaf is visited and the result
+//   equals the brute-force answer.
 #pragma once
 #include "b2_math.cuh"
 #include "bvh8.h"
@@ -24,8 +29,9 @@
 #define B2_NOFACE 0xFFFFFFFFu
 
 struct BvhView {
-    const uint4*  nodes;    // 5 x uint4 per node
+    const float4* nodes;    // B2_NODE_QUADS (14) x 16 B per node
     const float4* tris;     // 3 x float4 per triangle record
+    float bx, by, bz;       // max |vertex coordinate| per axis
 };
 
 struct HitRec {
@@ -36,20 +42,14 @@ struct HitRec {
 
 struct RaySetup {
     V3 o, d, idir;
+    V3 idn, cn, cf;         // near-plane slope (idir*C3'), near / far constants of the box test (see header)
     uint32_t oct;           // bit k set iff idir_k >= 0
+    uint32_t onx, ony, onz; // float4 offsets of the near planes inside a node (lo arrays for positive directions, hi arrays otherwise)
 };
 
-B2_DEV RaySetup ray_setup(V3 o, V3 d)
-{
-    RaySetup r; r.o = o; r.d = d;
-    float dx = d.x, dy = d.y, dz = d.z;
-    if (fabsf(dx) < 1e-18f) dx = copysignf(1e-18f, dx);
-    if (fabsf(dy) < 1e-18f) dy = copysignf(1e-18f, dy);
-    if (fabsf(dz) < 1e-18f) dz = copysignf(1e-18f, dz);
-    r.idir = mk3(dvd(1.0f, dx), dvd(1.0f, dy), dvd(1.0f, dz));
-    r.oct = (r.idir.x >= 0.f ? 1u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 4u : 0u);
-    return r;
-}
+#define B2_C3P 0.99951171875f          // 1 - 2^-11
+
+B2_DEV RaySetup ray_setup(V3 o, V3 d, const struct BvhView& bvh);
 
 // formula F on an exact float box
 B2_DEV void slab_F(const RaySetup& r, V3 lo, V3 hi, float& tn, float& tf)
@@ -102,72 +102,57 @@ B2_DEV V3 tri_ng(const BvhView& bvh, uint32_t tri_idx)
     return cross_fma(v_sub(mk3(b.x, b.y, b.z), v0), v_sub(mk3(c.x, c.y, c.z), v0));
 }
 
-// byte s of w as an exact float 2^23 + b: one PRMT, no I2F (the XU pipe was the busiest pipe with cvt, profiles/r01)
-template <int S> B2_DEV float byte_magic(uint32_t w, uint32_t k4b) { return u2f(prmt_imm<0x7540 + S>(w, k4b)); }
-
-#define B2_C3P 0.99951171875f          // 1 - 2^-11 : C3 folded into the near planes (see below)
+B2_DEV RaySetup ray_setup(V3 o, V3 d, const BvhView& bvh)
+{
+    RaySetup r; r.o = o; r.d = d;
+    float dx = d.x, dy = d.y, dz = d.z;
+    if (fabsf(dx) < 1e-18f) dx = copysignf(1e-18f, dx);
+    if (fabsf(dy) < 1e-18f) dy = copysignf(1e-18f, dy);
+    if (fabsf(dz) < 1e-18f) dz = copysignf(1e-18f, dz);
+    r.idir = mk3(dvd(1.0f, dx), dvd(1.0f, dy), dvd(1.0f, dz));
+    r.oct = (r.idir.x >= 0.f ? 1u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 4u : 0u);
+    const float k20 = 9.5367431640625e-07f;   // 2^-20
+    const float oix = o.x * r.idir.x, oiy = o.y * r.idir.y, oiz = o.z * r.idir.z;
+    const float dlx = (fabsf(oix) + bvh.bx * fabsf(r.idir.x)) * k20, dly = (fabsf(oiy) + bvh.by * fabsf(r.idir.y)) * k20, dlz = (fabsf(oiz) + bvh.bz * fabsf(r.idir.z)) * k20;
+    r.idn = mk3(r.idir.x * B2_C3P, r.idir.y * B2_C3P, r.idir.z * B2_C3P);
+    r.cn = mk3((oix + dlx) * B2_C3P, (oiy + dly) * B2_C3P, (oiz + dlz) * B2_C3P);
+    r.cf = mk3(oix - dlx, oiy - dly, oiz - dlz);
+    // node layout in float4 units: lo_x 0..1, lo_y 2..3, lo_z 4..5, hi_x 6..7, hi_y 8..9, hi_z 10..11
+    r.onx = (r.oct & 1u) ? 0u : 6u; r.ony = (r.oct & 2u) ? 2u : 8u; r.onz = (r.oct & 4u) ? 4u : 10u;
+    return r;
+}
 
 // Intersect the 8 children of one node; returns the hit mask: bits 31..24 inner children by priority (slot ^ oct), bits 23..0 leaf triangles.
-//
-// Per axis k (ad = scale*idir, ao = (p - o)*idir) the real-valued child planes are t = q*ad + ao, q in 0..255.  Computed form:
-//     far :  tf_k = fma(q', ad,       cf),  cf = (ao + dl) - 2^23*ad                q' = 2^23 + q (exact float, byte_magic)
-//     near:  tn_k = fma(q', ad*C3',   cn),  cn = (ao - dl)*C3' - 2^23*(ad*C3')      C3' = 1 - 2^-11
-//     dl = |ao|*2^-20 + |ad|*(1 + 2^-12)
-// The 2^23 offset of q' cancels exactly against the constant (same rounded ad); rounding the constant costs at most |ad|/2 and is
-// covered by the |ad| term of dl; the remaining dl >= 2^-20(|ao| + 256|ad|) dominates the FMA-path error and F's relative error
-// (trace.cuh header).  Scaling the near side by C3' makes  max(tn_x,tn_y,tn_z,0) <= min(tf_x,tf_y,tf_z,tbest*C1)  at least as
-// permissive as the oracle's visit rule V (tn <= tbest*C1 && tf >= max(0, tn*C3)) on the float box inside the quantised one.
-B2_DEV uint32_t node_test(const uint4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& imask)
+B2_DEV uint32_t node_test(const float4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& imask)
 {
-    const uint4 n0 = ldg(np + 0), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
-    const float px = u2f(n0.x), py = u2f(n0.y), pz = u2f(n0.z);
-    const float sx = u2f((n0.w & 0xffu) << 23), sy = u2f(((n0.w >> 8) & 0xffu) << 23), sz = u2f(((n0.w >> 16) & 0xffu) << 23);
-    imask = n0.w >> 24;
-    child_base = n1.x; tri_base = n1.y;
-
-    const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
-    const float aox = (px - r.o.x) * r.idir.x, aoy = (py - r.o.y) * r.idir.y, aoz = (pz - r.o.z) * r.idir.z;
-    const float k20 = 9.5367431640625e-07f, k1 = 1.000244140625f, two23 = 8388608.0f;
-    const float dlx = fmaf(fabsf(adx), k1, fabsf(aox) * k20), dly = fmaf(fabsf(ady), k1, fabsf(aoy) * k20), dlz = fmaf(fabsf(adz), k1, fabsf(aoz) * k20);
-    const float anx = adx * B2_C3P, any_ = ady * B2_C3P, anz = adz * B2_C3P;
-    const float cnx = fmaf(-two23, anx, (aox - dlx) * B2_C3P), cny = fmaf(-two23, any_, (aoy - dly) * B2_C3P), cnz = fmaf(-two23, anz, (aoz - dlz) * B2_C3P);
-    const float cfx = fmaf(-two23, adx, aox + dlx), cfy = fmaf(-two23, ady, aoy + dly), cfz = fmaf(-two23, adz, aoz + dlz);
-
-    // near/far byte planes by ray direction sign
-    const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
-    const uint32_t qnx0 = nx ? n3.z : n2.x, qnx1 = nx ? n3.w : n2.y, qfx0 = nx ? n2.x : n3.z, qfx1 = nx ? n2.y : n3.w;
-    const uint32_t qny0 = ny ? n4.x : n2.z, qny1 = ny ? n4.y : n2.w, qfy0 = ny ? n2.z : n4.x, qfy1 = ny ? n2.w : n4.y;
-    const uint32_t qnz0 = nz ? n4.z : n3.x, qnz1 = nz ? n4.w : n3.y, qfz0 = nz ? n3.x : n4.z, qfz1 = nz ? n3.y : n4.w;
-
+    // near planes: the "lo" arrays for positive directions, the "hi" arrays otherwise; far planes: the other one (offset 6 quads apart)
+    const float4 nxa = ldg(np + r.onx), nxb = ldg(np + r.onx + 1), fxa = ldg(np + (6u - r.onx)), fxb = ldg(np + (7u - r.onx));
+    const float4 nya = ldg(np + r.ony), nyb = ldg(np + r.ony + 1), fya = ldg(np + (10u - r.ony)), fyb = ldg(np + (11u - r.ony));
+    const float4 nza = ldg(np + r.onz), nzb = ldg(np + r.onz + 1), fza = ldg(np + (14u - r.onz)), fzb = ldg(np + (15u - r.onz));
+    const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
+    child_base = f2u(h0.x); tri_base = f2u(h0.y); imask = f2u(h1.x);
     // octant permutation of the priority bits of all inner children at once: meta ^= oct where (meta & 0x18) == 0x18
-    const uint32_t m0 = n1.z ^ ((((n1.z >> 3) & (n1.z >> 4)) & 0x01010101u) * r.oct);
-    const uint32_t m1 = n1.w ^ ((((n1.w >> 3) & (n1.w >> 4)) & 0x01010101u) * r.oct);
-
+    const uint32_t w0 = f2u(h0.z), w1 = f2u(h0.w);
+    const uint32_t m0 = w0 ^ ((((w0 >> 3) & (w0 >> 4)) & 0x01010101u) * r.oct);
+    const uint32_t m1 = w1 ^ ((((w1 >> 3) & (w1 >> 4)) & 0x01010101u) * r.oct);
     const float tlim = tbest * B2_C1;
-    const uint32_t k4b = opaque_const(0x4B000000u);
     uint32_t hitmask = 0;
-#define B2_CHILD(S, QNX, QNY, QNZ, QFX, QFY, QFZ, M)                                                    \
-    {                                                                                                    \
-        const float tnx = fmaf(byte_magic<(S) & 3>(QNX, k4b), anx, cnx);                                 \
-        const float tny = fmaf(byte_magic<(S) & 3>(QNY, k4b), any_, cny);                                \
-        const float tnz = fmaf(byte_magic<(S) & 3>(QNZ, k4b), anz, cnz);                                 \
-        const float tfx = fmaf(byte_magic<(S) & 3>(QFX, k4b), adx, cfx);                                 \
-        const float tfy = fmaf(byte_magic<(S) & 3>(QFY, k4b), ady, cfy);                                 \
-        const float tfz = fmaf(byte_magic<(S) & 3>(QFZ, k4b), adz, cfz);                                 \
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                       \
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlim));                                       \
-        const uint32_t meta = ((M) >> (8 * ((S) & 3))) & 0xffu;                                          \
-        const uint32_t bits = (meta >> 5) << (meta & 0x1fu);                                             \
-        hitmask |= (tn <= tf) ? bits : 0u;                                                               \
+#define B2_CHILD(S, NX, NY, NZ, FX, FY, FZ, M)                                                                        \
+    {                                                                                                                  \
+        const float tn = fmaxf(fmaxf(fmaf(NX, r.idn.x, -r.cn.x), fmaf(NY, r.idn.y, -r.cn.y)), fmaxf(fmaf(NZ, r.idn.z, -r.cn.z), 0.0f)); \
+        const float tf = fminf(fminf(fmaf(FX, r.idir.x, -r.cf.x), fmaf(FY, r.idir.y, -r.cf.y)), fminf(fmaf(FZ, r.idir.z, -r.cf.z), tlim)); \
+        const uint32_t meta = ((M) >> (8 * ((S) & 3))) & 0xffu;                                                        \
+        const uint32_t bits = (meta >> 5) << (meta & 0x1fu);                                                           \
+        hitmask |= (tn <= tf) ? bits : 0u;                                                                             \
     }
-    B2_CHILD(0, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
-    B2_CHILD(1, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
-    B2_CHILD(2, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
-    B2_CHILD(3, qnx0, qny0, qnz0, qfx0, qfy0, qfz0, m0)
-    B2_CHILD(4, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
-    B2_CHILD(5, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
-    B2_CHILD(6, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
-    B2_CHILD(7, qnx1, qny1, qnz1, qfx1, qfy1, qfz1, m1)
+    B2_CHILD(0, nxa.x, nya.x, nza.x, fxa.x, fya.x, fza.x, m0)
+    B2_CHILD(1, nxa.y, nya.y, nza.y, fxa.y, fya.y, fza.y, m0)
+    B2_CHILD(2, nxa.z, nya.z, nza.z, fxa.z, fya.z, fza.z, m0)
+    B2_CHILD(3, nxa.w, nya.w, nza.w, fxa.w, fya.w, fza.w, m0)
+    B2_CHILD(4, nxb.x, nyb.x, nzb.x, fxb.x, fyb.x, fzb.x, m1)
+    B2_CHILD(5, nxb.y, nyb.y, nzb.y, fxb.y, fyb.y, fzb.y, m1)
+    B2_CHILD(6, nxb.z, nyb.z, nzb.z, fxb.z, fyb.z, fzb.z, m1)
+    B2_CHILD(7, nxb.w, nyb.w, nzb.w, fxb.w, fyb.w, fzb.w, m1)
 #undef B2_CHILD
     return hitmask;
 }
@@ -190,7 +175,7 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
             const uint32_t node_idx = G.x + rel;
             if (G.y & 0xff000000u) stack[sp++] = G;
             uint32_t child_base, tri_base, imask;
-            const uint32_t hm = node_test(bvh.nodes + 5 * (size_t)node_idx, r, best.t, child_base, tri_base, imask);
+            const uint32_t hm = node_test(bvh.nodes + B2_NODE_QUADS * (size_t)node_idx, r, best.t, child_base, tri_base, imask);
             if (STATS) n_nodes++;
             G = make_uint2(child_base, (hm & 0xff000000u) | imask);
             Gt = make_uint2(tri_base, hm & 0x00ffffffu);

@@ -25,7 +25,11 @@ __attribute__((visibility("default"))) void emul_scene_info(void* p, uint32_t* n
 {
     EmulScene* s = (EmulScene*)p; *n_nodes = s->bvh.n_nodes; *n_tris = s->bvh.n_tris; *depth = s->bvh.max_depth; *sah = s->bvh.sah_cost;
 }
-static BvhView view(void* p) { EmulScene* s = (EmulScene*)p; BvhView v; v.nodes = (const uint4*)s->bvh.nodes; v.tris = (const float4*)s->bvh.tris; return v; }
+static BvhView view(void* p)
+{
+    EmulScene* s = (EmulScene*)p; BvhView v; v.nodes = (const float4*)s->bvh.nodes; v.tris = (const float4*)s->bvh.tris;
+    v.bx = s->bvh.abs_max[0]; v.by = s->bvh.abs_max[1]; v.bz = s->bvh.abs_max[2]; return v;
+}
 
 __attribute__((visibility("default"))) void emul_intersect(void* sc, const float* origs, const float* dirs, uint32_t n, float tfar,
                                                            float* t_out, uint32_t* face_out, float* ng_out, uint8_t* hit_out, double* mean_nodes, double* mean_tris, uint32_t* per_ray_nodes, uint32_t* per_ray_tris)
@@ -34,7 +38,7 @@ __attribute__((visibility("default"))) void emul_intersect(void* sc, const float
     unsigned long long tn = 0, tt = 0;
     #pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn, tt)
     for (int64_t i = 0; i < (int64_t)n; i++) {
-        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        const RaySetup r = ray_setup(mk3(origs[3 * i], origs[3 * i + 1], origs[3 * i + 2]), mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), bvh);
         HitRec h = trace_init(tfar);
         uint32_t nn = 0, nt = 0;
         trace_closest<true>(bvh, r, h, nn, nt);

@@ -33,8 +33,9 @@ def test_cpp_dropin_matches_oracle(po, synth):
     pf = [l.split() for l in out.stdout.splitlines() if l.startswith("PF")]
     # oracle for the same scenario
     osc = oracle_scene("uvsphere:40:60")
-    m = synth.vlp16_900()
-    m.range_min = 0.0
+    # the same float32 model parameters the C++ example computes (-15.0f * (float)M_PI / 180.0f, ...)
+    f, pi32 = np.float32, np.float32(np.pi)
+    m = synth.SphericalModel(float(f(-15.0) * pi32 / f(180.0)), float(f(2.0) * pi32 / f(180.0)), 16, float(-pi32), float(f(2.0) * pi32 / f(900.0)), 900, 0.0, 130.0)
     o, d = po.model_rays(m)
     I = synth.make_transform()
     ranges = osc.simulate(I, I, o, d, m.range_max)["ranges"]
