@@ -174,6 +174,7 @@ struct b2_rcc {
     DevBuf<b2_transform> d_poses, d_tdelta; DevBuf<uint32_t> d_ncorr; DevBuf<b2_cross_stats> d_bstats;
     HostPin* pin = nullptr;
     int red_grid = 0;
+    int fused_grid = 0;                 // blocks of the cooperative k_icp_loop (0: cooperative launch unavailable)
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
 };
 
@@ -189,6 +190,12 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     h->map = map; h->Tsb = tf_identity_pod();
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, map->device));
     h->red_grid = prop.multiProcessorCount;
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, map->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop, B2_ICP_BLOCK, 0) == cudaSuccess && per_sm > 0)
+            h->fused_grid = prop.multiProcessorCount;      // one block per SM
+    }
     int rc;
     if ((rc = h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)) || (rc = h->d_ticket.reserve(1)) || (rc = h->d_stats.reserve(1)) || (rc = h->d_icp.reserve(1))) { delete h; return rc; }
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
@@ -229,6 +236,14 @@ extern "C" int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms)
     float a = 0.f, b = 0.f;
     CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1])); CU(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
     if (find_ms) *find_ms = a; if (reduce_ms) *reduce_ms = b;
+    return B2_OK;
+}
+
+// profiling aid (not part of the public header): SM-clock durations of the last reduction's phases
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc* h, unsigned long long* out8)
+{
+    NOTNULL(h); NOTNULL(out8);
+    for (int i = 0; i < 8; i++) out8[i] = h->pin->icp.dbg[i];
     return B2_OK;
 }
 
@@ -456,8 +471,27 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
     // pre-transform of the first reduction, evaluated on the host with the same inline functions the kernels use (individually
     // rounded ops on both sides -> identical bits); saves a launch
     tf_store(&st.T_snew_sold, icp_pretransform(tf_from_pod(*Tbo), tf_from_pod(h->Tsb), tf_identity()));
+    {
+        const Tf Tos = tf_mul(tf_from_pod(*Tbo), tf_from_pod(h->Tsb));
+        tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros);
+    }
     CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
-    if (h->n > 0) {
+    static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 1; }();
+    if (h->n > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
+        // find, then ALL inner iterations in one cooperative kernel
+        if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
+        RES(launch_find(h, nullptr, h->d_icp.p));
+        if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+        int grid = std::min<int>(h->fused_grid, (int)((h->n + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
+        if (grid < 1) grid = 1;
+        RES(h->d_partials.reserve((size_t)2 * grid * (B2_NACC + 1)));
+        const float* dp = h->d_dpts.p; const uint8_t* dmk = h->d_dmask.p; const float* mp = h->d_mpts.p; const float* mn = h->d_mnrm.p; const uint8_t* mh = h->d_mhits.p;
+        uint32_t nel = h->n; IcpState* icp_dev = h->d_icp.p; uint32_t its = iterations; double* parts = h->d_partials.p;
+        void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts};
+        CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop, dim3(grid), dim3(B2_ICP_BLOCK), args, 0, h->stream));
+        LAUNCHED();
+        if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
+    } else if (h->n > 0) {
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         RES(launch_find(h, nullptr, h->d_icp.p));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));

@@ -1,6 +1,10 @@
 // kernels.cuh -- CUDA kernels of the ray-casting-correspondence path (sm_100a).  Compiled with -fmad=false: every FMA is explicit.
 #pragma once
+#include <cstddef>
 #include "trace.cuh"
+#if defined(__CUDACC__)
+#include <cooperative_groups.h>
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device-side CrossStatistics helpers (mirror oracle/oracle.c op for op; tolerance-level parity is all that is required,
@@ -152,7 +156,7 @@ __host__ __device__ __noinline__ bool polar_newton3(const double A[3][3], double
             const double d = y - X[i][j]; diff += d * d;
             X[i][j] = y;
         }
-        if (diff < 1e-30) {
+        if (diff < 1e-22) {
             for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] = X[i][j];
             return true;
         }
@@ -268,16 +272,67 @@ __device__ __forceinline__ void block_reduce_acc(P2LAcc& a, double* smem)
 // ---------------------------------------------------------------------------------------------------------------------
 // ICP state kept on the device between the kernels of one correctOnce (micp_localization.cpp:899-984)
 // ---------------------------------------------------------------------------------------------------------------------
-struct IcpState {
+struct alignas(16) IcpState {
     b2_transform Tom, Tbo, Tsb;          // inputs
     b2_transform T_onew_oold;            // :910, :963
     b2_transform T_snew_sold;            // pre-transform of the NEXT reduction (MICPSensor.hpp:178)
     b2_transform Tom_new;                // :972-984
+    b2_transform Tos, Tso;               // Tos = Tbo * Tsb (sensor -> odom), Tso = ~Tos: composed once per correctOnce on the host
     b2_cross_stats Cmerged_o;            // :918-937 (single sensor)
     b2_cross_stats stats_s;              // last sensor-frame statistics
     float max_dist;
     uint32_t iter;
+    float Ros[9];                        // rotation matrix of Tos, row-major
+    uint32_t pad_[1];
+    unsigned long long dbg[8];           // SM-clock stamps of the last reduction's tail (profiling aid, b2_rcc_debug_clocks)
 };
+
+// rotation matrix (row-major) of a unit quaternion
+B2_DEV void quat_to_mat(Q4 q, float R[9])
+{
+    const float x = q.x, y = q.y, z = q.z, w = q.w;
+    R[0] = sub(1.0f, mul(2.0f, add(mul(y, y), mul(z, z)))); R[1] = mul(2.0f, sub(mul(x, y), mul(z, w))); R[2] = mul(2.0f, add(mul(x, z), mul(y, w)));
+    R[3] = mul(2.0f, add(mul(x, y), mul(z, w))); R[4] = sub(1.0f, mul(2.0f, add(mul(x, x), mul(z, z)))); R[5] = mul(2.0f, sub(mul(y, z), mul(x, w)));
+    R[6] = mul(2.0f, sub(mul(x, z), mul(y, w))); R[7] = mul(2.0f, add(mul(y, z), mul(x, w))); R[8] = sub(1.0f, mul(2.0f, add(mul(x, x), mul(y, y))));
+}
+
+// Lean inner-iteration tail for the cooperative ICP loop.  Same mathematics as icp_step (micp_localization.cpp:926-963) with the
+// constant frame chain pre-composed: Cs_o = Tos * stats_s in one step (rotation-matrix form), the merge with the empty identity
+// statistics dropped (exact no-op), T_snew_sold = Tso * T_onew_oold * Tos, and Tom_new only after the last iteration.  Rounding
+// differs from the two-step chain at the 1e-7 level (covered by the 1e-5 tolerance on dT; n_meas may differ by a unit when a pair
+// sits within an ulp of max_dist).
+B2_DEV void icp_step_fast(IcpState* st, const CStats& s, bool last)
+{
+    const float* R = st->Ros;
+    const V3 t = mk3(st->Tos.t.x, st->Tos.t.y, st->Tos.t.z);
+    CStats o; o.n = s.n;
+    o.dm = mk3(R[0] * s.dm.x + R[1] * s.dm.y + R[2] * s.dm.z + t.x, R[3] * s.dm.x + R[4] * s.dm.y + R[5] * s.dm.z + t.y, R[6] * s.dm.x + R[7] * s.dm.y + R[8] * s.dm.z + t.z);
+    o.mm = mk3(R[0] * s.mm.x + R[1] * s.mm.y + R[2] * s.mm.z + t.x, R[3] * s.mm.x + R[4] * s.mm.y + R[5] * s.mm.z + t.y, R[6] * s.mm.x + R[7] * s.mm.y + R[8] * s.mm.z + t.z);
+    float RC[9];
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) RC[i * 3 + j] = R[i * 3 + 0] * s.C[j * 3 + 0] + R[i * 3 + 1] * s.C[j * 3 + 1] + R[i * 3 + 2] * s.C[j * 3 + 2];
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) o.C[j * 3 + i] = RC[i * 3 + 0] * R[j * 3 + 0] + RC[i * 3 + 1] * R[j * 3 + 1] + RC[i * 3 + 2] * R[j * 3 + 2];
+    const Tf T_inner = umeyama_dev(o);
+    const Tf T_onew_oold = tf_mul(tf_load(&st->T_onew_oold), T_inner);
+    tf_store(&st->T_onew_oold, T_onew_oold);
+    tf_store(&st->T_snew_sold, tf_mul(tf_mul(tf_load(&st->Tso), T_onew_oold), tf_load(&st->Tos)));
+    if (last) {
+        const Tf Tom = tf_load(&st->Tom);
+        Tf Tn = tf_mul(Tom, T_onew_oold);
+        if (o.n > 0) Tn.R = q_normalize(Tn.R); else Tn = Tom;
+        tf_store(&st->Tom_new, Tn);
+        cs_store(&st->Cmerged_o, o);
+        cs_store(&st->stats_s, s);
+    }
+    st->iter++;
+}
+
+static_assert(offsetof(IcpState, Tos) % 16 == 0 && offsetof(IcpState, Tso) % 16 == 0 && offsetof(IcpState, Cmerged_o) % 16 == 0 && sizeof(IcpState) % 16 == 0, "IcpState alignment");
 
 B2_DEV Tf icp_pretransform(Tf Tbo, Tf Tsb, Tf T_onew_oold)
 {
@@ -463,6 +518,7 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
 {
     __shared__ double smem[(B2_NACC + 1) * (B2_RED_BLOCK / 32)];
     __shared__ bool is_last;
+    const long long c0 = clock64();
     const Tf Tpre = icp ? tf_load(&icp->T_snew_sold) : tf_from_pod(Tpre_val);
     const float max_dist = icp ? icp->max_dist : max_dist_val;
     P2LAcc acc; acc_zero(acc);
@@ -487,6 +543,7 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    const long long c1 = clock64();
     // deterministic parallel sum of the block partials: thread (g, i) adds value i of blocks g, g+16, ...; then the 16 group sums in order
     __shared__ double s_part[16][B2_NACC + 1];
     {
@@ -504,11 +561,90 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        const long long c2 = clock64();
         const CStats st = acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5));
         if (out) cs_store(out, st);
-        if (icp) icp_step(icp, st);
+        const long long c3 = clock64();
+        if (icp) {
+            icp_step(icp, st);
+            const long long c4 = clock64();
+            icp->dbg[0] = (unsigned long long)(c1 - c0); icp->dbg[1] = (unsigned long long)(c2 - c1); icp->dbg[2] = (unsigned long long)(c3 - c2);
+            icp->dbg[3] = (unsigned long long)(c4 - c3);
+        }
         *ticket = 0u;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The `optimization_iterations` inner iterations of correctOnce (micp_localization.cpp:915-964) as ONE cooperative kernel: per
+// iteration a P2L pass over the n pairs (model buffers are L2-hot after find) -> FP64 block partials -> grid sync -> EVERY block sums
+// the partials in the same fixed order and runs the serial tail redundantly on its shared-memory copy of the ICP state.  One block
+// per SM; 5 iterations cost 5 grid syncs instead of 5 launches + 5 "last block" rounds.  Partials are double-buffered by parity.
+// ---------------------------------------------------------------------------------------------------------------------
+#define B2_ICP_BLOCK 256
+__global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, const float* __restrict__ mpts,
+                                                          const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
+                                                          uint32_t iterations, double* __restrict__ partials)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double smem[(B2_NACC + 1) * (B2_ICP_BLOCK / 32)];
+    __shared__ double s_part[16][B2_NACC + 1];
+    __shared__ __align__(16) IcpState s_icp;
+    for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(icp_g)[w];
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t it = 0; it < iterations; it++) {
+        const Tf Tpre = tf_load(&s_icp.T_snew_sold);
+        const float max_dist = s_icp.max_dist;
+        P2LAcc acc; acc_zero(acc);
+        for (uint32_t base = gid; base < n; base += 4u * stride) {
+            // up to 4 pairs per trip with all their loads issued before the first use
+            uint8_t dm[4], mm[4]; V3 d[4], I[4], N[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = base + (uint32_t)u * stride;
+                const bool in = i < n;
+                const uint32_t j = in ? i : base;
+                dm[u] = in ? dmask[j] : (uint8_t)0; mm[u] = mmask[j];
+                d[u] = mk3(dpts[3 * j], dpts[3 * j + 1], dpts[3 * j + 2]);
+                I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
+                N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                V3 D, M;
+                if ((dm[u] > 0) && (mm[u] > 0) && p2l_pair(Tpre, d[u], I[u], N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
+            }
+        }
+        block_reduce_acc<B2_ICP_BLOCK>(acc, smem);
+        double* part = partials + (size_t)(it & 1u) * gridDim.x * (B2_NACC + 1);
+        if (threadIdx.x == 0) {
+            double* p = part + (size_t)blockIdx.x * (B2_NACC + 1);
+            for (int i = 0; i < B2_NACC; i++) p[i] = acc.v[i];
+            p[B2_NACC] = (double)acc.n;
+            __threadfence();
+        }
+        grid.sync();
+        {
+            const uint32_t i = threadIdx.x & 15u, g = threadIdx.x >> 4;
+            double a = 0.0;
+            for (uint32_t b = g; b < gridDim.x; b += 16u) a += __ldcg(part + (size_t)b * (B2_NACC + 1) + i);
+            s_part[g][i] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < B2_NACC + 1) {
+            double a = 0.0;
+            #pragma unroll
+            for (int g = 0; g < 16; g++) a += s_part[g][threadIdx.x];
+            s_part[0][threadIdx.x] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) icp_step_fast(&s_icp, acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5)), it + 1 == iterations);
+        __syncthreads();
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(icp_g)[w] = reinterpret_cast<const uint32_t*>(&s_icp)[w];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -164,10 +164,23 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
     uint2 stack[B2_TRAVERSAL_STACK];
     int sp = 0;
     // root group: slot 0 of a virtual parent -> priority bit 24 + (0 ^ oct), imask bit 0
-    uint2 G = make_uint2(0u, (1u << (24 + r.oct)) | 1u);
-    uint2 Gt = make_uint2(0u, 0u);
+    uint2 G = make_uint2(0u, (1u << (24 + r.oct)) | 1u);      // pending inner children: (child_base, hit bits 31..24 | imask 7..0)
+    uint2 Gt = make_uint2(0u, 0u);                             // pending leaf triangles of the last visited node: (tri_base, bits 23..0)
+    // Each trip does ONE unit of work per lane -- a triangle test if one is pending, otherwise a node visit -- instead of a node visit
+    // followed by an inner loop over that node's triangles: a warp then never waits for the lane with the most triangles in a node
+    // (profiles/r01: the max-over-lanes triangle loop dominated the slowest warps' instruction streams).  The closest hit under the
+    // (t, face) rule does not depend on the order of the tests.
     while (true) {
-        if (G.y & 0xff000000u) {
+        if (Gt.y) {
+            const uint32_t i = 31u - (uint32_t)clz32(Gt.y);
+            Gt.y &= ~(1u << i);
+            tri_test(bvh, r, Gt.x + i, best);
+            if (STATS) n_tris++;
+        } else {
+            if (!(G.y & 0xff000000u)) {
+                if (sp == 0) break;
+                G = stack[--sp];
+            }
             const uint32_t bitpos = 31u - (uint32_t)clz32(G.y);
             G.y &= ~(1u << bitpos);
             const uint32_t slot = (bitpos - 24u) ^ r.oct;
@@ -179,18 +192,6 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
             if (STATS) n_nodes++;
             G = make_uint2(child_base, (hm & 0xff000000u) | imask);
             Gt = make_uint2(tri_base, hm & 0x00ffffffu);
-        } else {
-            Gt = G; G = make_uint2(0u, 0u);
-        }
-        while (Gt.y) {
-            const uint32_t i = 31u - (uint32_t)clz32(Gt.y);
-            Gt.y &= ~(1u << i);
-            tri_test(bvh, r, Gt.x + i, best);
-            if (STATS) n_tris++;
-        }
-        if (!(G.y & 0xff000000u)) {
-            if (sp == 0) break;
-            G = stack[--sp];
         }
     }
 }

@@ -1,0 +1,21 @@
+import os, sys, ctypes as C
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("B2_FUSED", "0")
+import rmcl_b200
+from rmcl_b200 import synth
+V, F = synth.building(1_000_000)
+gmap = rmcl_b200.Map(V, F)
+m = synth.c2_sensor()
+Tsb, Tgt, I = synth.scenario_tsb(), synth.building_gt_pose(), synth.make_transform()
+h = rmcl_b200.RCCB200Spherical(gmap)
+h.setTsb(Tsb); h.setModel(m); h.setParams(1.0, 0.15)
+h.find(Tgt)
+h.setRanges(synth.noisy_ranges(h.modelView()["ranges"], m.range_max))
+Tom = synth.compose(Tgt, synth.scenario_pose_offset())
+lib = rmcl_b200.load_library()
+for k in range(3):
+    h.correctOnce(Tom, I, 5, 0.0)
+    out = (C.c_ulonglong * 8)()
+    lib.b2_rcc_debug_clocks(h._h, out)
+    print("cycles: main+blockreduce+ticket %d | partial sum %d | finalize %d | icp_step %d" % (out[0], out[1], out[2], out[3]))

@@ -88,7 +88,7 @@ __attribute__((visibility("default"))) void emul_cs_transform(const b2_transform
 // whole correctOnce with the device functions (find_one + sequential reduce + icp_step)
 __attribute__((visibility("default"))) void emul_correct_once(void* sc, uint32_t n, const float* origs, uint32_t n_origs, const float* dirs, float range_max,
                                                               const float* dpts, const uint8_t* dmask, const b2_transform* Tom, const b2_transform* Tbo, const b2_transform* Tsb,
-                                                              uint32_t iterations, float max_dist, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+                                                              uint32_t iterations, float max_dist, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged, int fast_tail)
 {
     std::vector<float> mp(3 * (size_t)n), mn(3 * (size_t)n), mr(n); std::vector<uint8_t> mh(n); std::vector<uint32_t> mf(n);
     IcpState st; memset(&st, 0, sizeof(st));
@@ -97,12 +97,13 @@ __attribute__((visibility("default"))) void emul_correct_once(void* sc, uint32_t
     tf_store(&st.T_onew_oold, I);
     tf_store(&st.T_snew_sold, icp_pretransform(tf_load(&st.Tbo), tf_load(&st.Tsb), I));
     tf_store(&st.Tom_new, tf_load(&st.Tom));
+    { const Tf Tos = tf_mul(tf_load(&st.Tbo), tf_load(&st.Tsb)); tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros); }
     b2_transform Tbm; memset(&Tbm, 0, sizeof(Tbm)); tf_store(&Tbm, tf_mul(tf_load(&st.Tom), tf_load(&st.Tbo)));
     emul_find(sc, &Tbm, Tsb, n, origs, n_origs, dirs, range_max, mp.data(), mn.data(), mh.data(), mf.data(), mr.data());
     for (uint32_t it = 0; it < iterations; it++) {
         b2_cross_stats ss;
         emul_cross_statistics(&st.T_snew_sold, n, dpts, dmask, mp.data(), mn.data(), mh.data(), max_dist, &ss);
-        icp_step(&st, cs_load(&ss));
+        if (fast_tail) icp_step_fast(&st, cs_load(&ss), it + 1 == iterations); else icp_step(&st, cs_load(&ss));
     }
     *Tom_new = st.Tom_new; *T_onew_oold = st.T_onew_oold; *Cmerged = st.Cmerged_o;
 }

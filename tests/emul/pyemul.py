@@ -87,13 +87,13 @@ class Scene:
                         _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
         return out
 
-    def correct_once(self, origs_s, dirs_s, range_max, dpts, dmask, Tom, Tbo, Tsb, iterations, max_dist):
+    def correct_once(self, origs_s, dirs_s, range_max, dpts, dmask, Tom, Tbo, Tsb, iterations, max_dist, fast_tail=False):
         origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
         dpts, dmask = _f32(dpts), np.ascontiguousarray(dmask, np.uint8)
         Tn, Td, Cm = np.zeros((), TRANSFORM), np.zeros((), TRANSFORM), np.zeros((), CROSS_STATS)
         Tom, Tbo, Tsb = np.ascontiguousarray(Tom), np.ascontiguousarray(Tbo), np.ascontiguousarray(Tsb)
         lib().emul_correct_once(self._h, C.c_uint32(len(dirs_s)), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_max), _p(dpts), _p(dmask),
-                                _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm))
+                                _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm), C.c_int(int(fast_tail)))
         return Tn, Td, Cm
 
     def pf_update(self, poses, attrs, Tsb, beams, params):

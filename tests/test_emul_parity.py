@@ -75,6 +75,11 @@ def test_icp_chain_bit_exact(pe, po, synth):
     assert a[2]["n_meas"] == b[2]["n_meas"] and a[2]["n_meas"] > 5000
     assert np.abs(a[0]["t"] - b[0]["t"]).max() <= 1e-6 and np.abs(a[0]["R"] - b[0]["R"]).max() <= 1e-6
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()      # same algorithm, same order -> same bits
+    # the lean tail of the cooperative ICP loop (pre-composed frames): same result within float noise
+    c = esc.correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, fast_tail=True)
+    assert abs(int(c[2]["n_meas"]) - int(a[2]["n_meas"])) <= 2
+    assert np.abs(a[0]["t"] - c[0]["t"]).max() <= 2e-6 and np.abs(a[0]["R"] - c[0]["R"]).max() <= 2e-6
+    assert np.abs(a[1]["t"] - c[1]["t"]).max() <= 2e-6 and np.abs(a[1]["R"] - c[1]["R"]).max() <= 2e-6
 
 
 def test_pf_bit_exact(pe, po, synth):
