@@ -176,6 +176,7 @@ struct b2_rcc {
     int red_grid = 0;
     int fused_grid = 0;                 // blocks of the cooperative k_icp_loop (0: cooperative launch unavailable)
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
+    cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
 };
 
 static b2_transform tf_identity_pod() { b2_transform T; memset(&T, 0, sizeof(T)); T.R.w = 1.0f; return T; }
@@ -200,6 +201,8 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     if ((rc = h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)) || (rc = h->d_ticket.reserve(1)) || (rc = h->d_stats.reserve(1)) || (rc = h->d_icp.reserve(1))) { delete h; return rc; }
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
     CU(cudaMallocHost((void**)&h->pin, sizeof(HostPin)));
+    CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
     *out = h;
     return B2_OK;
 }
@@ -214,6 +217,8 @@ extern "C" int b2_rcc_destroy(b2_rcc* h)
     h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release();
     h->d_poses.release(); h->d_tdelta.release(); h->d_ncorr.release(); h->d_bstats.release();
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return B2_OK;
@@ -460,8 +465,26 @@ extern "C" int b2_rcc_download_dataset(b2_rcc* h, float* p, uint8_t* m)
 }
 
 static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double cp,
-                             b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+                             b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged, const float* ranges_host = nullptr, uint32_t n_ranges = 0)
 {
+    bool aux_used = false;
+    if (ranges_host) {
+        // the find kernel does not read the dataset: upload + unpack the scan on the side stream while it runs
+        if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
+        if (n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n_ranges, h->n);
+        if (h->n > 0) {
+            RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n));
+            CU(cudaEventRecord(h->ev_aux, h->stream));                    // order after whatever the main stream still has in flight
+            CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+            CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
+            k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max,
+                                                                          h->d_dpts.p, h->d_dmask.p);
+            LAUNCHED();
+            CU(cudaEventRecord(h->ev_aux, h->aux));
+            aux_used = true;
+        }
+        h->n_dataset = h->n;
+    }
     if (!h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
     if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
     IcpState& st = h->pin->icp;
@@ -480,8 +503,11 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
     if (h->n > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
         // find, then ALL inner iterations in one cooperative kernel
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
-        RES(launch_find(h, nullptr, h->d_icp.p));
+        b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
+        tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(*Tbo)));        // MICPSensor.hpp:148, same inline ops as the kernels
+        RES(launch_find(h, &Tbm_host, nullptr));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+        if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
         int grid = std::min<int>(h->fused_grid, (int)((h->n + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
         if (grid < 1) grid = 1;
         RES(h->d_partials.reserve((size_t)2 * grid * (B2_NACC + 1)));
@@ -492,6 +518,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         LAUNCHED();
         if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
     } else if (h->n > 0) {
+        if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         RES(launch_find(h, nullptr, h->d_icp.p));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
@@ -519,8 +546,8 @@ extern "C" int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges, uint32
 {
     NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
     CU(cudaSetDevice(h->map->device));
-    RES(ranges_to_dataset(h, ranges, n, 0));
-    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged);
+    if (n) NOTNULL(ranges);
+    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged, ranges, n);
 }
 
 extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t n_poses, int poses_on_device,

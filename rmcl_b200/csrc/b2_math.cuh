@@ -36,6 +36,7 @@ B2_DEV float u2f(uint32_t a) { return __uint_as_float(a); }
 B2_DEV int clz32(uint32_t a) { return __clz((int)a); }
 B2_DEV int popc32(uint32_t a) { return __popc(a); }
 template <typename T> B2_DEV T ldg(const T* p) { return __ldg(p); }
+B2_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 B2_DEV uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
 // PRMT with an IMMEDIATE selector and the second operand in a register (nvcc otherwise folds the constant operand into the
 // immediate slot and materialises every selector with a MOV)
@@ -56,6 +57,7 @@ B2_DEV float u2f(uint32_t a) { float f; memcpy(&f, &a, 4); return f; }
 B2_DEV int clz32(uint32_t a) { return a ? __builtin_clz(a) : 32; }
 B2_DEV int popc32(uint32_t a) { return __builtin_popcount(a); }
 template <typename T> B2_DEV T ldg(const T* p) { return *p; }
+B2_DEV void prefetch_l1(const void*) {}
 template <int SEL> inline uint32_t prmt_imm(uint32_t x, uint32_t y);
 inline uint32_t opaque_const(uint32_t v) { return v; }
 B2_DEV uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)

@@ -127,41 +127,53 @@ __host__ __device__ __noinline__ void svd3_dev(const double A[3][3], double U[3]
     }
 }
 
-// orthogonal polar factor of a 3x3 matrix with positive determinant; false if not applicable / not converged
+// orthogonal polar factor of a 3x3 matrix with positive determinant; false if not applicable / not converged.
+// Frobenius-scaled Newton iteration X <- (g X + X^-T / g) / 2 in FP32 (4-cycle ops, MUFU-based div/sqrt: ~3x shorter serial chain than
+// FP64 on the one thread that executes it), then one unscaled FP64 step that makes the result orthogonal to double precision.
+// Accuracy: FP32 rounding of the iterates perturbs the rotation by ~1e-7 rad (the reference's own rmagine SVD is FP32 as well); the
+// translation inherits ~1e-7 * |mean| -- two orders below the 1e-5 tolerance on dT.
 __host__ __device__ __noinline__ bool polar_newton3(const double A[3][3], double Q[3][3])
 {
-    double X[3][3];
     double fro = 0.0;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) fro += A[i][j] * A[i][j];
     if (!(fro > 0.0)) return false;
     const double inv_n = 1.0 / sqrt(fro);
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) X[i][j] = A[i][j] * inv_n;
-    for (int it = 0; it < 40; it++) {
-        // cofactor matrix = det * X^-T
-        double Cf[3][3];
+    float X[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) X[i][j] = (float)(A[i][j] * inv_n);
+    bool conv = false;
+    for (int it = 0; it < 40 && !conv; it++) {
+        float Cf[3][3];                                           // cofactor matrix = det * X^-T
         Cf[0][0] = X[1][1] * X[2][2] - X[1][2] * X[2][1]; Cf[0][1] = X[1][2] * X[2][0] - X[1][0] * X[2][2]; Cf[0][2] = X[1][0] * X[2][1] - X[1][1] * X[2][0];
         Cf[1][0] = X[0][2] * X[2][1] - X[0][1] * X[2][2]; Cf[1][1] = X[0][0] * X[2][2] - X[0][2] * X[2][0]; Cf[1][2] = X[0][1] * X[2][0] - X[0][0] * X[2][1];
         Cf[2][0] = X[0][1] * X[1][2] - X[0][2] * X[1][1]; Cf[2][1] = X[0][2] * X[1][0] - X[0][0] * X[1][2]; Cf[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
-        const double det = X[0][0] * Cf[0][0] + X[0][1] * Cf[0][1] + X[0][2] * Cf[0][2];
-        if (!(det > 1e-14)) return false;                         // reflection, singular or NaN: let the SVD decide
-        double nx = 0.0, nc = 0.0;
+        const float det = X[0][0] * Cf[0][0] + X[0][1] * Cf[0][1] + X[0][2] * Cf[0][2];
+        if (!(det > 1e-12f)) return false;                        // reflection, singular or NaN: let the SVD decide
+        float nx = 0.f, nc = 0.f;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { nx += X[i][j] * X[i][j]; nc += Cf[i][j] * Cf[i][j]; }
-        // Frobenius scaling g^2 = |X^-T|_F / |X|_F  with X^-T = Cf / det
-        const double g2 = sqrt(nc / nx) / det;
-        const double g = sqrt(g2);
-        const double a = 0.5 * g, b = 0.5 / (g * det);
-        double diff = 0.0;
+        const float g = sqrtf(sqrtf(nc / nx) / det);              // Frobenius scaling g^2 = |X^-T|_F / |X|_F
+        const float a = 0.5f * g, b = 0.5f / (g * det);
+        float diff = 0.f;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-            const double y = a * X[i][j] + b * Cf[i][j];
-            const double d = y - X[i][j]; diff += d * d;
+            const float y = a * X[i][j] + b * Cf[i][j];
+            const float d = y - X[i][j]; diff += d * d;
             X[i][j] = y;
         }
-        if (diff < 1e-22) {
-            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] = X[i][j];
-            return true;
-        }
+        conv = diff < 1e-10f;                                     // |dX|_F < 1e-5: the next (quadratic) steps finish the job
     }
-    return false;
+    if (!conv) return false;
+    double Y[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Y[i][j] = (double)X[i][j];
+    for (int it = 0; it < 1; it++) {                              // unscaled FP64 step: orthogonality 1e-6 -> 1e-12
+        double Cf[3][3];
+        Cf[0][0] = Y[1][1] * Y[2][2] - Y[1][2] * Y[2][1]; Cf[0][1] = Y[1][2] * Y[2][0] - Y[1][0] * Y[2][2]; Cf[0][2] = Y[1][0] * Y[2][1] - Y[1][1] * Y[2][0];
+        Cf[1][0] = Y[0][2] * Y[2][1] - Y[0][1] * Y[2][2]; Cf[1][1] = Y[0][0] * Y[2][2] - Y[0][2] * Y[2][0]; Cf[1][2] = Y[0][1] * Y[2][0] - Y[0][0] * Y[2][1];
+        Cf[2][0] = Y[0][1] * Y[1][2] - Y[0][2] * Y[1][1]; Cf[2][1] = Y[0][2] * Y[1][0] - Y[0][0] * Y[1][2]; Cf[2][2] = Y[0][0] * Y[1][1] - Y[0][1] * Y[1][0];
+        const double det = Y[0][0] * Cf[0][0] + Y[0][1] * Cf[0][1] + Y[0][2] * Cf[0][2];
+        const double b = 0.5 / det;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Y[i][j] = 0.5 * Y[i][j] + b * Cf[i][j];
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] = Y[i][j];
+    return true;
 }
 
 __host__ __device__ __noinline__ Tf umeyama_dev(const CStats& s)
@@ -581,7 +593,7 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
 // the partials in the same fixed order and runs the serial tail redundantly on its shared-memory copy of the ICP state.  One block
 // per SM; 5 iterations cost 5 grid syncs instead of 5 launches + 5 "last block" rounds.  Partials are double-buffered by parity.
 // ---------------------------------------------------------------------------------------------------------------------
-#define B2_ICP_BLOCK 256
+#define B2_ICP_BLOCK 512
 __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, const float* __restrict__ mpts,
                                                           const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
                                                           uint32_t iterations, double* __restrict__ partials)
@@ -589,12 +601,13 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double smem[(B2_NACC + 1) * (B2_ICP_BLOCK / 32)];
-    __shared__ double s_part[16][B2_NACC + 1];
+    __shared__ double s_part[B2_ICP_BLOCK / 16][B2_NACC + 1];
     __shared__ __align__(16) IcpState s_icp;
     for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(icp_g)[w];
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t it = 0; it < iterations; it++) {
+        const long long c0 = clock64();
         const Tf Tpre = tf_load(&s_icp.T_snew_sold);
         const float max_dist = s_icp.max_dist;
         P2LAcc acc; acc_zero(acc);
@@ -625,22 +638,33 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
             p[B2_NACC] = (double)acc.n;
             __threadfence();
         }
+        const long long c1 = clock64();
         grid.sync();
+        const long long c2 = clock64();
         {
+            constexpr uint32_t NG = B2_ICP_BLOCK / 16;               // thread (g, i) adds value i of blocks g, g+NG, ...
             const uint32_t i = threadIdx.x & 15u, g = threadIdx.x >> 4;
             double a = 0.0;
-            for (uint32_t b = g; b < gridDim.x; b += 16u) a += __ldcg(part + (size_t)b * (B2_NACC + 1) + i);
+            for (uint32_t b = g; b < gridDim.x; b += NG) a += __ldcg(part + (size_t)b * (B2_NACC + 1) + i);
             s_part[g][i] = a;
         }
         __syncthreads();
         if (threadIdx.x < B2_NACC + 1) {
             double a = 0.0;
             #pragma unroll
-            for (int g = 0; g < 16; g++) a += s_part[g][threadIdx.x];
+            for (int g = 0; g < B2_ICP_BLOCK / 16; g++) a += s_part[g][threadIdx.x];
             s_part[0][threadIdx.x] = a;
         }
         __syncthreads();
-        if (threadIdx.x == 0) icp_step_fast(&s_icp, acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5)), it + 1 == iterations);
+        if (threadIdx.x == 0) {
+            const long long c3 = clock64();
+            icp_step_fast(&s_icp, acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5)), it + 1 == iterations);
+            if (it == 1) {
+                const long long c4 = clock64();
+                s_icp.dbg[0] = (unsigned long long)(c1 - c0); s_icp.dbg[1] = (unsigned long long)(c2 - c1);
+                s_icp.dbg[2] = (unsigned long long)(c3 - c2); s_icp.dbg[3] = (unsigned long long)(c4 - c3);
+            }
+        }
         __syncthreads();
     }
     if (blockIdx.x == 0)

@@ -176,7 +176,8 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
             Gt.y &= ~(1u << i);
             tri_test(bvh, r, Gt.x + i, best);
             if (STATS) n_tris++;
-        } else {
+        }
+        if (!Gt.y) {                                           // last pending triangle done (or none): visit a node in the same trip
             if (!(G.y & 0xff000000u)) {
                 if (sp == 0) break;
                 G = stack[--sp];

@@ -1,7 +1,6 @@
 import os, sys, ctypes as C
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("B2_FUSED", "0")
 import rmcl_b200
 from rmcl_b200 import synth
 V, F = synth.building(1_000_000)
@@ -18,4 +17,4 @@ for k in range(3):
     h.correctOnce(Tom, I, 5, 0.0)
     out = (C.c_ulonglong * 8)()
     lib.b2_rcc_debug_clocks(h._h, out)
-    print("cycles: main+blockreduce+ticket %d | partial sum %d | finalize %d | icp_step %d" % (out[0], out[1], out[2], out[3]))
+    print("cycles (coop loop, iteration 1, block 0): pass+blockreduce %d | grid.sync %d | partial sum %d | tail %d" % (out[0], out[1], out[2], out[3]))

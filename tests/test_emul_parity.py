@@ -61,7 +61,7 @@ def test_find_all_models_bit_exact(pe, po, synth):
         assert 0.3 < r1["hits"].mean() <= 1.0
 
 
-def test_icp_chain_bit_exact(pe, po, synth):
+def test_icp_chain_parity(pe, po, synth):
     osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
     m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 31, 32, -np.pi, 2 * np.pi / 256, 256, 0.5, 120.0)
     o, d = po.model_rays(m)
@@ -74,7 +74,9 @@ def test_icp_chain_bit_exact(pe, po, synth):
     b = esc.correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0)
     assert a[2]["n_meas"] == b[2]["n_meas"] and a[2]["n_meas"] > 5000
     assert np.abs(a[0]["t"] - b[0]["t"]).max() <= 1e-6 and np.abs(a[0]["R"] - b[0]["R"]).max() <= 1e-6
-    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()      # same algorithm, same order -> same bits
+    assert np.abs(a[1]["t"] - b[1]["t"]).max() <= 1e-6 and np.abs(a[1]["R"] - b[1]["R"]).max() <= 1e-6
+    # (the chain was bit-identical while the device used the oracle's FP64 Jacobi SVD; the FP32 Newton polar iteration that replaced it
+    #  on the critical path agrees to ~1e-7)
     # the lean tail of the cooperative ICP loop (pre-composed frames): same result within float noise
     c = esc.correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, fast_tail=True)
     assert abs(int(c[2]["n_meas"]) - int(a[2]["n_meas"])) <= 2
