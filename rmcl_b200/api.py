@@ -123,8 +123,10 @@ def _devptr(x):
 class Map:
     """Triangle mesh + in-HBM BVH; stands in for rm::EmbreeMap / rm::OptixMap (rm::import_embree_map, micp_localization.cpp:188)."""
 
-    def __init__(self, verts, faces, device=0, build_mode=B2_BUILD_HOST_SAH):
+    def __init__(self, verts, faces, device=0, build_mode=None):
         lib = load_library()
+        if build_mode is None:
+            build_mode = int(os.environ.get("B2_BUILD_MODE", B2_BUILD_HOST_SAH))
         verts = _f32(verts).reshape(-1, 3)
         faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
         h = C.c_void_p()

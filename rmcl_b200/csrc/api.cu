@@ -1,6 +1,7 @@
 // api.cu -- C ABI (include/rmcl_b200.h) over the sm_100a kernels.  No CPU fallback anywhere: every entry point either runs
 // the CUDA path or fails with B2_ERR_CUDA.
 #include "kernels.cuh"
+#include "lbvh.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -63,10 +64,32 @@ extern "C" int b2_mesh_create(const float* verts, uint32_t nv, const uint32_t* f
     NOTNULL(out); *out = nullptr;
     if (nf == 0 || nv == 0) return fail(B2_ERR_NO_MAP, "EMPTY MAP: %u vertices, %u faces", nv, nf);
     NOTNULL(verts); NOTNULL(faces);
-    if (build_mode != B2_BUILD_HOST_SAH) return fail(B2_ERR_UNSUPPORTED, "build_mode %d not available in this build", build_mode);
+    if (build_mode != B2_BUILD_HOST_SAH && build_mode != B2_BUILD_DEVICE_LBVH) return fail(B2_ERR_UNSUPPORTED, "unknown build_mode %d", build_mode);
     int ndev = 0; CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
+    if (build_mode == B2_BUILD_DEVICE_LBVH) {
+        for (size_t i = 0; i < 3 * (size_t)nf; i++) if (faces[i] >= nv) return fail(B2_ERR_INVALID, "BVH build failed: face index out of range");
+        for (size_t i = 0; i < 3 * (size_t)nv; i++) if (!std::isfinite(verts[i])) return fail(B2_ERR_INVALID, "BVH build failed: non-finite vertex");
+        const auto t0 = std::chrono::steady_clock::now();
+        float* d_v = nullptr; uint32_t* d_f = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d_v, sizeof(float) * 3 * (size_t)nv);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_f, sizeof(uint32_t) * 3 * (size_t)nf);
+        if (e == cudaSuccess) e = cudaMemcpy(d_v, verts, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_f, faces, sizeof(uint32_t) * 3 * (size_t)nf, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(d_v); cudaFree(d_f); return fail(B2_ERR_CUDA, "mesh upload failed: %s", cudaGetErrorString(e)); }
+        b2_mesh* m = new (std::nothrow) b2_mesh();
+        if (!m) { cudaFree(d_v); cudaFree(d_f); return fail(B2_ERR_OOM, "out of host memory"); }
+        const char* err = "";
+        const int rc = lbvh_build_device(d_v, nv, d_f, nf, &m->d_nodes, &m->n_nodes, &m->d_tris, &m->n_tris, &m->max_depth, m->abs_max, &err);
+        g_launches.fetch_add(5 + m->max_depth);
+        cudaFree(d_v); cudaFree(d_f);
+        if (rc != 0) { delete m; return fail(rc == -5 ? B2_ERR_INVALID : B2_ERR_CUDA, "BVH build failed: %s (%s)", err, cudaGetErrorString(cudaGetLastError())); }
+        m->device = device; m->build_mode = build_mode; m->n_faces = nf; m->n_verts = nv; m->sah = 0.f;
+        m->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *out = m;
+        return B2_OK;
+    }
     const auto t0 = std::chrono::steady_clock::now();
     B2BvhHost hb; const char* err = "";
     const int rc = b2_build_bvh8_host(verts, nv, faces, nf, &hb, &err);

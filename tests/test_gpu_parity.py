@@ -305,3 +305,38 @@ def test_full_size_properties_c3(po, synth):
     out2 = up.update(P[:2000], out[:2000], Tsb, beams, prm)
     both = up.update(P[:2000], A[:2000], Tsb, np.concatenate([beams, beams]), prm)
     assert (out2["likelihood"]["n_meas"] == 360).all() and out2.tobytes() == both.tobytes()
+
+
+@pytest.mark.parametrize("name,lo,hi,n", [("cube29", -9.5, 9.5, 30000), ("building:200000", 1.0, 2.9, 100000), ("uvsphere:40:60", -6.0, 6.0, 30000)])
+def test_device_lbvh_build_bit_exact(po, synth, name, lo, hi, n):
+    """Map built entirely on the device (Morton + radix sort + Karras hierarchy + wide collapse): same answers as the oracle (and hence as
+    the host SAH build) -- the hit definition does not depend on the tree."""
+    import rmcl_b200
+    V, F = mesh(name)
+    lb = rmcl_b200.Map(V, F, device=0, build_mode=rmcl_b200.api.B2_BUILD_DEVICE_LBVH)
+    info = lb.info()
+    assert info["n_leaf_tris"] == len(F) and info["build_mode"] == 1 and 0 < info["max_depth"] < 36
+    o, d = random_rays(n, lo, hi, seed=9)
+    t1, f1, n1, h1 = oracle_scene(name).intersect(o, d)
+    t2, f2, n2, h2 = lb.intersect(o, d)
+    assert np.array_equal(h1, h2) and np.array_equal(f1, f2) and np.array_equal(t1, t2) and np.array_equal(n1, n2)
+    # a full sensor path on the device-built map
+    if name.startswith("building"):
+        m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 31, 32, -np.pi, 2 * np.pi / 256, 256, 0.5, 120.0)
+        oo, dd = po.model_rays(m)
+        ref = oracle_scene(name).simulate(synth.building_gt_pose(), synth.scenario_tsb(), oo, dd, m.range_max)
+        h = rmcl_b200.RCCB200Spherical(lb)
+        h.setTsb(synth.scenario_tsb())
+        h.setModel(m)
+        h.find(synth.building_gt_pose())
+        mv = h.modelView()
+        assert all(np.array_equal(mv[k], ref[k], equal_nan=True) for k in ref)
+    # degenerate inputs: one triangle, coincident triangles
+    one = rmcl_b200.Map(np.array([[5, -1, -1], [5, 1, -1], [5, 0, 1]], np.float32), np.array([[0, 1, 2]], np.uint32), build_mode=1)
+    t, f, ng, hit = one.intersect([[0, 0, 0]], [[1, 0, 0]])
+    assert hit[0] == 1 and f[0] == 0
+    Vd = np.tile(np.array([[5, -1, -1], [5, 1, -1], [5, 0, 1]], np.float32), (5, 1))
+    Fd = np.arange(15, dtype=np.uint32).reshape(5, 3)[::-1].copy()
+    dup = rmcl_b200.Map(Vd, Fd, build_mode=1)
+    t, f, ng, hit = dup.intersect([[0, 0, 0]], [[1, 0, 0]])
+    assert hit[0] == 1 and f[0] == 0                                       # tie -> smallest face id
