@@ -144,7 +144,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": "C2: MICP-L correctOnce, 1 pose x 128x1024 spherical scan, building mesh", "n_faces": args.faces, "rays_per_step_per_gpu": 131072,
               "inner_iterations": ITERATIONS, "poses_per_gpu": 1, "parallelism": f"pose-shard x{world} (map replicated, no collective)",
-              "l2": "flushed between timed steps (256 MiB write)"}
+              "l2": "flushed between timed steps (256 MiB write)", "map_build": "device LBVH (B2_BUILD_MODE=0 selects the host SAH build)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -315,7 +315,7 @@ def main():
                     "ms_per_step": e2e_ms_max / args.steps, "timer": "host wall clock around the synchronous C-ABI call"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": {"fused_kernel_or_find": float(np.mean(find_ms)), "separate_reduce_launches": float(np.mean(red_ms)), "find_alone": find_s * 1e3},
-            "map": {"n_nodes": info["n_nodes"], "bvh_mb": info["bvh_bytes"] / 1e6, "build_ms": info["build_ms"], "max_depth": info["max_depth"]},
+            "map": {"n_nodes": info["n_nodes"], "bvh_mb": info["bvh_bytes"] / 1e6, "build_ms": info["build_ms"], "max_depth": info["max_depth"], "build_mode": info["build_mode"]},
             "result_check": {"n_meas": int(Cm["n_meas"]), "dt_norm": float(np.linalg.norm(Td["t"]))},
             "extra": extra}
     print(json.dumps(line))

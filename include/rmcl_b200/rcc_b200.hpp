@@ -28,7 +28,7 @@ inline void b2_check(int rc, const char* what)
 // stands in for rm::EmbreeMap / rm::OptixMap; shared between sensors and plugins like the reference's map container (micp_localization.cpp:545)
 class B200Map {
 public:
-    B200Map(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces, int device = 0, int build_mode = B2_BUILD_HOST_SAH)
+    B200Map(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces, int device = 0, int build_mode = B2_BUILD_DEVICE_LBVH)
     { b2_check(b2_mesh_create(verts_xyz, n_vertices, faces_ijk, n_faces, device, build_mode, &m_), "B200Map"); }
     ~B200Map() { b2_mesh_destroy(m_); }
     B200Map(const B200Map&) = delete; B200Map& operator=(const B200Map&) = delete;

@@ -126,7 +126,7 @@ class Map:
     def __init__(self, verts, faces, device=0, build_mode=None):
         lib = load_library()
         if build_mode is None:
-            build_mode = int(os.environ.get("B2_BUILD_MODE", B2_BUILD_HOST_SAH))
+            build_mode = int(os.environ.get("B2_BUILD_MODE", B2_BUILD_DEVICE_LBVH))     # device build: faster to build AND to trace
         verts = _f32(verts).reshape(-1, 3)
         faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
         h = C.c_void_p()

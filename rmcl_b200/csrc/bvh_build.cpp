@@ -35,7 +35,7 @@ struct Prim { Box box; float c[3]; };
 
 constexpr int   kBins = 32;
 constexpr float kCNode = 1.0f;      // cost of visiting one wide node
-constexpr float kCPrim = 0.35f;     // cost of testing one triangle
+static float kCPrim = 0.35f;        // cost of testing one triangle relative to visiting one wide node (B2_SAH_CPRIM overrides)
 constexpr float kInf = 1e30f;
 
 struct Builder {
@@ -156,6 +156,7 @@ int b2_build_bvh8_host(const float* verts, uint32_t nv, const uint32_t* faces, u
     static const char* e_depth = "BVH too deep for the traversal stack";
     static const char* e_oom = "out of host memory";
     *out = B2BvhHost();
+    if (const char* e = getenv("B2_SAH_CPRIM")) kCPrim = (float)atof(e);
     if (nf == 0 || nv == 0) { *err = e_empty; return -3; }
     for (uint32_t i = 0; i < 3 * nf; i++) if (faces[i] >= nv) { *err = e_index; return -1; }
     for (size_t i = 0; i < 3 * (size_t)nv; i++) if (!std::isfinite(verts[i])) { *err = e_nan; return -1; }

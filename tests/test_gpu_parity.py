@@ -50,6 +50,20 @@ def test_closest_hit_bit_exact(po, name, lo, hi, n):
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
 
 
+@pytest.mark.parametrize("name,lo,hi", [("cube29", -9.5, 9.5), ("building:200000", 1.0, 2.9)])
+def test_host_sah_build_bit_exact(po, name, lo, hi):
+    """the alternative host SAH builder (build_mode 0) gives the same answers as the default device build and the oracle"""
+    import rmcl_b200
+    V, F = mesh(name)
+    sah = rmcl_b200.Map(V, F, device=0, build_mode=rmcl_b200.api.B2_BUILD_HOST_SAH)
+    o, d = random_rays(50000, lo, hi, seed=11)
+    t1, f1, n1, h1 = oracle_scene(name).intersect(o, d)
+    t2, f2, n2, h2 = sah.intersect(o, d)
+    t3, f3, n3, h3 = gpu_map(name).intersect(o, d)
+    assert np.array_equal(f1, f2) and np.array_equal(t1, t2) and np.array_equal(n1, n2) and np.array_equal(h1, h2)
+    assert np.array_equal(f1, f3) and np.array_equal(t1, t3)
+
+
 def test_c1_find_golden(po, synth):
     """C1: 32x32 spherical on the 10 092-triangle cube, against the committed golden vectors."""
     g = np.load(os.path.join(GOLD, "c1_cube.npz"))
