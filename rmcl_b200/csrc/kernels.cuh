@@ -127,6 +127,14 @@ __host__ __device__ __noinline__ void svd3_dev(const double A[3][3], double U[3]
     }
 }
 
+#if B2_ON_DEVICE
+B2_DEV float b2_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+B2_DEV float b2_rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+B2_DEV float b2_rcp_approx(float x) { return 1.0f / x; }
+B2_DEV float b2_rsqrt_approx(float x) { return 1.0f / std::sqrt(x); }
+#endif
+
 // orthogonal polar factor of a 3x3 matrix with positive determinant; false if not applicable / not converged.
 // Frobenius-scaled Newton iteration X <- (g X + X^-T / g) / 2 in FP32 (4-cycle ops, MUFU-based div/sqrt: ~3x shorter serial chain than
 // FP64 on the one thread that executes it), then one unscaled FP64 step that makes the result orthogonal to double precision.
@@ -148,17 +156,27 @@ __host__ __device__ __noinline__ bool polar_newton3(const double A[3][3], double
         Cf[2][0] = X[0][1] * X[1][2] - X[0][2] * X[1][1]; Cf[2][1] = X[0][2] * X[1][0] - X[0][0] * X[1][2]; Cf[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
         const float det = X[0][0] * Cf[0][0] + X[0][1] * Cf[0][1] + X[0][2] * Cf[0][2];
         if (!(det > 1e-12f)) return false;                        // reflection, singular or NaN: let the SVD decide
-        float nx = 0.f, nc = 0.f;
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { nx += X[i][j] * X[i][j]; nc += Cf[i][j] * Cf[i][j]; }
-        const float g = sqrtf(sqrtf(nc / nx) / det);              // Frobenius scaling g^2 = |X^-T|_F / |X|_F
-        const float a = 0.5f * g, b = 0.5f / (g * det);
+        float a, b;
+        if (it < 3) {
+            // Frobenius scaling g^2 = |X^-T|_F / |X|_F only matters while X is far from orthogonal; approximate reciprocal / rsqrt are
+            // enough (any g > 0 keeps the iteration convergent, and its errors are corrected by the following steps)
+            float nx = 0.f, nc = 0.f;
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { nx += X[i][j] * X[i][j]; nc += Cf[i][j] * Cf[i][j]; }
+            const float rdet = b2_rcp_approx(det);
+            const float q = nc * b2_rcp_approx(nx);                                  // (|Cf|/|X|)^2
+            const float g2 = q * b2_rsqrt_approx(q) * rdet;                          // sqrt(q) / det
+            const float rg = b2_rsqrt_approx(g2);                                    // 1 / g
+            a = 0.5f * g2 * rg; b = 0.5f * rg * rdet;
+        } else {
+            a = 0.5f; b = 0.5f * b2_rcp_approx(det);
+        }
         float diff = 0.f;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
             const float y = a * X[i][j] + b * Cf[i][j];
             const float d = y - X[i][j]; diff += d * d;
             X[i][j] = y;
         }
-        conv = diff < 1e-10f;                                     // |dX|_F < 1e-5: the next (quadratic) steps finish the job
+        conv = (it >= 3) && diff < 1e-10f;                        // |dX|_F < 1e-5 on an unscaled step: the FP64 step finishes the job
     }
     if (!conv) return false;
     double Y[3][3];
@@ -192,23 +210,26 @@ __host__ __device__ __noinline__ Tf umeyama_dev(const CStats& s)
         const double sgn = (det3d(U) * det3d(V) < 0.0) ? -1.0 : 1.0;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
     }
-    double q[4];
-    const double tr = R[0][0] + R[1][1] + R[2][2];
-    if (tr > 0.0) {
-        const double sc = sqrt(tr + 1.0) * 2.0; q[3] = 0.25 * sc;
-        q[0] = (R[2][1] - R[1][2]) / sc; q[1] = (R[0][2] - R[2][0]) / sc; q[2] = (R[1][0] - R[0][1]) / sc;
-    } else if (R[0][0] > R[1][1] && R[0][0] > R[2][2]) {
-        const double sc = sqrt(1.0 + R[0][0] - R[1][1] - R[2][2]) * 2.0; q[3] = (R[2][1] - R[1][2]) / sc;
-        q[0] = 0.25 * sc; q[1] = (R[0][1] + R[1][0]) / sc; q[2] = (R[0][2] + R[2][0]) / sc;
-    } else if (R[1][1] > R[2][2]) {
-        const double sc = sqrt(1.0 + R[1][1] - R[0][0] - R[2][2]) * 2.0; q[3] = (R[0][2] - R[2][0]) / sc;
-        q[0] = (R[0][1] + R[1][0]) / sc; q[1] = 0.25 * sc; q[2] = (R[1][2] + R[2][1]) / sc;
+    // rotation matrix -> quaternion in FP32 (the reference's rm::Quaternion::set(Matrix3x3) is FP32 as well); R is orthogonal to 1e-12
+    float Rf[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rf[i][j] = (float)R[i][j];
+    float q[4];
+    const float tr = Rf[0][0] + Rf[1][1] + Rf[2][2];
+    if (tr > 0.0f) {
+        const float sc = sqrt_rn(tr + 1.0f) * 2.0f; q[3] = 0.25f * sc;
+        q[0] = dvd(Rf[2][1] - Rf[1][2], sc); q[1] = dvd(Rf[0][2] - Rf[2][0], sc); q[2] = dvd(Rf[1][0] - Rf[0][1], sc);
+    } else if (Rf[0][0] > Rf[1][1] && Rf[0][0] > Rf[2][2]) {
+        const float sc = sqrt_rn(1.0f + Rf[0][0] - Rf[1][1] - Rf[2][2]) * 2.0f; q[3] = dvd(Rf[2][1] - Rf[1][2], sc);
+        q[0] = 0.25f * sc; q[1] = dvd(Rf[0][1] + Rf[1][0], sc); q[2] = dvd(Rf[0][2] + Rf[2][0], sc);
+    } else if (Rf[1][1] > Rf[2][2]) {
+        const float sc = sqrt_rn(1.0f + Rf[1][1] - Rf[0][0] - Rf[2][2]) * 2.0f; q[3] = dvd(Rf[0][2] - Rf[2][0], sc);
+        q[0] = dvd(Rf[0][1] + Rf[1][0], sc); q[1] = 0.25f * sc; q[2] = dvd(Rf[1][2] + Rf[2][1], sc);
     } else {
-        const double sc = sqrt(1.0 + R[2][2] - R[0][0] - R[1][1]) * 2.0; q[3] = (R[1][0] - R[0][1]) / sc;
-        q[0] = (R[0][2] + R[2][0]) / sc; q[1] = (R[1][2] + R[2][1]) / sc; q[2] = 0.25 * sc;
+        const float sc = sqrt_rn(1.0f + Rf[2][2] - Rf[0][0] - Rf[1][1]) * 2.0f; q[3] = dvd(Rf[1][0] - Rf[0][1], sc);
+        q[0] = dvd(Rf[0][2] + Rf[2][0], sc); q[1] = dvd(Rf[1][2] + Rf[2][1], sc); q[2] = 0.25f * sc;
     }
-    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    out.R.x = (float)(q[0] / n); out.R.y = (float)(q[1] / n); out.R.z = (float)(q[2] / n); out.R.w = (float)(q[3] / n);
+    Q4 qq; qq.x = q[0]; qq.y = q[1]; qq.z = q[2]; qq.w = q[3];
+    out.R = q_normalize(qq);
     out.t = v_sub(s.mm, q_rot(out.R, s.dm));
     return out;
 }
@@ -255,31 +276,60 @@ B2_DEV CStats acc_finalize(const double* v, uint32_t n)
     return s;
 }
 
-// block-level sum of the accumulators; result valid in thread 0.  smem: double[(B2_NACC+1) * 32]
+// block-level sum of the accumulators; result valid in thread 0.  smem: double[(B2_NACC+1) * (BLOCK/32)]
+//
+// Warp stage = reduce-scatter: at each of four steps a lane hands half of its remaining values to its partner and adds the partner's half
+// of the values it keeps, so 16 values cost 8+4+2+1 (+1 final) = 16 64-bit shuffles instead of 16 x 5 = 80 for 16 independent butterflies
+// (the FP64 shuffles of the plain version were the longest part of the reduction pass: profiles/r01, clock stamps in k_icp_loop).
+// After the four steps lane l holds value index ((l>>1) & 15) summed over the 16 lanes that share its bit 0; one xor-1 step completes it.
+#if defined(__CUDACC__)
+template <int H>
+__device__ __forceinline__ void rs_step(double (&v)[16], int offset, bool upper)
+{
+    #pragma unroll
+    for (int i = 0; i < H; i++) {
+        const double send = upper ? v[i] : v[i + H];
+        const double keep = upper ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+    }
+}
 template <int BLOCK>
 __device__ __forceinline__ void block_reduce_acc(P2LAcc& a, double* smem)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = BLOCK / 32;
+    double v[16];
     #pragma unroll
-    for (int i = 0; i < B2_NACC; i++) a.v[i] = warp_sum(a.v[i]);
+    for (int i = 0; i < B2_NACC; i++) v[i] = a.v[i];
+    v[15] = 0.0;
+    rs_step<8>(v, 16, (lane & 16) != 0);      // keeps values [8,16) if bit 4 set else [0,8)
+    rs_step<4>(v, 8, (lane & 8) != 0);
+    rs_step<2>(v, 4, (lane & 4) != 0);
+    rs_step<1>(v, 2, (lane & 2) != 0);
+    const double tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     a.n = warp_sum_u32(a.n);
-    if (lane == 0) {
-        #pragma unroll
-        for (int i = 0; i < B2_NACC; i++) smem[i * NW + warp] = a.v[i];
-        smem[B2_NACC * NW + warp] = (double)a.n;
-    }
+    if ((lane & 1) == 0 && vidx < B2_NACC) smem[vidx * NW + warp] = tot;
+    if (lane == 0) smem[B2_NACC * NW + warp] = (double)a.n;
     __syncthreads();
     if (warp == 0) {
-        #pragma unroll
-        for (int i = 0; i <= B2_NACC; i++) {
-            double x = lane < NW ? smem[i * NW + lane] : 0.0;
-            x = warp_sum(x);
-            if (i < B2_NACC) a.v[i] = x; else a.n = (uint32_t)(x + 0.5);
+        // lane i < 16 sums value i over the NW warps (fixed order)
+        if (lane <= B2_NACC) {
+            double x = 0.0;
+            #pragma unroll
+            for (int w = 0; w < NW; w++) x += smem[lane * NW + w];
+            smem[lane * NW] = x;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            #pragma unroll
+            for (int i = 0; i < B2_NACC; i++) a.v[i] = smem[i * NW];
+            a.n = (uint32_t)(smem[B2_NACC * NW] + 0.5);
         }
     }
     __syncthreads();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ICP state kept on the device between the kernels of one correctOnce (micp_localization.cpp:899-984)
@@ -611,11 +661,11 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
         const Tf Tpre = tf_load(&s_icp.T_snew_sold);
         const float max_dist = s_icp.max_dist;
         P2LAcc acc; acc_zero(acc);
-        for (uint32_t base = gid; base < n; base += 4u * stride) {
-            // up to 4 pairs per trip with all their loads issued before the first use
-            uint8_t dm[4], mm[4]; V3 d[4], I[4], N[4];
+        for (uint32_t base = gid; base < n; base += 2u * stride) {
+            // up to 2 pairs per trip with all their loads issued before the first use
+            uint8_t dm[2], mm[2]; V3 d[2], I[2], N[2];
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const uint32_t i = base + (uint32_t)u * stride;
                 const bool in = i < n;
                 const uint32_t j = in ? i : base;
@@ -625,7 +675,7 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
                 N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
             }
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 V3 D, M;
                 if ((dm[u] > 0) && (mm[u] > 0) && p2l_pair(Tpre, d[u], I[u], N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
             }
