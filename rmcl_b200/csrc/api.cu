@@ -181,8 +181,8 @@ extern "C" int b2_mesh_intersect_stats(const b2_mesh* m, const float* origs, con
 // ---------------------------------------------------------------------------------------------------------------------
 // RCC handle
 // ---------------------------------------------------------------------------------------------------------------------
-struct HostPin {            // pinned staging for small results
-    b2_transform T[3]; b2_cross_stats S[2]; IcpState icp;
+struct HostPin {            // pinned (mapped) staging for small results
+    b2_transform T[3]; b2_cross_stats S[2]; IcpState icp; IcpState icp_out; volatile unsigned int flag; unsigned int pad[3];
 };
 
 struct b2_rcc {
@@ -198,6 +198,7 @@ struct b2_rcc {
     HostPin* pin = nullptr;
     int red_grid = 0;
     int fused_grid = 0;                 // blocks of the cooperative k_icp_loop (0: cooperative launch unavailable)
+    unsigned int seq = 0;               // completion sequence number written by k_icp_loop into pin->flag
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
 };
@@ -223,7 +224,8 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     int rc;
     if ((rc = h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)) || (rc = h->d_ticket.reserve(1)) || (rc = h->d_stats.reserve(1)) || (rc = h->d_icp.reserve(1))) { delete h; return rc; }
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
-    CU(cudaMallocHost((void**)&h->pin, sizeof(HostPin)));
+    CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
+    memset((void*)h->pin, 0, sizeof(HostPin));
     CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
     *out = h;
@@ -492,22 +494,27 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
 {
     bool aux_used = false;
     if (ranges_host) {
-        // the find kernel does not read the dataset: upload + unpack the scan on the side stream while it runs
         if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
         if (n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n_ranges, h->n);
         if (h->n > 0) {
             RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n));
-            CU(cudaEventRecord(h->ev_aux, h->stream));                    // order after whatever the main stream still has in flight
+            CU(cudaEventRecord(h->ev_aux, h->stream));                    // the side stream starts after whatever the main stream had in flight BEFORE this call
             CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
-            CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
-            k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max,
-                                                                          h->d_dpts.p, h->d_dmask.p);
-            LAUNCHED();
-            CU(cudaEventRecord(h->ev_aux, h->aux));
-            aux_used = true;
         }
         h->n_dataset = h->n;
     }
+    // the find kernel does not read the dataset: the scan is uploaded + unpacked on the side stream WHILE it runs (and the host-side
+    // cost of issuing the copy is hidden behind the already launched find)
+    auto upload_scan = [&]() -> int {
+        if (!ranges_host || h->n == 0) return B2_OK;
+        CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
+        k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max,
+                                                                      h->d_dpts.p, h->d_dmask.p);
+        LAUNCHED();
+        CU(cudaEventRecord(h->ev_aux, h->aux));
+        aux_used = true;
+        return B2_OK;
+    };
     if (!h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
     if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
     IcpState& st = h->pin->icp;
@@ -521,35 +528,54 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         const Tf Tos = tf_mul(tf_from_pod(*Tbo), tf_from_pod(h->Tsb));
         tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros);
     }
-    CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
     static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 1; }();
+    static const int use_spin = [] { const char* e = getenv("B2_SPIN"); return e ? atoi(e) : 1; }();
+    bool waited = false;
     if (h->n > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
-        // find, then ALL inner iterations in one cooperative kernel
+        // find, then ALL inner iterations in one cooperative kernel; state in by kernel parameter, result out through mapped pinned memory
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
         tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(*Tbo)));        // MICPSensor.hpp:148, same inline ops as the kernels
         RES(launch_find(h, &Tbm_host, nullptr));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+        RES(upload_scan());
         if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
         int grid = std::min<int>(h->fused_grid, (int)((h->n + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
         if (grid < 1) grid = 1;
         RES(h->d_partials.reserve((size_t)2 * grid * (B2_NACC + 1)));
         const float* dp = h->d_dpts.p; const uint8_t* dmk = h->d_dmask.p; const float* mp = h->d_mpts.p; const float* mn = h->d_mnrm.p; const uint8_t* mh = h->d_mhits.p;
         uint32_t nel = h->n; IcpState* icp_dev = h->d_icp.p; uint32_t its = iterations; double* parts = h->d_partials.p;
-        void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts};
+        IcpState* host_out = use_spin ? &h->pin->icp_out : nullptr; volatile unsigned int* host_flag = use_spin ? &h->pin->flag : nullptr;
+        unsigned int seq = ++h->seq; if (seq == 0) seq = ++h->seq;
+        void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts, &st, &host_out, &host_flag, &seq};
         CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop, dim3(grid), dim3(B2_ICP_BLOCK), args, 0, h->stream));
         LAUNCHED();
         if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
+        if (use_spin) {
+            // spin on the completion flag the kernel writes into mapped host memory (a stream synchronise costs several microseconds more)
+            const auto t_start = std::chrono::steady_clock::now();
+            unsigned long long spins = 0;
+            while (h->pin->flag != seq) {
+                if ((++spins & 0xfffffull) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 5.0) break;
+            }
+            if (h->pin->flag == seq) { memcpy(&st, (const void*)&h->pin->icp_out, sizeof(IcpState)); waited = true; }
+        }
     } else if (h->n > 0) {
+        RES(upload_scan());
         if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
+        CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         RES(launch_find(h, nullptr, h->d_icp.p));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
         for (uint32_t it = 0; it < iterations; it++) RES(launch_reduce(h, nullptr, 0.f, h->d_icp.p, nullptr));
         if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
+    } else {
+        CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
     }
-    CU(cudaMemcpyAsync(&st, h->d_icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    if (!waited) {
+        CU(cudaMemcpyAsync(&st, h->d_icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     if (Tom_new) *Tom_new = st.Tom_new;
     if (T_onew_oold) *T_onew_oold = st.T_onew_oold;
     if (Cmerged) *Cmerged = st.Cmerged_o;

@@ -646,14 +646,16 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
 #define B2_ICP_BLOCK 512
 __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, const float* __restrict__ mpts,
                                                           const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
-                                                          uint32_t iterations, double* __restrict__ partials)
+                                                          uint32_t iterations, double* __restrict__ partials, const __grid_constant__ IcpState init,
+                                                          IcpState* host_out, volatile unsigned int* host_flag, unsigned int seq)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double smem[(B2_NACC + 1) * (B2_ICP_BLOCK / 32)];
     __shared__ double s_part[B2_ICP_BLOCK / 16][B2_NACC + 1];
     __shared__ __align__(16) IcpState s_icp;
-    for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(icp_g)[w];
+    // the initial state arrives as a kernel parameter (no H2D copy in front of the launch)
+    for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(&init)[w];
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t it = 0; it < iterations; it++) {
@@ -717,8 +719,18 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
         }
         __syncthreads();
     }
-    if (blockIdx.x == 0)
-        for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(icp_g)[w] = reinterpret_cast<const uint32_t*>(&s_icp)[w];
+    if (blockIdx.x == 0) {
+        for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) {
+            const uint32_t x = reinterpret_cast<const uint32_t*>(&s_icp)[w];
+            reinterpret_cast<uint32_t*>(icp_g)[w] = x;
+            if (host_out) reinterpret_cast<volatile uint32_t*>(host_out)[w] = x;      // mapped pinned host memory: result lands without a D2H copy
+        }
+        if (host_flag) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) { *host_flag = seq; __threadfence_system(); }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
