@@ -367,7 +367,9 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
             tot += a.elapsed_time(bb)
     ms = maxr(tot) / steps
     # end to end with host particles
-    Ph, Ah = P[b:e].copy(), A[b:e].copy()
+    # pinned host staging (like the scan of the headline step)
+    Ph = torch.from_numpy(P[b:e].view(np.uint8).copy()).pin_memory().numpy().view(P.dtype).reshape(-1)
+    Ah = torch.from_numpy(A[b:e].view(np.uint8).copy()).pin_memory().numpy().view(A.dtype).reshape(-1)
     t0 = time.perf_counter()
     for _ in range(3):
         up.update(Ph, Ah, Tsb, beams, prm)
