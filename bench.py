@@ -55,17 +55,25 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_indices):
+        self.gpus = ",".join(str(g) for g in gpu_indices)
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_mark = None
 
     def start(self):
+        """ONE sampler process (rank 0) for all GPUs of the job, started well before the timed region: nvidia-smi start-up takes NVML /
+        driver locks for ~a second and would otherwise stall the first launches of every rank."""
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpus}", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        """samples before this wall-clock instant are outside the timed region and are dropped"""
+        import datetime
+        self.t_mark = datetime.datetime.now()
 
     def stop(self):
         if self.p is None:
@@ -77,17 +85,21 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
+        import datetime
         sm, smax, reasons = [], [], set()
         for line in open(self.f.name):
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t_mark is not None and ts < self.t_mark:
+                    continue
+                sm.append(float(c[2]))
+                smax.append(float(c[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.f.name)
@@ -172,6 +184,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
 
     # ---- set-up (untimed): map build (host SAH -> HBM), model, synthetic scan produced by the library itself at T_gt ----
     V, F = synth.building(args.faces)
@@ -204,9 +219,9 @@ def main():
         h.correctOnce(Tom, I, ITERATIONS, 0.0)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     find_ms, red_ms = [], []
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.mark()
     launches0 = rmcl_b200.kernel_launch_count()
     for a, b in ev:
         flush.fill_(2)                      # untimed L2 flush
@@ -246,7 +261,7 @@ def main():
         Tn2, Td2, Cm2 = h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
         e2e_s += time.perf_counter() - t0
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
