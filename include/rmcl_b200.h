@@ -76,6 +76,8 @@ enum {
     B2_ERR_UNSUPPORTED = -5
 };
 enum { B2_BUILD_HOST_SAH = 0, B2_BUILD_DEVICE_LBVH = 1 };
+/* correspondence type of a b2_rcc handle: ray casting (RCCEmbree*, default) or closest point (CPCEmbree) */
+enum { B2_CORR_RCC = 0, B2_CORR_CPC = 1 };
 
 B2_API const char* b2_last_error(void);
 B2_API int         b2_version(void);
@@ -117,6 +119,12 @@ B2_API int b2_rcc_set_dataset(b2_rcc* h, const float* points_xyz, const uint8_t*
 B2_API int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device);
 /* RCC..::find(Tbm_est), rmcl/src/rmcl/registration/RCCEmbree.cpp:26-36,58-68,89-99,121-131 */
 B2_API int b2_rcc_find(b2_rcc* h, const b2_transform* Tbm_est);
+/* CPCEmbree (rmcl/include/rmcl/registration/CPCEmbree.hpp:20-54, find at rmcl/src/rmcl/registration/CPCEmbree.cpp:17-43): with
+ * B2_CORR_CPC, b2_rcc_find runs one closest-point query per DATASET point (mask not consulted, as in the reference) instead of tracing
+ * the sensor model: Pm = Tsm*d_i; cp = map.closestPoint(Pm); hits = cp.d <= max_dist; points = Tms*cp.p; normals = Tms.R*cp.n.
+ * No sensor model is needed; the model buffers get n_dataset entries (ranges = cp.d), so b2_rcc_cross_statistics and
+ * b2_rcc_correct_once work unchanged.  b2_rcc_correct_once_ranges is refused in this mode. */
+B2_API int b2_rcc_set_correspondence_type(b2_rcc* h, int type);
 /* Correspondences{CPU,CUDA}::computeCrossStatistics, rmcl/src/rmcl/registration/CorrespondencesCPU.cpp:10-39 (CUDA twin CorrespondencesCUDA.cpp:9-30) */
 B2_API int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T_snew_sold, double convergence_progress, b2_cross_stats* out_host);
 /* modelView()/datasetView(), Correspondences.hpp:47-62: device pointers (points/normals packed xyz, hits/mask u8) + our extra face ids / ranges */
@@ -157,6 +165,13 @@ B2_API int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_parti
 /* ParticleUpdater<RAM>::update: HOST poses/attrs; copies in, updates, copies attrs back (end-to-end entry point) */
 B2_API int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses_host, b2_particle_attr* attrs_host, uint32_t n_particles,
                                     const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
+
+/* rest of the particle-filter cycle on the device, so that particles never leave HBM between stages:
+ * TFMotionUpdaterGPU / particle_move_and_forget (rmcl_ros/src/rmcl/particle_motion.cu:11-46): pose = pose * T_bnew_bold, n_meas -= forget_rate * n_meas */
+B2_API int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n_particles, const b2_transform* T_bnew_bold, double forget_rate);
+/* compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92): sum and max (initial 0) of likelihood.mean over the LOCAL particles; with particles
+ * sharded across GPUs the caller all-reduces the 8 bytes (SUM, MAX) -- the one exchange step of the cycle.  Results to HOST. */
+B2_API int b2_pf_likelihood_stats(b2_pf* h, const b2_particle_attr* attrs_dev, uint32_t n_particles, float* sum_out, float* max_out);
 
 /* ---------------------------------------------------------------- introspection ------------------------------ */
 /* CUDA-event timing of the kernels inside b2_rcc_correct_once*(): when enabled, events are recorded on the handle's stream around the

@@ -148,6 +148,13 @@ public:
     }
 };
 
+// rmcl::CPCEmbree twin (rmcl/include/rmcl/registration/CPCEmbree.hpp:20-54): closest-point correspondences on the same map BVH.
+// find() = one closest-point query per dataset point (CPCEmbree.cpp:17-43); no sensor model.
+class CPCB200 : public CorrespondencesB200 {
+public:
+    explicit CPCB200(B200MapPtr map) : CorrespondencesB200(std::move(map)) { b2_check(b2_rcc_set_correspondence_type(h_, B2_CORR_CPC), "CPCB200"); }
+};
+
 // --- v1 batched corrector API (lidar_corrector_embree_benchmark.cpp:86-133) -------------------------------------------------------
 struct CorrectionResultsB200 { std::vector<rm::Transform> Tdelta; std::vector<uint32_t> Ncorr; };
 template <typename RCC> class CorrectorB200 : public RCC {
@@ -201,6 +208,19 @@ public:
         b2_check(b2_pf_sensor_update(h_, reinterpret_cast<const b2_transform*>(poses.raw()), reinterpret_cast<b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
                                      reinterpret_cast<const b2_transform*>(&Tsb_), reinterpret_cast<const b2_range_meas*>(beams_.data()), (uint32_t)beams_.size(), &config), "update");
         return {};
+    }
+    // rest of the cycle on the device (particles stay in HBM): TFMotionUpdaterGPU (particle_motion.cu:36-46) and compute_stats (resampling.cu:84-92)
+    void motionUpdate(rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs, const rm::Transform& T_bnew_bold, double forget_rate)
+    {
+        b2_check(b2_pf_motion_update(h_, reinterpret_cast<b2_transform*>(poses.raw()), reinterpret_cast<b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
+                                     reinterpret_cast<const b2_transform*>(&T_bnew_bold), forget_rate), "motionUpdate");
+    }
+    struct SimpleLikelihoodStats { float sum = 0.0f; float max = -1.0f; };                       // resampling.cuh:26-30
+    SimpleLikelihoodStats computeStats(rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs)
+    {
+        SimpleLikelihoodStats s;
+        b2_check(b2_pf_likelihood_stats(h_, reinterpret_cast<const b2_particle_attr*>(attrs.raw()), (uint32_t)attrs.size(), &s.sum, &s.max), "computeStats");
+        return s;
     }
 private:
     B200MapPtr map_;

@@ -738,7 +738,9 @@ void orc_micp_correct_once(const orc_scene* s,
     uint8_t* mh = (uint8_t*)malloc((size_t)n);
     /* MICPSensor_::findCorrespondences (MICPSensor.hpp:146-151): Tbm = Tom * Tbo */
     const orc_transform Tbm = T_mul(*Tom, *Tbo);
-    orc_simulate(s, &Tbm, Tsb, n, origs_s, n_origs, dirs_s, range_max, mp, mn, mh, NULL, NULL);
+    /* dirs_s == NULL selects closest-point correspondences (CPCEmbree::find, hits against the NON-adaptive params.max_dist) */
+    if (dirs_s) orc_simulate(s, &Tbm, Tsb, n, origs_s, n_origs, dirs_s, range_max, mp, mn, mh, NULL, NULL);
+    else        orc_cpc_find(s, &Tbm, Tsb, n, dataset_pts, max_dist, 0, mp, mn, mh, NULL, NULL);
 
     const float md = orc_adaptive_max_dist(max_dist, adaptive_max_dist_min, convergence_progress);
     orc_transform T_onew_oold = T_identity();
@@ -862,6 +864,156 @@ void orc_pf_update(const orc_scene* s, uint32_t n_particles, const orc_transform
         for (uint32_t b = 0; b < n_beams; b++) orc_pf_sensor_update_one(s, &Tsm, &beams_s[b], p, &a);
         attrs[i] = a;
     }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* closest-point correspondences: CPCEmbree::find (rmcl/src/rmcl/registration/CPCEmbree.cpp:17-43)       */
+/* ------------------------------------------------------------------------------------------------ */
+/* Stand-in for rm::EmbreeMap::closestPoint (Embree point query).  BVH-independent definition, mirrored op for op by the kernels:
+ *   candidate(tri) = closest point on the triangle (C. Ericson's region tests, plain individually rounded ops), d2 = |p - q|^2;
+ *   box bound      b2(box) = |max(lo - q, q - hi, 0)|^2  (monotone in the box);
+ *   lim(d2)        = (sqrt(d2) + DELTA)^2, DELTA = 2^-16 * (1 + max|q_k|): dominates the rounding error of the candidate point;
+ *   a candidate counts iff b2(triangle AABB) <= lim(d2); result = argmin (d2, face id); a node may be skipped only if b2(node) > lim(best). */
+static inline float cp_b2(const float lo[3], const float hi[3], const float q[3])
+{
+    float acc[3];
+    for (int k = 0; k < 3; k++) { float a = lo[k] - q[k], b = q[k] - hi[k]; float m = a > b ? a : b; acc[k] = m > 0.0f ? m : 0.0f; }
+    return (acc[0] * acc[0] + acc[1] * acc[1]) + acc[2] * acc[2];
+}
+static inline float cp_lim(float d2, float delta) { float s = sqrtf(d2) + delta; return s * s; }
+static inline float dot_plain(const float a[3], const float b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+static void cp_triangle(const float a[3], const float b[3], const float c[3], const float p[3], float out[3])
+{
+    float ab[3], ac[3], ap[3], bp[3], cp[3];
+    for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+    const float d1 = dot_plain(ab, ap), d2 = dot_plain(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { for (int k = 0; k < 3; k++) out[k] = a[k]; return; }
+    for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+    const float d3 = dot_plain(ab, bp), d4 = dot_plain(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { for (int k = 0; k < 3; k++) out[k] = b[k]; return; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { const float v = d1 / (d1 - d3); for (int k = 0; k < 3; k++) out[k] = a[k] + ab[k] * v; return; }
+    for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+    const float d5 = dot_plain(ab, cp), d6 = dot_plain(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { for (int k = 0; k < 3; k++) out[k] = c[k]; return; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { const float w = d2 / (d2 - d6); for (int k = 0; k < 3; k++) out[k] = a[k] + ac[k] * w; return; }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int k = 0; k < 3; k++) out[k] = b[k] + (c[k] - b[k]) * w;
+        return;
+    }
+    const float denom = 1.0f / ((va + vb) + vc);
+    const float v = vb * denom, w = vc * denom;
+    for (int k = 0; k < 3; k++) out[k] = (a[k] + ab[k] * v) + ac[k] * w;
+}
+
+static int cp_candidate(const orc_scene* s, uint32_t f, const float q[3], float delta, float* d2_out, float p_out[3])
+{
+    const float* a = s->verts + 3 * (size_t)s->faces[3 * (size_t)f + 0];
+    const float* b = s->verts + 3 * (size_t)s->faces[3 * (size_t)f + 1];
+    const float* c = s->verts + 3 * (size_t)s->faces[3 * (size_t)f + 2];
+    float p[3]; cp_triangle(a, b, c, q, p);
+    const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = fmin3(a[k], b[k], c[k]); hi[k] = fmax3(a[k], b[k], c[k]); }
+    if (!(cp_b2(lo, hi, q) <= cp_lim(d2, delta))) return 0;
+    *d2_out = d2; p_out[0] = p[0]; p_out[1] = p[1]; p_out[2] = p[2];
+    return 1;
+}
+
+int orc_closest_point(const orc_scene* s, const float q[3], int brute, float* d_out, float p_out[3], float n_out[3], uint32_t* face_out)
+{
+    float qa = fabsf(q[0]); if (fabsf(q[1]) > qa) qa = fabsf(q[1]); if (fabsf(q[2]) > qa) qa = fabsf(q[2]);
+    const float delta = 1.52587890625e-05f * (1.0f + qa);
+    float best = INFINITY, bp[3] = {0, 0, 0}; uint32_t bf = ORC_NOFACE;
+    if (s->nf == 0) return 0;
+    if (!(isfinite(q[0]) && isfinite(q[1]) && isfinite(q[2]))) return 0;   /* no candidate can count for a non-finite query (every comparison fails) */
+    if (brute) {
+        for (uint32_t f = 0; f < s->nf; f++) {
+            float d2, p[3];
+            if (cp_candidate(s, f, q, delta, &d2, p) && (d2 < best || (d2 == best && f < bf))) { best = d2; bf = f; bp[0] = p[0]; bp[1] = p[1]; bp[2] = p[2]; }
+        }
+    } else {
+        uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const bvh_node* nd = &s->nodes[stack[--sp]];
+            if (cp_b2(nd->lo, nd->hi, q) > cp_lim(best, delta)) continue;
+            if (nd->count) {
+                for (uint32_t i = 0; i < nd->count; i++) {
+                    const uint32_t f = s->prim[nd->left_first + i]; float d2, p[3];
+                    if (cp_candidate(s, f, q, delta, &d2, p) && (d2 < best || (d2 == best && f < bf))) { best = d2; bf = f; bp[0] = p[0]; bp[1] = p[1]; bp[2] = p[2]; }
+                }
+            } else if (sp + 2 <= 128) {
+                const bvh_node* l = &s->nodes[nd->left_first]; const bvh_node* r = l + 1;
+                if (cp_b2(l->lo, l->hi, q) <= cp_b2(r->lo, r->hi, q)) { stack[sp++] = nd->left_first + 1; stack[sp++] = nd->left_first; }
+                else { stack[sp++] = nd->left_first; stack[sp++] = nd->left_first + 1; }
+            }
+        }
+    }
+    if (bf == ORC_NOFACE) return 0;
+    if (d_out) *d_out = sqrtf(best);
+    if (p_out) { p_out[0] = bp[0]; p_out[1] = bp[1]; p_out[2] = bp[2]; }
+    if (face_out) *face_out = bf;
+    if (n_out) { float ng[3]; tri_ng(s, bf, ng); orc_vec3 n = v3_normalize(v3(ng[0], ng[1], ng[2])); n_out[0] = n.x; n_out[1] = n.y; n_out[2] = n.z; }
+    return 1;
+}
+
+/* CPCEmbree::find: per dataset point (mask NOT consulted, CPCEmbree.cpp:33-42): Pm = Tsm * d_i; cp = closestPoint(Pm);
+ * hits = cp.d <= max_dist; points = Tms * cp.p; normals = Tms.R * cp.n */
+void orc_cpc_find(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb, uint32_t n, const float* dataset_pts, float max_dist, int brute,
+                  float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* dists)
+{
+    const orc_transform Tsm = T_mul(*Tbm, *Tsb);
+    const orc_transform Tms = T_inv(Tsm);
+    #pragma omp parallel for schedule(dynamic, 128)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const orc_vec3 Pm = T_apply(Tsm, v3(dataset_pts[3 * i], dataset_pts[3 * i + 1], dataset_pts[3 * i + 2]));
+        const float q[3] = {Pm.x, Pm.y, Pm.z};
+        float d, p[3], nn[3]; uint32_t f;
+        if (orc_closest_point(s, q, brute, &d, p, nn, &f)) {
+            put3(points, (size_t)i, T_apply(Tms, v3(p[0], p[1], p[2])));
+            put3(normals, (size_t)i, q_rot(Tms.R, v3(nn[0], nn[1], nn[2])));
+            if (hits) hits[i] = d <= max_dist;
+            if (face_ids) face_ids[i] = f;
+            if (dists) dists[i] = d;
+        } else {
+            put3(points, (size_t)i, v3(NAN, NAN, NAN)); put3(normals, (size_t)i, v3(NAN, NAN, NAN));
+            if (hits) hits[i] = 0;
+            if (face_ids) face_ids[i] = ORC_NOFACE;
+            if (dists) dists[i] = INFINITY;
+        }
+    }
+}
+
+/* TFMotionUpdaterGPU: particle_move_and_forget_kernel (rmcl_ros/src/rmcl/particle_motion.cu:11-34): pose = pose * T_bnew_bold;
+ * n_meas -= forget_rate * n_meas (uint32 -= double: computed in double, truncated on the store) */
+void orc_pf_motion_update(uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        poses[i] = T_mul(poses[i], *T_bnew_bold);
+        const uint32_t nm = attrs[i].likelihood.n_meas;
+        attrs[i].likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
+    }
+}
+
+/* compute_stats / simple_stats_kernel<512> with ONE block (rmcl_ros/src/rmcl/resampling.cu:41-92; GladiatorResamplerGPU sizes `stats` to 1):
+ * lane tid accumulates L[tid], L[tid+512], ... in FP32 (sum) and max with initial 0, then a pairwise tree over the 512 lanes. */
+void orc_pf_likelihood_stats(uint32_t n, const orc_particle_attr* attrs, float* sum_out, float* max_out)
+{
+    float sum[512], mx[512];
+    for (uint32_t t = 0; t < 512; t++) { sum[t] = 0.0f; mx[t] = 0.0f; }
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t t = i % 512u; const float L = attrs[i].likelihood.mean;
+        sum[t] += L; if (L > mx[t]) mx[t] = L;
+    }
+    for (uint32_t s = 256; s > 0; s >>= 1)
+        for (uint32_t t = 0; t < s; t++) { sum[t] = sum[t] + sum[t + s]; if (mx[t + s] > mx[t]) mx[t] = mx[t + s]; }
+    *sum_out = sum[0]; *max_out = mx[0];
 }
 
 int orc_num_threads(void)

@@ -125,6 +125,15 @@ void  orc_pf_update(const orc_scene* s, uint32_t n_particles, const orc_transfor
                     const orc_transform* Tsb, uint32_t n_beams, const orc_range_meas* beams_s, const orc_pf_params* p);
 void  orc_gaussian1d_add(orc_gaussian1d* a, const orc_gaussian1d* b);                                               /* rm::Gaussian1D::operator+= */
 
+/* closest-point correspondences: rm::EmbreeMap::closestPoint + CPCEmbree::find (rmcl/src/rmcl/registration/CPCEmbree.cpp:17-43) */
+int   orc_closest_point(const orc_scene* s, const float q[3], int brute, float* d_out, float p_out[3], float n_out[3], uint32_t* face_out);
+void  orc_cpc_find(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb, uint32_t n, const float* dataset_pts, float max_dist, int brute,
+                   float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* dists);
+
+/* rest of the PF cycle: motion update (particle_motion.cu:11-46) and likelihood statistics (resampling.cu:41-92) */
+void  orc_pf_motion_update(uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate);
+void  orc_pf_likelihood_stats(uint32_t n, const orc_particle_attr* attrs, float* sum_out, float* max_out);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -120,11 +120,14 @@ class Scene:
 
     def micp_correct_once(self, origs_s, dirs_s, range_max, dataset_pts, dataset_mask, Tom, Tbo, Tsb, iterations=5, max_dist=1.0,
                           adaptive_max_dist_min=0.15, convergence_progress=0.0, f64_accum=False):
-        origs_s = _f32(origs_s).reshape(-1, 3)
-        dirs_s = _f32(dirs_s).reshape(-1, 3)
-        n = dirs_s.shape[0]
         dp = _f32(dataset_pts).reshape(-1, 3)
         dm = np.ascontiguousarray(dataset_mask, np.uint8)
+        if dirs_s is None:                      # closest-point correspondences (CPCEmbree): one query per dataset point
+            origs_s, n = np.zeros((1, 3), np.float32), dp.shape[0]
+        else:
+            origs_s = _f32(origs_s).reshape(-1, 3)
+            dirs_s = _f32(dirs_s).reshape(-1, 3)
+            n = dirs_s.shape[0]
         Tn = np.zeros((), TRANSFORM)
         Td = np.zeros((), TRANSFORM)
         Cm = np.zeros((), CROSS_STATS)
@@ -150,6 +153,17 @@ class Scene:
                                 C.c_float(range_min), C.c_float(range_max), _p(ranges), C.c_float(max_dist), C.c_int(int(f64_accum)),
                                 _p(Td), _p(nc), _p(st))
         return Td, nc, st
+
+    # ---- closest-point correspondences (CPCEmbree::find) -------------------------------------
+    def cpc_find(self, Tbm, Tsb, dataset_pts, max_dist, brute=False):
+        dp = _f32(dataset_pts).reshape(-1, 3)
+        n = len(dp)
+        out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
+                   face_ids=np.empty(n, np.uint32), dists=np.empty(n, np.float32))
+        Tbm, Tsb = _tf(Tbm), _tf(Tsb)
+        lib().orc_cpc_find(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(dp), C.c_float(max_dist), C.c_int(int(brute)),
+                           _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["dists"]))
+        return out
 
     # ---- particle filter --------------------------------------------------------------------
     def pf_update(self, poses, attrs, Tsb, beams, params: PFParams):
@@ -251,3 +265,18 @@ def transform_inv(a):
     out = np.zeros((), TRANSFORM)
     lib().orc_transform_inv(_p(a), _p(out))
     return out
+
+
+def pf_motion_update(poses, attrs, T_bnew_bold, forget_rate):
+    poses = _tf(poses).reshape(-1).copy()
+    attrs = np.ascontiguousarray(attrs).copy()
+    T = _tf(T_bnew_bold)
+    lib().orc_pf_motion_update(C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(T), C.c_double(forget_rate))
+    return poses, attrs
+
+
+def pf_likelihood_stats(attrs):
+    attrs = np.ascontiguousarray(attrs)
+    s, m = C.c_float(), C.c_float()
+    lib().orc_pf_likelihood_stats(C.c_uint32(len(attrs)), _p(attrs), C.byref(s), C.byref(m))
+    return s.value, m.value

@@ -5,10 +5,10 @@ host-side mirror of the reference's operator interface over it (rmcl::RCC..::fin
 v1 correct(), ParticleUpdater::update).  There is no CPU fallback: importing works anywhere, but every compute call needs
 the CUDA library and a GPU and raises otherwise.
 """
-from .api import (B2Error, Map, RCCB200, RCCB200Spherical, RCCB200Pinhole, RCCB200O1Dn, RCCB200OnDn, SphereCorrectorB200, PinholeCorrectorB200,
+from .api import (B2Error, Map, RCCB200, RCCB200Spherical, RCCB200Pinhole, RCCB200O1Dn, RCCB200OnDn, CPCB200, SphereCorrectorB200, PinholeCorrectorB200,
                   O1DnCorrectorB200, OnDnCorrectorB200, PCDSensorUpdaterB200, PFParams, umeyama_transform, kernel_launch_count, lib_path, load_library)
 from . import synth
 
-__all__ = ["B2Error", "Map", "RCCB200", "RCCB200Spherical", "RCCB200Pinhole", "RCCB200O1Dn", "RCCB200OnDn", "SphereCorrectorB200",
+__all__ = ["B2Error", "Map", "RCCB200", "RCCB200Spherical", "RCCB200Pinhole", "RCCB200O1Dn", "RCCB200OnDn", "CPCB200", "SphereCorrectorB200",
            "PinholeCorrectorB200", "O1DnCorrectorB200", "OnDnCorrectorB200", "PCDSensorUpdaterB200", "PFParams", "umeyama_transform",
            "kernel_launch_count", "lib_path", "load_library", "synth"]

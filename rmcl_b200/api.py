@@ -60,7 +60,8 @@ EXPORTS = [
     "b2_rcc_set_model_pinhole", "b2_rcc_set_model_o1dn", "b2_rcc_set_model_ondn", "b2_rcc_set_params", "b2_rcc_set_dataset", "b2_rcc_set_ranges",
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
-    "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing",
+    "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
+    "b2_rcc_set_correspondence_type",
 ]
 
 
@@ -259,7 +260,9 @@ class RCCB200:
         return out
 
     def modelView(self):                           # Correspondences.hpp:47-54 (host copies)
-        n = self.n
+        nn = C.c_uint32()
+        _chk(load_library().b2_rcc_model_view(self._h, None, None, None, None, None, C.byref(nn)))
+        n = nn.value
         out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
                    face_ids=np.empty(n, np.uint32), ranges=np.empty(n, np.float32))
         _chk(load_library().b2_rcc_download_model(self._h, _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"])))
@@ -325,6 +328,19 @@ class RCCB200OnDn(RCCB200):
     """rmcl::RCCEmbreeOnDn twin (RCCEmbree.hpp:68-83)."""
 
 
+class CPCB200(RCCB200):
+    """rmcl::CPCEmbree twin (rmcl/include/rmcl/registration/CPCEmbree.hpp:20-54): closest-point correspondences.  find() runs one
+    closest-point query per dataset point on the same map BVH (CPCEmbree.cpp:17-43); no sensor model.  computeCrossStatistics /
+    correctOnce are the shared Correspondences_ code."""
+
+    def __init__(self, map_: Map):
+        super().__init__(map_)
+        _chk(load_library().b2_rcc_set_correspondence_type(self._h, C.c_int(1)))
+
+    def setModel(self, m):
+        raise B2Error(-1, "CPCB200 has no sensor model (closest-point correspondences use the dataset points)")
+
+
 # v1 names used by the legacy benchmarks (lidar_corrector_{embree,optix}_benchmark.cpp:86)
 SphereCorrectorB200 = RCCB200Spherical
 PinholeCorrectorB200 = RCCB200Pinhole
@@ -382,3 +398,25 @@ class PCDSensorUpdaterB200:
         assert attrs.dtype.itemsize == 36
         _chk(lib.b2_pf_sensor_update_host(self._h, _p(poses), _p(attrs), C.c_uint32(len(poses)), _p(Tsb), _p(beams), C.c_uint32(len(beams)), C.byref(prm)))
         return attrs
+
+    def motionUpdate(self, particle_poses, particle_attrs, T_bnew_bold, forget_rate):
+        """TFMotionUpdaterGPU (rmcl_ros/src/rmcl/particle_motion.cu:11-46): in place on torch CUDA tensors."""
+        n = particle_poses.numel() * particle_poses.element_size() // 32
+        _chk(load_library().b2_pf_motion_update(self._h, _devptr(particle_poses), _devptr(particle_attrs), C.c_uint32(n), _p(_tf(T_bnew_bold)), C.c_double(forget_rate)))
+
+    def likelihoodStats(self, particle_attrs, dist=None):
+        """compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92) of the local particles; with `dist` (torch.distributed, particles sharded
+        across ranks) the 8 bytes are all-reduced (SUM / MAX) -- the only exchange step of the particle-filter cycle."""
+        n = particle_attrs.numel() * particle_attrs.element_size() // 36
+        s, m = C.c_float(), C.c_float()
+        _chk(load_library().b2_pf_likelihood_stats(self._h, _devptr(particle_attrs), C.c_uint32(n), C.byref(s), C.byref(m)))
+        s, m = s.value, m.value
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            import torch
+            dev = particle_attrs.device if dist.get_backend() == "nccl" else "cpu"
+            ts = torch.tensor([s], dtype=torch.float64, device=dev)
+            tm = torch.tensor([m], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            s, m = float(ts[0]), float(tm[0])
+        return s, m

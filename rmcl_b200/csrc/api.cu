@@ -201,6 +201,8 @@ struct b2_rcc {
     unsigned int seq = 0;               // completion sequence number written by k_icp_loop into pin->flag
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
+    int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
+    uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
 };
 
 static b2_transform tf_identity_pod() { b2_transform T; memset(&T, 0, sizeof(T)); T.R.w = 1.0f; return T; }
@@ -403,6 +405,18 @@ static ModelBuffers model_buffers(const b2_rcc* h)
 
 static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* icp_dev)
 {
+    static const int prefetch_mode_cp = [] { const char* e = getenv("B2_FIND_PREFETCH"); return e ? atoi(e) : 1; }();
+    if (h->corr_type == B2_CORR_CPC) {
+        // CPCEmbree::find (CPCEmbree.cpp:17-43): one closest-point query per dataset point
+        const uint32_t n = h->n_dataset;
+        if (n == 0) { h->n_model = 0; h->found = true; return B2_OK; }
+        RES(reserve_model(h, n));
+        k_cpc_find<<<(n + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode_cp, icp_dev,
+                                                                                             Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, h->d_dpts.p, n, h->max_dist, model_buffers(h));
+        LAUNCHED();
+        h->n_model = n; h->found = true;
+        return B2_OK;
+    }
     if (!h->has_model) return fail(B2_ERR_INVALID, "find before setModel");
     if (h->n == 0) return B2_OK;
     RES(reserve_model(h, h->n));
@@ -411,6 +425,14 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h));
     LAUNCHED();
     h->n_model = h->n; h->found = true;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_correspondence_type(b2_rcc* h, int type)
+{
+    NOTNULL(h);
+    if (type != B2_CORR_RCC && type != B2_CORR_CPC) return fail(B2_ERR_INVALID, "unknown correspondence type %d", type);
+    h->corr_type = type; h->found = false;
     return B2_OK;
 }
 
@@ -493,6 +515,8 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
                              b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged, const float* ranges_host = nullptr, uint32_t n_ranges = 0)
 {
     bool aux_used = false;
+    const bool cpc = h->corr_type == B2_CORR_CPC;
+    if (ranges_host && cpc) return fail(B2_ERR_INVALID, "correctOnce(ranges) needs ray-casting correspondences (the handle is in closest-point mode)");
     if (ranges_host) {
         if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
         if (n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n_ranges, h->n);
@@ -515,8 +539,9 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         aux_used = true;
         return B2_OK;
     };
-    if (!h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
-    if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
+    if (!cpc && !h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
+    const uint32_t nw = h->work_n();
+    if (h->n_dataset != nw) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
     IcpState& st = h->pin->icp;
     memset(&st, 0, sizeof(st));
     st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = h->Tsb; st.max_dist = adaptive_max_dist(h, cp);
@@ -531,7 +556,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
     static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 1; }();
     static const int use_spin = [] { const char* e = getenv("B2_SPIN"); return e ? atoi(e) : 1; }();
     bool waited = false;
-    if (h->n > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
+    if (nw > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
         // find, then ALL inner iterations in one cooperative kernel; state in by kernel parameter, result out through mapped pinned memory
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
@@ -540,11 +565,11 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
         RES(upload_scan());
         if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
-        int grid = std::min<int>(h->fused_grid, (int)((h->n + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
+        int grid = std::min<int>(h->fused_grid, (int)((nw + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
         if (grid < 1) grid = 1;
         RES(h->d_partials.reserve((size_t)2 * grid * (B2_NACC + 1)));
         const float* dp = h->d_dpts.p; const uint8_t* dmk = h->d_dmask.p; const float* mp = h->d_mpts.p; const float* mn = h->d_mnrm.p; const uint8_t* mh = h->d_mhits.p;
-        uint32_t nel = h->n; IcpState* icp_dev = h->d_icp.p; uint32_t its = iterations; double* parts = h->d_partials.p;
+        uint32_t nel = nw; IcpState* icp_dev = h->d_icp.p; uint32_t its = iterations; double* parts = h->d_partials.p;
         IcpState* host_out = use_spin ? &h->pin->icp_out : nullptr; volatile unsigned int* host_flag = use_spin ? &h->pin->flag : nullptr;
         unsigned int seq = ++h->seq; if (seq == 0) seq = ++h->seq;
         void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts, &st, &host_out, &host_flag, &seq};
@@ -560,7 +585,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
             }
             if (h->pin->flag == seq) { memcpy(&st, (const void*)&h->pin->icp_out, sizeof(IcpState)); waited = true; }
         }
-    } else if (h->n > 0) {
+    } else if (nw > 0) {
         RES(upload_scan());
         if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
         CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
@@ -668,6 +693,7 @@ struct b2_pf {
     b2_mesh* map = nullptr; cudaStream_t stream = 0;
     DevBuf<PfBeam> d_beams; PfBeam* h_beams = nullptr; size_t h_beams_cap = 0;
     DevBuf<b2_transform> d_poses; DevBuf<b2_particle_attr> d_attrs;
+    DevBuf<double> d_part; DevBuf<unsigned int> d_ticket; DevBuf<float> d_out; float* h_out = nullptr; int n_sm = 0;
     int smem_optin = 0;
 };
 
@@ -681,6 +707,10 @@ extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
     h->map = map;
     CU(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device));
     h->smem_optin -= 1024;              // room for the kernel's static shared memory
+    CU(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, map->device));
+    { int rc2; if ((rc2 = h->d_part.reserve(2 * (size_t)h->n_sm * 4)) || (rc2 = h->d_ticket.reserve(1)) || (rc2 = h->d_out.reserve(2))) { delete h; return rc2; } }
+    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
+    CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
     CU(cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     *out = h;
     return B2_OK;
@@ -690,8 +720,9 @@ extern "C" int b2_pf_destroy(b2_pf* h)
     if (!h) return B2_OK;
     cudaSetDevice(h->map->device);
     cudaStreamSynchronize(h->stream);
-    h->d_beams.release(); h->d_poses.release(); h->d_attrs.release();
+    h->d_beams.release(); h->d_poses.release(); h->d_attrs.release(); h->d_part.release(); h->d_ticket.release(); h->d_out.release();
     if (h->h_beams) cudaFreeHost(h->h_beams);
+    if (h->h_out) cudaFreeHost(h->h_out);
     delete h;
     return B2_OK;
 }
@@ -764,5 +795,35 @@ extern "C" int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses, b2_
     RES(pf_update_impl(h, h->d_poses.p, h->d_attrs.p, n, Tsb, beams, n_beams, prm));
     CU(cudaMemcpyAsync(attrs, h->d_attrs.p, sizeof(b2_particle_attr) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+extern "C" int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* T, double forget_rate)
+{
+    NOTNULL(h); NOTNULL(T);
+    if (n == 0) return B2_OK;
+    NOTNULL(poses_dev); NOTNULL(attrs_dev);
+    CU(cudaSetDevice(h->map->device));
+    k_pf_motion<<<(n + 255) / 256, 256, 0, h->stream>>>(poses_dev, attrs_dev, n, *T, forget_rate);
+    LAUNCHED();
+    return B2_OK;
+}
+
+extern "C" int b2_pf_likelihood_stats(b2_pf* h, const b2_particle_attr* attrs_dev, uint32_t n, float* sum_out, float* max_out)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    float s = 0.f, m = 0.f;
+    if (n > 0) {
+        NOTNULL(attrs_dev);
+        const uint32_t grid = std::min<uint32_t>((uint32_t)h->n_sm * 4u, (n + 255) / 256);
+        k_pf_stats<<<grid, 256, 0, h->stream>>>(attrs_dev, n, h->d_part.p, h->d_ticket.p, h->d_out.p);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(h->h_out, h->d_out.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        s = h->h_out[0]; m = h->h_out[1];
+    }
+    if (sum_out) *sum_out = s;
+    if (max_out) *max_out = m;
     return B2_OK;
 }

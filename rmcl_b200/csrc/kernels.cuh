@@ -568,6 +568,45 @@ __global__ void __launch_bounds__(B2_FIND_BLOCK) k_rcc_find(BvhView bvh, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// CPCEmbree::find (CPCEmbree.cpp:17-43): one thread per dataset point (the mask is NOT consulted, as in the reference);
+//   Pm = Tsm * d_i;  cp = closestPoint(Pm);  hits = cp.d <= max_dist;  points = Tms * cp.p;  normals = Tms.R * cp.n
+// The model buffers get one entry per dataset point, so computeCrossStatistics / the ICP loop run unchanged on them.
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV void cpc_find_one(const BvhView& bvh, Tf Tsm, Tf Tms, const float* __restrict__ dpts, float max_dist, uint32_t i, const ModelBuffers& out)
+{
+    const V3 q = tf_apply(Tsm, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]));
+    CpBest best; uint32_t nn = 0, nt = 0;
+    closest_point<false>(bvh, q, best, nn, nt);
+    if (best.face != B2_NOFACE) {
+        const float d = sqrtf(best.d2);
+        const V3 p = tf_apply(Tms, best.p);
+        const V3 ns = q_rot(Tms.R, v_normalize(tri_ng(bvh, best.tri)));
+        out.pts[3 * i] = p.x; out.pts[3 * i + 1] = p.y; out.pts[3 * i + 2] = p.z;
+        out.nrm[3 * i] = ns.x; out.nrm[3 * i + 1] = ns.y; out.nrm[3 * i + 2] = ns.z;
+        out.hits[i] = d <= max_dist ? 1 : 0; out.faces[i] = best.face; out.ranges[i] = d;
+    } else {
+        const float qnan = u2f(0x7fc00000u);
+        out.pts[3 * i] = qnan; out.pts[3 * i + 1] = qnan; out.pts[3 * i + 2] = qnan;
+        out.nrm[3 * i] = qnan; out.nrm[3 * i + 1] = qnan; out.nrm[3 * i + 2] = qnan;
+        out.hits[i] = 0; out.faces[i] = B2_NOFACE; out.ranges[i] = u2f(0x7f800000u);
+    }
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(B2_FIND_BLOCK) k_cpc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const IcpState* __restrict__ icp,
+                                                            b2_transform Tbm_val, b2_transform Tsb_val, const float* __restrict__ dpts, uint32_t n, float max_dist,
+                                                            ModelBuffers out)
+{
+    prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Tf Tbm = icp ? tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo)) : tf_from_pod(Tbm_val);
+    const Tf Tsm = tf_mul(Tbm, tf_from_pod(Tsb_val));
+    cpc_find_one(bvh, Tsm, tf_inv(Tsm), dpts, max_dist, i, out);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Correspondences*::computeCrossStatistics (CorrespondencesCPU.cpp:10-39): N-element masked reduction -> CrossStatistics.
 // Deterministic: per-block partials, the last block to finish sums them in block order.  With `icp` set, the last block also
 // performs the rest of the inner iteration (frame changes, Umeyama, compose) so one correctOnce needs 1 + iterations launches.
@@ -883,4 +922,45 @@ __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const
         pf_merge(lk, s_eval + threadIdx.x * n_beams, n_beams);
         ap->likelihood = lk;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rest of the PF cycle
+// ---------------------------------------------------------------------------------------------------------------------
+// particle_move_and_forget_kernel (rmcl_ros/src/rmcl/particle_motion.cu:11-34): HBM stream, 2 x (32 + 36) B per particle
+__global__ void k_pf_motion(b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n, b2_transform T_val, double forget_rate)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tf_store(poses + i, tf_mul(tf_load(poses + i), tf_from_pod(T_val)));
+    const uint32_t nm = attrs[i].likelihood.n_meas;
+    attrs[i].likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
+}
+
+// compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92) over all SMs: FP64 block sums + max, the last block combines in block order
+__global__ void __launch_bounds__(256) k_pf_stats(const b2_particle_attr* __restrict__ attrs, uint32_t n, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                  float* __restrict__ out /* [sum, max] */)
+{
+    __shared__ double s_sum[8]; __shared__ float s_max[8]; __shared__ bool is_last;
+    double sum = 0.0; float mx = 0.0f;                                                     // max starts at 0 like the reference (:54)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const float L = attrs[i].likelihood.mean; sum += (double)L; mx = fmaxf(mx, L); }
+    sum = warp_sum(sum);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0; float m = 0.0f;
+        for (int w = 0; w < 8; w++) { a += s_sum[w]; m = fmaxf(m, s_max[w]); }
+        partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = (double)m;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    double a = 0.0, m = 0.0;
+    for (uint32_t b = 0; b < gridDim.x; b++) { a += __ldcg(partials + 2 * b); m = fmax(m, __ldcg(partials + 2 * b + 1)); }
+    out[0] = (float)a; out[1] = (float)m;
+    *ticket = 0u;
 }

@@ -198,3 +198,150 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
 }
 
 B2_DEV HitRec trace_init(float tfar) { HitRec h; h.t = tfar; h.face = B2_NOFACE; h.tri = 0u; return h; }
+
+// =====================================================================================================================
+// Closest point on the map (stand-in for rm::EmbreeMap::closestPoint / Embree point queries behind CPCEmbree::find,
+// rmcl/src/rmcl/registration/CPCEmbree.cpp:33-42).  Same BVH8F nodes, distance test instead of slab test.
+//
+// RESULT DEFINITION (identical to oracle/oracle.c:orc_closest_point, independent of the acceleration structure):
+//   candidate(tri) = closest point on the triangle (Ericson's region tests, individually rounded ops), d2 = |p - q|^2
+//   b2(box)        = |max(lo - q, q - hi, 0)|^2                      monotone: a larger box never has a larger b2
+//   lim(d2)        = (sqrt(d2) + DELTA)^2,  DELTA = 2^-16 (1 + max_k |q_k|)
+//   a candidate COUNTS iff b2(triangle AABB) <= lim(d2);   result = argmin (d2, face id) over counting candidates.
+// CULLING: a child is skipped only if b2(child box) > lim(best d2).  Child boxes are exact float AABBs of the triangles below, so
+//   b2(child) <= b2(triangle AABB) <= lim(d2_tri) <= lim(best) for every triangle that could still win or tie: its leaf is visited.
+// Stack: one entry per level as for rays -- (child_base, pending inner children | imask) with the spare 16 bits holding a bf16 LOWER
+//   bound of the group's smallest b2 (float truncated toward zero), so a whole group is dropped at pop time once lim has shrunk.
+// =====================================================================================================================
+struct CpBest {
+    float d2, lim;
+    uint32_t face, tri;
+    V3 p;
+};
+
+B2_DEV float cp_lim(float d2, float delta) { const float s = add(sqrtf(d2), delta); return mul(s, s); }
+B2_DEV float cp_axis(float lo, float hi, float q) { return fmaxf(fmaxf(sub(lo, q), sub(q, hi)), 0.0f); }
+B2_DEV float cp_b2(float ax, float ay, float az) { return add(add(mul(ax, ax), mul(ay, ay)), mul(az, az)); }
+B2_DEV float dot_plain(V3 a, V3 b) { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
+
+B2_DEV V3 cp_triangle(V3 a, V3 b, V3 c, V3 p)
+{
+    const V3 ab = v_sub(b, a), ac = v_sub(c, a), ap = v_sub(p, a);
+    const float d1 = dot_plain(ab, ap), d2 = dot_plain(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) return a;
+    const V3 bp = v_sub(p, b);
+    const float d3 = dot_plain(ab, bp), d4 = dot_plain(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) return b;
+    const float vc = sub(mul(d1, d4), mul(d3, d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { const float v = dvd(d1, sub(d1, d3)); return mk3(add(a.x, mul(ab.x, v)), add(a.y, mul(ab.y, v)), add(a.z, mul(ab.z, v))); }
+    const V3 cp = v_sub(p, c);
+    const float d5 = dot_plain(ab, cp), d6 = dot_plain(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) return c;
+    const float vb = sub(mul(d5, d2), mul(d1, d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { const float w = dvd(d2, sub(d2, d6)); return mk3(add(a.x, mul(ac.x, w)), add(a.y, mul(ac.y, w)), add(a.z, mul(ac.z, w))); }
+    const float va = sub(mul(d3, d6), mul(d5, d4));
+    const float e43 = sub(d4, d3), e56 = sub(d5, d6);
+    if (va <= 0.0f && e43 >= 0.0f && e56 >= 0.0f) {
+        const float w = dvd(e43, add(e43, e56));
+        return mk3(add(b.x, mul(sub(c.x, b.x), w)), add(b.y, mul(sub(c.y, b.y), w)), add(b.z, mul(sub(c.z, b.z), w)));
+    }
+    const float denom = dvd(1.0f, add(add(va, vb), vc));
+    const float v = mul(vb, denom), w = mul(vc, denom);
+    return mk3(add(add(a.x, mul(ab.x, v)), mul(ac.x, w)), add(add(a.y, mul(ab.y, v)), mul(ac.y, w)), add(add(a.z, mul(ab.z, v)), mul(ac.z, w)));
+}
+
+B2_DEV void cp_tri_test(const BvhView& bvh, V3 q, float delta, uint32_t tri_idx, CpBest& best)
+{
+    const float4 a = ldg(bvh.tris + 3 * (size_t)tri_idx + 0);
+    const float4 b = ldg(bvh.tris + 3 * (size_t)tri_idx + 1);
+    const float4 c = ldg(bvh.tris + 3 * (size_t)tri_idx + 2);
+    const V3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(b.x, b.y, b.z), v2 = mk3(c.x, c.y, c.z);
+    const V3 p = cp_triangle(v0, v1, v2, q);
+    const float dx = sub(p.x, q.x), dy = sub(p.y, q.y), dz = sub(p.z, q.z);
+    const float d2 = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+    const uint32_t face = f2u(a.w);
+    if (!(d2 < best.d2 || (d2 == best.d2 && face < best.face))) return;
+    const float ax = cp_axis(fminf(fminf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.x, v1.x), v2.x), q.x);
+    const float ay = cp_axis(fminf(fminf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.y, v1.y), v2.y), q.y);
+    const float az = cp_axis(fminf(fminf(v0.z, v1.z), v2.z), fmaxf(fmaxf(v0.z, v1.z), v2.z), q.z);
+    const float lim = cp_lim(d2, delta);
+    if (!(cp_b2(ax, ay, az) <= lim)) return;
+    best.d2 = d2; best.lim = lim; best.face = face; best.tri = tri_idx; best.p = p;
+}
+
+B2_DEV float cp_delta(V3 q) { return mul(1.52587890625e-05f, add(1.0f, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z)))); }
+
+template <bool STATS>
+B2_DEV void closest_point(const BvhView& bvh, V3 q, CpBest& best, uint32_t& n_nodes, uint32_t& n_tris)
+{
+    best.d2 = u2f(0x7f800000u); best.lim = u2f(0x7f800000u); best.face = B2_NOFACE; best.tri = 0u; best.p = mk3(0.f, 0.f, 0.f);
+    // a non-finite query has no counting candidate (every comparison fails); do not walk the tree for it
+    if (!(fabsf(q.x) < u2f(0x7f800000u) && fabsf(q.y) < u2f(0x7f800000u) && fabsf(q.z) < u2f(0x7f800000u))) return;
+    const float delta = cp_delta(q);
+    uint2 stack[B2_TRAVERSAL_STACK];
+    int sp = 0;
+    uint32_t node_idx = 0;
+    while (true) {
+        const float4* __restrict__ np = bvh.nodes + B2_NODE_QUADS * (size_t)node_idx;
+        const float4 lxa = ldg(np + 0), lxb = ldg(np + 1), lya = ldg(np + 2), lyb = ldg(np + 3), lza = ldg(np + 4), lzb = ldg(np + 5);
+        const float4 hxa = ldg(np + 6), hxb = ldg(np + 7), hya = ldg(np + 8), hyb = ldg(np + 9), hza = ldg(np + 10), hzb = ldg(np + 11);
+        const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
+        const uint32_t child_base = f2u(h0.x), tri_base = f2u(h0.y), imask = f2u(h1.x), m0 = f2u(h0.z), m1 = f2u(h0.w);
+        if (STATS) n_nodes++;
+        float b2[8];
+        b2[0] = cp_b2(cp_axis(lxa.x, hxa.x, q.x), cp_axis(lya.x, hya.x, q.y), cp_axis(lza.x, hza.x, q.z));
+        b2[1] = cp_b2(cp_axis(lxa.y, hxa.y, q.x), cp_axis(lya.y, hya.y, q.y), cp_axis(lza.y, hza.y, q.z));
+        b2[2] = cp_b2(cp_axis(lxa.z, hxa.z, q.x), cp_axis(lya.z, hya.z, q.y), cp_axis(lza.z, hza.z, q.z));
+        b2[3] = cp_b2(cp_axis(lxa.w, hxa.w, q.x), cp_axis(lya.w, hya.w, q.y), cp_axis(lza.w, hza.w, q.z));
+        b2[4] = cp_b2(cp_axis(lxb.x, hxb.x, q.x), cp_axis(lyb.x, hyb.x, q.y), cp_axis(lzb.x, hzb.x, q.z));
+        b2[5] = cp_b2(cp_axis(lxb.y, hxb.y, q.x), cp_axis(lyb.y, hyb.y, q.y), cp_axis(lzb.y, hzb.y, q.z));
+        b2[6] = cp_b2(cp_axis(lxb.z, hxb.z, q.x), cp_axis(lyb.z, hyb.z, q.y), cp_axis(lzb.z, hzb.z, q.z));
+        b2[7] = cp_b2(cp_axis(lxb.w, hxb.w, q.x), cp_axis(lyb.w, hyb.w, q.y), cp_axis(lzb.w, hzb.w, q.z));
+        // leaf children first (their triangles shrink lim before the inner children are judged)
+        uint32_t tbits = 0;
+        #pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const uint32_t meta = ((s < 4 ? m0 : m1) >> (8 * (s & 3))) & 0xffu;
+            const uint32_t bits = ((meta >> 5) << (meta & 0x1fu)) & 0x00ffffffu;          // empty slots and inner children contribute nothing
+            tbits |= (b2[s] <= best.lim) ? bits : 0u;
+        }
+        while (tbits) {
+            const uint32_t i = 31u - (uint32_t)clz32(tbits);
+            tbits &= ~(1u << i);
+            cp_tri_test(bvh, q, delta, tri_base + i, best);
+            if (STATS) n_tris++;
+        }
+        // inner children within lim: descend into the nearest, park the others as one group
+        uint32_t hit = 0, near_slot = 0; float near_b2 = u2f(0x7f800000u), rest_b2 = u2f(0x7f800000u);
+        #pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const bool in = ((imask >> s) & 1u) && (b2[s] <= best.lim);
+            if (in) {
+                hit |= 1u << s;
+                if (b2[s] < near_b2) { rest_b2 = near_b2; near_b2 = b2[s]; near_slot = (uint32_t)s; }
+                else rest_b2 = fminf(rest_b2, b2[s]);
+            }
+        }
+        if (hit) {
+            hit &= ~(1u << near_slot);
+            if (hit) stack[sp++] = make_uint2(child_base, (hit << 24) | (f2u(rest_b2) >> 16 << 8) | imask);
+            node_idx = child_base + popc32(imask & ((1u << near_slot) - 1u));
+            continue;
+        }
+        // pop: next child of the youngest group whose lower bound is still within lim
+        bool found = false;
+        while (sp > 0) {
+            uint2 G = stack[sp - 1];
+            const float lb = u2f(((G.y >> 8) & 0xffffu) << 16);
+            if (!(lb <= best.lim)) { sp--; continue; }
+            const uint32_t bitpos = 31u - (uint32_t)clz32(G.y);
+            const uint32_t slot = bitpos - 24u;
+            G.y &= ~(1u << bitpos);
+            if (G.y & 0xff000000u) stack[sp - 1] = G; else sp--;
+            node_idx = G.x + popc32(G.y & 0xffu & ((1u << slot) - 1u));
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+}

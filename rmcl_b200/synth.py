@@ -339,6 +339,12 @@ def compose(a, b):
     return out
 
 
+def transform_points(T, pts):
+    """T * p for an (n, 3) array, float64 inside, float32 out (host-side convenience for tests / bench set-up only)."""
+    q, t = np.asarray(T["R"], np.float64), np.asarray(T["t"], np.float64)
+    return (_qrot(q, np.asarray(pts, np.float64)) + t).astype(np.float32)
+
+
 def inverse(a):
     qa, ta = np.asarray(a["R"], np.float64), np.asarray(a["t"], np.float64)
     qi = qa * np.array([-1, -1, -1, 1.0])

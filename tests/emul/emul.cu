@@ -66,6 +66,28 @@ __attribute__((visibility("default"))) void emul_find(void* sc, const b2_transfo
     for (int64_t i = 0; i < (int64_t)n; i++) find_one(bvh, Tsm, m, (uint32_t)i, (uint64_t)i, out);
 }
 
+__attribute__((visibility("default"))) void emul_cpc_find(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* dpts, float max_dist,
+                                                          float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* dists, double* mean_nodes, double* mean_tris)
+{
+    const BvhView bvh = view(sc);
+    ModelBuffers out; out.pts = pts; out.nrm = nrm; out.hits = hits; out.faces = faces; out.ranges = dists;
+    const Tf Tsm = tf_mul(tf_from_pod(*Tbm), tf_from_pod(*Tsb));
+    const Tf Tms = tf_inv(Tsm);
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) cpc_find_one(bvh, Tsm, Tms, dpts, max_dist, (uint32_t)i, out);
+    if (mean_nodes || mean_tris) {
+        unsigned long long tn = 0, tt = 0;
+        #pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn, tt)
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            CpBest b; uint32_t nn = 0, nt = 0;
+            closest_point<true>(bvh, tf_apply(Tsm, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2])), b, nn, nt);
+            tn += nn; tt += nt;
+        }
+        if (mean_nodes) *mean_nodes = (double)tn / (double)(n ? n : 1);
+        if (mean_tris) *mean_tris = (double)tt / (double)(n ? n : 1);
+    }
+}
+
 // sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
 __attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
                                                                   const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)

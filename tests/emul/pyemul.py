@@ -87,6 +87,18 @@ class Scene:
                         _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
         return out
 
+    def cpc_find(self, Tbm, Tsb, dataset_pts, max_dist):
+        dp = _f32(dataset_pts).reshape(-1, 3)
+        n = len(dp)
+        out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
+                   face_ids=np.empty(n, np.uint32), dists=np.empty(n, np.float32))
+        Tbm, Tsb = np.ascontiguousarray(Tbm), np.ascontiguousarray(Tsb)
+        mn, mt = C.c_double(), C.c_double()
+        lib().emul_cpc_find(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(dp), C.c_float(max_dist), _p(out["points"]), _p(out["normals"]), _p(out["hits"]),
+                            _p(out["face_ids"]), _p(out["dists"]), C.byref(mn), C.byref(mt))
+        out["work"] = (mn.value, mt.value)
+        return out
+
     def correct_once(self, origs_s, dirs_s, range_max, dpts, dmask, Tom, Tbo, Tsb, iterations, max_dist, fast_tail=False):
         origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
         dpts, dmask = _f32(dpts), np.ascontiguousarray(dmask, np.uint8)

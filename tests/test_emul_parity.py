@@ -128,3 +128,17 @@ def test_umeyama_fast_path_and_fallback(pe, po):
     z = np.zeros((), po.CROSS_STATS)
     I = pe.umeyama(z)
     assert np.allclose(I["R"], [0, 0, 0, 1]) and np.allclose(I["t"], 0)
+
+
+@pytest.mark.parametrize("name,lo,hi", [("cube29", [-12] * 3, [12] * 3), ("building:60000", [-2, -2, -1], [62, 42, 4]), ("uvsphere:40:60", [-7] * 3, [7] * 3)])
+def test_cpc_bit_exact(pe, po, synth, name, lo, hi):
+    """Closest-point traversal of the 8-wide BVH (trace.cuh:closest_point) == the oracle's definition, bit for bit."""
+    osc, esc = oracle_scene(name), emul_scene(name)
+    rng = np.random.default_rng(5)
+    q = rng.uniform(lo, hi, (20000, 3)).astype(np.float32)
+    q[::997] = np.nan
+    Tbm, Tsb = synth.make_transform([0.3, -0.2, 0.1], [0.1, 0.05, 0.7]), synth.make_transform([0.1, 0, 0.2], [0, 0, 0.1])
+    a, b = osc.cpc_find(Tbm, Tsb, q, 0.8), esc.cpc_find(Tbm, Tsb, q, 0.8)
+    for k in ("points", "normals", "hits", "face_ids", "dists"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert 0 < a["hits"].mean() < 1

@@ -354,3 +354,92 @@ def test_device_lbvh_build_bit_exact(po, synth, name, lo, hi, n):
     dup = rmcl_b200.Map(Vd, Fd, build_mode=1)
     t, f, ng, hit = dup.intersect([[0, 0, 0]], [[1, 0, 0]])
     assert hit[0] == 1 and f[0] == 0                                       # tie -> smallest face id
+
+
+def test_pf_motion_and_stats_gpu(po, synth):
+    """SURVEY 8f2 on the device: motion update bit-exact (same quaternion op order), statistics max exact / sum to FP32 noise."""
+    import torch
+    import rmcl_b200
+    P, A = synth.pf_particles(100_003)
+    rng = np.random.default_rng(1)
+    A["likelihood"]["mean"] = rng.uniform(0, 0.2, len(A)).astype(np.float32)
+    A["likelihood"]["n_meas"] = rng.integers(0, 10001, len(A)).astype(np.uint32)
+    T = synth.make_transform((0.1, -0.02, 0.0), (0, 0, 0.05))
+    Pr, Ar = po.pf_motion_update(P, A, T, 0.03)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map("cube29"))
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+    up.motionUpdate(Pd, Ad, T, 0.03)
+    torch.cuda.synchronize()
+    Pg = Pd.cpu().numpy().view(synth.TRANSFORM_DTYPE).reshape(-1)
+    Ag = Ad.cpu().numpy().view(synth.PARTICLE_ATTR_DTYPE).reshape(-1)
+    assert np.array_equal(Pg["R"], Pr["R"]) and np.array_equal(Pg["t"], Pr["t"])
+    assert Ag.tobytes() == Ar.tobytes()
+    s, m = up.likelihoodStats(Ad)
+    sr, mr = po.pf_likelihood_stats(Ar)
+    assert m == mr and abs(s - sr) <= 2e-6 * abs(sr) + 1e-6
+    s0, m0 = up.likelihoodStats(Ad[:0])
+    assert s0 == 0.0 and m0 == 0.0
+
+
+@pytest.mark.parametrize("name,lo,hi", [("cube29", [-12] * 3, [12] * 3), ("building:1000000", [-1, -1, -0.5], [61, 41, 3.5])])
+def test_cpc_find_bit_exact(po, synth, name, lo, hi):
+    """SURVEY 8f3: CPCEmbree::find (CPCEmbree.cpp:17-43) through the C ABI == oracle, bit for bit (points, normals, hits, faces, distances)."""
+    import rmcl_b200
+    osc = oracle_scene(name)
+    rng = np.random.default_rng(11)
+    q = rng.uniform(lo, hi, (100000, 3)).astype(np.float32)
+    q[::1009] = np.nan                                               # masked-out dataset entries may hold anything; the mask is not consulted
+    Tbm, Tsb = synth.make_transform([0.3, -0.2, 0.1], [0.02, 0.01, 0.7]), synth.scenario_tsb()
+    h = rmcl_b200.CPCB200(gpu_map(name))
+    h.setTsb(Tsb); h.setParams(0.8, 0.15)
+    h.setDataset(q)
+    h.find(Tbm)
+    mv, ref = h.modelView(), osc.cpc_find(Tbm, Tsb, q, 0.8)
+    assert len(mv["hits"]) == len(q)
+    assert np.array_equal(mv["hits"], ref["hits"]) and np.array_equal(mv["face_ids"], ref["face_ids"])
+    assert np.array_equal(mv["ranges"], ref["dists"]) and np.array_equal(mv["points"], ref["points"], equal_nan=True)
+    assert np.array_equal(mv["normals"], ref["normals"], equal_nan=True)
+    assert 0.05 < ref["hits"].mean() < 0.95
+    # cross statistics on the closest-point pairs
+    I = synth.make_transform()
+    dm = np.ones(len(q), np.uint8)
+    st = h.computeCrossStatistics(I, 0.0)
+    r = po.statistics_p2l(I, q, dm, ref["points"], ref["normals"], ref["hits"], 0.8, f64=True)
+    assert st["n_meas"] == r["n_meas"] and np.abs(st["dataset_mean"] - r["dataset_mean"]).max() <= 5e-6
+    with pytest.raises(rmcl_b200.B2Error):
+        h.setModel(synth.c1_sensor())
+    with pytest.raises(rmcl_b200.B2Error):
+        h.correctOnce(Tbm, I, 5, 0.0, ranges=np.ones(8, np.float32))
+    # empty dataset
+    h.setDataset(np.zeros((0, 3), np.float32))
+    h.find(Tbm)
+    assert len(h.modelView()["hits"]) == 0
+
+
+def test_cpc_correct_once(po, synth):
+    """MICP-L correctOnce with closest-point correspondences: find + 5 inner iterations on the device vs the oracle chain."""
+    import rmcl_b200
+    name, m = "building:1000000", synth.c2_sensor()
+    osc = oracle_scene(name)
+    o, d = po.model_rays(m)
+    Tgt, Tsb = synth.building_gt_pose(), synth.scenario_tsb()
+    ranges = synth.noisy_ranges(osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max)
+    dp, dm, _ = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
+    Tbo = synth.make_transform((0.05, 0.02, 0.0), (0, 0, 0.1))
+    Tom = synth.compose(synth.compose(Tgt, synth.scenario_pose_offset()), synth.inverse(Tbo))
+    h = rmcl_b200.CPCB200(gpu_map(name))
+    h.setTsb(Tsb); h.setParams(1.0, 0.15)
+    h.setDataset(dp, dm)
+    for cp in (0.0, 0.6):
+        ref = osc.micp_correct_once(None, None, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, cp, f64_accum=True)
+        Tn, Td, Cm = h.correctOnce(Tom, Tbo, 5, cp)
+        assert abs(int(Cm["n_meas"]) - int(ref[2]["n_meas"])) <= 2
+        assert np.abs(Tn["t"] - ref[0]["t"]).max() <= TOL_DT and quat_close(Tn["R"], ref[0]["R"], TOL_DT)
+        assert np.abs(Td["t"] - ref[1]["t"]).max() <= TOL_DT and quat_close(Td["R"], ref[1]["R"], TOL_DT)
+    # a scan already on the map: every point has distance ~0 -> (near-)identity update
+    clean = osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"]
+    dp2, dm2, _ = po.dataset_from_ranges(o, d, clean, m.range_min, m.range_max)
+    h.setDataset(dp2, dm2)
+    Tn, Td, Cm = h.correctOnce(Tgt, synth.make_transform(), 5, 0.0)
+    assert np.abs(Td["t"]).max() < 1e-4 and quat_close(Td["R"], [0, 0, 0, 1], 1e-5) and Cm["n_meas"] > 100000

@@ -238,3 +238,76 @@ def test_dataset_from_ranges_mask(po, synth):
     pts, mask, nv = po.dataset_from_ranges(o, d, r, m.range_min, m.range_max)
     assert mask[0] == 0 and mask[1] == 0 and mask[2] == 1 and nv == m.size - 2
     assert np.array_equal(pts[5], d[5] * np.float32(5.0))
+
+
+def test_pf_motion_and_stats(po, synth):
+    """particle_move_and_forget (particle_motion.cu:11-34) and compute_stats (resampling.cu:41-92) restated."""
+    P, A = synth.pf_particles(3000)
+    rng = np.random.default_rng(1)
+    A["likelihood"]["mean"] = rng.uniform(0, 0.2, len(A)).astype(np.float32)
+    A["likelihood"]["n_meas"] = rng.integers(0, 10001, len(A)).astype(np.uint32)
+    T = synth.make_transform((0.1, -0.02, 0.0), (0, 0, 0.05))
+    P2, A2 = po.pf_motion_update(P, A, T, 0.03)
+    ref = synth.compose(P, np.broadcast_to(T, P.shape))
+    assert np.abs(P2["t"] - ref["t"]).max() < 1e-5 and np.abs(np.abs((P2["R"] * ref["R"]).sum(1)) - 1).max() < 1e-6
+    nm = A["likelihood"]["n_meas"].astype(np.float64)
+    assert np.array_equal(A2["likelihood"]["n_meas"], (nm - 0.03 * nm).astype(np.uint32))       # uint -= double truncates (quirk D3)
+    assert np.array_equal(A2["likelihood"]["mean"], A["likelihood"]["mean"])
+    s, m = po.pf_likelihood_stats(A)
+    assert m == A["likelihood"]["mean"].max() and abs(s - A["likelihood"]["mean"].astype(np.float64).sum()) < 1e-3
+    s0, m0 = po.pf_likelihood_stats(A[:0])
+    assert s0 == 0.0 and m0 == 0.0                                                              # max starts at 0 (resampling.cu:54)
+
+
+def test_closest_point_oracle(po, synth):
+    """closest-point correspondences (CPCEmbree.cpp:17-43) restated; BVH walk == brute force, closed forms on the cube."""
+    I = synth.make_transform()
+    rng = np.random.default_rng(3)
+    for name, lo, hi in (("cube29", [-12] * 3, [12] * 3), ("building:60000", [-2, -2, -1], [62, 42, 4])):
+        sc = oracle_scene(name)
+        q = rng.uniform(lo, hi, (3000, 3)).astype(np.float32)
+        a, b = sc.cpc_find(I, I, q, 1.0, brute=False), sc.cpc_find(I, I, q, 1.0, brute=True)
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+    sc = oracle_scene("cube29")
+    q = rng.uniform(-9.9, 9.9, (2000, 3)).astype(np.float32)
+    r = sc.cpc_find(I, I, q, 1.0)
+    d_true = 10.0 - np.abs(q).max(1)                                     # inside the cube (half extent 10): distance to the nearest face
+    assert np.abs(r["dists"] - d_true).max() <= 2e-6
+    assert np.array_equal(r["hits"], (r["dists"] <= 1.0).astype(np.uint8))
+    ax = np.abs(q).argmax(1)
+    sign = np.sign(q[np.arange(len(q)), ax])
+    assert np.allclose(np.abs(r["normals"][np.arange(len(q)), ax]), 1.0, atol=1e-6)             # the face normal, axis aligned
+    assert np.allclose(r["points"][np.arange(len(q)), ax], 10.0 * sign, atol=1e-5)
+    # sensor-frame output: a rigid change of frame must not change distances, and points come back in the sensor frame
+    Tbm, Tsb = synth.make_transform([0.4, -0.3, 0.2], [0.1, -0.05, 0.6]), synth.make_transform([0.1, 0, 0.3], [0, 0.02, 0])
+    Tsm = synth.compose(Tbm, Tsb)
+    qs = synth.transform_points(synth.inverse(Tsm), q)                  # the same map-frame queries expressed in the sensor frame
+    r2 = sc.cpc_find(Tbm, Tsb, qs, 1.0)
+    assert np.abs(r2["dists"] - d_true).max() <= 2e-5
+    assert np.abs(synth.transform_points(Tsm, r2["points"]) - r["points"]).max() <= 5e-5
+    # tie rule (d2, face id), surface point, far point, non-finite query
+    V = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    F = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    s2 = po.Scene(V, F)
+    t = s2.cpc_find(I, I, np.array([[0.5, 0.5, 0.25], [0.25, 0.5, 0.0], [5, 5, 5], [np.nan, 0, 0]], np.float32), 1.0)
+    assert t["face_ids"][0] == 0 and abs(t["dists"][0] - 0.25) < 1e-7 and t["hits"][0] == 1    # on the shared diagonal: lower face id wins
+    assert t["face_ids"][1] == 1 and t["dists"][1] == 0.0 and t["hits"][1] == 1
+    assert t["hits"][2] == 0 and t["face_ids"][2] == 0 and abs(t["dists"][2] - np.sqrt(16 + 16 + 25)) < 1e-5
+    assert t["hits"][3] == 0 and t["face_ids"][3] == 0xFFFFFFFF and np.isnan(t["points"][3]).all()
+
+
+def test_cpc_correct_once_converges(po, synth):
+    """ICP with closest-point correspondences pulls a perturbed scan back onto the map (same inner loop as MICP-L, CPC find)."""
+    sc = oracle_scene("cube29")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    Tgt, Tsb = synth.make_transform([0.3, -0.2, 0.1], [0, 0, 0.3]), synth.make_transform([0.0, 0, 0.2], [0, 0, 0])
+    sim = sc.simulate(Tgt, Tsb, o, d, m.range_max)
+    dp, dm, _ = po.dataset_from_ranges(o, d, sim["ranges"], m.range_min, m.range_max)
+    I = synth.make_transform()
+    Tom = synth.compose(Tgt, synth.make_transform([0.15, -0.1, 0.05], [0.01, -0.01, 0.04]))
+    e0 = np.abs(Tom["t"] - Tgt["t"]).max()
+    for _ in range(6):
+        Tom, Td, Cm = sc.micp_correct_once(None, None, m.range_max, dp, dm, Tom, I, Tsb, 5, 1.0, 0.15, 0.0, f64_accum=True)
+    assert Cm["n_meas"] > 0.9 * dm.sum()
+    assert np.abs(Tom["t"] - Tgt["t"]).max() < 0.2 * e0

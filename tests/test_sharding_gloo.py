@@ -47,9 +47,17 @@ def _worker(rank, world, port, q):
         prm = po.PFParams.defaults()
         local = sc.pf_update(P[b:e], A[b:e], Tsb, beams, prm)
         full = gather_records(local, dist, dst=0)
+        # the one exchange step of the cycle: {sum, max} of likelihood.mean, all-reduced over the shards
+        import torch
+        ls, lm = po.pf_likelihood_stats(local)
+        ts, tm = torch.tensor([ls], dtype=torch.float64), torch.tensor([lm], dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         if rank == 0:
             ref = sc.pf_update(P, A, Tsb, beams, prm)
-            q.put(("ok", full.tobytes() == ref.tobytes(), len(full)))
+            rs, rm = po.pf_likelihood_stats(ref)
+            stats_ok = float(tm[0]) == rm and abs(float(ts[0]) - rs) <= 1e-5 * abs(rs) + 1e-6
+            q.put(("ok", full.tobytes() == ref.tobytes() and stats_ok, len(full)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
