@@ -392,6 +392,34 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     out["c3_pf"] = {"workload": f"C3: particle-filter sensor update, {n_part} particles x 180 beams per GPU, 1M-triangle mesh", "rays_per_s": n_part * world * 180 / (ms * 1e-3),
                     "ms_per_step": ms, "e2e_rays_per_s": n_part * world * 180 / e2e, "e2e_ms_per_step": e2e * 1e3,
                     "h2d_bytes_per_step": n_part * (32 + 36) + 180 * 32, "d2h_bytes_per_step": n_part * 36}
+    # ---- the whole particle-filter cycle on the device: motion -> sensor update -> stats (8-byte all-reduce) -> Gladiator
+    # resampling (all-gather of the particle set when sharded); particles never leave HBM
+    glad = rmcl_b200.GladiatorConfig.defaults()
+    Tmo = synth.make_transform((0.02, 0.0, 0.0), (0.0, 0.0, 0.01))
+    Pc, Ac = Pd.clone(), A0.clone()
+    tot = 0.0
+    for i in range(warm + steps):
+        flush.fill_(4)
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        up.motionUpdate(Pc, Ac, Tmo, 0.01)
+        up.update(Pc, Ac, Tsb, beams, prm)
+        up.likelihoodStats(Ac, dist if world > 1 else None)
+        if world > 1:
+            Pn, An = up.resampleSharded(Pc, Ac, dist, glad, seed=1234, step=i)
+        else:
+            Pn, An = torch.empty_like(Pc), torch.empty_like(Ac)
+            up.resample(Pc, Ac, Pn, An, glad, seed=1234, step=i)
+        bb.record(stream)
+        torch.cuda.synchronize()
+        Pc, Ac = Pn, An
+        if i >= warm:
+            tot += a.elapsed_time(bb)
+    ms_cycle = maxr(tot) / steps
+    out["c3_pf_cycle"] = {"workload": f"C3 full cycle on the device: motion + sensor update ({n_part} particles x 180 beams per GPU) + stats + Gladiator resampling",
+                          "rays_per_s": n_part * world * 180 / (ms_cycle * 1e-3), "ms_per_cycle": ms_cycle,
+                          "exchange": "none" if world == 1 else f"all-reduce 16 B + all-gather {n_part * world * 68} B per cycle (NCCL)"}
     # ---- v1 batched correct ----
     hv = rmcl_b200.SphereCorrectorB200(gmap)
     hv.setStream(stream.cuda_stream)

@@ -52,6 +52,7 @@ typedef struct {
     float real_miss_sim_miss_error;   /* 0.0   */
     float range_min, range_max;       /* sensor_range 0.05 .. 80.0 */
     int   ng_mode;                    /* 0: raw un-normalised geometric normal (Embree path, :57-68); 1: unit normal (OptiX path, BeamEvaluateProgram.cu:104-113) */
+    int   correspondence_type;        /* 0: ray casting (evaluate_rcc, :18-86); 1: closest point (evaluate_cpc, :88-95; selected at :219-222) */
 } b2_pf_params;
 
 typedef struct {
@@ -172,6 +173,22 @@ B2_API int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_at
 /* compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92): sum and max (initial 0) of likelihood.mean over the LOCAL particles; with particles
  * sharded across GPUs the caller all-reduces the 8 bytes (SUM, MAX) -- the one exchange step of the cycle.  Results to HOST. */
 B2_API int b2_pf_likelihood_stats(b2_pf* h, const b2_particle_attr* attrs_dev, uint32_t n_particles, float* sum_out, float* max_out);
+
+/* GladiatorResamplerGPU / gladiator_resample (rmcl_ros/src/rmcl/resampling.cu:108-221; config GladiatorResamplerConfig.hpp:7-20): each
+ * champion i draws a random opponent; if the opponent's likelihood.mean is larger, the champion's slot receives a perturbed copy of the
+ * opponent (Gaussian noise on t and on the Euler angles) whose n_meas is reduced by the forget rate; else it keeps its own state.
+ * poses/attrs hold ALL n_all particles (on one GPU: the local ones; sharded: the all-gathered set -- the one exchange step of this stage);
+ * this call produces the champions first .. first+n_local-1 into poses_new/attrs_new (n_local entries; must not alias the inputs).
+ * Draws come from Philox4x32-10 keyed by (seed, step, global particle index) unless raw_dev/normals_dev (n_local, n_local x 6) supply them. */
+typedef struct {
+    float min_noise_tx, min_noise_ty, min_noise_tz, min_noise_roll, min_noise_pitch, min_noise_yaw;
+    float likelihood_forget_per_meter, likelihood_forget_per_radian;     /* reference defaults 0.3, 0.2 */
+} b2_gladiator_config;
+B2_API int b2_pf_resample_gladiator(b2_pf* h, const b2_transform* poses_dev, const b2_particle_attr* attrs_dev, uint32_t n_all, uint32_t first, uint32_t n_local,
+                                    b2_transform* poses_new_dev, b2_particle_attr* attrs_new_dev, const b2_gladiator_config* cfg, uint64_t seed, uint32_t step,
+                                    const uint32_t* raw_dev, const float* normals_dev);
+/* the draws b2_pf_resample_gladiator would use (replaces init_curand / curand(), resampling.cu:13-30,134-143): raw u32 + 6 normals per particle */
+B2_API int b2_pf_gladiator_randoms(b2_pf* h, uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* raw_dev, float* normals_dev);
 
 /* ---------------------------------------------------------------- introspection ------------------------------ */
 /* CUDA-event timing of the kernels inside b2_rcc_correct_once*(): when enabled, events are recorded on the handle's stream around the

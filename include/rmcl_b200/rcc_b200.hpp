@@ -185,7 +185,7 @@ inline rm::Transform umeyama_transform(const rm::CrossStatistics& s, int device 
 // --- particle filter sensor update ------------------------------------------------------------------------------------------------
 class PCDSensorUpdaterB200 {
 public:
-    b2_pf_params config{2.0f, 100.0f, 100.0f, 0.0f, 0.05f, 80.0f, 0};                           // PCDSensorUpdaterEmbree.cpp:122-134
+    b2_pf_params config{2.0f, 100.0f, 100.0f, 0.0f, 0.05f, 80.0f, 0, 0};                         // PCDSensorUpdaterEmbree.cpp:122-134
     explicit PCDSensorUpdaterB200(B200MapPtr map) : map_(std::move(map))
     {
         if (!map_) throw std::runtime_error("NO MAP");
@@ -221,6 +221,17 @@ public:
         SimpleLikelihoodStats s;
         b2_check(b2_pf_likelihood_stats(h_, reinterpret_cast<const b2_particle_attr*>(attrs.raw()), (uint32_t)attrs.size(), &s.sum, &s.max), "computeStats");
         return s;
+    }
+    // GladiatorResamplerGPU::resample (resampling.cu:201-221; config GladiatorResamplerConfig.hpp:7-20).  `poses/attrs` = all particles
+    // opponents are drawn from; the outputs receive champions first .. first+poses_new.size()-1 (single GPU: first = 0, same sizes).
+    b2_gladiator_config resampler_config{0.03f, 0.03f, 0.0f, 0.0f, 0.0f, 0.01f, 0.3f, 0.2f};
+    void resample(rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs,
+                  rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses_new, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs_new,
+                  uint64_t seed = 1234, uint32_t step = 0, uint32_t first = 0)
+    {
+        b2_check(b2_pf_resample_gladiator(h_, reinterpret_cast<const b2_transform*>(poses.raw()), reinterpret_cast<const b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
+                                          first, (uint32_t)poses_new.size(), reinterpret_cast<b2_transform*>(poses_new.raw()), reinterpret_cast<b2_particle_attr*>(attrs_new.raw()),
+                                          &resampler_config, seed, step, nullptr, nullptr), "resample");
     }
 private:
     B200MapPtr map_;

@@ -843,7 +843,13 @@ void orc_pf_sensor_update_one(const orc_scene* s, const orc_transform* Tsm, cons
     mm.orig = T_apply(*Tsm, meas_s->orig);
     mm.range = meas_s->range;
     memset(&mm.cov, 0, sizeof(mm.cov));
-    const float error = orc_pf_evaluate_rcc(s, &mm, p);
+    float error;
+    if (p->correspondence_type == 1) {                               /* evaluate_cpc (:88-95): distance of meas_m.mean() to the surface */
+        const orc_vec3 q = v3_add(mm.orig, v3_scale(mm.dir, mm.range));     /* RangeMeasurement.hpp:17-20 */
+        const float qa[3] = {q.x, q.y, q.z};
+        float d;
+        error = orc_closest_point(s, qa, 0, &d, NULL, NULL, NULL) ? d : INFINITY;
+    } else error = orc_pf_evaluate_rcc(s, &mm, p);
     /* :224  exp(-(e*e)/sq/2) / sqrt(2*sq*M_PI): float numerator argument, double exp / sqrt, stored to float */
     const float arg = -(error * error) / sigma_dist_quad / 2;
     const float eval = (float)(exp((double)arg) / sqrt((double)(2 * sigma_dist_quad) * M_PI));
@@ -1014,6 +1020,92 @@ void orc_pf_likelihood_stats(uint32_t n, const orc_particle_attr* attrs, float* 
     for (uint32_t s = 256; s > 0; s >>= 1)
         for (uint32_t t = 0; t < s; t++) { sum[t] = sum[t] + sum[t + s]; if (mx[t + s] > mx[t]) mx[t] = mx[t + s]; }
     *sum_out = sum[0]; *max_out = mx[0];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Gladiator resampling (resampling.cu:108-199)                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c[4] = {ctr_in[0], ctr_in[1], ctr_in[2], ctr_in[3]}, k[2] = {key_in[0], key_in[1]};
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+static inline float u01_open(uint32_t r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f; }   /* (0,1), exact in float */
+
+void orc_pf_gladiator_randoms(uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* raw_out, float* normals_out)
+{
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        uint32_t r[8];
+        const uint32_t c0[4] = {first + (uint32_t)i, 0u, step, 0u}, c1[4] = {first + (uint32_t)i, 0u, step, 1u};
+        orc_philox4x32_10(c0, key, r); orc_philox4x32_10(c1, key, r + 4);
+        raw_out[i] = r[0];
+        for (int p = 0; p < 3; p++) {                                  /* Box-Muller on (r[1+2p], r[2+2p]) */
+            const float u1 = u01_open(r[1 + 2 * p]), u2 = u01_open(r[2 + 2 * p]);
+            const float rad = sqrtf(-2.0f * logf(u1)), ang = 6.283185307179586f * u2;
+            normals_out[6 * i + 2 * p] = rad * cosf(ang);
+            normals_out[6 * i + 2 * p + 1] = rad * sinf(ang);
+        }
+    }
+}
+
+/* rm::EulerAngles <- Quaternion and back [RM-recalled: the standard ZYX conversions] */
+static inline void quat_to_euler(orc_quat q, float* roll, float* pitch, float* yaw)
+{
+    const float sinr_cosp = 2.0f * (q.w * q.x + q.y * q.z), cosr_cosp = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
+    *roll = atan2f(sinr_cosp, cosr_cosp);
+    const float sinp = 2.0f * (q.w * q.y - q.z * q.x);
+    *pitch = fabsf(sinp) >= 1.0f ? copysignf(1.5707963267948966f, sinp) : asinf(sinp);
+    const float siny_cosp = 2.0f * (q.w * q.z + q.x * q.y), cosy_cosp = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
+    *yaw = atan2f(siny_cosp, cosy_cosp);
+}
+static inline orc_quat euler_to_quat(float roll, float pitch, float yaw)
+{
+    const float cr = cosf(roll * 0.5f), sr = sinf(roll * 0.5f), cp = cosf(pitch * 0.5f), sp = sinf(pitch * 0.5f), cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f);
+    orc_quat q;
+    q.w = cr * cp * cy + sr * sp * sy;
+    q.x = sr * cp * cy - cr * sp * sy;
+    q.y = cr * sp * cy + sr * cp * sy;
+    q.z = cr * cp * sy - sr * sp * cy;
+    return q;
+}
+
+void orc_pf_gladiator_resample(uint32_t n_all, const orc_transform* poses, const orc_particle_attr* attrs, uint32_t first, uint32_t n_local,
+                               const uint32_t* raw, const float* normals, const orc_gladiator_config* cfg,
+                               orc_transform* poses_new, orc_particle_attr* attrs_new)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n_local; i++) {
+        const uint32_t champion = first + (uint32_t)i;
+        const uint32_t enemy = raw[i] % n_all;                                   /* :137 */
+        const float Lc = attrs[champion].likelihood.mean, Le = attrs[enemy].likelihood.mean;
+        if (Le > Lc) {                                                            /* :150 */
+            const orc_transform pose = poses[enemy];
+            orc_transform pn = pose; orc_particle_attr an = attrs[enemy];
+            const float* N = normals + 6 * (size_t)i;
+            pn.t.x += N[0] * cfg->min_noise_tx; pn.t.y += N[1] * cfg->min_noise_ty; pn.t.z += N[2] * cfg->min_noise_tz;    /* :166-168 */
+            float roll, pitch, yaw; quat_to_euler(pn.R, &roll, &pitch, &yaw);
+            roll += N[3] * cfg->min_noise_roll; pitch += N[4] * cfg->min_noise_pitch; yaw += N[5] * cfg->min_noise_yaw;    /* :169-173 */
+            pn.R = euler_to_quat(roll, pitch, yaw);
+            const orc_transform diff = T_mul(T_inv(pose), pn);                    /* :175 */
+            const float trans_dist = v3_l2norm(diff.t);                           /* :178 (l2norm; the CPU variant squares it, quirk D7) */
+            const float rot_dist = sqrtf(((diff.R.x * diff.R.x + diff.R.y * diff.R.y) + diff.R.z * diff.R.z) + diff.R.w * diff.R.w);   /* :179 Quaternion::l2norm [RM-recalled]: the 4-norm, ~1 */
+            const float frs = (float)(1.0 - pow(1.0 - (double)cfg->likelihood_forget_per_meter, (double)trans_dist));      /* :182 */
+            const float frr = (float)(1.0 - pow(1.0 - (double)cfg->likelihood_forget_per_radian, (double)rot_dist));       /* :183 */
+            const float forget = frs > frr ? frs : frr;
+            const float remember = (float)(1.0 - (double)forget);                 /* :185 */
+            an.likelihood.n_meas = (uint32_t)((float)an.likelihood.n_meas * remember);     /* :187 uint *= float */
+            poses_new[i] = pn; attrs_new[i] = an;
+        } else { poses_new[i] = poses[champion]; attrs_new[i] = attrs[champion]; }
+    }
 }
 
 int orc_num_threads(void)

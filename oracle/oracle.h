@@ -44,6 +44,7 @@ typedef struct {
     float real_miss_sim_miss_error;   /* 0.0   */
     float range_min, range_max;       /* 0.05, 80.0 */
     int   ng_mode;                    /* 0 = raw (un-normalised) Ng like the Embree path (quirk D1), 1 = unit normal like the OptiX path */
+    int   correspondence_type;        /* 0 = ray casting (evaluate_rcc, :18-86), 1 = closest point (evaluate_cpc, :88-95, selected at :219-222) */
 } orc_pf_params;
 
 typedef struct orc_scene orc_scene;
@@ -133,6 +134,22 @@ void  orc_cpc_find(const orc_scene* s, const orc_transform* Tbm, const orc_trans
 /* rest of the PF cycle: motion update (particle_motion.cu:11-46) and likelihood statistics (resampling.cu:41-92) */
 void  orc_pf_motion_update(uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate);
 void  orc_pf_likelihood_stats(uint32_t n, const orc_particle_attr* attrs, float* sum_out, float* max_out);
+
+/* Gladiator resampling, device variant (rmcl_ros/src/rmcl/resampling.cu:108-199; config GladiatorResamplerConfig.hpp:7-20).
+ * The reference draws from cuRAND XORWOW (curand_init(1234, idx, 0), :20); its skip-ahead tables are not in the tree, and its own CPU
+ * variant uses std::mt19937 (GladiatorResamplerCPU.cpp:96-109), so the random stream is an implementation detail: here the draws are
+ * Philox4x32-10 (Salmon et al., SC'11) with counter (global particle index, 0, step, block) and key = seed, one raw u32 (opponent) and
+ * six Box-Muller normals per particle.  The resampling itself is a pure function of (particles, draws). */
+typedef struct {
+    float min_noise_tx, min_noise_ty, min_noise_tz, min_noise_roll, min_noise_pitch, min_noise_yaw;
+    float likelihood_forget_per_meter, likelihood_forget_per_radian;     /* defaults 0.3, 0.2 */
+} orc_gladiator_config;
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_pf_gladiator_randoms(uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* raw_out, float* normals_out /* n x 6 */);
+/* champions first .. first+n_local-1 of the n_all particles; opponent = raw % n_all; outputs have n_local entries */
+void orc_pf_gladiator_resample(uint32_t n_all, const orc_transform* poses, const orc_particle_attr* attrs, uint32_t first, uint32_t n_local,
+                               const uint32_t* raw, const float* normals, const orc_gladiator_config* cfg,
+                               orc_transform* poses_new, orc_particle_attr* attrs_new);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

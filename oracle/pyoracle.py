@@ -22,12 +22,13 @@ RANGE_MEAS = np.dtype([("orig", np.float32, 3), ("dir", np.float32, 3), ("range"
 
 class PFParams(C.Structure):
     _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
-                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int)]
+                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int),
+                ("correspondence_type", C.c_int)]
 
     @staticmethod
-    def defaults(ng_mode=0):
+    def defaults(ng_mode=0, correspondence_type=0):
         # rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:122-134
-        return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode)
+        return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode, correspondence_type)
 
 
 def build(force=False):
@@ -175,6 +176,39 @@ class Scene:
         Tsb = _tf(Tsb)
         lib().orc_pf_update(self._h, C.c_uint32(poses.shape[0]), _p(poses), _p(attrs), _p(Tsb), C.c_uint32(beams.shape[0]), _p(beams), C.byref(params))
         return attrs
+
+
+class GladiatorConfig(C.Structure):
+    """GladiatorResamplerConfig (rmcl_ros/include/rmcl_ros/rmcl/GladiatorResamplerConfig.hpp:7-20)."""
+    _fields_ = [("min_noise_tx", C.c_float), ("min_noise_ty", C.c_float), ("min_noise_tz", C.c_float), ("min_noise_roll", C.c_float),
+                ("min_noise_pitch", C.c_float), ("min_noise_yaw", C.c_float), ("likelihood_forget_per_meter", C.c_float),
+                ("likelihood_forget_per_radian", C.c_float)]
+
+    @staticmethod
+    def defaults():
+        return GladiatorConfig(0.03, 0.03, 0.0, 0.0, 0.0, 0.01, 0.3, 0.2)
+
+
+def philox4x32_10(ctr, key):
+    c, k, o = np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), np.zeros(4, np.uint32)
+    lib().orc_philox4x32_10(_p(c), _p(k), _p(o))
+    return o
+
+
+def pf_gladiator_randoms(seed, step, first, n):
+    raw, nrm = np.empty(n, np.uint32), np.empty((n, 6), np.float32)
+    lib().orc_pf_gladiator_randoms(C.c_uint64(seed), C.c_uint32(step), C.c_uint32(first), C.c_uint32(n), _p(raw), _p(nrm))
+    return raw, nrm
+
+
+def pf_gladiator_resample(poses, attrs, first, n_local, raw, normals, cfg):
+    poses, attrs = _tf(poses).reshape(-1), np.ascontiguousarray(attrs)
+    raw, normals = np.ascontiguousarray(raw, np.uint32), _f32(normals).reshape(-1, 6)
+    assert len(raw) == n_local and len(normals) == n_local
+    Pn, An = np.zeros(n_local, TRANSFORM), np.zeros(n_local, attrs.dtype)
+    lib().orc_pf_gladiator_resample(C.c_uint32(len(poses)), _p(poses), _p(attrs), C.c_uint32(first), C.c_uint32(n_local), _p(raw), _p(normals),
+                                    C.byref(cfg), _p(Pn), _p(An))
+    return Pn, An
 
 
 def spherical_dirs(m):

@@ -42,11 +42,23 @@ class _PinholeModel(C.Structure):
 class PFParams(C.Structure):
     """PCDSensorUpdaterEmbree config (rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:122-134)."""
     _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
-                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int)]
+                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int),
+                ("correspondence_type", C.c_int)]       # 0: ray casting (evaluate_rcc), 1: closest point (evaluate_cpc, :88-95,219-222)
 
     @staticmethod
-    def defaults(ng_mode=0):
-        return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode)
+    def defaults(ng_mode=0, correspondence_type=0):
+        return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode, correspondence_type)
+
+
+class GladiatorConfig(C.Structure):
+    """GladiatorResamplerConfig (rmcl_ros/include/rmcl_ros/rmcl/GladiatorResamplerConfig.hpp:7-20)."""
+    _fields_ = [("min_noise_tx", C.c_float), ("min_noise_ty", C.c_float), ("min_noise_tz", C.c_float), ("min_noise_roll", C.c_float),
+                ("min_noise_pitch", C.c_float), ("min_noise_yaw", C.c_float), ("likelihood_forget_per_meter", C.c_float),
+                ("likelihood_forget_per_radian", C.c_float)]
+
+    @staticmethod
+    def defaults():
+        return GladiatorConfig(0.03, 0.03, 0.0, 0.0, 0.0, 0.01, 0.3, 0.2)
 
 
 class _MeshInfo(C.Structure):
@@ -61,7 +73,7 @@ EXPORTS = [
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
-    "b2_rcc_set_correspondence_type",
+    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms",
 ]
 
 
@@ -420,3 +432,37 @@ class PCDSensorUpdaterB200:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             s, m = float(ts[0]), float(tm[0])
         return s, m
+
+
+    def gladiatorRandoms(self, seed, step, first, n, device=None):
+        """The draws resample() uses for champions first..first+n-1 (raw u32 opponent word + 6 normals each), as torch CUDA tensors."""
+        import torch
+        dev = device if device is not None else torch.device("cuda", self.map.device)
+        raw = torch.empty(n, dtype=torch.int32, device=dev)
+        nrm = torch.empty((n, 6), dtype=torch.float32, device=dev)
+        _chk(load_library().b2_pf_gladiator_randoms(self._h, C.c_uint64(seed), C.c_uint32(step), C.c_uint32(first), C.c_uint32(n), _devptr(raw), _devptr(nrm)))
+        return raw, nrm
+
+    def resample(self, particle_poses, particle_attrs, particle_poses_new, particle_attrs_new, config=None, seed=1234, step=0, first=0, raw=None, normals=None):
+        """GladiatorResamplerGPU::resample (rmcl_ros/src/rmcl/resampling.cu:108-221) on torch CUDA tensors.  `particle_poses/attrs` hold all
+        particles opponents are drawn from; the outputs receive champions first .. first+len(out)-1 (single GPU: first = 0, same length)."""
+        cfg = config or GladiatorConfig.defaults()
+        n_all = particle_poses.numel() * particle_poses.element_size() // 32
+        n_local = particle_poses_new.numel() * particle_poses_new.element_size() // 32
+        _chk(load_library().b2_pf_resample_gladiator(self._h, _devptr(particle_poses), _devptr(particle_attrs), C.c_uint32(n_all), C.c_uint32(first), C.c_uint32(n_local),
+                                                     _devptr(particle_poses_new), _devptr(particle_attrs_new), C.byref(cfg), C.c_uint64(seed), C.c_uint32(step),
+                                                     _devptr(raw) if raw is not None else None, _devptr(normals) if normals is not None else None))
+        return particle_poses_new, particle_attrs_new
+
+    def resampleSharded(self, poses_local, attrs_local, dist, config=None, seed=1234, step=0):
+        """Particles sharded over ranks (equal contiguous slices in rank order): all-gather the particle set (the exchange step of this
+        stage: 68 B per particle over NVLink), then every rank resamples its own champions against GLOBAL opponents.  Draws are keyed by the
+        global particle index, so the result equals the single-GPU resample of the concatenated set.  (n, 8) / (n, 9) float32 CUDA tensors."""
+        import torch
+        from .shard import gladiator_resample_sharded
+
+        def run(P_all, A_all, first, n_local):
+            P_new, A_new = torch.empty_like(poses_local), torch.empty_like(attrs_local)
+            return self.resample(P_all, A_all, P_new, A_new, config, seed, step, first=first)
+
+        return gladiator_resample_sharded(run, poses_local, attrs_local, dist, sync=lambda: torch.cuda.synchronize(poses_local.device))

@@ -711,7 +711,8 @@ extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
     { int rc2; if ((rc2 = h->d_part.reserve(2 * (size_t)h->n_sm * 4)) || (rc2 = h->d_ticket.reserve(1)) || (rc2 = h->d_out.reserve(2))) { delete h; return rc2; } }
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
     CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
-    CU(cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     *out = h;
     return B2_OK;
 }
@@ -766,7 +767,8 @@ static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_a
     ppb = std::max(1u, std::min(ppb, want));
     ppb = std::min(ppb, (uint32_t)B2_PF_BLOCK);
     const uint32_t grid = (n + ppb - 1) / ppb;
-    k_pf_update<<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    if (prm->correspondence_type == 1) k_pf_update<1><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    else                               k_pf_update<0><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
     LAUNCHED();
     return B2_OK;
 }
@@ -805,6 +807,34 @@ extern "C" int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particl
     NOTNULL(poses_dev); NOTNULL(attrs_dev);
     CU(cudaSetDevice(h->map->device));
     k_pf_motion<<<(n + 255) / 256, 256, 0, h->stream>>>(poses_dev, attrs_dev, n, *T, forget_rate);
+    LAUNCHED();
+    return B2_OK;
+}
+
+extern "C" int b2_pf_resample_gladiator(b2_pf* h, const b2_transform* poses_dev, const b2_particle_attr* attrs_dev, uint32_t n_all, uint32_t first, uint32_t n_local,
+                                        b2_transform* poses_new_dev, b2_particle_attr* attrs_new_dev, const b2_gladiator_config* cfg, uint64_t seed, uint32_t step,
+                                        const uint32_t* raw_dev, const float* normals_dev)
+{
+    NOTNULL(h); NOTNULL(cfg);
+    if ((uint64_t)first + n_local > n_all) return fail(B2_ERR_INVALID, "champion range %u+%u exceeds the %u particles", first, n_local, n_all);
+    if ((raw_dev == nullptr) != (normals_dev == nullptr)) return fail(B2_ERR_INVALID, "raw_dev and normals_dev must be given together");
+    if (n_local == 0) return B2_OK;
+    NOTNULL(poses_dev); NOTNULL(attrs_dev); NOTNULL(poses_new_dev); NOTNULL(attrs_new_dev);
+    if ((const void*)poses_dev == (const void*)poses_new_dev || (const void*)attrs_dev == (const void*)attrs_new_dev)
+        return fail(B2_ERR_INVALID, "resampling is not in place: outputs must not alias the inputs (resampling.cu:112-117 double-buffers)");
+    CU(cudaSetDevice(h->map->device));
+    k_pf_gladiator<<<(n_local + 255) / 256, 256, 0, h->stream>>>(poses_dev, attrs_dev, n_all, first, n_local, poses_new_dev, attrs_new_dev, *cfg, seed, step, raw_dev, normals_dev);
+    LAUNCHED();
+    return B2_OK;
+}
+
+extern "C" int b2_pf_gladiator_randoms(b2_pf* h, uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* raw_dev, float* normals_dev)
+{
+    NOTNULL(h);
+    if (n == 0) return B2_OK;
+    NOTNULL(raw_dev); NOTNULL(normals_dev);
+    CU(cudaSetDevice(h->map->device));
+    k_pf_gladiator_randoms<<<(n + 255) / 256, 256, 0, h->stream>>>(seed, step, first, n, raw_dev, normals_dev);
     LAUNCHED();
     return B2_OK;
 }

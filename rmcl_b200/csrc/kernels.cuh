@@ -860,10 +860,19 @@ B2_DEV void gaussian1d_add(b2_gaussian1d& a, float b_mean, float b_sigma, uint32
 }
 
 // Gaussian evaluation of one (particle, beam) pair: sensorUpdate() up to `eval` (PCDSensorUpdaterEmbree.cpp:197-224)
+template <int CORR>
 B2_DEV float pf_eval_one(const BvhView& bvh, Tf Tsm, const PfBeam& b, const b2_pf_params& prm, float sigma_quad, double denom)
 {
     const V3 orig_m = tf_apply(Tsm, mk3(b.ox, b.oy, b.oz));                                // RangeMeasurement.hpp:29-42
     const V3 dir_m = q_rot(Tsm.R, mk3(b.dx, b.dy, b.dz));
+    if (CORR == 1) {
+        // evaluate_cpc (:88-95): error = distance of meas_m.mean() = orig + dir*range (RangeMeasurement.hpp:17-20) to the surface
+        CpBest best; uint32_t nn = 0, nt = 0;
+        closest_point<false>(bvh, v_add(orig_m, v_scale(dir_m, b.range)), best, nn, nt);
+        const float error = best.face != B2_NOFACE ? sqrtf(best.d2) : u2f(0x7f800000u);
+        const float arg = dvd(dvd(-mul(error, error), sigma_quad), 2.0f);                  // :224
+        return (float)(exp((double)arg) / denom);
+    }
     const bool real_hit = (prm.range_min <= b.range) && (b.range <= prm.range_max);        // :27
     const RaySetup r = ray_setup(orig_m, dir_m, bvh);
     HitRec h = trace_init(u2f(0x7f800000u));                                               // tfar = +inf (:38)
@@ -900,6 +909,7 @@ B2_DEV void pf_merge(b2_gaussian1d& lk, const float* e, uint32_t n_beams)
 #define B2_PF_BLOCK 128
 // 72 registers (7 blocks/SM) measured 8 % faster than the uncapped 84 (6 blocks/SM); a persistent-lane variant with dynamic ray fetch
 // (idle lanes claim new rays) was measured SLOWER (2.3 vs 3.3 G rays/s: the extra live state and warp votes cost more than the refill gains)
+template <int CORR>
 __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n_particles,
                                                            b2_transform Tsb_val, const PfBeam* __restrict__ beams, uint32_t n_beams, b2_pf_params prm, uint32_t ppb)
 {
@@ -913,7 +923,7 @@ __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const
         const uint32_t pl = w / n_beams, bi = w % n_beams;
         const Tf Tsm = tf_mul(tf_load(poses + p0 + pl), Tsb);                              // :337-338
         const PfBeam b = beams[bi];
-        s_eval[pl * n_beams + b.slot] = pf_eval_one(bvh, Tsm, b, prm, sigma_quad, denom);
+        s_eval[pl * n_beams + b.slot] = pf_eval_one<CORR>(bvh, Tsm, b, prm, sigma_quad, denom);
     }
     __syncthreads();
     if (threadIdx.x < np) {
@@ -936,6 +946,104 @@ __global__ void k_pf_motion(b2_transform* __restrict__ poses, b2_particle_attr* 
     const uint32_t nm = attrs[i].likelihood.n_meas;
     attrs[i].likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gladiator resampling (rmcl_ros/src/rmcl/resampling.cu:108-199).  Draws: Philox4x32-10 (Salmon et al., SC'11), counter =
+// (global particle index, 0, step, block), key = seed -- one raw u32 (opponent) + three Box-Muller pairs per particle; a function
+// of the GLOBAL index only, so the result does not depend on how particles are sharded over GPUs.  See DESIGN.md for why the
+// reference's cuRAND XORWOW stream is not reproduced.
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    #pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+B2_DEV float u01_open(uint32_t r) { return mul(add((float)(r >> 8), 0.5f), 5.9604644775390625e-08f); }
+B2_DEV void gladiator_draws(uint64_t seed, uint32_t step, uint32_t gidx, uint32_t& raw, float N[6])
+{
+    uint32_t r[8];
+    philox4x32_10(gidx, 0u, step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    philox4x32_10(gidx, 0u, step, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r + 4);
+    raw = r[0];
+    #pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const float u1 = u01_open(r[1 + 2 * p]), u2 = u01_open(r[2 + 2 * p]);
+        const float rad = sqrtf(mul(-2.0f, logf(u1))), ang = mul(6.283185307179586f, u2);
+        N[2 * p] = mul(rad, cosf(ang)); N[2 * p + 1] = mul(rad, sinf(ang));
+    }
+}
+// rm::EulerAngles <-> Quaternion [RM-recalled: standard ZYX conversions], op order as in oracle/oracle.c
+B2_DEV void quat_to_euler(Q4 q, float& roll, float& pitch, float& yaw)
+{
+    roll = atan2f(mul(2.0f, add(mul(q.w, q.x), mul(q.y, q.z))), sub(1.0f, mul(2.0f, add(mul(q.x, q.x), mul(q.y, q.y)))));
+    const float sinp = mul(2.0f, sub(mul(q.w, q.y), mul(q.z, q.x)));
+    pitch = fabsf(sinp) >= 1.0f ? copysignf(1.5707963267948966f, sinp) : asinf(sinp);
+    yaw = atan2f(mul(2.0f, add(mul(q.w, q.z), mul(q.x, q.y))), sub(1.0f, mul(2.0f, add(mul(q.y, q.y), mul(q.z, q.z)))));
+}
+B2_DEV Q4 euler_to_quat(float roll, float pitch, float yaw)
+{
+    const float cr = cosf(mul(roll, 0.5f)), sr = sinf(mul(roll, 0.5f)), cp = cosf(mul(pitch, 0.5f)), sp = sinf(mul(pitch, 0.5f)), cy = cosf(mul(yaw, 0.5f)), sy = sinf(mul(yaw, 0.5f));
+    Q4 q;
+    q.w = add(mul(mul(cr, cp), cy), mul(mul(sr, sp), sy));
+    q.x = sub(mul(mul(sr, cp), cy), mul(mul(cr, sp), sy));
+    q.y = add(mul(mul(cr, sp), cy), mul(mul(sr, cp), sy));
+    q.z = sub(mul(mul(cr, cp), sy), mul(mul(sr, sp), cy));
+    return q;
+}
+// one champion: poses/attrs are the n_all particles, champion = global index, outputs are written at out_p / out_a
+B2_DEV void gladiator_one(const b2_transform* poses, const b2_particle_attr* attrs, uint32_t n_all, uint32_t champion, uint32_t raw, const float N[6],
+                          const b2_gladiator_config& cfg, b2_transform* out_p, b2_particle_attr* out_a)
+{
+    const uint32_t enemy = raw % n_all;                                                    // :137
+    const float Lc = attrs[champion].likelihood.mean, Le = attrs[enemy].likelihood.mean;
+    if (!(Le > Lc)) { *out_p = poses[champion]; *out_a = attrs[champion]; return; }       // :150, :193-196
+    b2_transform pn = poses[enemy]; b2_particle_attr an = attrs[enemy];
+    const Tf pose = tf_from_pod(pn);
+    Tf pnew = pose;
+    pnew.t = mk3(add(pose.t.x, mul(N[0], cfg.min_noise_tx)), add(pose.t.y, mul(N[1], cfg.min_noise_ty)), add(pose.t.z, mul(N[2], cfg.min_noise_tz)));   // :166-168
+    float roll, pitch, yaw; quat_to_euler(pose.R, roll, pitch, yaw);
+    pnew.R = euler_to_quat(add(roll, mul(N[3], cfg.min_noise_roll)), add(pitch, mul(N[4], cfg.min_noise_pitch)), add(yaw, mul(N[5], cfg.min_noise_yaw)));   // :169-173
+    const Tf diff = tf_mul(tf_inv(pose), pnew);                                            // :175
+    const float trans_dist = v_l2norm(diff.t);                                             // :178
+    const float rot_dist = sqrtf(add(add(add(mul(diff.R.x, diff.R.x), mul(diff.R.y, diff.R.y)), mul(diff.R.z, diff.R.z)), mul(diff.R.w, diff.R.w)));   // :179
+    const float frs = (float)(1.0 - pow(1.0 - (double)cfg.likelihood_forget_per_meter, (double)trans_dist));    // :182
+    const float frr = (float)(1.0 - pow(1.0 - (double)cfg.likelihood_forget_per_radian, (double)rot_dist));     // :183
+    const float forget = frs > frr ? frs : frr;
+    const float remember = (float)(1.0 - (double)forget);                                  // :185
+    an.likelihood.n_meas = (uint32_t)mul((float)an.likelihood.n_meas, remember);           // :187
+    pn.R.x = pnew.R.x; pn.R.y = pnew.R.y; pn.R.z = pnew.R.z; pn.R.w = pnew.R.w; pn.t.x = pnew.t.x; pn.t.y = pnew.t.y; pn.t.z = pnew.t.z;   // stamp: the enemy's
+    *out_p = pn; *out_a = an;
+}
+
+#ifdef __CUDACC__
+// HBM stream: 68 B in (+68 B gathered from the opponent when it wins) and 68 B out per particle
+__global__ void __launch_bounds__(256) k_pf_gladiator(const b2_transform* __restrict__ poses, const b2_particle_attr* __restrict__ attrs, uint32_t n_all, uint32_t first,
+                                                      uint32_t n_local, b2_transform* __restrict__ poses_new, b2_particle_attr* __restrict__ attrs_new,
+                                                      b2_gladiator_config cfg, uint64_t seed, uint32_t step, const uint32_t* __restrict__ raw_in, const float* __restrict__ normals_in)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    uint32_t raw; float N[6];
+    if (raw_in) { raw = raw_in[i]; for (int k = 0; k < 6; k++) N[k] = normals_in[6 * (size_t)i + k]; }
+    else gladiator_draws(seed, step, first + i, raw, N);
+    gladiator_one(poses, attrs, n_all, first + i, raw, N, cfg, poses_new + i, attrs_new + i);
+}
+__global__ void k_pf_gladiator_randoms(uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* __restrict__ raw_out, float* __restrict__ normals_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t raw; float N[6];
+    gladiator_draws(seed, step, first + i, raw, N);
+    raw_out[i] = raw;
+    for (int k = 0; k < 6; k++) normals_out[6 * (size_t)i + k] = N[k];
+}
+#endif
 
 // compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92) over all SMs: FP64 block sums + max, the last block combines in block order
 __global__ void __launch_bounds__(256) k_pf_stats(const b2_particle_attr* __restrict__ attrs, uint32_t n, double* __restrict__ partials, unsigned int* __restrict__ ticket,

@@ -88,6 +88,19 @@ __attribute__((visibility("default"))) void emul_cpc_find(void* sc, const b2_tra
     }
 }
 
+__attribute__((visibility("default"))) void emul_gladiator(uint32_t n_all, const b2_transform* poses, const b2_particle_attr* attrs, uint32_t first, uint32_t n_local,
+                                                           const b2_gladiator_config* cfg, uint64_t seed, uint32_t step, b2_transform* poses_new, b2_particle_attr* attrs_new,
+                                                           uint32_t* raw_out, float* normals_out)
+{
+    for (uint32_t i = 0; i < n_local; i++) {
+        uint32_t raw; float N[6];
+        gladiator_draws(seed, step, first + i, raw, N);
+        if (raw_out) raw_out[i] = raw;
+        if (normals_out) for (int k = 0; k < 6; k++) normals_out[6 * (size_t)i + k] = N[k];
+        gladiator_one(poses, attrs, n_all, first + i, raw, N, *cfg, poses_new + i, attrs_new + i);
+    }
+}
+
 // sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
 __attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
                                                                   const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)
@@ -144,7 +157,7 @@ __attribute__((visibility("default"))) void emul_pf_update(void* sc, uint32_t n_
     for (int64_t p = 0; p < (int64_t)n_particles; p++) {
         std::vector<float> e(n_beams);
         const Tf Tsm = tf_mul(tf_load(poses + p), tf_from_pod(*Tsb));
-        for (uint32_t j = 0; j < n_beams; j++) e[pb[j].slot] = pf_eval_one(bvh, Tsm, pb[j], *prm, sigma_quad, denom);
+        for (uint32_t j = 0; j < n_beams; j++) e[pb[j].slot] = prm->correspondence_type == 1 ? pf_eval_one<1>(bvh, Tsm, pb[j], *prm, sigma_quad, denom) : pf_eval_one<0>(bvh, Tsm, pb[j], *prm, sigma_quad, denom);
         b2_gaussian1d lk = attrs[p].likelihood;
         pf_merge(lk, e.data(), n_beams);
         attrs[p].likelihood = lk;

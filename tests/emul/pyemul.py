@@ -16,7 +16,8 @@ CROSS_STATS = np.dtype([("dataset_mean", np.float32, 3), ("model_mean", np.float
 
 class PFParams(C.Structure):
     _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
-                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int)]
+                ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int),
+                ("correspondence_type", C.c_int)]
 
 
 def build(force=False):
@@ -114,9 +115,18 @@ class Scene:
         beams = np.ascontiguousarray(beams)
         Tsb = np.ascontiguousarray(Tsb)
         prm = PFParams(params.dist_sigma, params.real_hit_sim_miss_error, params.real_miss_sim_hit_error, params.real_miss_sim_miss_error,
-                       params.range_min, params.range_max, params.ng_mode)
+                       params.range_min, params.range_max, params.ng_mode, getattr(params, "correspondence_type", 0))
         lib().emul_pf_update(self._h, C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(Tsb), C.c_uint32(len(beams)), _p(beams), C.byref(prm))
         return attrs
+
+
+def gladiator(poses, attrs, first, n_local, cfg, seed, step):
+    poses, attrs = np.ascontiguousarray(poses), np.ascontiguousarray(attrs)
+    Pn, An = np.zeros(n_local, poses.dtype), np.zeros(n_local, attrs.dtype)
+    raw, nrm = np.zeros(n_local, np.uint32), np.zeros((n_local, 6), np.float32)
+    lib().emul_gladiator(C.c_uint32(len(poses)), _p(poses), _p(attrs), C.c_uint32(first), C.c_uint32(n_local), C.byref(cfg), C.c_uint64(seed), C.c_uint32(step),
+                         _p(Pn), _p(An), _p(raw), _p(nrm))
+    return Pn, An, raw, nrm
 
 
 def cross_statistics(Tpre, dpts, dmask, mpts, mnrm, mmask, max_dist):

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_pod_sizes_match_header():
     import rmcl_b200
     from rmcl_b200 import api, synth
-    assert ctypes.sizeof(api.PFParams) == 28 and ctypes.sizeof(api._SphericalModel) == 32 and ctypes.sizeof(api._PinholeModel) == 32
+    assert ctypes.sizeof(api.PFParams) == 32 and ctypes.sizeof(api.GladiatorConfig) == 32 and ctypes.sizeof(api._SphericalModel) == 32 and ctypes.sizeof(api._PinholeModel) == 32
     assert synth.TRANSFORM_DTYPE.itemsize == 32 and synth.CROSS_STATS_DTYPE.itemsize == 64
 
 

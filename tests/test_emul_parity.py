@@ -142,3 +142,31 @@ def test_cpc_bit_exact(pe, po, synth, name, lo, hi):
     for k in ("points", "normals", "hits", "face_ids", "dists"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
     assert 0 < a["hits"].mean() < 1
+
+
+def test_pf_cpc_bit_exact(pe, po, synth):
+    """PF sensor update with correspondence_type == 1 (evaluate_cpc, PCDSensorUpdaterEmbree.cpp:88-95): attrs bit-identical to the oracle."""
+    osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    Tsb = synth.scenario_tsb()
+    pts = osc.simulate(synth.building_gt_pose(), Tsb, o, d, 80.0)["points"]
+    beams = synth.pf_beams(pts, 40)
+    P, A = synth.pf_particles(300)
+    prm = po.PFParams.defaults(0, 1)
+    a, b = osc.pf_update(P, A, Tsb, beams, prm), esc.pf_update(P, A, Tsb, beams, prm)
+    assert a.tobytes() == b.tobytes()
+    assert not np.array_equal(a["likelihood"]["mean"], osc.pf_update(P, A, Tsb, beams, po.PFParams.defaults(0, 0))["likelihood"]["mean"])
+
+
+def test_gladiator_bit_exact(pe, po, synth):
+    """Device resampling code (kernels.cuh: philox4x32_10, gladiator_draws, gladiator_one) on the CPU == the oracle, bit for bit."""
+    from test_oracle import _glad_particles
+    n = 20000
+    P, A = _glad_particles(synth, n)
+    cfg = po.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    raw, nrm = po.pf_gladiator_randoms(99, 7, 1000, n - 1000)
+    Pn, An = po.pf_gladiator_resample(P, A, 1000, n - 1000, raw, nrm, cfg)
+    Pe, Ae, rawe, nrme = pe.gladiator(P, A, 1000, n - 1000, cfg, 99, 7)
+    assert np.array_equal(raw, rawe) and np.array_equal(nrm, nrme)
+    assert Pn.tobytes() == Pe.tobytes() and An.tobytes() == Ae.tobytes()

@@ -205,8 +205,9 @@ def test_correct_batch_v1(po, synth):
     assert abs(Tc["t"][0, 2]) < 0.2
 
 
-@pytest.mark.parametrize("ng_mode", [0, 1])
-def test_pf_sensor_update(po, synth, ng_mode):
+@pytest.mark.parametrize("ng_mode,corr", [(0, 0), (1, 0), (0, 1)])
+def test_pf_sensor_update(po, synth, ng_mode, corr):
+    """corr 0: evaluate_rcc (PCDSensorUpdaterEmbree.cpp:18-86); corr 1: evaluate_cpc (:88-95), the closest-point error."""
     import rmcl_b200
     name = "building:200000"
     osc = oracle_scene(name)
@@ -218,10 +219,10 @@ def test_pf_sensor_update(po, synth, ng_mode):
     beams["range"][:3] = (0.01, 200.0, 90.0)                     # real misses (out of sensor range) exercise the penalty branches
     P, A = synth.pf_particles(5000)
     A["likelihood"]["n_meas"][:10] = 9990                        # clamp at MAX_N_MEAS
-    prm = po.PFParams.defaults(ng_mode)
+    prm = po.PFParams.defaults(ng_mode, corr)
     ref = osc.pf_update(P, A, Tsb, beams, prm)
     up = rmcl_b200.PCDSensorUpdaterB200(gpu_map(name))
-    out = up.update(P, A, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    out = up.update(P, A, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode, corr))
     assert np.array_equal(out["likelihood"]["n_meas"], ref["likelihood"]["n_meas"])
     assert np.array_equal(out["state_sigma"], ref["state_sigma"])
     assert np.abs(out["likelihood"]["mean"] - ref["likelihood"]["mean"]).max() <= TOL_LIK
@@ -229,14 +230,14 @@ def test_pf_sensor_update(po, synth, ng_mode):
     frac_exact = np.mean(out["likelihood"]["mean"] == ref["likelihood"]["mean"])
     assert frac_exact > 0.99
     # sharding invariance: the two halves computed separately equal the whole, bit for bit
-    a = up.update(P[:2500], A[:2500], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
-    b = up.update(P[2500:], A[2500:], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    a = up.update(P[:2500], A[:2500], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode, corr))
+    b = up.update(P[2500:], A[2500:], Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode, corr))
     assert np.concatenate([a, b]).tobytes() == out.tobytes()
     # device-resident variant (ParticleUpdater<VRAM_CUDA>)
     import torch
     Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
     Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
-    up.update(Pd, Ad, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode))
+    up.update(Pd, Ad, Tsb, beams, rmcl_b200.PFParams.defaults(ng_mode, corr))
     torch.cuda.synchronize()
     assert Ad.cpu().numpy().view(synth.PARTICLE_ATTR_DTYPE).reshape(-1).tobytes() == out.tobytes()
 
@@ -443,3 +444,55 @@ def test_cpc_correct_once(po, synth):
     h.setDataset(dp2, dm2)
     Tn, Td, Cm = h.correctOnce(Tgt, synth.make_transform(), 5, 0.0)
     assert np.abs(Td["t"]).max() < 1e-4 and quat_close(Td["R"], [0, 0, 0, 1], 1e-5) and Cm["n_meas"] > 100000
+
+
+def test_gladiator_resample_gpu(po, synth):
+    """gladiator_resample (resampling.cu:108-221) on the device.  Integer work (Philox words, opponent choice, win/lose decision,
+    copied fields) is bit-exact; the perturbed pose goes through device sinf/cosf/atan2f/logf (<= 2 ulp from glibc): tolerance 2e-6."""
+    import torch
+    import rmcl_b200
+    from test_oracle import _glad_particles
+    n = 200000
+    P, A = _glad_particles(synth, n)
+    cfg_o = po.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    cfg = rmcl_b200.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map("cube29"))
+    raw_o, nrm_o = po.pf_gladiator_randoms(1234, 3, 0, n)
+    raw_d, nrm_d = up.gladiatorRandoms(1234, 3, 0, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(raw_d.cpu().numpy().view(np.uint32), raw_o)                               # Philox4x32-10: bit-exact
+    assert np.abs(nrm_d.cpu().numpy() - nrm_o).max() <= 4e-6                                        # Box-Muller through device logf/sinf/cosf
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+
+    def to_np(Pt, At):
+        torch.cuda.synchronize()
+        return Pt.cpu().numpy().view(P.dtype).reshape(-1), At.cpu().numpy().view(A.dtype).reshape(-1)
+
+    ref_P, ref_A = po.pf_gladiator_resample(P, A, 0, n, raw_o, nrm_o, cfg_o)
+    for external in (True, False):
+        Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
+        if external:   # the oracle's draws uploaded: isolates the resampling arithmetic from the generator
+            up.resample(Pd, Ad, Pn, An, cfg, raw=torch.from_numpy(raw_o.view(np.int32)).cuda(), normals=torch.from_numpy(nrm_o).cuda())
+        else:
+            up.resample(Pd, Ad, Pn, An, cfg, seed=1234, step=3)
+        gP, gA = to_np(Pn, An)
+        assert np.array_equal(gA["likelihood"]["mean"], ref_A["likelihood"]["mean"]) and np.array_equal(gA["state_sigma"], ref_A["state_sigma"])
+        assert np.array_equal(gP["stamp"], ref_P["stamp"])                                          # who won where: exact
+        if external:
+            assert np.array_equal(gP["t"], ref_P["t"])                                              # t + N*noise: two individually rounded ops, bit-exact
+        else:
+            assert np.abs(gP["t"] - ref_P["t"]).max() <= 8e-6                                       # device normals differ by ulps -> at most 1 ulp of |t| <= 64
+        assert np.abs(gP["R"] - ref_P["R"]).max() <= 2e-6
+        dn = np.abs(gA["likelihood"]["n_meas"].astype(np.int64) - ref_A["likelihood"]["n_meas"].astype(np.int64))
+        assert dn.max() <= 1 and (dn == 0).mean() > 0.999                                           # uint *= float truncation next to an ulp of pow()
+    whole_P, whole_A = gP, gA
+    # sharding invariance on the device: champions [0, h) and [h, n) against all n opponents == the whole, bit for bit
+    h = n // 2
+    Pa, Aa, Pb, Ab = torch.empty_like(Pd[:h]), torch.empty_like(Ad[:h]), torch.empty_like(Pd[h:]), torch.empty_like(Ad[h:])
+    up.resample(Pd, Ad, Pa, Aa, cfg, seed=1234, step=3, first=0)
+    up.resample(Pd, Ad, Pb, Ab, cfg, seed=1234, step=3, first=h)
+    a, b = to_np(Pa, Aa), to_np(Pb, Ab)
+    assert np.concatenate([a[0], b[0]]).tobytes() == whole_P.tobytes() and np.concatenate([a[1], b[1]]).tobytes() == whole_A.tobytes()
+    with pytest.raises(rmcl_b200.B2Error):
+        up.resample(Pd, Ad, Pd, Ad, cfg)                                                            # in place is refused

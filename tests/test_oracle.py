@@ -311,3 +311,58 @@ def test_cpc_correct_once_converges(po, synth):
         Tom, Td, Cm = sc.micp_correct_once(None, None, m.range_max, dp, dm, Tom, I, Tsb, 5, 1.0, 0.15, 0.0, f64_accum=True)
     assert Cm["n_meas"] > 0.9 * dm.sum()
     assert np.abs(Tom["t"] - Tgt["t"]).max() < 0.2 * e0
+
+
+def _glad_particles(synth, n, seed=0):
+    P, A = synth.pf_particles(n)
+    rng = np.random.default_rng(seed)
+    A["likelihood"]["mean"] = rng.uniform(0, 0.2, n).astype(np.float32)
+    A["likelihood"]["n_meas"] = rng.integers(0, 10001, n).astype(np.uint32)
+    A["state_sigma"] = rng.uniform(0, 1, (n, 6)).astype(np.float32)
+    P["R"] = np.stack([synth.quat_from_rpy(*r) for r in rng.uniform(-0.3, 0.3, (n, 3))]).astype(np.float32)
+    P["stamp"] = np.arange(n)
+    return P, A
+
+
+def test_philox_known_answers(po):
+    """Philox4x32-10 against the published Random123 known-answer vectors (kat_vectors: zeros, all ones, digits of pi)."""
+    assert [hex(x) for x in po.philox4x32_10([0] * 4, [0] * 2)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in po.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in po.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    raw, nrm = po.pf_gladiator_randoms(1234, 0, 0, 200000)
+    assert np.abs(nrm.mean(0)).max() < 0.01 and np.abs(nrm.std(0) - 1).max() < 0.01 and np.isfinite(nrm).all()
+    assert np.abs(np.corrcoef(nrm.T) - np.eye(6)).max() < 0.01
+    assert abs((raw % 7 == 0).mean() - 1 / 7) < 0.005
+    # keyed by the GLOBAL index: a shard's draws are a slice of the whole
+    r2, n2 = po.pf_gladiator_randoms(1234, 0, 5000, 1000)
+    assert np.array_equal(r2, raw[5000:6000]) and np.array_equal(n2, nrm[5000:6000])
+    assert not np.array_equal(po.pf_gladiator_randoms(1234, 1, 0, 100)[0], raw[:100])
+
+
+def test_gladiator_resample_oracle(po, synth):
+    """gladiator_resample_kernel (resampling.cu:108-199) restated as a pure function of (particles, draws)."""
+    n = 20000
+    P, A = _glad_particles(synth, n)
+    cfg = po.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    raw, nrm = po.pf_gladiator_randoms(1234, 3, 0, n)
+    Pn, An = po.pf_gladiator_resample(P, A, 0, n, raw, nrm, cfg)
+    enemy = raw % n
+    won = A["likelihood"]["mean"][enemy] > A["likelihood"]["mean"]
+    assert 0.4 < won.mean() < 0.6
+    assert Pn[~won].tobytes() == P[~won].tobytes() and An[~won].tobytes() == A[~won].tobytes()          # champion stays champion (:193-196)
+    assert np.array_equal(An["likelihood"]["mean"][won], A["likelihood"]["mean"][enemy][won])           # the likelihood is kept (:177)
+    assert np.array_equal(An["state_sigma"][won], A["state_sigma"][enemy][won]) and np.array_equal(Pn["stamp"][won], P["stamp"][enemy][won])
+    dt = Pn["t"][won] - P["t"][enemy][won]
+    assert np.abs(dt - nrm[won][:, :3] * np.array([0.03, 0.03, 0.01], np.float32)).max() < 1e-5            # :166-168
+    assert np.abs(np.linalg.norm(Pn["R"][won].astype(np.float64), axis=1) - 1).max() < 1e-6
+    # forget rule (:178-187): rot_dist is the quaternion 4-norm (~1), so forget_rate >= likelihood_forget_per_radian
+    tr = np.linalg.norm(dt.astype(np.float64), axis=1)
+    forget = np.maximum(1 - 0.7 ** tr, 0.2)
+    expect = A["likelihood"]["n_meas"][enemy][won] * (1 - forget)
+    assert np.abs(An["likelihood"]["n_meas"][won] - expect).max() <= 1.01
+    # sharding invariance: two halves with global indices == the whole
+    h = n // 2
+    a = po.pf_gladiator_resample(P, A, 0, h, raw[:h], nrm[:h], cfg)
+    b = po.pf_gladiator_resample(P, A, h, n - h, raw[h:], nrm[h:], cfg)
+    assert np.concatenate([a[0], b[0]]).tobytes() == Pn.tobytes() and np.concatenate([a[1], b[1]]).tobytes() == An.tobytes()

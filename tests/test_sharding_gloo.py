@@ -53,11 +53,31 @@ def _worker(rank, world, port, q):
         ts, tm = torch.tensor([ls], dtype=torch.float64), torch.tensor([lm], dtype=torch.float64)
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        # resampling: the stage WITH an exchange (opponents come from all particles): all-gather, then resample the own champions.
+        # The product passes its CUDA kernel as `resample_fn`; here the CPU emulation of the same device code stands in.
+        from rmcl_b200.shard import gladiator_resample_sharded
+        n_eq = 100                                                                  # equal shard sizes
+        Pq, Aq = P[:n_eq].copy(), sc.pf_update(P[:n_eq], A[:n_eq], Tsb, beams, prm)
+        cfg = po.GladiatorConfig.defaults()
+        lb, le = shard_range(n_eq, rank, world)
+
+        def resample_fn(P_all, A_all, first, n_local):
+            Pa = P_all.numpy().view(Pq.dtype).reshape(-1)
+            Aa = A_all.numpy().view(Aq.dtype).reshape(-1)
+            Pn, An, _, _ = pyemul.gladiator(Pa, Aa, first, n_local, cfg, 1234, 5)
+            return Pn, An
+
+        Pl = torch.from_numpy(Pq[lb:le].view(np.float32).reshape(-1, 8).copy())
+        Al = torch.from_numpy(Aq[lb:le].view(np.float32).reshape(-1, 9).copy())
+        Pn, An = gladiator_resample_sharded(resample_fn, Pl, Al, dist)
+        Pfull, Afull = gather_records(Pn, dist, dst=0), gather_records(An, dist, dst=0)
         if rank == 0:
             ref = sc.pf_update(P, A, Tsb, beams, prm)
             rs, rm = po.pf_likelihood_stats(ref)
             stats_ok = float(tm[0]) == rm and abs(float(ts[0]) - rs) <= 1e-5 * abs(rs) + 1e-6
-            q.put(("ok", full.tobytes() == ref.tobytes() and stats_ok, len(full)))
+            Pr, Ar, _, _ = pyemul.gladiator(Pq, Aq, 0, n_eq, cfg, 1234, 5)
+            res_ok = Pfull.tobytes() == Pr.tobytes() and Afull.tobytes() == Ar.tobytes() and not np.array_equal(Ar["likelihood"]["mean"], Aq["likelihood"]["mean"])
+            q.put(("ok", full.tobytes() == ref.tobytes() and stats_ok and res_ok, len(full)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
