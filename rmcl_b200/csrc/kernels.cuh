@@ -697,11 +697,34 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
     for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(&init)[w];
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // With at most two pairs per thread (C2: 131 072 pairs on 148 x 512 threads) the pairs are loaded ONCE and stay in registers for
+    // all iterations: only the pre-transform changes between passes, so later passes touch no memory at all.
+    const bool cached = n <= 2u * stride;
+    bool c_ok[2] = {false, false}; V3 c_d[2], c_I[2], c_N[2];
+    if (cached) {
+        #pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t i = gid + (uint32_t)u * stride;
+            const bool in = i < n;
+            const uint32_t j = in ? i : 0u;
+            c_ok[u] = in && (dmask[j] > 0) && (mmask[j] > 0);
+            c_d[u] = mk3(dpts[3 * j], dpts[3 * j + 1], dpts[3 * j + 2]);
+            c_I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
+            c_N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
+        }
+    }
     for (uint32_t it = 0; it < iterations; it++) {
         const long long c0 = clock64();
         const Tf Tpre = tf_load(&s_icp.T_snew_sold);
         const float max_dist = s_icp.max_dist;
         P2LAcc acc; acc_zero(acc);
+        if (cached) {
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                V3 D, M;
+                if (c_ok[u] && p2l_pair(Tpre, c_d[u], c_I[u], c_N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
+            }
+        } else
         for (uint32_t base = gid; base < n; base += 2u * stride) {
             // up to 2 pairs per trip with all their loads issued before the first use
             uint8_t dm[2], mm[2]; V3 d[2], I[2], N[2];

@@ -280,68 +280,86 @@ B2_DEV void closest_point(const BvhView& bvh, V3 q, CpBest& best, uint32_t& n_no
     const float delta = cp_delta(q);
     uint2 stack[B2_TRAVERSAL_STACK];
     int sp = 0;
-    uint32_t node_idx = 0;
+    uint32_t next = 0u; float next_b2 = 0.0f; bool have_next = true;        // node to visit once the pending leaves are done (root first)
+    uint32_t tbits = 0u, tri_base = 0u;                                       // pending triangles of the leaf child being tested
+    uint32_t lmask = 0u, m0 = 0u, m1 = 0u;                                    // pending leaf children (slots) of the last visited node, its meta bytes
+    float b2[8];                                                              // child bounds of the last visited node (registers: static indexing only)
+    #pragma unroll
+    for (int s = 0; s < 8; s++) b2[s] = 0.0f;
+    // One unit of work per trip and lane -- a triangle test if one is pending, else a node visit -- as in trace_closest: a warp never
+    // waits for the lane with the most triangles in a node.  Leaf children are taken NEAREST FIRST and judged against the bound as it
+    // stands then, so once a close triangle is found the remaining leaves of the node are dropped untested.  The order of the tests
+    // does not change the result (argmin over counting candidates); it only changes how early the bound shrinks.
     while (true) {
-        const float4* __restrict__ np = bvh.nodes + B2_NODE_QUADS * (size_t)node_idx;
-        const float4 lxa = ldg(np + 0), lxb = ldg(np + 1), lya = ldg(np + 2), lyb = ldg(np + 3), lza = ldg(np + 4), lzb = ldg(np + 5);
-        const float4 hxa = ldg(np + 6), hxb = ldg(np + 7), hya = ldg(np + 8), hyb = ldg(np + 9), hza = ldg(np + 10), hzb = ldg(np + 11);
-        const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
-        const uint32_t child_base = f2u(h0.x), tri_base = f2u(h0.y), imask = f2u(h1.x), m0 = f2u(h0.z), m1 = f2u(h0.w);
-        if (STATS) n_nodes++;
-        float b2[8];
-        b2[0] = cp_b2(cp_axis(lxa.x, hxa.x, q.x), cp_axis(lya.x, hya.x, q.y), cp_axis(lza.x, hza.x, q.z));
-        b2[1] = cp_b2(cp_axis(lxa.y, hxa.y, q.x), cp_axis(lya.y, hya.y, q.y), cp_axis(lza.y, hza.y, q.z));
-        b2[2] = cp_b2(cp_axis(lxa.z, hxa.z, q.x), cp_axis(lya.z, hya.z, q.y), cp_axis(lza.z, hza.z, q.z));
-        b2[3] = cp_b2(cp_axis(lxa.w, hxa.w, q.x), cp_axis(lya.w, hya.w, q.y), cp_axis(lza.w, hza.w, q.z));
-        b2[4] = cp_b2(cp_axis(lxb.x, hxb.x, q.x), cp_axis(lyb.x, hyb.x, q.y), cp_axis(lzb.x, hzb.x, q.z));
-        b2[5] = cp_b2(cp_axis(lxb.y, hxb.y, q.x), cp_axis(lyb.y, hyb.y, q.y), cp_axis(lzb.y, hzb.y, q.z));
-        b2[6] = cp_b2(cp_axis(lxb.z, hxb.z, q.x), cp_axis(lyb.z, hyb.z, q.y), cp_axis(lzb.z, hzb.z, q.z));
-        b2[7] = cp_b2(cp_axis(lxb.w, hxb.w, q.x), cp_axis(lyb.w, hyb.w, q.y), cp_axis(lzb.w, hzb.w, q.z));
-        // leaf children first (their triangles shrink lim before the inner children are judged)
-        uint32_t tbits = 0;
-        #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            const uint32_t meta = ((s < 4 ? m0 : m1) >> (8 * (s & 3))) & 0xffu;
-            const uint32_t bits = ((meta >> 5) << (meta & 0x1fu)) & 0x00ffffffu;          // empty slots and inner children contribute nothing
-            tbits |= (b2[s] <= best.lim) ? bits : 0u;
+        if (!tbits && lmask) {
+            uint32_t sel = 0u; float bsel = u2f(0x7f800000u);
+            #pragma unroll
+            for (int s = 0; s < 8; s++) if (((lmask >> s) & 1u) && b2[s] < bsel) { bsel = b2[s]; sel = (uint32_t)s; }
+            if (bsel <= best.lim) {
+                lmask &= ~(1u << sel);
+                const uint32_t meta = ((sel < 4u ? m0 : m1) >> (8u * (sel & 3u))) & 0xffu;
+                tbits = (meta >> 5) << (meta & 0x1fu);
+            } else lmask = 0u;                                                // every other pending leaf is at least as far
         }
-        while (tbits) {
+        if (tbits) {
             const uint32_t i = 31u - (uint32_t)clz32(tbits);
             tbits &= ~(1u << i);
             cp_tri_test(bvh, q, delta, tri_base + i, best);
             if (STATS) n_tris++;
         }
-        // inner children within lim: descend into the nearest, park the others as one group
-        uint32_t hit = 0, near_slot = 0; float near_b2 = u2f(0x7f800000u), rest_b2 = u2f(0x7f800000u);
-        #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            const bool in = ((imask >> s) & 1u) && (b2[s] <= best.lim);
-            if (in) {
-                hit |= 1u << s;
-                if (b2[s] < near_b2) { rest_b2 = near_b2; near_b2 = b2[s]; near_slot = (uint32_t)s; }
-                else rest_b2 = fminf(rest_b2, b2[s]);
+        if (!tbits && !lmask) {
+            // the node chosen at the previous visit was judged before that node's triangles were tested: judge it again
+            if (have_next && !(next_b2 <= best.lim)) have_next = false;
+            while (!have_next && sp > 0) {
+                // next child of the youngest group whose lower bound is still within lim
+                uint2 G = stack[sp - 1];
+                const float lb = u2f(((G.y >> 8) & 0xffffu) << 16);
+                if (!(lb <= best.lim)) { sp--; continue; }
+                const uint32_t bitpos = 31u - (uint32_t)clz32(G.y);
+                const uint32_t slot = bitpos - 24u;
+                G.y &= ~(1u << bitpos);
+                if (G.y & 0xff000000u) stack[sp - 1] = G; else sp--;
+                next = G.x + popc32(G.y & 0xffu & ((1u << slot) - 1u));
+                next_b2 = 0.0f; have_next = true;
+            }
+            if (!have_next) break;
+            const float4* __restrict__ np = bvh.nodes + B2_NODE_QUADS * (size_t)next;
+            const float4 lxa = ldg(np + 0), lxb = ldg(np + 1), lya = ldg(np + 2), lyb = ldg(np + 3), lza = ldg(np + 4), lzb = ldg(np + 5);
+            const float4 hxa = ldg(np + 6), hxb = ldg(np + 7), hya = ldg(np + 8), hyb = ldg(np + 9), hza = ldg(np + 10), hzb = ldg(np + 11);
+            const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
+            const uint32_t child_base = f2u(h0.x), imask = f2u(h1.x);
+            tri_base = f2u(h0.y); m0 = f2u(h0.z); m1 = f2u(h0.w);
+            if (STATS) n_nodes++;
+            b2[0] = cp_b2(cp_axis(lxa.x, hxa.x, q.x), cp_axis(lya.x, hya.x, q.y), cp_axis(lza.x, hza.x, q.z));
+            b2[1] = cp_b2(cp_axis(lxa.y, hxa.y, q.x), cp_axis(lya.y, hya.y, q.y), cp_axis(lza.y, hza.y, q.z));
+            b2[2] = cp_b2(cp_axis(lxa.z, hxa.z, q.x), cp_axis(lya.z, hya.z, q.y), cp_axis(lza.z, hza.z, q.z));
+            b2[3] = cp_b2(cp_axis(lxa.w, hxa.w, q.x), cp_axis(lya.w, hya.w, q.y), cp_axis(lza.w, hza.w, q.z));
+            b2[4] = cp_b2(cp_axis(lxb.x, hxb.x, q.x), cp_axis(lyb.x, hyb.x, q.y), cp_axis(lzb.x, hzb.x, q.z));
+            b2[5] = cp_b2(cp_axis(lxb.y, hxb.y, q.x), cp_axis(lyb.y, hyb.y, q.y), cp_axis(lzb.y, hzb.y, q.z));
+            b2[6] = cp_b2(cp_axis(lxb.z, hxb.z, q.x), cp_axis(lyb.z, hyb.z, q.y), cp_axis(lzb.z, hzb.z, q.z));
+            b2[7] = cp_b2(cp_axis(lxb.w, hxb.w, q.x), cp_axis(lyb.w, hyb.w, q.y), cp_axis(lzb.w, hzb.w, q.z));
+            // children within lim: leaf children become pending; descend into the nearest inner child next, park the other inner children
+            // as one group (judged again when popped)
+            uint32_t hit = 0, near_slot = 0; float near_b2 = u2f(0x7f800000u), rest_b2 = u2f(0x7f800000u);
+            #pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const uint32_t meta = ((s < 4 ? m0 : m1) >> (8 * (s & 3))) & 0xffu;
+                const bool within = b2[s] <= best.lim;
+                const bool inner = (imask >> s) & 1u;
+                if (within && !inner && meta != 0u) lmask |= 1u << s;                      // empty slots have meta 0
+                if (within && inner) {
+                    hit |= 1u << s;
+                    if (b2[s] < near_b2) { rest_b2 = near_b2; near_b2 = b2[s]; near_slot = (uint32_t)s; }
+                    else rest_b2 = fminf(rest_b2, b2[s]);
+                }
+            }
+            have_next = hit != 0u;
+            if (hit) {
+                hit &= ~(1u << near_slot);
+                if (hit) stack[sp++] = make_uint2(child_base, (hit << 24) | (f2u(rest_b2) >> 16 << 8) | imask);
+                next = child_base + popc32(imask & ((1u << near_slot) - 1u));
+                next_b2 = near_b2;
             }
         }
-        if (hit) {
-            hit &= ~(1u << near_slot);
-            if (hit) stack[sp++] = make_uint2(child_base, (hit << 24) | (f2u(rest_b2) >> 16 << 8) | imask);
-            node_idx = child_base + popc32(imask & ((1u << near_slot) - 1u));
-            continue;
-        }
-        // pop: next child of the youngest group whose lower bound is still within lim
-        bool found = false;
-        while (sp > 0) {
-            uint2 G = stack[sp - 1];
-            const float lb = u2f(((G.y >> 8) & 0xffffu) << 16);
-            if (!(lb <= best.lim)) { sp--; continue; }
-            const uint32_t bitpos = 31u - (uint32_t)clz32(G.y);
-            const uint32_t slot = bitpos - 24u;
-            G.y &= ~(1u << bitpos);
-            if (G.y & 0xff000000u) stack[sp - 1] = G; else sp--;
-            node_idx = G.x + popc32(G.y & 0xffu & ((1u << slot) - 1u));
-            found = true;
-            break;
-        }
-        if (!found) break;
     }
 }

@@ -42,4 +42,16 @@ Td = torch.from_numpy(T.view(np.float32).reshape(-1, 8).copy()).cuda()
 for _ in range(2):
     hv.correct(Td)
 torch.cuda.synchronize()
+# closest-point correspondences on the same scan; 8(f2): the rest of the PF cycle
+ds = h.datasetView()
+hc = rmcl_b200.CPCB200(gmap)
+hc.setTsb(Tsb); hc.setParams(1.0, 0.15); hc.setDataset(ds["points"], ds["mask"])
+for _ in range(2):
+    hc.correctOnce(Tom, I, 5, 0.0)
+up.update(Pd, Ad, Tsb, beams, rmcl_b200.PFParams.defaults(0, 1))
+up.motionUpdate(Pd, Ad, synth.make_transform((0.02, 0, 0), (0, 0, 0.01)), 0.01)
+up.likelihoodStats(Ad)
+Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
+up.resample(Pd, Ad, Pn, An)
+torch.cuda.synchronize()
 print("done", rmcl_b200.kernel_launch_count())

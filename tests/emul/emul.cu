@@ -67,7 +67,7 @@ __attribute__((visibility("default"))) void emul_find(void* sc, const b2_transfo
 }
 
 __attribute__((visibility("default"))) void emul_cpc_find(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* dpts, float max_dist,
-                                                          float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* dists, double* mean_nodes, double* mean_tris)
+                                                          float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* dists, double* mean_nodes, double* mean_tris, uint32_t* per_nodes, uint32_t* per_tris)
 {
     const BvhView bvh = view(sc);
     ModelBuffers out; out.pts = pts; out.nrm = nrm; out.hits = hits; out.faces = faces; out.ranges = dists;
@@ -82,6 +82,8 @@ __attribute__((visibility("default"))) void emul_cpc_find(void* sc, const b2_tra
             CpBest b; uint32_t nn = 0, nt = 0;
             closest_point<true>(bvh, tf_apply(Tsm, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2])), b, nn, nt);
             tn += nn; tt += nt;
+            if (per_nodes) per_nodes[i] = nn;
+            if (per_tris) per_tris[i] = nt;
         }
         if (mean_nodes) *mean_nodes = (double)tn / (double)(n ? n : 1);
         if (mean_tris) *mean_tris = (double)tt / (double)(n ? n : 1);

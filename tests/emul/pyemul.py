@@ -95,9 +95,11 @@ class Scene:
                    face_ids=np.empty(n, np.uint32), dists=np.empty(n, np.float32))
         Tbm, Tsb = np.ascontiguousarray(Tbm), np.ascontiguousarray(Tsb)
         mn, mt = C.c_double(), C.c_double()
+        pn, pt = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
         lib().emul_cpc_find(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(dp), C.c_float(max_dist), _p(out["points"]), _p(out["normals"]), _p(out["hits"]),
-                            _p(out["face_ids"]), _p(out["dists"]), C.byref(mn), C.byref(mt))
+                            _p(out["face_ids"]), _p(out["dists"]), C.byref(mn), C.byref(mt), _p(pn), _p(pt))
         out["work"] = (mn.value, mt.value)
+        out["per_query"] = (pn, pt)
         return out
 
     def correct_once(self, origs_s, dirs_s, range_max, dpts, dmask, Tom, Tbo, Tsb, iterations, max_dist, fast_tail=False):
