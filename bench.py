@@ -149,8 +149,23 @@ def cpu_reference_leg(args, steps, warmup):
     return m.size / dt, dt, host_threads(), m.size
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else printed during the run (NCCL banners, library chatter)
+    was diverted to stderr by main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                   # fd 1 -> stderr for the rest of the run (C libraries included)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,7 +185,7 @@ def main():
                                  "sample": f"{steps} full C2 correctOnce steps (131072 rays + 5 reductions each) on the CPU oracle, OpenMP over rays and over reduction chunks, threads = min(CPU affinity, cgroup CPU quota); Embree/rmagine not buildable here",
                                  "host_logical_cpus": os.cpu_count()},
                 "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -333,7 +348,7 @@ def main():
             "map": {"n_nodes": info["n_nodes"], "bvh_mb": info["bvh_bytes"] / 1e6, "build_ms": info["build_ms"], "max_depth": info["max_depth"], "build_mode": info["build_mode"]},
             "result_check": {"n_meas": int(Cm["n_meas"]), "dt_norm": float(np.linalg.norm(Td["t"]))},
             "extra": extra}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -385,6 +400,7 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     # pinned host staging (like the scan of the headline step)
     Ph = torch.from_numpy(P[b:e].view(np.uint8).copy()).pin_memory().numpy().view(P.dtype).reshape(-1)
     Ah = torch.from_numpy(A[b:e].view(np.uint8).copy()).pin_memory().numpy().view(A.dtype).reshape(-1)
+    up.update(Ph, Ah, Tsb, beams, prm)               # untimed: first call sizes the staging buffers
     t0 = time.perf_counter()
     for _ in range(3):
         up.update(Ph, Ah, Tsb, beams, prm)
