@@ -89,6 +89,13 @@ B2_API int         b2_device_count(int* n);
  * rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:158): vertices/faces in HOST memory -> BVH resident in HBM of `device`. */
 B2_API int b2_mesh_create(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces,
                           int device, int build_mode, b2_mesh** out);
+/* rm::import_embree_map(file) (rmcl_ros/src/nodes/micp_localization.cpp:188, rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:158): mesh file ->
+ * map.  Self-contained readers for Stanford PLY (ascii / binary_little_endian) and Wavefront OBJ; polygons are fan-triangulated.
+ * COLLADA (.dae) needs assimp and is refused with B2_ERR_INVALID. */
+B2_API int b2_mesh_create_from_file(const char* path, int device, int build_mode, b2_mesh** out);
+/* the import step alone (host only, no device needed): malloc'ed vertex / face arrays, released with b2_mesh_file_free */
+B2_API int b2_mesh_file_load(const char* path, float** verts_xyz, uint32_t* nv, uint32_t** faces_ijk, uint32_t* nf);
+B2_API void b2_mesh_file_free(float* verts_xyz, uint32_t* faces_ijk);
 B2_API int b2_mesh_destroy(b2_mesh* m);
 B2_API int b2_mesh_get_info(const b2_mesh* m, b2_mesh_info* info);
 /* closest hit for arbitrary rays (host arrays in, host arrays out): t in (0,tfar], tie -> smaller face id.
@@ -128,6 +135,13 @@ B2_API int b2_rcc_find(b2_rcc* h, const b2_transform* Tbm_est);
 B2_API int b2_rcc_set_correspondence_type(b2_rcc* h, int type);
 /* Correspondences{CPU,CUDA}::computeCrossStatistics, rmcl/src/rmcl/registration/CorrespondencesCPU.cpp:10-39 (CUDA twin CorrespondencesCUDA.cpp:9-30) */
 B2_API int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T_snew_sold, double convergence_progress, b2_cross_stats* out_host);
+/* Scan-vs-map segmentation: the classification of ScanMapSegmentationEmbreeNode::scanCB (rmcl_ros/src/nodes/filter/
+ * scan_map_segmentation_embree.cpp:84-187).  Call after b2_rcc_set_ranges (the real scan) and b2_rcc_find(T_sensor_map with Tsb = identity,
+ * or Tbm with the handle's Tsb): compares real and simulated ranges / normals per ray and returns the two outlier clouds in raster order
+ * (HOST buffers of cap_* points x 3 floats; n_* receive the full counts even when the capacity is smaller) and optionally one label per
+ * ray (0 none, 1 outlier_scan, 2 outlier_map). */
+B2_API int b2_rcc_segment(b2_rcc* h, float min_dist_outlier_scan, float min_dist_outlier_map, float* outlier_scan_host, uint32_t cap_scan, uint32_t* n_scan,
+                          float* outlier_map_host, uint32_t cap_map, uint32_t* n_map, uint8_t* labels_host);
 /* modelView()/datasetView(), Correspondences.hpp:47-62: device pointers (points/normals packed xyz, hits/mask u8) + our extra face ids / ranges */
 B2_API int b2_rcc_model_view(b2_rcc* h, float** points, float** normals, uint8_t** hits, uint32_t** face_ids, float** ranges, uint32_t* n);
 B2_API int b2_rcc_dataset_view(b2_rcc* h, float** points, uint8_t** mask, uint32_t* n);

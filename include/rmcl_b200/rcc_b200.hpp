@@ -30,6 +30,9 @@ class B200Map {
 public:
     B200Map(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces, int device = 0, int build_mode = B2_BUILD_DEVICE_LBVH)
     { b2_check(b2_mesh_create(verts_xyz, n_vertices, faces_ijk, n_faces, device, build_mode, &m_), "B200Map"); }
+    // rm::import_embree_map(file) twin (micp_localization.cpp:188): .ply / .obj
+    explicit B200Map(const std::string& mesh_file, int device = 0, int build_mode = B2_BUILD_DEVICE_LBVH)
+    { b2_check(b2_mesh_create_from_file(mesh_file.c_str(), device, build_mode, &m_), "B200Map"); }
     ~B200Map() { b2_mesh_destroy(m_); }
     B200Map(const B200Map&) = delete; B200Map& operator=(const B200Map&) = delete;
     b2_mesh* handle() const { return m_; }
@@ -102,6 +105,18 @@ public:
                                      reinterpret_cast<b2_transform*>(T_onew_oold), reinterpret_cast<b2_cross_stats*>(Cmerged_o)), "correctOnce");
         outdated = false;
         return out;
+    }
+    // ScanMapSegmentationEmbreeNode::scanCB classification (scan_map_segmentation_embree.cpp:110-187): after setRanges(real scan) + find(pose)
+    struct Segmentation { std::vector<rm::Vector3f> outlier_scan, outlier_map; };
+    Segmentation segment(float min_dist_outlier_scan, float min_dist_outlier_map)
+    {
+        uint32_t n = 0, ns = 0, nm = 0;
+        b2_check(b2_rcc_model_view(h_, nullptr, nullptr, nullptr, nullptr, nullptr, &n), "segment");
+        Segmentation r; r.outlier_scan.resize(n); r.outlier_map.resize(n);
+        b2_check(b2_rcc_segment(h_, min_dist_outlier_scan, min_dist_outlier_map, reinterpret_cast<float*>(r.outlier_scan.data()), n, &ns,
+                                reinterpret_cast<float*>(r.outlier_map.data()), n, &nm, nullptr), "segment");
+        r.outlier_scan.resize(ns); r.outlier_map.resize(nm);
+        return r;
     }
     void setStream(void* cuda_stream) { b2_check(b2_rcc_set_stream(h_, cuda_stream), "setStream"); }
     b2_rcc* handle() const { return h_; }

@@ -1108,6 +1108,41 @@ void orc_pf_gladiator_resample(uint32_t n_all, const orc_transform* poses, const
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* scan-vs-map segmentation (scan_map_segmentation_embree.cpp:110-187)                               */
+/* ------------------------------------------------------------------------------------------------ */
+void orc_segment(uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max,
+                 const float* ranges_real, const float* ranges_sim, const float* normals_sim, float min_dist_outlier_scan, float min_dist_outlier_map,
+                 float* outlier_scan, uint32_t* n_scan, float* outlier_map, uint32_t* n_map, uint8_t* labels)
+{
+    uint32_t ns = 0, nm = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t oi = n_origs == 1 ? 0 : i;
+        const orc_vec3 dir = v3(dirs_s[3 * i], dirs_s[3 * i + 1], dirs_s[3 * i + 2]);
+        const orc_vec3 orig = v3(origs_s[3 * oi], origs_s[3 * oi + 1], origs_s[3 * oi + 2]);
+        const float rr = ranges_real[i], rs = ranges_sim[i];
+        const int real_valid = (range_min <= rr) && (rr <= range_max);           /* model.range.inside, :121-122 */
+        const int sim_valid = (range_min <= rs) && (rs <= range_max);
+        int label = 0; orc_vec3 p = v3(0, 0, 0);
+        if (real_valid) {
+            const orc_vec3 preal = v3_add(v3_scale(dir, rr), orig);              /* :126 */
+            if (sim_valid) {
+                const orc_vec3 pint = v3_scale(dir, rs);                          /* :130 -- without the origin, as in the reference */
+                const orc_vec3 nint = v3_normalize(v3(normals_sim[3 * i], normals_sim[3 * i + 1], normals_sim[3 * i + 2]));   /* :131-132 */
+                const float spd = v3_dot(v3_sub(preal, pint), nint);              /* :134 */
+                const orc_vec3 pmesh = v3_add(preal, v3_scale(nint, spd));        /* :135 */
+                const float plane_distance = v3_l2norm(v3_sub(pmesh, preal));     /* :136 */
+                if (rr < rs) { if (plane_distance > min_dist_outlier_scan) { label = 1; p = preal; } }     /* :138-149 */
+                else         { if (plane_distance > min_dist_outlier_map)  { label = 2; p = pint; } }      /* :150-161 */
+            } else { label = 1; p = preal; }                                       /* :164-171 */
+        } else if (sim_valid) { label = 2; p = v3_add(v3_scale(dir, rs), orig); }  /* :173-182 */
+        if (labels) labels[i] = (uint8_t)label;
+        if (label == 1) { put3(outlier_scan, ns, p); ns++; }
+        if (label == 2) { put3(outlier_map, nm, p); nm++; }
+    }
+    *n_scan = ns; *n_map = nm;
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

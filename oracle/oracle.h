@@ -151,6 +151,13 @@ void orc_pf_gladiator_resample(uint32_t n_all, const orc_transform* poses, const
                                const uint32_t* raw, const float* normals, const orc_gladiator_config* cfg,
                                orc_transform* poses_new, orc_particle_attr* attrs_new);
 
+/* scan-vs-map segmentation: the classification loop of ScanMapSegmentationEmbreeNode (rmcl_ros/src/nodes/filter/
+ * scan_map_segmentation_embree.cpp:110-187) given the simulated ranges + normals (sensor frame) and the real ranges.  Outputs the two
+ * outlier clouds in raster order (n x 3 capacity each) and, optionally, a per-ray label (0 none, 1 scan outlier, 2 map outlier). */
+void orc_segment(uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max,
+                 const float* ranges_real, const float* ranges_sim, const float* normals_sim, float min_dist_outlier_scan, float min_dist_outlier_map,
+                 float* outlier_scan, uint32_t* n_scan, float* outlier_map, uint32_t* n_map, uint8_t* labels);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -73,7 +73,7 @@ EXPORTS = [
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
-    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms",
+    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free",
 ]
 
 
@@ -90,8 +90,9 @@ def load_library():
     lib.b2_last_error.restype = C.c_char_p
     lib.b2_kernel_launch_count.restype = C.c_uint64
     for name in EXPORTS:
-        if name not in ("b2_last_error", "b2_kernel_launch_count"):
+        if name not in ("b2_last_error", "b2_kernel_launch_count", "b2_mesh_file_free"):
             getattr(lib, name).restype = C.c_int
+    lib.b2_mesh_file_free.restype = None
     _lib = lib
     return lib
 
@@ -133,6 +134,19 @@ def _devptr(x):
     raise TypeError(type(x))
 
 
+def read_mesh_file(path):
+    """Import step of Map.from_file alone (host only): -> (vertices (nv,3) float32, faces (nf,3) uint32)."""
+    lib = load_library()
+    v, f, nv, nf = C.POINTER(C.c_float)(), C.POINTER(C.c_uint32)(), C.c_uint32(), C.c_uint32()
+    _chk(lib.b2_mesh_file_load(os.fsencode(path), C.byref(v), C.byref(nv), C.byref(f), C.byref(nf)))
+    try:
+        V = np.ctypeslib.as_array(v, (nv.value, 3)).copy()
+        F = np.ctypeslib.as_array(f, (nf.value, 3)).copy()
+    finally:
+        lib.b2_mesh_file_free(v, f)
+    return V, F
+
+
 class Map:
     """Triangle mesh + in-HBM BVH; stands in for rm::EmbreeMap / rm::OptixMap (rm::import_embree_map, micp_localization.cpp:188)."""
 
@@ -146,6 +160,18 @@ class Map:
         _chk(lib.b2_mesh_create(_p(verts), C.c_uint32(len(verts)), _p(faces), C.c_uint32(len(faces)), C.c_int(device), C.c_int(build_mode), C.byref(h)))
         self._h = h
         self.device = device
+
+    @classmethod
+    def from_file(cls, path, device=0, build_mode=None):
+        """rm::import_embree_map(file) twin: .ply (ascii / binary little endian) or .obj."""
+        lib = load_library()
+        if build_mode is None:
+            build_mode = int(os.environ.get("B2_BUILD_MODE", B2_BUILD_DEVICE_LBVH))
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _chk(lib.b2_mesh_create_from_file(os.fsencode(path), C.c_int(device), C.c_int(build_mode), C.byref(h)))
+        self._h, self.device = h, device
+        return self
 
     def close(self):
         if getattr(self, "_h", None):
@@ -286,6 +312,18 @@ class RCCB200:
         out = dict(points=np.empty((n.value, 3), np.float32), mask=np.empty(n.value, np.uint8))
         _chk(load_library().b2_rcc_download_dataset(self._h, _p(out["points"]), _p(out["mask"])))
         return out
+
+    def segment(self, min_dist_outlier_scan=0.15, min_dist_outlier_map=0.15):
+        """ScanMapSegmentationEmbreeNode::scanCB classification (scan_map_segmentation_embree.cpp:110-187) after setRanges(real scan) and
+        find(pose): -> (outlier_scan (k,3), outlier_map (m,3), labels (n,))."""
+        nn = C.c_uint32()
+        _chk(load_library().b2_rcc_model_view(self._h, None, None, None, None, None, C.byref(nn)))
+        n = nn.value
+        a, b, lab = np.zeros((max(n, 1), 3), np.float32), np.zeros((max(n, 1), 3), np.float32), np.zeros(max(n, 1), np.uint8)
+        na, nb = C.c_uint32(), C.c_uint32()
+        _chk(load_library().b2_rcc_segment(self._h, C.c_float(min_dist_outlier_scan), C.c_float(min_dist_outlier_map), _p(a), C.c_uint32(n), C.byref(na),
+                                           _p(b), C.c_uint32(n), C.byref(nb), _p(lab)))
+        return a[: na.value].copy(), b[: nb.value].copy(), lab[:n].copy()
 
     def correctOnce(self, Tom, Tbo, iterations=5, convergence_progress=0.0, ranges=None):
         """MICPLocalizationNode::correctOnce for this sensor (micp_localization.cpp:899-984), fully on the device.

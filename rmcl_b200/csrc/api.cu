@@ -110,6 +110,32 @@ extern "C" int b2_mesh_create(const float* verts, uint32_t nv, const uint32_t* f
     return B2_OK;
 }
 
+int b2_load_mesh_file(const char* path, std::vector<float>& V, std::vector<uint32_t>& F, const char** err_out);   // mesh_io.cpp
+
+extern "C" int b2_mesh_file_load(const char* path, float** verts, uint32_t* nv, uint32_t** faces, uint32_t* nf)
+{
+    NOTNULL(path); NOTNULL(verts); NOTNULL(nv); NOTNULL(faces); NOTNULL(nf);
+    *verts = nullptr; *faces = nullptr; *nv = 0; *nf = 0;
+    std::vector<float> V; std::vector<uint32_t> F; const char* err = "";
+    const int rc = b2_load_mesh_file(path, V, F, &err);
+    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : B2_ERR_INVALID, "mesh import of '%s' failed: %s", path, err);
+    float* v = (float*)malloc(sizeof(float) * V.size()); uint32_t* f = (uint32_t*)malloc(sizeof(uint32_t) * F.size());
+    if (!v || !f) { free(v); free(f); return fail(B2_ERR_OOM, "out of host memory"); }
+    memcpy(v, V.data(), sizeof(float) * V.size()); memcpy(f, F.data(), sizeof(uint32_t) * F.size());
+    *verts = v; *faces = f; *nv = (uint32_t)(V.size() / 3); *nf = (uint32_t)(F.size() / 3);
+    return B2_OK;
+}
+extern "C" void b2_mesh_file_free(float* verts, uint32_t* faces) { free(verts); free(faces); }
+
+extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_mode, b2_mesh** out)
+{
+    NOTNULL(out); *out = nullptr; NOTNULL(path);
+    std::vector<float> V; std::vector<uint32_t> F; const char* err = "";
+    const int rc = b2_load_mesh_file(path, V, F, &err);
+    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : B2_ERR_INVALID, "mesh import of '%s' failed: %s", path, err);
+    return b2_mesh_create(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), device, build_mode, out);
+}
+
 extern "C" int b2_mesh_destroy(b2_mesh* m)
 {
     if (!m) return B2_OK;
@@ -201,6 +227,8 @@ struct b2_rcc {
     unsigned int seq = 0;               // completion sequence number written by k_icp_loop into pin->flag
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
+    uint32_t n_ranges_in = 0;           // real ranges resident in d_ranges_in (set_ranges / correct_once_ranges), needed by b2_rcc_segment
+    DevBuf<uint32_t> d_seg_counts, d_seg_offsets, d_seg_totals; DevBuf<float> d_seg_scan, d_seg_map; DevBuf<uint8_t> d_seg_labels;
     int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
     uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
 };
@@ -373,7 +401,7 @@ static int ranges_to_dataset(b2_rcc* h, const float* ranges, uint32_t n, int src
     CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges, sizeof(float) * n, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     k_dataset_from_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, n, h->range_min, h->range_max, h->d_dpts.p, h->d_dmask.p);
     LAUNCHED();
-    h->n_dataset = n;
+    h->n_dataset = n; h->n_ranges_in = n;
     return B2_OK;
 }
 
@@ -473,6 +501,39 @@ extern "C" int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T, double 
     return B2_OK;
 }
 
+extern "C" int b2_rcc_segment(b2_rcc* h, float min_dist_outlier_scan, float min_dist_outlier_map, float* outlier_scan, uint32_t cap_scan, uint32_t* n_scan,
+                              float* outlier_map, uint32_t cap_map, uint32_t* n_map, uint8_t* labels)
+{
+    NOTNULL(h); NOTNULL(n_scan); NOTNULL(n_map);
+    *n_scan = 0; *n_map = 0;
+    CU(cudaSetDevice(h->map->device));
+    if (h->corr_type != B2_CORR_RCC || !h->has_model) return fail(B2_ERR_INVALID, "segmentation needs a ray-casting handle with a sensor model");
+    if (!h->found || h->n_model != h->n) return fail(B2_ERR_INVALID, "segmentation before find");
+    if (h->n_ranges_in != h->n) return fail(B2_ERR_INVALID, "segmentation needs the real ranges (set_ranges), have %u of %u", h->n_ranges_in, h->n);
+    const uint32_t n = h->n;
+    if (n == 0) return B2_OK;
+    const uint32_t blocks = (n + B2_SEG_BLOCK - 1) / B2_SEG_BLOCK;
+    RES(h->d_seg_counts.reserve(2 * (size_t)blocks)); RES(h->d_seg_offsets.reserve(2 * (size_t)blocks)); RES(h->d_seg_totals.reserve(2));
+    RES(h->d_seg_scan.reserve(3 * (size_t)n)); RES(h->d_seg_map.reserve(3 * (size_t)n)); RES(h->d_seg_labels.reserve(n));
+    const RayModel m = ray_model(h);
+    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->d_mnrm.p, min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, nullptr, nullptr, nullptr, nullptr);
+    LAUNCHED();
+    k_segment_scan<<<1, 1024, 0, h->stream>>>(h->d_seg_counts.p, blocks, h->d_seg_offsets.p, h->d_seg_totals.p);
+    LAUNCHED();
+    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->d_mnrm.p, min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, h->d_seg_offsets.p,
+                                                      h->d_seg_scan.p, h->d_seg_map.p, h->d_seg_labels.p);
+    LAUNCHED();
+    uint32_t tot[2] = {0, 0};
+    CU(cudaMemcpyAsync(tot, h->d_seg_totals.p, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *n_scan = tot[0]; *n_map = tot[1];
+    if (outlier_scan && std::min(tot[0], cap_scan)) CU(cudaMemcpyAsync(outlier_scan, h->d_seg_scan.p, sizeof(float) * 3 * (size_t)std::min(tot[0], cap_scan), cudaMemcpyDeviceToHost, h->stream));
+    if (outlier_map && std::min(tot[1], cap_map)) CU(cudaMemcpyAsync(outlier_map, h->d_seg_map.p, sizeof(float) * 3 * (size_t)std::min(tot[1], cap_map), cudaMemcpyDeviceToHost, h->stream));
+    if (labels) CU(cudaMemcpyAsync(labels, h->d_seg_labels.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
 extern "C" int b2_rcc_model_view(b2_rcc* h, float** p, float** nr, uint8_t** hi, uint32_t** f, float** r, uint32_t* n)
 {
     NOTNULL(h);
@@ -525,7 +586,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
             CU(cudaEventRecord(h->ev_aux, h->stream));                    // the side stream starts after whatever the main stream had in flight BEFORE this call
             CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
         }
-        h->n_dataset = h->n;
+        h->n_dataset = h->n; h->n_ranges_in = h->n;
     }
     // the find kernel does not read the dataset: the scan is uploaded + unpacked on the side stream WHILE it runs (and the host-side
     // cost of issuing the copy is hidden behind the already launched find)

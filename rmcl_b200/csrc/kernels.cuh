@@ -607,6 +607,89 @@ __global__ void __launch_bounds__(B2_FIND_BLOCK) k_cpc_find(BvhView bvh, uint32_
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------------
+// scan-vs-map segmentation: classification loop of ScanMapSegmentationEmbreeNode
+// (rmcl_ros/src/nodes/filter/scan_map_segmentation_embree.cpp:110-187) on the model buffers left by find() and the real ranges.
+// label 0: neither cloud, 1: outlier_scan (point = preal), 2: outlier_map (point = pint)
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV uint32_t segment_classify(const RayModel& model, uint32_t i, float rr, float rs, V3 nsim, float min_scan, float min_map, V3& p)
+{
+    const uint32_t oi = model.n_origs == 1 ? 0 : i;
+    const V3 dir = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
+    const V3 orig = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
+    const bool real_valid = (model.range_min <= rr) && (rr <= model.range_max);           // model.range.inside, :121-122
+    const bool sim_valid = (model.range_min <= rs) && (rs <= model.range_max);
+    p = mk3(0.f, 0.f, 0.f);
+    if (real_valid) {
+        const V3 preal = v_add(v_scale(dir, rr), orig);                                   // :126
+        if (!sim_valid) { p = preal; return 1u; }                                         // :164-171
+        const V3 pint = v_scale(dir, rs);                                                 // :130 (no origin, as in the reference)
+        const V3 nint = v_normalize(nsim);                                                // :131-132
+        const float spd = v_dot(v_sub(preal, pint), nint);                                // :134
+        const V3 pmesh = v_add(preal, v_scale(nint, spd));                                // :135
+        const float plane_distance = v_l2norm(v_sub(pmesh, preal));                       // :136
+        if (rr < rs) { if (plane_distance > min_scan) { p = preal; return 1u; } }         // :138-149
+        else         { if (plane_distance > min_map)  { p = pint;  return 2u; } }         // :150-161
+        return 0u;
+    }
+    if (sim_valid) { p = v_add(v_scale(dir, rs), orig); return 2u; }                      // :173-182
+    return 0u;
+}
+
+#ifdef __CUDACC__
+#define B2_SEG_BLOCK 256
+// pass 1 (counts != nullptr, out_* == nullptr): per-block counts of both classes.  pass 3: recompute and write each outlier at
+// block offset + its rank inside the block, so both clouds come out in raster order like the reference's push_back loop.
+__global__ void __launch_bounds__(B2_SEG_BLOCK) k_segment(RayModel model, const float* __restrict__ ranges_real, const float* __restrict__ ranges_sim,
+                                                          const float* __restrict__ normals_sim, float min_scan, float min_map, uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ offsets, float* __restrict__ out_scan, float* __restrict__ out_map, uint8_t* __restrict__ labels)
+{
+    __shared__ uint32_t s_cnt[2][B2_SEG_BLOCK / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t label = 0u; V3 p = mk3(0.f, 0.f, 0.f);
+    if (i < model.n) label = segment_classify(model, i, ranges_real[i], ranges_sim[i], mk3(normals_sim[3 * i], normals_sim[3 * i + 1], normals_sim[3 * i + 2]), min_scan, min_map, p);
+    const uint32_t b1 = __ballot_sync(0xffffffffu, label == 1u), b2 = __ballot_sync(0xffffffffu, label == 2u);
+    if (lane == 0) { s_cnt[0][warp] = __popc(b1); s_cnt[1][warp] = __popc(b2); }
+    __syncthreads();
+    uint32_t before1 = 0u, before2 = 0u, tot1 = 0u, tot2 = 0u;
+    #pragma unroll
+    for (uint32_t w = 0; w < B2_SEG_BLOCK / 32; w++) { if (w < warp) { before1 += s_cnt[0][w]; before2 += s_cnt[1][w]; } tot1 += s_cnt[0][w]; tot2 += s_cnt[1][w]; }
+    if (!out_scan) {
+        if (threadIdx.x == 0) { counts[2 * blockIdx.x] = tot1; counts[2 * blockIdx.x + 1] = tot2; }
+        return;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+    if (label == 1u) { const size_t o = (size_t)offsets[2 * blockIdx.x] + before1 + __popc(b1 & lt); out_scan[3 * o] = p.x; out_scan[3 * o + 1] = p.y; out_scan[3 * o + 2] = p.z; }
+    if (label == 2u) { const size_t o = (size_t)offsets[2 * blockIdx.x + 1] + before2 + __popc(b2 & lt); out_map[3 * o] = p.x; out_map[3 * o + 1] = p.y; out_map[3 * o + 2] = p.z; }
+    if (labels && i < model.n) labels[i] = (uint8_t)label;
+}
+// pass 2: exclusive scan of the per-block counts (one block; a few thousand entries at most), totals to totals[0..1]
+__global__ void __launch_bounds__(1024) k_segment_scan(const uint32_t* __restrict__ counts, uint32_t n_blocks, uint32_t* __restrict__ offsets, uint32_t* __restrict__ totals)
+{
+    __shared__ uint32_t s[2][1024];
+    __shared__ uint32_t carry[2];
+    if (threadIdx.x == 0) { carry[0] = 0u; carry[1] = 0u; }
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
+        const uint32_t b = base + threadIdx.x;
+        const uint32_t v0 = b < n_blocks ? counts[2 * b] : 0u, v1 = b < n_blocks ? counts[2 * b + 1] : 0u;
+        s[0][threadIdx.x] = v0; s[1][threadIdx.x] = v1;
+        __syncthreads();
+        for (uint32_t d = 1; d < 1024u; d <<= 1) {                      // Hillis-Steele inclusive scan
+            const uint32_t a0 = threadIdx.x >= d ? s[0][threadIdx.x - d] : 0u, a1 = threadIdx.x >= d ? s[1][threadIdx.x - d] : 0u;
+            __syncthreads();
+            s[0][threadIdx.x] += a0; s[1][threadIdx.x] += a1;
+            __syncthreads();
+        }
+        if (b < n_blocks) { offsets[2 * b] = carry[0] + s[0][threadIdx.x] - v0; offsets[2 * b + 1] = carry[1] + s[1][threadIdx.x] - v1; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry[0] += s[0][1023]; carry[1] += s[1][1023]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Correspondences*::computeCrossStatistics (CorrespondencesCPU.cpp:10-39): N-element masked reduction -> CrossStatistics.
 // Deterministic: per-block partials, the last block to finish sums them in block order.  With `icp` set, the last block also
 // performs the rest of the inner iteration (frame changes, Umeyama, compose) so one correctOnce needs 1 + iterations launches.

@@ -103,6 +103,22 @@ __attribute__((visibility("default"))) void emul_gladiator(uint32_t n_all, const
     }
 }
 
+__attribute__((visibility("default"))) void emul_segment(uint32_t n, const float* origs, uint32_t n_origs, const float* dirs, float range_min, float range_max, const float* rr,
+                                                         const float* rs, const float* nsim, float min_scan, float min_map, float* out_scan, uint32_t* n_scan, float* out_map,
+                                                         uint32_t* n_map, uint8_t* labels)
+{
+    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = range_min; m.range_max = range_max; m.width = n; m.height = 1;
+    uint32_t a = 0, b = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        V3 p;
+        const uint32_t l = segment_classify(m, i, rr[i], rs[i], mk3(nsim[3 * i], nsim[3 * i + 1], nsim[3 * i + 2]), min_scan, min_map, p);
+        labels[i] = (uint8_t)l;
+        if (l == 1u) { out_scan[3 * a] = p.x; out_scan[3 * a + 1] = p.y; out_scan[3 * a + 2] = p.z; a++; }
+        if (l == 2u) { out_map[3 * b] = p.x; out_map[3 * b + 1] = p.y; out_map[3 * b + 2] = p.z; b++; }
+    }
+    *n_scan = a; *n_map = b;
+}
+
 // sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
 __attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
                                                                   const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)

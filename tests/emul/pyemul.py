@@ -122,6 +122,17 @@ class Scene:
         return attrs
 
 
+def segment(origs_s, dirs_s, range_min, range_max, ranges_real, ranges_sim, normals_sim, min_scan, min_map):
+    origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
+    n = len(dirs_s)
+    rr, rs, ns_ = _f32(ranges_real).reshape(-1), _f32(ranges_sim).reshape(-1), _f32(normals_sim).reshape(-1, 3)
+    a, b, lab = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+    na, nb = C.c_uint32(), C.c_uint32()
+    lib().emul_segment(C.c_uint32(n), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_min), C.c_float(range_max), _p(rr), _p(rs), _p(ns_),
+                       C.c_float(min_scan), C.c_float(min_map), _p(a), C.byref(na), _p(b), C.byref(nb), _p(lab))
+    return a[: na.value].copy(), b[: nb.value].copy(), lab
+
+
 def gladiator(poses, attrs, first, n_local, cfg, seed, step):
     poses, attrs = np.ascontiguousarray(poses), np.ascontiguousarray(attrs)
     Pn, An = np.zeros(n_local, poses.dtype), np.zeros(n_local, attrs.dtype)

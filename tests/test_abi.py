@@ -60,3 +60,48 @@ def test_product_does_not_reference_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read().lower()
+
+
+def _write_ply(path, V, F, binary):
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat " + (b"binary_little_endian" if binary else b"ascii") + b" 1.0\ncomment test\n")
+        f.write(f"element vertex {len(V)}\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\n".encode())
+        f.write(f"element face {len(F)}\nproperty list uchar int vertex_indices\nend_header\n".encode())
+        for v in V:
+            f.write(struct.pack("<fffB", *v, 7) if binary else f"{v[0]!r} {v[1]!r} {v[2]!r} 7\n".encode())
+        for t in F:
+            f.write(struct.pack("<B" + "i" * len(t), len(t), *t) if binary else (" ".join(map(str, [len(t), *t])) + "\n").encode())
+
+
+def test_mesh_file_import(tmp_path):
+    """SURVEY 8f4: rm::import_embree_map stand-in -- PLY (ascii, binary) and OBJ readers, polygons fan-triangulated, errors reported."""
+    import rmcl_b200
+    from rmcl_b200 import synth
+    V, F = synth.cube(3)
+    V = V.astype(np.float32)
+    for binary in (False, True):
+        p = str(tmp_path / f"m{int(binary)}.ply")
+        _write_ply(p, [tuple(float(x) for x in v) for v in V], [tuple(int(i) for i in t) for t in F], binary)
+        V2, F2 = rmcl_b200.read_mesh_file(p)
+        assert np.array_equal(V2, V) and np.array_equal(F2, F)
+    q = str(tmp_path / "quad.ply")
+    _write_ply(q, [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0.5, 2, 0)], [(0, 1, 2, 3), (3, 2, 4)], False)
+    Vq, Fq = rmcl_b200.read_mesh_file(q)
+    assert Fq.tolist() == [[0, 1, 2], [0, 2, 3], [3, 2, 4]]
+    o = str(tmp_path / "m.obj")
+    with open(o, "w") as f:
+        f.write("# test\n" + "".join(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n" for v in V.tolist()) + "vn 0 0 1\n")
+        f.write("".join(f"f {t[0] + 1}//1 {t[1] + 1}//1 {t[2] + 1}//1\n" for t in F.tolist()[:-1]))
+        t = F.tolist()[-1]
+        f.write(f"f {t[0] - len(V)} {t[1] - len(V)} {t[2] - len(V)}\n")               # negative (relative) indices
+    Vo, Fo = rmcl_b200.read_mesh_file(o)
+    assert np.array_equal(Vo, V) and np.array_equal(Fo, F)
+    for bad, txt in (("x.dae", "<COLLADA/>"), ("empty.ply", "ply\nformat ascii 1.0\nelement vertex 0\nproperty float x\nproperty float y\nproperty float z\nend_header\n"),
+                     ("oob.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")):
+        bp = tmp_path / bad
+        bp.write_text(txt)
+        with pytest.raises(rmcl_b200.B2Error):
+            rmcl_b200.read_mesh_file(str(bp))
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.read_mesh_file(str(tmp_path / "missing.ply"))

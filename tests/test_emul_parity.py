@@ -170,3 +170,11 @@ def test_gladiator_bit_exact(pe, po, synth):
     Pe, Ae, rawe, nrme = pe.gladiator(P, A, 1000, n - 1000, cfg, 99, 7)
     assert np.array_equal(raw, rawe) and np.array_equal(nrm, nrme)
     assert Pn.tobytes() == Pe.tobytes() and An.tobytes() == Ae.tobytes()
+
+
+def test_segmentation_bit_exact(pe, po, synth):
+    from test_oracle import _segmentation_case
+    sc, m, o, d, T, Tsb, sim, real = _segmentation_case(po, synth)
+    ra = po.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
+    rb = pe.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
+    assert all(np.array_equal(x, y) for x, y in zip(ra, rb))

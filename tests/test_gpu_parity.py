@@ -496,3 +496,46 @@ def test_gladiator_resample_gpu(po, synth):
     assert np.concatenate([a[0], b[0]]).tobytes() == whole_P.tobytes() and np.concatenate([a[1], b[1]]).tobytes() == whole_A.tobytes()
     with pytest.raises(rmcl_b200.B2Error):
         up.resample(Pd, Ad, Pd, Ad, cfg)                                                            # in place is refused
+
+
+@pytest.mark.parametrize("name", ["cube29", "building:200000"])
+def test_segmentation_gpu(po, synth, name):
+    """scan-vs-map segmentation through the C ABI == oracle: labels and both outlier clouds (raster order), bit for bit."""
+    import rmcl_b200
+    from test_oracle import _segmentation_case
+    osc = oracle_scene(name)
+    m = synth.c2_sensor() if name != "cube29" else synth.c1_sensor()
+    o, d = po.model_rays(m)
+    T = synth.building_gt_pose() if name != "cube29" else synth.make_transform([0.5, -0.3, 0.2], [0, 0, 0.4])
+    Tsb = synth.scenario_tsb()
+    sim = osc.simulate(T, Tsb, o, d, m.range_max)
+    rng = np.random.default_rng(4)
+    real = sim["ranges"] + rng.normal(0, 0.01, len(o if len(o) > 1 else d)).astype(np.float32)
+    k = rng.permutation(len(real))
+    real[k[:300]] *= 0.6; real[k[300:600]] *= 1.3; real[k[600:650]] = m.range_max + 1; real[k[650:670]] = 0.0
+    h = _rcc(synth, name, m, Tsb)
+    h.setRanges(real)
+    h.find(T)
+    a, b, lab = h.segment(0.15, 0.1)
+    ra, rb, rl = po.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
+    assert np.array_equal(lab, rl) and np.array_equal(a, ra) and np.array_equal(b, rb)
+    assert len(a) >= 300 and len(b) >= 300
+    h2 = _rcc(synth, name, m, Tsb)
+    with pytest.raises(rmcl_b200.B2Error):
+        h2.segment()                                                     # before find / without ranges
+
+
+def test_map_from_file_gpu(tmp_path, synth):
+    """Map.from_file (rm::import_embree_map twin): the imported mesh traces exactly like the in-memory one."""
+    import rmcl_b200
+    from test_abi import _write_ply
+    V, F = mesh("cube29")
+    p = str(tmp_path / "cube.ply")
+    _write_ply(p, [tuple(float(x) for x in v) for v in V], [tuple(int(i) for i in t) for t in F], True)
+    o, d = random_rays(20000, -9.5, 9.5, seed=3)
+    a = rmcl_b200.Map.from_file(p).intersect(o, d)
+    b = gpu_map("cube29").intersect(o, d)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    (tmp_path / "bad.dae").write_text("<COLLADA/>")
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map.from_file(str(tmp_path / "bad.dae"))

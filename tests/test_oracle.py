@@ -366,3 +366,46 @@ def test_gladiator_resample_oracle(po, synth):
     a = po.pf_gladiator_resample(P, A, 0, h, raw[:h], nrm[:h], cfg)
     b = po.pf_gladiator_resample(P, A, h, n - h, raw[h:], nrm[h:], cfg)
     assert np.concatenate([a[0], b[0]]).tobytes() == Pn.tobytes() and np.concatenate([a[1], b[1]]).tobytes() == An.tobytes()
+
+
+def _segmentation_case(po, synth, name="cube29"):
+    """A scan of the map with an extra obstacle in front of a wall (scan outliers), a range pushed behind the wall (map outliers),
+    dropped returns and out-of-range values."""
+    sc = oracle_scene(name)
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    T, Tsb = synth.make_transform([0.5, -0.3, 0.2], [0, 0, 0.4]), synth.make_transform()
+    sim = sc.simulate(T, Tsb, o, d, m.range_max)
+    real = sim["ranges"].copy()
+    rng = np.random.default_rng(2)
+    real += rng.normal(0, 0.01, len(real)).astype(np.float32)
+    k = rng.permutation(len(real))
+    real[k[:100]] *= 0.6                  # something in front of the surface
+    real[k[100:200]] *= 1.3               # the ray cut the surface
+    real[k[200:230]] = m.range_max + 1    # no return
+    real[k[230:240]] = 0.0                # below range.min
+    return sc, m, o, d, T, Tsb, sim, real
+
+
+def test_segmentation_oracle(po, synth):
+    """scan_map_segmentation_embree.cpp:110-187 restated; labels against an independent numpy evaluation."""
+    sc, m, o, d, T, Tsb, sim, real = _segmentation_case(po, synth)
+    a, b, lab = po.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.15)
+    rv = (real >= m.range_min) & (real <= m.range_max)
+    sv = (sim["ranges"] >= m.range_min) & (sim["ranges"] <= m.range_max)
+    n = sim["normals"].astype(np.float64)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    preal, pint = d.astype(np.float64) * real[:, None] + o, d.astype(np.float64) * sim["ranges"][:, None]
+    pd = np.abs(((preal - pint) * n).sum(1))
+    expect = np.zeros(len(real), np.uint8)
+    both = rv & sv
+    margin = np.abs(pd - 0.15) > 1e-4                                   # away from the threshold the float and double evaluations agree
+    expect[both & (real < sim["ranges"]) & (pd > 0.15)] = 1
+    expect[both & ~(real < sim["ranges"]) & (pd > 0.15)] = 2
+    expect[rv & ~sv] = 1
+    expect[~rv & sv] = 2
+    assert np.array_equal(lab[margin | ~both], expect[margin | ~both])
+    assert (lab == 1).sum() == len(a) >= 100 and (lab == 2).sum() == len(b) >= 100
+    assert np.allclose(a, preal[lab == 1], atol=1e-5)                     # raster order
+    far = (lab == 2) & rv
+    assert np.allclose(b[(lab == 2).nonzero()[0].searchsorted(far.nonzero()[0])], pint[far], atol=1e-5)
