@@ -96,6 +96,8 @@ B2_API int b2_mesh_create_from_file(const char* path, int device, int build_mode
 /* the import step alone (host only, no device needed): malloc'ed vertex / face arrays, released with b2_mesh_file_free */
 B2_API int b2_mesh_file_load(const char* path, float** verts_xyz, uint32_t* nv, uint32_t** faces_ijk, uint32_t* nf);
 B2_API void b2_mesh_file_free(float* verts_xyz, uint32_t* faces_ijk);
+/* Drops the creator's reference.  b2_rcc / b2_pf handles created on the map hold their own references (the reference shares its map through
+ * rm::EmbreeMapPtr, a shared_ptr, micp_localization.cpp:545), so map and handles may be destroyed in any order. */
 B2_API int b2_mesh_destroy(b2_mesh* m);
 B2_API int b2_mesh_get_info(const b2_mesh* m, b2_mesh_info* info);
 /* closest hit for arbitrary rays (host arrays in, host arrays out): t in (0,tfar], tie -> smaller face id.
@@ -209,6 +211,8 @@ B2_API int b2_pf_gladiator_randoms(b2_pf* h, uint64_t seed, uint32_t step, uint3
  * find kernel and around the reduction/Umeyama kernels; b2_rcc_last_timing returns the two durations of the most recent call (ms). */
 B2_API int b2_rcc_enable_timing(b2_rcc* h, int enable);
 B2_API int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms);
+/* the calling thread's pending CUDA runtime error as text ("" if none), without clearing it: no entry point of this library leaves one behind */
+B2_API const char* b2_peek_cuda_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 B2_API uint64_t b2_kernel_launch_count(void);
 

@@ -73,7 +73,7 @@ EXPORTS = [
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
-    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free",
+    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error",
 ]
 
 
@@ -90,9 +90,10 @@ def load_library():
     lib.b2_last_error.restype = C.c_char_p
     lib.b2_kernel_launch_count.restype = C.c_uint64
     for name in EXPORTS:
-        if name not in ("b2_last_error", "b2_kernel_launch_count", "b2_mesh_file_free"):
+        if name not in ("b2_last_error", "b2_kernel_launch_count", "b2_mesh_file_free", "b2_peek_cuda_error"):
             getattr(lib, name).restype = C.c_int
     lib.b2_mesh_file_free.restype = None
+    lib.b2_peek_cuda_error.restype = C.c_char_p
     _lib = lib
     return lib
 

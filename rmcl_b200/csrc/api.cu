@@ -30,10 +30,13 @@ static int fail(int code, const char* fmt, ...)
 extern "C" const char* b2_last_error(void) { return g_err; }
 extern "C" int b2_version(void) { return 100; }
 extern "C" uint64_t b2_kernel_launch_count(void) { return g_launches.load(); }
+// pending (not yet consumed) CUDA runtime error of the calling thread, "" if none; does not clear it (test hygiene: no entry point may leave one behind)
+extern "C" const char* b2_peek_cuda_error(void) { const cudaError_t e = cudaPeekAtLastError(); return e == cudaSuccess ? "" : cudaGetErrorString(e); }
 extern "C" int b2_device_count(int* n) { NOTNULL(n); CU(cudaGetDeviceCount(n)); return B2_OK; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct b2_mesh {
+    std::atomic<int> refs{1};           // the creator's reference + one per b2_rcc / b2_pf handle: the BVH stays resident until the last user is gone
     int device = 0; int build_mode = 0;
     B2Node8* d_nodes = nullptr; B2Tri* d_tris = nullptr;
     uint32_t n_nodes = 0, n_tris = 0, n_faces = 0, n_verts = 0, max_depth = 0;
@@ -136,15 +139,18 @@ extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_
     return b2_mesh_create(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), device, build_mode, out);
 }
 
-extern "C" int b2_mesh_destroy(b2_mesh* m)
+static void mesh_unref(b2_mesh* m)
 {
-    if (!m) return B2_OK;
+    if (!m || m->refs.fetch_sub(1) != 1) return;
     cudaSetDevice(m->device);
     if (m->d_nodes) cudaFree(m->d_nodes);
     if (m->d_tris) cudaFree(m->d_tris);
     delete m;
-    return B2_OK;
+    (void)cudaGetLastError();
 }
+// Drops the creator's reference.  Handles created on the map keep it alive (rm::EmbreeMapPtr is a shared_ptr in the reference as well,
+// micp_localization.cpp:545), so the order in which a garbage collector destroys map and handles does not matter.
+extern "C" int b2_mesh_destroy(b2_mesh* m) { mesh_unref(m); return B2_OK; }
 
 extern "C" int b2_mesh_get_info(const b2_mesh* m, b2_mesh_info* info)
 {
@@ -258,6 +264,7 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     memset((void*)h->pin, 0, sizeof(HostPin));
     CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+    map->refs.fetch_add(1);             // released in b2_rcc_destroy
     *out = h;
     return B2_OK;
 }
@@ -275,7 +282,11 @@ extern "C" int b2_rcc_destroy(b2_rcc* h)
     if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    h->d_seg_counts.release(); h->d_seg_offsets.release(); h->d_seg_totals.release(); h->d_seg_scan.release(); h->d_seg_map.release(); h->d_seg_labels.release();
+    b2_mesh* map = h->map;
     delete h;
+    (void)cudaGetLastError();
+    mesh_unref(map);
     return B2_OK;
 }
 
@@ -774,6 +785,7 @@ extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
     CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
     CU(cudaFuncSetAttribute(k_pf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     CU(cudaFuncSetAttribute(k_pf_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    map->refs.fetch_add(1);             // released in b2_pf_destroy
     *out = h;
     return B2_OK;
 }
@@ -785,7 +797,10 @@ extern "C" int b2_pf_destroy(b2_pf* h)
     h->d_beams.release(); h->d_poses.release(); h->d_attrs.release(); h->d_part.release(); h->d_ticket.release(); h->d_out.release();
     if (h->h_beams) cudaFreeHost(h->h_beams);
     if (h->h_out) cudaFreeHost(h->h_out);
+    b2_mesh* map = h->map;
     delete h;
+    (void)cudaGetLastError();
+    mesh_unref(map);
     return B2_OK;
 }
 extern "C" int b2_pf_set_stream(b2_pf* h, void* s) { NOTNULL(h); h->stream = (cudaStream_t)s; return B2_OK; }

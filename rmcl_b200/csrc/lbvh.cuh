@@ -225,7 +225,8 @@ static int lbvh_build_device(const float* d_verts, uint32_t nv, const uint32_t* 
         cudaFree(tbox); cudaFree(nbox); cudaFree(cent); cudaFree(bounds); cudaFree(flags); cudaFree(codes); cudaFree(ids); cudaFree(codes_s); cudaFree(ids_s);
         cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(first); cudaFree(last); cudaFree(root_of); cudaFree(counters); cudaFree(cub_tmp);
     };
-#define LB(call) do { if ((call) != cudaSuccess) { freeall(); cudaFree(nodes8); cudaFree(tris8); return rc; } } while (0)
+    static thread_local char e_detail[256];
+#define LB(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(e_detail, sizeof(e_detail), "CUDA error in the device BVH build: %s at lbvh.cuh:%d", cudaGetErrorString(e_), __LINE__); *err = e_detail; (void)cudaGetLastError(); freeall(); cudaFree(nodes8); cudaFree(tris8); return rc; } } while (0)
     const size_t N = (size_t)nf;
     LB(cudaMalloc(&tbox, sizeof(LbvhBox) * N)); LB(cudaMalloc(&nbox, sizeof(LbvhBox) * (2 * N)));
     LB(cudaMalloc(&cent, sizeof(float) * 3 * N)); LB(cudaMalloc(&bounds, sizeof(unsigned int) * 9)); LB(cudaMalloc(&flags, sizeof(unsigned int) * N));

@@ -98,3 +98,20 @@ def random_rays(n, lo, hi, seed=0):
     d = rng.normal(size=(n, 3))
     d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     return o, d
+
+
+@pytest.fixture(autouse=True)
+def _no_pending_cuda_error(request):
+    """GPU hygiene: no entry point of the library may leave an unconsumed CUDA runtime error behind (the next caller's
+    cudaGetLastError() would trip over it) -- neither during a test nor when its handles are garbage-collected afterwards."""
+    gpu = "gpu" in request.keywords and _has_gpu()
+    if gpu:
+        import gc
+        import rmcl_b200
+        gc.collect()
+        msg = rmcl_b200.load_library().b2_peek_cuda_error().decode()
+        assert msg == "", f"pending CUDA error before the test (left by the destruction of earlier handles): {msg}"
+    yield
+    if gpu:
+        msg = rmcl_b200.load_library().b2_peek_cuda_error().decode()
+        assert msg == "", f"pending CUDA error after the test: {msg}"

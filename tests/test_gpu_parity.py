@@ -539,3 +539,18 @@ def test_map_from_file_gpu(tmp_path, synth):
     (tmp_path / "bad.dae").write_text("<COLLADA/>")
     with pytest.raises(rmcl_b200.B2Error):
         rmcl_b200.Map.from_file(str(tmp_path / "bad.dae"))
+
+
+def test_destroy_order_gpu(synth):
+    """The map may be destroyed before the handles created on it (shared ownership, like rm::EmbreeMapPtr): no dangling access, no pending error."""
+    import rmcl_b200
+    V, F = mesh("cube29")
+    m = rmcl_b200.Map(V, F)
+    h = rmcl_b200.RCCB200Spherical(m)
+    up = rmcl_b200.PCDSensorUpdaterB200(m)
+    h.setModel(synth.c1_sensor())
+    m.close()                                       # creator's reference gone; the handles keep the BVH alive
+    h.find(synth.make_transform())
+    assert h.modelView()["hits"].sum() > 0
+    h.close(); up.close()
+    assert rmcl_b200.load_library().b2_peek_cuda_error() == b""
