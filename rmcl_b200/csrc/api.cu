@@ -318,6 +318,17 @@ extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc
     return B2_OK;
 }
 
+// profiling aid (not part of the public header): per-warp {start, end} %globaltimer stamps of the NEXT k_rcc_find launches.
+// buf_dev: device buffer of 2 x ceil(n_rays / 32) u64, or nullptr to switch the stamps off again.
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_find_warp_times(b2_rcc* h, unsigned long long* buf_dev)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyToSymbol(g_find_warp_times, &buf_dev, sizeof(buf_dev)));
+    return B2_OK;
+}
+
 extern "C" int b2_rcc_set_stream(b2_rcc* h, void* s) { NOTNULL(h); h->stream = (cudaStream_t)s; return B2_OK; }
 extern "C" int b2_rcc_set_tsb(b2_rcc* h, const b2_transform* Tsb) { NOTNULL(h); NOTNULL(Tsb); h->Tsb = *Tsb; return B2_OK; }
 extern "C" int b2_rcc_set_params(b2_rcc* h, float max_dist, float amin) { NOTNULL(h); h->max_dist = max_dist; h->adaptive_max_dist_min = amin; return B2_OK; }

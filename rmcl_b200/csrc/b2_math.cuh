@@ -76,6 +76,17 @@ B2_DEV V3 v_scale(V3 a, float s) { return mk3(mul(a.x, s), mul(a.y, s), mul(a.z,
 B2_DEV V3 v_neg(V3 a) { return mk3(-a.x, -a.y, -a.z); }
 // rm::Vector3::dot: x*o.x + y*o.y + z*o.z (left to right)
 B2_DEV float v_dot(V3 a, V3 b) { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
+// (a0, a1) * b + c for two values at once.  Device: one packed FFMA2 (sm_100 fma.rn.f32x2; b and c are broadcast operands, the pair
+// (a0, a1) should be an even-aligned register pair such as the .xy / .zw halves of a 128-bit load).  Host: two fmaf.  Same bits either way.
+B2_DEV void fma2_bcast(float a0, float a1, float b, float c, float& d0, float& d1)
+{
+#if B2_ON_DEVICE
+    asm("{ .reg .b64 ra, rb, rc, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %4};\n\t mov.b64 rc, {%5, %5};\n\t fma.rn.f32x2 rd, ra, rb, rc;\n\t mov.b64 {%0, %1}, rd; }"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+#else
+    d0 = fmaf(a0, b, c); d1 = fmaf(a1, b, c);
+#endif
+}
 B2_DEV float v_l2norm(V3 a) { return sqrt_rn(add(add(mul(a.x, a.x), mul(a.y, a.y)), mul(a.z, a.z))); }
 B2_DEV V3 v_normalize(V3 a) { const float n = v_l2norm(a); return mk3(dvd(a.x, n), dvd(a.y, n), dvd(a.z, n)); }
 

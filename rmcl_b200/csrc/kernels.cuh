@@ -551,20 +551,33 @@ __device__ __forceinline__ void prefetch_map_l2(const BvhView& bvh, uint32_t n_n
 }
 
 #define B2_FIND_BLOCK 64
-__global__ void __launch_bounds__(B2_FIND_BLOCK) k_rcc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const b2_transform* __restrict__ Tbm_dev,
-                                                            const IcpState* __restrict__ icp, b2_transform Tbm_val, b2_transform Tsb_val, RayModel model, uint32_t n_poses,
-                                                            ModelBuffers out)
+// profiling aid: when set (b2_rcc_debug_find_warp_times), lane 0 of every warp stores {start, end} in %globaltimer nanoseconds
+__device__ unsigned long long* g_find_warp_times = nullptr;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// 14 blocks per SM (72 registers): the 2048 blocks of the C2 scan are resident in ONE wave on 148 SMs (13.84 per SM); with the 76
+// registers ptxas picks on its own only 13 fit and the last blocks wait for a slot (measured 54.0 -> 51.7 us).  A variant with 16 rays
+// per warp (half-empty warps, shorter max-over-lanes trip count) was measured slower (71 us: the idle lanes still own registers).
+__global__ void __launch_bounds__(B2_FIND_BLOCK, 14) k_rcc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const b2_transform* __restrict__ Tbm_dev,
+                                                                const IcpState* __restrict__ icp, b2_transform Tbm_val, b2_transform Tsb_val, RayModel model, uint32_t n_poses,
+                                                                ModelBuffers out)
 {
-    prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g_find_warp_times && (threadIdx.x & 31u) == 0u) g_find_warp_times[2 * (gid >> 5)] = globaltimer_ns();      // nothing stays live across the trace
+    prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint64_t total = (uint64_t)model.n * n_poses;
-    if (gid >= total) return;
-    const uint32_t pose = (uint32_t)(gid / model.n), i = tile_order((uint32_t)(gid % model.n), model.width, model.height);
-    Tf Tbm;
-    if (icp) Tbm = tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo));           // MICPSensor.hpp:148
-    else if (Tbm_dev) Tbm = tf_load(Tbm_dev + pose);
-    else Tbm = tf_from_pod(Tbm_val);
-    find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, (uint64_t)pose * model.n + i, out);
+    if (gid < total) {
+        const uint32_t pose = (uint32_t)(gid / model.n), i = tile_order((uint32_t)(gid % model.n), model.width, model.height);
+        Tf Tbm;
+        if (icp) Tbm = tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo));           // MICPSensor.hpp:148
+        else if (Tbm_dev) Tbm = tf_load(Tbm_dev + pose);
+        else Tbm = tf_from_pod(Tbm_val);
+        find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, (uint64_t)pose * model.n + i, out);
+    }
+    if (g_find_warp_times) {
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0u) g_find_warp_times[2 * (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1] = globaltimer_ns();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

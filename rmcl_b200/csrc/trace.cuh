@@ -11,7 +11,7 @@
 //   result = argmin (t, face id) over HITs with t <= tfar.
 // CULLING: a child box (exact float AABB of the triangles below it) is skipped only if NOT
 //       max(tn'_x, tn'_y, tn'_z, 0) <= min(tf'_x, tf'_y, tf'_z, fl(tbest*C1))
-//   with  tf'_k = fma(far_plane_k,  idir_k,      -cf_k),  cf_k = oi_k - dl_k                 oi_k = fl(o_k * idir_k)
+//   with  tf'_k = fma(far_plane_k,  idir_k,      -cf_k),  cf_k = oi_k - dl_k            (two children per FFMA2 on the device)                 oi_k = fl(o_k * idir_k)
 //         tn'_k = fma(near_plane_k, idir_k*C3',  -cn_k),  cn_k = (oi_k + dl_k) * C3'         C3' = 1 - 2^-11
 //         dl_k  = 2^-20 * (|oi_k| + B_k * |idir_k|)        B_k = max |vertex coordinate| on axis k
 //   All constants are per RAY (RaySetup); a node visit is 48 FMAs + min/max, no per-node setup.  dl_k bounds the FMA-path error
@@ -42,7 +42,7 @@ struct HitRec {
 
 struct RaySetup {
     V3 o, d, idir;
-    V3 idn, cn, cf;         // near-plane slope (idir*C3'), near / far constants of the box test (see header)
+    V3 idn, ncn, ncf;       // near-plane slope (idir*C3'), NEGATED near / far constants of the box test (see header): the FMA addends
     uint32_t oct;           // bit k set iff idir_k >= 0
     uint32_t onx, ony, onz; // float4 offsets of the near planes inside a node (lo arrays for positive directions, hi arrays otherwise)
 };
@@ -115,8 +115,8 @@ B2_DEV RaySetup ray_setup(V3 o, V3 d, const BvhView& bvh)
     const float oix = o.x * r.idir.x, oiy = o.y * r.idir.y, oiz = o.z * r.idir.z;
     const float dlx = (fabsf(oix) + bvh.bx * fabsf(r.idir.x)) * k20, dly = (fabsf(oiy) + bvh.by * fabsf(r.idir.y)) * k20, dlz = (fabsf(oiz) + bvh.bz * fabsf(r.idir.z)) * k20;
     r.idn = mk3(r.idir.x * B2_C3P, r.idir.y * B2_C3P, r.idir.z * B2_C3P);
-    r.cn = mk3((oix + dlx) * B2_C3P, (oiy + dly) * B2_C3P, (oiz + dlz) * B2_C3P);
-    r.cf = mk3(oix - dlx, oiy - dly, oiz - dlz);
+    r.ncn = mk3(-((oix + dlx) * B2_C3P), -((oiy + dly) * B2_C3P), -((oiz + dlz) * B2_C3P));
+    r.ncf = mk3(-(oix - dlx), -(oiy - dly), -(oiz - dlz));
     // node layout in float4 units: lo_x 0..1, lo_y 2..3, lo_z 4..5, hi_x 6..7, hi_y 8..9, hi_z 10..11
     r.onx = (r.oct & 1u) ? 0u : 6u; r.ony = (r.oct & 2u) ? 2u : 8u; r.onz = (r.oct & 4u) ? 4u : 10u;
     return r;
@@ -137,23 +137,27 @@ B2_DEV uint32_t node_test(const float4* __restrict__ np, const RaySetup& r, floa
     const uint32_t m1 = w1 ^ ((((w1 >> 3) & (w1 >> 4)) & 0x01010101u) * r.oct);
     const float tlim = tbest * B2_C1;
     uint32_t hitmask = 0;
-#define B2_CHILD(S, NX, NY, NZ, FX, FY, FZ, M)                                                                        \
+    // Two children per step: Blackwell's packed FP32 FMA (FFMA2, PTX fma.rn.f32x2) evaluates one plane of two neighbouring slots in ONE
+    // issue slot -- the operand pair is the register pair the 128-bit node load delivered, slope and addend are scalar broadcasts.  Each
+    // half is an ordinary round-to-nearest FMA, so the results are those of the scalar code (and of the CPU emulation) bit for bit.
+#define B2_PAIR(S, NX0, NX1, NY0, NY1, NZ0, NZ1, FX0, FX1, FY0, FY1, FZ0, FZ1, M)                                     \
     {                                                                                                                  \
-        const float tn = fmaxf(fmaxf(fmaf(NX, r.idn.x, -r.cn.x), fmaf(NY, r.idn.y, -r.cn.y)), fmaxf(fmaf(NZ, r.idn.z, -r.cn.z), 0.0f)); \
-        const float tf = fminf(fminf(fmaf(FX, r.idir.x, -r.cf.x), fmaf(FY, r.idir.y, -r.cf.y)), fminf(fmaf(FZ, r.idir.z, -r.cf.z), tlim)); \
-        const uint32_t meta = ((M) >> (8 * ((S) & 3))) & 0xffu;                                                        \
-        const uint32_t bits = (meta >> 5) << (meta & 0x1fu);                                                           \
-        hitmask |= (tn <= tf) ? bits : 0u;                                                                             \
+        float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;                                              \
+        fma2_bcast(NX0, NX1, r.idn.x, r.ncn.x, nx0, nx1); fma2_bcast(NY0, NY1, r.idn.y, r.ncn.y, ny0, ny1);            \
+        fma2_bcast(NZ0, NZ1, r.idn.z, r.ncn.z, nz0, nz1);                                                              \
+        fma2_bcast(FX0, FX1, r.idir.x, r.ncf.x, fx0, fx1); fma2_bcast(FY0, FY1, r.idir.y, r.ncf.y, fy0, fy1);          \
+        fma2_bcast(FZ0, FZ1, r.idir.z, r.ncf.z, fz0, fz1);                                                             \
+        const float tn0 = fmaxf(fmaxf(nx0, ny0), fmaxf(nz0, 0.0f)), tn1 = fmaxf(fmaxf(nx1, ny1), fmaxf(nz1, 0.0f));    \
+        const float tf0 = fminf(fminf(fx0, fy0), fminf(fz0, tlim)), tf1 = fminf(fminf(fx1, fy1), fminf(fz1, tlim));    \
+        const uint32_t meta0 = ((M) >> (8 * ((S) & 3))) & 0xffu, meta1 = ((M) >> (8 * (((S) + 1) & 3))) & 0xffu;       \
+        hitmask |= (tn0 <= tf0) ? ((meta0 >> 5) << (meta0 & 0x1fu)) : 0u;                                              \
+        hitmask |= (tn1 <= tf1) ? ((meta1 >> 5) << (meta1 & 0x1fu)) : 0u;                                              \
     }
-    B2_CHILD(0, nxa.x, nya.x, nza.x, fxa.x, fya.x, fza.x, m0)
-    B2_CHILD(1, nxa.y, nya.y, nza.y, fxa.y, fya.y, fza.y, m0)
-    B2_CHILD(2, nxa.z, nya.z, nza.z, fxa.z, fya.z, fza.z, m0)
-    B2_CHILD(3, nxa.w, nya.w, nza.w, fxa.w, fya.w, fza.w, m0)
-    B2_CHILD(4, nxb.x, nyb.x, nzb.x, fxb.x, fyb.x, fzb.x, m1)
-    B2_CHILD(5, nxb.y, nyb.y, nzb.y, fxb.y, fyb.y, fzb.y, m1)
-    B2_CHILD(6, nxb.z, nyb.z, nzb.z, fxb.z, fyb.z, fzb.z, m1)
-    B2_CHILD(7, nxb.w, nyb.w, nzb.w, fxb.w, fyb.w, fzb.w, m1)
-#undef B2_CHILD
+    B2_PAIR(0, nxa.x, nxa.y, nya.x, nya.y, nza.x, nza.y, fxa.x, fxa.y, fya.x, fya.y, fza.x, fza.y, m0)
+    B2_PAIR(2, nxa.z, nxa.w, nya.z, nya.w, nza.z, nza.w, fxa.z, fxa.w, fya.z, fya.w, fza.z, fza.w, m0)
+    B2_PAIR(4, nxb.x, nxb.y, nyb.x, nyb.y, nzb.x, nzb.y, fxb.x, fxb.y, fyb.x, fyb.y, fzb.x, fzb.y, m1)
+    B2_PAIR(6, nxb.z, nxb.w, nyb.z, nyb.w, nzb.z, nzb.w, fxb.z, fxb.w, fyb.z, fyb.w, fzb.z, fzb.w, m1)
+#undef B2_PAIR
     return hitmask;
 }
 
