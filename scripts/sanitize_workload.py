@@ -1,0 +1,48 @@
+"""Small run of every entry point for compute-sanitizer (memcheck / racecheck / initcheck):
+   compute-sanitizer --tool memcheck python scripts/sanitize_workload.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rmcl_b200
+from rmcl_b200 import synth
+
+V, F = synth.building(20000)
+for mode in (1, 0):
+    gmap = rmcl_b200.Map(V, F, build_mode=mode)
+    m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 15, 16, -np.pi, 2 * np.pi / 128, 128, 0.5, 120.0)
+    Tsb, Tgt, I = synth.scenario_tsb(), synth.building_gt_pose(), synth.make_transform()
+    h = rmcl_b200.RCCB200Spherical(gmap)
+    h.setTsb(Tsb); h.setModel(m); h.setParams(1.0, 0.15)
+    h.find(Tgt)
+    ranges = synth.noisy_ranges(h.modelView()["ranges"], m.range_max)
+    h.setRanges(ranges)
+    Tom = synth.compose(Tgt, synth.scenario_pose_offset())
+    h.correctOnce(Tom, I, 5, 0.0)
+    h.correctOnce(Tom, I, 5, 0.3, ranges=ranges)
+    h.find(Tom); h.computeCrossStatistics(I, 0.0); h.segment(0.15, 0.15)
+    T = synth.transforms(7); T[:] = Tom
+    h.correct(T)
+    ds = h.datasetView()
+    hc = rmcl_b200.CPCB200(gmap); hc.setTsb(Tsb); hc.setParams(1.0, 0.15); hc.setDataset(ds["points"], ds["mask"])
+    hc.find(Tom); hc.correctOnce(Tom, I, 3, 0.0)
+    gmap.intersect(np.zeros((33, 3), np.float32) + [30, 20, 1], np.random.default_rng(0).normal(size=(33, 3)))
+    beams = synth.pf_beams(h.modelView()["points"], 20)
+    P, A = synth.pf_particles(333)
+    up = rmcl_b200.PCDSensorUpdaterB200(gmap)
+    A1 = up.update(P, A, Tsb, beams)
+    up.update(P, A, Tsb, beams, rmcl_b200.PFParams.defaults(1, 1))
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A1.view(np.float32).reshape(-1, 9).copy()).cuda()
+    up.motionUpdate(Pd, Ad, synth.make_transform((0.02, 0, 0), (0, 0, 0.01)), 0.01)
+    up.update(Pd, Ad, Tsb, beams)
+    up.likelihoodStats(Ad)
+    Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
+    up.resample(Pd, Ad, Pn, An)
+    rmcl_b200.umeyama_transform(h.computeCrossStatistics(I, 0.0).reshape(1))
+    torch.cuda.synchronize()
+    del h, hc, up, gmap
+print("sanitize workload done", rmcl_b200.kernel_launch_count())
