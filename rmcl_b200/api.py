@@ -326,23 +326,44 @@ class RCCB200:
                                            _p(b), C.c_uint32(n), C.byref(nb), _p(lab)))
         return a[: na.value].copy(), b[: nb.value].copy(), lab[:n].copy()
 
+    _CO_OUT = np.dtype([("Tn", TRANSFORM_DTYPE), ("Td", TRANSFORM_DTYPE), ("Cm", CROSS_STATS_DTYPE)])
+
+    def _co_scratch(self):
+        """Persistent argument block of correctOnce: at ~10 kHz call rates the per-call numpy/ctypes object churn of the generic path
+        (~12 us) would be a tenth of the step; here the arguments go into one preallocated 192-byte block and the addresses are plain ints."""
+        sc = getattr(self, "_co", None)
+        if sc is None:
+            buf = (C.c_char * 192)()                  # Tom 0:32 | Tbo 32:64 | Tom_new 64:96 | T_onew_oold 96:128 | Cmerged_o 128:192
+            base = C.addressof(buf)
+            lib = load_library()
+            lib.b2_rcc_correct_once.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.b2_rcc_correct_once_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+            sc = self._co = (buf, memoryview(buf).cast("B"), base, lib.b2_rcc_correct_once, lib.b2_rcc_correct_once_ranges)
+        return sc
+
     def correctOnce(self, Tom, Tbo, iterations=5, convergence_progress=0.0, ranges=None):
         """MICPLocalizationNode::correctOnce for this sensor (micp_localization.cpp:899-984), fully on the device.
         With `ranges` (host array) the scan upload is part of the call (end-to-end entry point)."""
-        Tn, Td, Cm = np.zeros((), TRANSFORM_DTYPE), np.zeros((), TRANSFORM_DTYPE), np.zeros((), CROSS_STATS_DTYPE)
-        lib = load_library()
+        buf, mv, base, f_once, f_ranges = self._co_scratch()
+        a, b = np.asarray(Tom).tobytes(), np.asarray(Tbo).tobytes()
+        if len(a) != 32 or len(b) != 32:
+            raise TypeError("expected 32-byte Transform records (synth.TRANSFORM_DTYPE)")
+        mv[0:32] = a
+        mv[32:64] = b
         if ranges is None:
-            _chk(lib.b2_rcc_correct_once(self._h, _p(_tf(Tom)), _p(_tf(Tbo)), C.c_uint32(iterations), C.c_double(convergence_progress), _p(Tn), _p(Td), _p(Cm)))
+            rc = f_once(self._h, base, base + 32, iterations, convergence_progress, base + 64, base + 96, base + 128)
         else:
             if hasattr(ranges, "data_ptr"):       # pinned / pageable HOST torch tensor
-                rp, rn = C.c_void_p(ranges.data_ptr()), ranges.numel()
+                rp, rn = ranges.data_ptr(), ranges.numel()
             else:
                 ranges = _f32(ranges).reshape(-1)
-                rp, rn = _p(ranges), len(ranges)
-            _chk(lib.b2_rcc_correct_once_ranges(self._h, rp, C.c_uint32(rn), _p(_tf(Tom)), _p(_tf(Tbo)), C.c_uint32(iterations),
-                                                C.c_double(convergence_progress), _p(Tn), _p(Td), _p(Cm)))
+                rp, rn = ranges.ctypes.data, len(ranges)
+            rc = f_ranges(self._h, rp, rn, base, base + 32, iterations, convergence_progress, base + 64, base + 96, base + 128)
+        if rc != 0:
+            _chk(rc)
         self.outdated = False
-        return Tn, Td, Cm
+        out = np.frombuffer(bytearray(mv[64:192]), self._CO_OUT)
+        return out["Tn"][0], out["Td"][0], out["Cm"][0]
 
     def correct(self, Tbm):
         """v1 {Sphere,Pinhole,O1Dn}Corrector::correct(Tbm[N]) -> (Tdelta[N], Ncorr[N], stats_b[N])

@@ -560,9 +560,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 // per warp (half-empty warps, shorter max-over-lanes trip count) was measured slower (71 us: the idle lanes still own registers).
 __global__ void __launch_bounds__(B2_FIND_BLOCK, 14) k_rcc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const b2_transform* __restrict__ Tbm_dev,
                                                                 const IcpState* __restrict__ icp, b2_transform Tbm_val, b2_transform Tsb_val, RayModel model, uint32_t n_poses,
-                                                                ModelBuffers out)
+                                                                ModelBuffers out, int early_dependents)
 {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // let a dependent kernel launched with programmatic stream serialization (k_icp_loop) become resident as SMs drain; it still waits
+    // (griddepcontrol.wait) for this grid to complete and flush before it reads the model buffers
+    if (early_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (g_find_warp_times && (threadIdx.x & 31u) == 0u) g_find_warp_times[2 * (gid >> 5)] = globaltimer_ns();      // nothing stays live across the trace
     prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint64_t total = (uint64_t)model.n * n_poses;
@@ -779,13 +782,42 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
 // per SM; 5 iterations cost 5 grid syncs instead of 5 launches + 5 "last block" rounds.  Partials are double-buffered by parity.
 // ---------------------------------------------------------------------------------------------------------------------
 #define B2_ICP_BLOCK 512
+// Grid barrier without a cooperative launch: a monotonically increasing arrival counter in global memory; barrier number k (1-based,
+// counted from the launch) is passed when the counter reaches base + k * gridDim.x.  Needs all blocks co-resident, which the host
+// guarantees by launching at most one block per SM on an otherwise drained stream (blocks of an unrelated kernel only delay residency,
+// they never wait on us).  A block that waits longer than ~2 s gives up and raises the abort word so that a scheduling surprise ends in
+// an error code, never in a hung GPU.
+__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int target, unsigned int* abort_word)
+{
+    __shared__ bool s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // arrive with release, poll with acquire (gpu scope): no stand-alone fences on the critical path
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        bool ok = true;
+        const long long t0 = clock64();
+        unsigned int spins = 0, v;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if ((++spins & 0x3ffu) == 0u && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile unsigned int*>(abort_word) != 0u)) { ok = false; atomicExch(abort_word, 1u); break; }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok;
+}
+
+template <bool COOP>
 __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, const float* __restrict__ mpts,
                                                           const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
                                                           uint32_t iterations, double* __restrict__ partials, const __grid_constant__ IcpState init,
-                                                          IcpState* host_out, volatile unsigned int* host_flag, unsigned int seq)
+                                                          IcpState* host_out, volatile unsigned int* host_flag, unsigned int seq,
+                                                          unsigned int* bar_counter, unsigned int bar_base, unsigned int* bar_abort)
 {
     namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    const long long k0 = clock64();
+    const unsigned long long g0 = globaltimer_ns();
     __shared__ double smem[(B2_NACC + 1) * (B2_ICP_BLOCK / 32)];
     __shared__ double s_part[B2_ICP_BLOCK / 16][B2_NACC + 1];
     __shared__ __align__(16) IcpState s_icp;
@@ -795,6 +827,9 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
     const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     // With at most two pairs per thread (C2: 131 072 pairs on 148 x 512 threads) the pairs are loaded ONCE and stay in registers for
     // all iterations: only the pre-transform changes between passes, so later passes touch no memory at all.
+    // Launched with programmatic stream serialization (see api.cu): the blocks may become resident while the find kernel is still
+    // draining; everything above overlapped with its tail, everything below reads its output.
+    if (!COOP) asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool cached = n <= 2u * stride;
     bool c_ok[2] = {false, false}; V3 c_d[2], c_I[2], c_N[2];
     if (cached) {
@@ -809,6 +844,7 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
             c_N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
         }
     }
+    const long long k1 = clock64();
     for (uint32_t it = 0; it < iterations; it++) {
         const long long c0 = clock64();
         const Tf Tpre = tf_load(&s_icp.T_snew_sold);
@@ -849,7 +885,8 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
             __threadfence();
         }
         const long long c1 = clock64();
-        grid.sync();
+        if (COOP) cg::this_grid().sync();
+        else if (!grid_barrier(bar_counter, bar_base + (it + 1u) * gridDim.x, bar_abort)) return;       // gave up: the host sees no completion flag and reports the error
         const long long c2 = clock64();
         {
             constexpr uint32_t NG = B2_ICP_BLOCK / 16;               // thread (g, i) adds value i of blocks g, g+NG, ...
@@ -878,6 +915,8 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
         __syncthreads();
     }
     if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) { s_icp.dbg[4] = (unsigned long long)(k1 - k0); s_icp.dbg[5] = (unsigned long long)(clock64() - k0); s_icp.dbg[6] = g0; s_icp.dbg[7] = globaltimer_ns(); }
+        __syncthreads();
         for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) {
             const uint32_t x = reinterpret_cast<const uint32_t*>(&s_icp)[w];
             reinterpret_cast<uint32_t*>(icp_g)[w] = x;
