@@ -608,20 +608,33 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
     bool aux_used = false;
     const bool cpc = h->corr_type == B2_CORR_CPC;
     if (ranges_host && cpc) return fail(B2_ERR_INVALID, "correctOnce(ranges) needs ray-casting correspondences (the handle is in closest-point mode)");
+    static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 2; }();
+    static const int use_zc = [] { const char* e = getenv("B2_ZEROCOPY"); return e ? atoi(e) : 1; }();
+    // Zero-copy scan: when the caller's buffer is pinned host memory the ICP-loop kernel reads it directly (and unpacks it) instead of
+    // memcpy + unpack kernel + cross-stream event.  Needs the register-cached loop (<= 2 pairs per thread) and the fused path.
+    const float* zc_ranges = nullptr;
     if (ranges_host) {
         if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
         if (n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n_ranges, h->n);
+        if (use_zc && use_coop && h->fused_grid > 0 && iterations > 0 && h->n > 0 && h->n <= 2u * (uint32_t)h->fused_grid * B2_ICP_BLOCK) {
+            // asked on every call (about a microsecond): an address can change from pinned to pageable between calls
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, ranges_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) zc_ranges = (const float*)pa.devicePointer;
+            (void)cudaGetLastError();
+        }
         if (h->n > 0) {
             RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n));
-            CU(cudaEventRecord(h->ev_aux, h->stream));                    // the side stream starts after whatever the main stream had in flight BEFORE this call
-            CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+            if (!zc_ranges) {
+                CU(cudaEventRecord(h->ev_aux, h->stream));                // the side stream starts after whatever the main stream had in flight BEFORE this call
+                CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+            }
         }
         h->n_dataset = h->n; h->n_ranges_in = h->n;
     }
     // the find kernel does not read the dataset: the scan is uploaded + unpacked on the side stream WHILE it runs (and the host-side
     // cost of issuing the copy is hidden behind the already launched find)
     auto upload_scan = [&]() -> int {
-        if (!ranges_host || h->n == 0) return B2_OK;
+        if (!ranges_host || h->n == 0 || zc_ranges) return B2_OK;
         CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
         k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max,
                                                                       h->d_dpts.p, h->d_dmask.p);
@@ -644,7 +657,6 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         const Tf Tos = tf_mul(tf_from_pod(*Tbo), tf_from_pod(h->Tsb));
         tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros);
     }
-    static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 2; }();
     bool barrier_used = false;
     static const int use_spin = [] { const char* e = getenv("B2_SPIN"); return e ? atoi(e) : 1; }();
     bool waited = false;
@@ -654,7 +666,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
         tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(*Tbo)));        // MICPSensor.hpp:148, same inline ops as the kernels
         static const int use_pdl = [] { const char* e = getenv("B2_PDL"); return e ? atoi(e) : 1; }();
-        h->pdl_next = use_coop == 2 && use_pdl && !h->timing && h->corr_type == B2_CORR_RCC;      // event records between the two kernels would serialise them anyway
+        h->pdl_next = use_coop == 2 && use_pdl && !h->timing && h->corr_type == B2_CORR_RCC && (!ranges_host || zc_ranges);      // event records between the two kernels would serialise them anyway
         const int rc_find = launch_find(h, &Tbm_host, nullptr);
         h->pdl_next = false;
         RES(rc_find);
@@ -671,8 +683,9 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
         // B2_FUSED=2 (default): ordinary launch + software grid barrier (one block per SM, all resident) -- measured ~10 us less launch
         // overhead per step than the cooperative launch (B2_FUSED=1), which stays available
         unsigned int* bar = h->d_bar.p; unsigned int bar_base = h->bar_base; unsigned int* bar_abort = h->d_bar.p + 1;
+        RayModel zc_model = ray_model(h); float* zc_dpts = h->d_dpts.p; uint8_t* zc_dmask = h->d_dmask.p; float* zc_rin = h->d_ranges_in.p;
         if (use_coop == 1) {
-            void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts, &st, &host_out, &host_flag, &seq, &bar, &bar_base, &bar_abort};
+            void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts, &st, &host_out, &host_flag, &seq, &bar, &bar_base, &bar_abort, &zc_ranges, &zc_model, &zc_dpts, &zc_dmask, &zc_rin};
             CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop<true>, dim3(grid), dim3(B2_ICP_BLOCK), args, 0, h->stream));
         } else {
             cudaLaunchConfig_t cfg{};
@@ -681,7 +694,7 @@ static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transf
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = (h->pdl_armed && !aux_used) ? 1 : 0;      // with a scan upload in flight the kernel also waits on the side stream's event
             cfg.attrs = attr; cfg.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, dp, dmk, mp, mn, mh, nel, icp_dev, its, parts, st, host_out, host_flag, seq, bar, bar_base, bar_abort));
+            CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, dp, dmk, mp, mn, mh, nel, icp_dev, its, parts, st, host_out, host_flag, seq, bar, bar_base, bar_abort, zc_ranges, zc_model, zc_dpts, zc_dmask, zc_rin));
             h->bar_base += its * (unsigned int)grid;
             barrier_used = true;
         }

@@ -813,7 +813,9 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
                                                           const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
                                                           uint32_t iterations, double* __restrict__ partials, const __grid_constant__ IcpState init,
                                                           IcpState* host_out, volatile unsigned int* host_flag, unsigned int seq,
-                                                          unsigned int* bar_counter, unsigned int bar_base, unsigned int* bar_abort)
+                                                          unsigned int* bar_counter, unsigned int bar_base, unsigned int* bar_abort,
+                                                          const float* __restrict__ zc_ranges, RayModel zc_model, float* __restrict__ dpts_out, uint8_t* __restrict__ dmask_out,
+                                                          float* __restrict__ ranges_out)
 {
     namespace cg = cooperative_groups;
     const long long k0 = clock64();
@@ -827,10 +829,25 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
     const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     // With at most two pairs per thread (C2: 131 072 pairs on 148 x 512 threads) the pairs are loaded ONCE and stay in registers for
     // all iterations: only the pre-transform changes between passes, so later passes touch no memory at all.
+    const bool cached = n <= 2u * stride;
+    // End-to-end entry (zc_ranges != nullptr, host passes it only in the cached case): the scan is read straight from the caller's pinned
+    // host buffer (zero copy over PCIe / C2C) and unpacked here exactly like k_dataset_from_ranges does (MICPSphericalSensorCPU.cpp:181-233).
+    // None of this depends on the find kernel, so with the programmatic launch it overlaps find's tail; no H2D copy, no unpack launch,
+    // no cross-stream event on the host's critical path.
+    float zr[2] = {0.f, 0.f}; V3 zdir[2], zorg[2];
+    if (zc_ranges) {
+        #pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t i = gid + (uint32_t)u * stride;
+            const uint32_t j = i < n ? i : 0u, oj = zc_model.n_origs == 1 ? 0u : j;
+            zr[u] = __ldcs(zc_ranges + j);
+            zdir[u] = mk3(zc_model.dirs[3 * j], zc_model.dirs[3 * j + 1], zc_model.dirs[3 * j + 2]);
+            zorg[u] = mk3(zc_model.origs[3 * oj], zc_model.origs[3 * oj + 1], zc_model.origs[3 * oj + 2]);
+        }
+    }
     // Launched with programmatic stream serialization (see api.cu): the blocks may become resident while the find kernel is still
     // draining; everything above overlapped with its tail, everything below reads its output.
     if (!COOP) asm volatile("griddepcontrol.wait;" ::: "memory");
-    const bool cached = n <= 2u * stride;
     bool c_ok[2] = {false, false}; V3 c_d[2], c_I[2], c_N[2];
     if (cached) {
         #pragma unroll
@@ -838,6 +855,19 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
             const uint32_t i = gid + (uint32_t)u * stride;
             const bool in = i < n;
             const uint32_t j = in ? i : 0u;
+            if (zc_ranges) {
+                const float r = zr[u];
+                c_d[u] = mk3(add(mul(zdir[u].x, r), zorg[u].x), add(mul(zdir[u].y, r), zorg[u].y), add(mul(zdir[u].z, r), zorg[u].z));
+                const bool valid = !(r < zc_model.range_min || r > zc_model.range_max);
+                c_ok[u] = in && valid && (mmask[j] > 0);
+                if (in) {          // keep the handle's dataset / scan buffers coherent for datasetView(), computeCrossStatistics(), segment()
+                    dpts_out[3 * j] = c_d[u].x; dpts_out[3 * j + 1] = c_d[u].y; dpts_out[3 * j + 2] = c_d[u].z;
+                    dmask_out[j] = valid ? 1 : 0; ranges_out[j] = r;
+                }
+                c_I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
+                c_N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
+                continue;
+            }
             c_ok[u] = in && (dmask[j] > 0) && (mmask[j] > 0);
             c_d[u] = mk3(dpts[3 * j], dpts[3 * j + 1], dpts[3 * j + 2]);
             c_I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);

@@ -151,8 +151,15 @@ def test_c2_micp_correct_once(po, synth):
     for cp in (0.0, 0.6):
         ref64 = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, cp, f64_accum=True)
         ref32 = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, cp, f64_accum=False)
-        for via_ranges in (False, True):
-            Tn, Td, Cm = h.correctOnce(Tom, Tbo, 5, cp, ranges=ranges if via_ranges else None)
+        import torch
+        pinned = torch.from_numpy(ranges.copy()).pin_memory()          # pinned host scan: read by the kernel directly (zero copy), unpacked on the device
+        for via_ranges in (False, True, "pinned"):
+            if via_ranges == "pinned":
+                h.setRanges(np.full_like(ranges, 3.0))                    # scramble the resident dataset: the call must rebuild it from the pinned scan
+            Tn, Td, Cm = h.correctOnce(Tom, Tbo, 5, cp, ranges=None if via_ranges is False else (pinned if via_ranges == "pinned" else ranges))
+            if via_ranges == "pinned":
+                ds2 = h.datasetView()
+                assert np.array_equal(ds2["points"], dp) and np.array_equal(ds2["mask"], dm)
             assert abs(int(Cm["n_meas"]) - int(ref64[2]["n_meas"])) <= 2                      # gate decisions (exact unless an ulp flips one)
             assert np.abs(Tn["t"] - ref64[0]["t"]).max() <= TOL_DT and quat_close(Tn["R"], ref64[0]["R"], TOL_DT)
             assert np.abs(Td["t"] - ref64[1]["t"]).max() <= TOL_DT and quat_close(Td["R"], ref64[1]["R"], TOL_DT)
