@@ -106,6 +106,17 @@ public:
         outdated = false;
         return out;
     }
+    // same, with the scan's ranges on the HOST (end-to-end entry): a pinned buffer is read in place by the kernel, a pageable one is uploaded
+    rm::Transform correctOnceRanges(const float* ranges_host, size_t n, const rm::Transform& Tom, const rm::Transform& Tbo, unsigned iterations = 5,
+                                    double convergence_progress = 0.0, rm::Transform* T_onew_oold = nullptr, rm::CrossStatistics* Cmerged_o = nullptr)
+    {
+        sync_params();
+        rm::Transform out;
+        b2_check(b2_rcc_correct_once_ranges(h_, ranges_host, (uint32_t)n, tf(&Tom), tf(&Tbo), iterations, convergence_progress, reinterpret_cast<b2_transform*>(&out),
+                                            reinterpret_cast<b2_transform*>(T_onew_oold), reinterpret_cast<b2_cross_stats*>(Cmerged_o)), "correctOnceRanges");
+        outdated = false;
+        return out;
+    }
     // ScanMapSegmentationEmbreeNode::scanCB classification (scan_map_segmentation_embree.cpp:110-187): after setRanges(real scan) + find(pose)
     struct Segmentation { std::vector<rm::Vector3f> outlier_scan, outlier_map; };
     Segmentation segment(float min_dist_outlier_scan, float min_dist_outlier_map)
