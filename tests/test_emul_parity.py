@@ -178,3 +178,35 @@ def test_segmentation_bit_exact(pe, po, synth):
     ra = po.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
     rb = pe.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
     assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_soup_bit_exact(pe, po, seed):
+    """Triangle soups with the awkward cases mixed in -- degenerate (zero-area) triangles, duplicates, slivers, coplanar sheets, coordinates
+    from millimetres to hundreds of metres: ray hits and closest points of the device traversal code equal the oracle's brute force."""
+    import pyemul
+    rng = np.random.default_rng(100 + seed)
+    n = 400
+    scale = [1e-3, 1.0, 300.0, 1.0][seed]
+    c = rng.uniform(-1, 1, (n, 1, 3)) * scale
+    tri = c + rng.normal(0, 0.15 * scale, (n, 3, 3))
+    tri[:20, 2] = tri[:20, 1]                                   # zero-area (two equal vertices)
+    tri[20:40] = tri[40:60]                                     # exact duplicates (tie -> lower face id)
+    tri[60:80, :, 2] = 0.25 * scale                             # a coplanar sheet
+    tri[80:100, 2] = tri[80:100, 0] + (tri[80:100, 1] - tri[80:100, 0]) * 0.5 + rng.normal(0, 1e-6 * scale, (20, 3))   # slivers
+    V = tri.reshape(-1, 3).astype(np.float32)
+    F = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    osc, esc = po.Scene(V, F), pyemul.Scene(V, F)
+    o = (rng.uniform(-1.5, 1.5, (4000, 3)) * scale).astype(np.float32)
+    d = rng.normal(size=(4000, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:300, rng.integers(0, 3)] = 0.0                           # axis-parallel components
+    tb, fb, nb, hb = osc.intersect(o, d, brute=True)
+    te, fe, ne, he, _ = esc.intersect(o, d)
+    assert np.array_equal(hb, he) and np.array_equal(fb, fe) and np.array_equal(tb, te) and np.array_equal(nb, ne)
+    assert 0.05 < hb.mean() < 0.99
+    I = np.zeros((), pyemul.TRANSFORM); I["R"][3] = 1.0
+    q = (rng.uniform(-1.5, 1.5, (3000, 3)) * scale).astype(np.float32)
+    q[:200] = V[rng.integers(0, len(V), 200)]                   # queries ON vertices
+    a, b = osc.cpc_find(I, I, q, 0.1 * scale, brute=True), esc.cpc_find(I, I, q, 0.1 * scale)
+    for k in ("points", "hits", "face_ids", "dists"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
