@@ -777,12 +777,7 @@ extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t
     const uint64_t grid = (uint64_t)bpp * n_poses;
     if (grid > 0x7fffffffull) return fail(B2_ERR_INVALID, "too many poses");
     RES(h->d_partials.reserve((size_t)std::max<uint64_t>(grid, (uint64_t)h->red_grid) * (B2_NACC + 1)));
-    static const int batch_minb = [] { const char* e = getenv("B2_BATCH_MINB"); return e ? atoi(e) : 4; }();
-    if (batch_minb >= 6)      k_rcc_fused_batch<6><<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
-                                                                       bpp, rays_per_block, h->d_partials.p);
-    else if (batch_minb == 5) k_rcc_fused_batch<5><<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
-                                                                       bpp, rays_per_block, h->d_partials.p);
-    else                      k_rcc_fused_batch<4><<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
+    k_rcc_fused_batch<<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
                                                                        bpp, rays_per_block, h->d_partials.p);
     LAUNCHED();
     b2_transform* td = Tdelta; uint32_t* nc = ncorr; b2_cross_stats* sb = stats_b;

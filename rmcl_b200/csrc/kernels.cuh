@@ -965,8 +965,8 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restri
 // grid = n_poses * blocks_per_pose; each block handles `rays_per_block` consecutive rays of one pose
 // ---------------------------------------------------------------------------------------------------------------------
 #define B2_FUSED_BLOCK 128
-template <int MINB>
-__global__ void __launch_bounds__(B2_FUSED_BLOCK, MINB) k_rcc_fused_batch(BvhView bvh, const b2_transform* __restrict__ Tbm_dev, b2_transform Tsb_val, RayModel model,
+// 6 blocks per SM (80 registers, a few spilled values): 2.5 % faster than the uncapped 128 registers / 4 blocks (3.06 -> 2.98 ms per 1000-pose call)
+__global__ void __launch_bounds__(B2_FUSED_BLOCK, 6) k_rcc_fused_batch(BvhView bvh, const b2_transform* __restrict__ Tbm_dev, b2_transform Tsb_val, RayModel model,
                                                                     const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, float max_dist,
                                                                     uint32_t blocks_per_pose, uint32_t rays_per_block, double* __restrict__ partials)
 {
