@@ -433,6 +433,28 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     out["c3_pf"] = {"workload": f"C3: particle-filter sensor update, {n_part} particles x 180 beams per GPU, 1M-triangle mesh", "rays_per_s": n_part * world * 180 / (ms * 1e-3),
                     "ms_per_step": ms, "e2e_rays_per_s": n_part * world * 180 / e2e, "e2e_ms_per_step": e2e * 1e3,
                     "h2d_bytes_per_step": n_part * (32 + 36) + 180 * 32, "d2h_bytes_per_step": n_part * 36}
+    # ---- C5 (BASELINE.json configs[4]): 1M particles x 360 beams sharded 8 ways = 125 000 x 360 per GPU; runs when 8 ranks are present
+    #      (B2_BENCH_C5=1 forces the per-GPU share on fewer GPUs)
+    if world == 8 or os.environ.get("B2_BENCH_C5") == "1":
+        beams5 = synth.pf_beams(pts, 360)
+        P5, A5 = synth.pf_particles(125_000 * world, seed=7)
+        b5, e5 = shard_range(len(P5), rank, world)
+        P5d = torch.from_numpy(P5[b5:e5].view(np.float32).reshape(-1, 8).copy()).cuda()
+        A50 = torch.from_numpy(A5[b5:e5].view(np.float32).reshape(-1, 9).copy()).cuda()
+        tot5 = 0.0
+        for i in range(2 + 5):
+            A5d = A50.clone()
+            flush.fill_(4)
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            up.update(P5d, A5d, Tsb, beams5, prm)
+            bb.record(stream)
+            torch.cuda.synchronize()
+            if i >= 2:
+                tot5 += a.elapsed_time(bb)
+        ms5 = maxr(tot5) / 5
+        out["c5_pf"] = {"workload": f"C5: particle-filter sensor update, {125_000 * world} particles x {len(beams5)} beams over {world} GPU(s), 1M-triangle mesh",
+                        "rays_per_s": 125_000 * world * len(beams5) / (ms5 * 1e-3), "ms_per_step": ms5}
     # ---- the whole particle-filter cycle on the device: motion -> sensor update -> stats (8-byte all-reduce) -> Gladiator
     # resampling (all-gather of the particle set when sharded); particles never leave HBM
     glad = rmcl_b200.GladiatorConfig.defaults()

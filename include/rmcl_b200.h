@@ -96,6 +96,11 @@ B2_API int b2_mesh_create_from_file(const char* path, int device, int build_mode
 /* the import step alone (host only, no device needed): malloc'ed vertex / face arrays, released with b2_mesh_file_free */
 B2_API int b2_mesh_file_load(const char* path, float** verts_xyz, uint32_t* nv, uint32_t** faces_ijk, uint32_t* nf);
 B2_API void b2_mesh_file_free(float* verts_xyz, uint32_t* faces_ijk);
+/* BVH blob: the built map as one host buffer (header + nodes + leaf triangle records), so that a map is built once and
+ * shipped to the other ranks (broadcast) or cached on disk; b2_mesh_create_from_blob validates the header and every index before uploading. */
+B2_API int b2_mesh_blob_size(const b2_mesh* m, uint64_t* bytes);
+B2_API int b2_mesh_export_blob(const b2_mesh* m, void* dst_host, uint64_t capacity);
+B2_API int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, int device, b2_mesh** out);
 /* Drops the creator's reference.  b2_rcc / b2_pf handles created on the map hold their own references (the reference shares its map through
  * rm::EmbreeMapPtr, a shared_ptr, micp_localization.cpp:545), so map and handles may be destroyed in any order. */
 B2_API int b2_mesh_destroy(b2_mesh* m);

@@ -73,7 +73,7 @@ EXPORTS = [
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
-    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error",
+    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob",
 ]
 
 
@@ -171,6 +171,23 @@ class Map:
         self = cls.__new__(cls)
         h = C.c_void_p()
         _chk(lib.b2_mesh_create_from_file(os.fsencode(path), C.c_int(device), C.c_int(build_mode), C.byref(h)))
+        self._h, self.device = h, device
+        return self
+
+    def export_blob(self):
+        """The built BVH as bytes (numpy uint8): build once, broadcast / cache, `Map.from_blob` on the receiving side."""
+        n = C.c_uint64()
+        _chk(load_library().b2_mesh_blob_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _chk(load_library().b2_mesh_export_blob(self._h, _p(buf), C.c_uint64(n.value)))
+        return buf
+
+    @classmethod
+    def from_blob(cls, blob, device=0):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _chk(load_library().b2_mesh_create_from_blob(_p(blob), C.c_uint64(blob.size), C.c_int(device), C.byref(h)))
         self._h, self.device = h, device
         return self
 

@@ -139,6 +139,83 @@ extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_
     return b2_mesh_create(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), device, build_mode, out);
 }
 
+// ---- BVH blob: build once, ship to the other ranks / to disk (b2_mesh_bvh_blob for broadcast) ---------------------------
+struct B2BlobHeader {
+    char     magic[8];                 // "B2BVH8F\0"
+    uint32_t version, node_bytes, tri_bytes, n_nodes, n_tris, n_faces, n_verts, max_depth;
+    int32_t  build_mode;
+    float    abs_max[3], sah;
+    uint32_t pad;                      // 64 bytes: the node array that follows stays 16-byte aligned inside an aligned buffer
+};
+static_assert(sizeof(B2BlobHeader) == 64, "blob header must be 64 bytes");
+static const char kBlobMagic[8] = {'B', '2', 'B', 'V', 'H', '8', 'F', 0};
+
+extern "C" int b2_mesh_blob_size(const b2_mesh* m, uint64_t* bytes)
+{
+    NOTNULL(m); NOTNULL(bytes);
+    *bytes = sizeof(B2BlobHeader) + (uint64_t)m->n_nodes * sizeof(B2Node8) + (uint64_t)m->n_tris * sizeof(B2Tri);
+    return B2_OK;
+}
+
+extern "C" int b2_mesh_export_blob(const b2_mesh* m, void* dst_host, uint64_t capacity)
+{
+    NOTNULL(m); NOTNULL(dst_host);
+    uint64_t need = 0; b2_mesh_blob_size(m, &need);
+    if (capacity < need) return fail(B2_ERR_INVALID, "blob buffer too small: %llu < %llu bytes", (unsigned long long)capacity, (unsigned long long)need);
+    CU(cudaSetDevice(m->device));
+    B2BlobHeader hd; memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, kBlobMagic, 8);
+    hd.version = 1; hd.node_bytes = sizeof(B2Node8); hd.tri_bytes = sizeof(B2Tri); hd.n_nodes = m->n_nodes; hd.n_tris = m->n_tris; hd.n_faces = m->n_faces;
+    hd.n_verts = m->n_verts; hd.max_depth = m->max_depth; hd.build_mode = m->build_mode; hd.sah = m->sah;
+    for (int k = 0; k < 3; k++) hd.abs_max[k] = m->abs_max[k];
+    char* p = static_cast<char*>(dst_host);
+    memcpy(p, &hd, sizeof(hd));
+    CU(cudaMemcpy(p + sizeof(hd), m->d_nodes, (size_t)m->n_nodes * sizeof(B2Node8), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p + sizeof(hd) + (size_t)m->n_nodes * sizeof(B2Node8), m->d_tris, (size_t)m->n_tris * sizeof(B2Tri), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+extern "C" int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, int device, b2_mesh** out)
+{
+    NOTNULL(out); *out = nullptr; NOTNULL(blob_host);
+    if (bytes < sizeof(B2BlobHeader)) return fail(B2_ERR_INVALID, "BVH blob truncated (%llu bytes)", (unsigned long long)bytes);
+    B2BlobHeader hd; memcpy(&hd, blob_host, sizeof(hd));
+    if (memcmp(hd.magic, kBlobMagic, 8) != 0 || hd.version != 1 || hd.node_bytes != sizeof(B2Node8) || hd.tri_bytes != sizeof(B2Tri))
+        return fail(B2_ERR_INVALID, "not a BVH blob of this library version");
+    const uint64_t need = sizeof(hd) + (uint64_t)hd.n_nodes * sizeof(B2Node8) + (uint64_t)hd.n_tris * sizeof(B2Tri);
+    if (hd.n_nodes == 0 || hd.n_tris == 0) return fail(B2_ERR_NO_MAP, "EMPTY MAP in BVH blob");
+    if (bytes < need || hd.max_depth > B2_TRAVERSAL_STACK - 4) return fail(B2_ERR_INVALID, "BVH blob inconsistent (%llu of %llu bytes, depth %u)", (unsigned long long)bytes, (unsigned long long)need, hd.max_depth);
+    // structural check of the indices the traversal follows (a corrupt blob must not turn into out-of-bounds device reads)
+    const B2Node8* nodes = reinterpret_cast<const B2Node8*>(static_cast<const char*>(blob_host) + sizeof(hd));
+    for (uint32_t i = 0; i < hd.n_nodes; i++) {
+        uint32_t n_inner = 0, tri_end = 0;
+        for (int sl = 0; sl < 8; sl++) {
+            const uint8_t meta = nodes[i].meta[sl];
+            if ((nodes[i].imask >> sl) & 1u) n_inner++;
+            else if (meta) { const uint32_t cnt = (meta >> 5) == 7 ? 3 : ((meta >> 5) == 3 ? 2 : 1); tri_end = std::max(tri_end, (uint32_t)(meta & 0x1fu) + cnt); }
+        }
+        if ((n_inner && (uint64_t)nodes[i].child_base + n_inner > hd.n_nodes) || (tri_end && (uint64_t)nodes[i].tri_base + tri_end > hd.n_tris))
+            return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u points outside the arrays", i);
+    }
+    int ndev = 0; CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    const auto t0 = std::chrono::steady_clock::now();
+    b2_mesh* m = new (std::nothrow) b2_mesh();
+    if (!m) return fail(B2_ERR_OOM, "out of host memory");
+    m->device = device; m->build_mode = hd.build_mode; m->n_nodes = hd.n_nodes; m->n_tris = hd.n_tris; m->n_faces = hd.n_faces; m->n_verts = hd.n_verts;
+    m->max_depth = hd.max_depth; m->sah = hd.sah;
+    for (int k = 0; k < 3; k++) m->abs_max[k] = hd.abs_max[k];
+    cudaError_t e = cudaMalloc((void**)&m->d_nodes, sizeof(B2Node8) * (size_t)hd.n_nodes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_tris, sizeof(B2Tri) * (size_t)hd.n_tris);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_nodes, nodes, sizeof(B2Node8) * (size_t)hd.n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_tris, reinterpret_cast<const char*>(nodes) + sizeof(B2Node8) * (size_t)hd.n_nodes, sizeof(B2Tri) * (size_t)hd.n_tris, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { if (m->d_nodes) cudaFree(m->d_nodes); if (m->d_tris) cudaFree(m->d_tris); delete m; (void)cudaGetLastError(); return fail(B2_ERR_CUDA, "BVH blob upload failed: %s", cudaGetErrorString(e)); }
+    m->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = m;
+    return B2_OK;
+}
+
 static void mesh_unref(b2_mesh* m)
 {
     if (!m || m->refs.fetch_sub(1) != 1) return;

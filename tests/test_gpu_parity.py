@@ -561,3 +561,22 @@ def test_destroy_order_gpu(synth):
     assert h.modelView()["hits"].sum() > 0
     h.close(); up.close()
     assert rmcl_b200.load_library().b2_peek_cuda_error() == b""
+
+
+def test_bvh_blob_roundtrip_gpu(synth):
+    """build once, ship the BVH blob; the re-created map traces bit-identically; corrupt blobs are refused."""
+    import rmcl_b200
+    m = gpu_map("cube29")
+    blob = m.export_blob()
+    assert blob[:7].tobytes() == b"B2BVH8F" and len(blob) == 64 + m.info()["bvh_bytes"]
+    m2 = rmcl_b200.Map.from_blob(blob)
+    assert {k: v for k, v in m2.info().items() if k != "build_ms"} == {k: v for k, v in m.info().items() if k != "build_ms"}
+    o, d = random_rays(20000, -9.5, 9.5, seed=5)
+    assert all(np.array_equal(x, y) for x, y in zip(m.intersect(o, d), m2.intersect(o, d)))
+    bad = blob.copy(); bad[64 + 192:64 + 196] = 0xff                          # child_base of the root node far outside the node array
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map.from_blob(bad)
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map.from_blob(blob[: len(blob) // 2])
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map.from_blob(np.zeros(100, np.uint8))
