@@ -189,8 +189,11 @@ B2_API int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses_host, b2
                                     const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
 
 /* rest of the particle-filter cycle on the device, so that particles never leave HBM between stages:
- * TFMotionUpdaterGPU / particle_move_and_forget (rmcl_ros/src/rmcl/particle_motion.cu:11-46): pose = pose * T_bnew_bold, n_meas -= forget_rate * n_meas */
-B2_API int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n_particles, const b2_transform* T_bnew_bold, double forget_rate);
+ * TFMotionUpdaterGPU / particle_move_and_forget (rmcl_ros/src/rmcl/particle_motion.cu:11-46): pose = pose * T_bnew_bold, n_meas -= forget_rate * n_meas.
+ * check_collision != 0 adds the wall check of the CPU updater (TFMotionUpdaterCPU.cpp:17-50,205-216): a ray from the old to the new position; a hit
+ * sets the particle's likelihood to {0, 0, MAX_N_MEAS}. */
+B2_API int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n_particles, const b2_transform* T_bnew_bold, double forget_rate,
+                               int check_collision);
 /* compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92): sum and max (initial 0) of likelihood.mean over the LOCAL particles; with particles
  * sharded across GPUs the caller all-reduces the 8 bytes (SUM, MAX) -- the one exchange step of the cycle.  Results to HOST. */
 B2_API int b2_pf_likelihood_stats(b2_pf* h, const b2_particle_attr* attrs_dev, uint32_t n_particles, float* sum_out, float* max_out);

@@ -236,10 +236,11 @@ public:
         return {};
     }
     // rest of the cycle on the device (particles stay in HBM): TFMotionUpdaterGPU (particle_motion.cu:36-46) and compute_stats (resampling.cu:84-92)
-    void motionUpdate(rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs, const rm::Transform& T_bnew_bold, double forget_rate)
+    void motionUpdate(rm::MemoryView<rm::Transform, rm::VRAM_CUDA> poses, rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs, const rm::Transform& T_bnew_bold, double forget_rate,
+                      bool check_collision = false)       // true: the wall check of TFMotionUpdaterCPU (TFMotionUpdaterCPU.cpp:205-216)
     {
         b2_check(b2_pf_motion_update(h_, reinterpret_cast<b2_transform*>(poses.raw()), reinterpret_cast<b2_particle_attr*>(attrs.raw()), (uint32_t)poses.size(),
-                                     reinterpret_cast<const b2_transform*>(&T_bnew_bold), forget_rate), "motionUpdate");
+                                     reinterpret_cast<const b2_transform*>(&T_bnew_bold), forget_rate, check_collision ? 1 : 0), "motionUpdate");
     }
     struct SimpleLikelihoodStats { float sum = 0.0f; float max = -1.0f; };                       // resampling.cuh:26-30
     SimpleLikelihoodStats computeStats(rm::MemoryView<ParticleAttributes, rm::VRAM_CUDA> attrs)

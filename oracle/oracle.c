@@ -999,11 +999,31 @@ void orc_cpc_find(const orc_scene* s, const orc_transform* Tbm, const orc_transf
  * n_meas -= forget_rate * n_meas (uint32 -= double: computed in double, truncated on the store) */
 void orc_pf_motion_update(uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate)
 {
+    orc_pf_motion_update_collide(NULL, n, poses, attrs, T_bnew_bold, forget_rate);
+}
+
+/* TFMotionUpdaterCPU::update inner loop (rmcl_ros/src/rmcl/TFMotionUpdaterCPU.cpp:184-224) with the optional wall check
+ * collision_in_between (:17-50): a ray from the old to the new position, tfar = their distance (skipped below 1e-5 m); a hit sets the
+ * likelihood to {0, 0, MAX_N_MEAS}.  s == NULL: no map, no check (the GPU updater, particle_motion.cu:11-34). */
+void orc_pf_motion_update_collide(const orc_scene* s, uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate)
+{
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; i++) {
-        poses[i] = T_mul(poses[i], *T_bnew_bold);
-        const uint32_t nm = attrs[i].likelihood.n_meas;
-        attrs[i].likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
+        const orc_transform pose_old = poses[i];
+        const orc_transform pose_new = T_mul(pose_old, *T_bnew_bold);
+        orc_particle_attr a = attrs[i];
+        const uint32_t nm = a.likelihood.n_meas;
+        a.likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
+        if (s) {
+            orc_vec3 vec = v3_sub(pose_new.t, pose_old.t);
+            const float length = v3_l2norm(vec);
+            if (!(length < 0.00001f)) {
+                vec = v3(vec.x / length, vec.y / length, vec.z / length);
+                const float o[3] = {pose_old.t.x, pose_old.t.y, pose_old.t.z}, d[3] = {vec.x, vec.y, vec.z};
+                if (orc_intersect(s, o, d, length, 0, NULL, NULL, NULL)) { a.likelihood.mean = 0.0f; a.likelihood.sigma = 0.0f; a.likelihood.n_meas = 10000u; }
+            }
+        }
+        poses[i] = pose_new; attrs[i] = a;
     }
 }
 

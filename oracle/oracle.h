@@ -133,6 +133,7 @@ void  orc_cpc_find(const orc_scene* s, const orc_transform* Tbm, const orc_trans
 
 /* rest of the PF cycle: motion update (particle_motion.cu:11-46) and likelihood statistics (resampling.cu:41-92) */
 void  orc_pf_motion_update(uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate);
+void  orc_pf_motion_update_collide(const orc_scene* s, uint32_t n, orc_transform* poses, orc_particle_attr* attrs, const orc_transform* T_bnew_bold, double forget_rate);   /* + wall check, TFMotionUpdaterCPU.cpp:17-50,184-224 */
 void  orc_pf_likelihood_stats(uint32_t n, const orc_particle_attr* attrs, float* sum_out, float* max_out);
 
 /* Gladiator resampling, device variant (rmcl_ros/src/rmcl/resampling.cu:108-199; config GladiatorResamplerConfig.hpp:7-20).

@@ -312,11 +312,12 @@ def transform_inv(a):
     return out
 
 
-def pf_motion_update(poses, attrs, T_bnew_bold, forget_rate):
+def pf_motion_update(poses, attrs, T_bnew_bold, forget_rate, scene=None):
+    """scene: a Scene -> walls are checked (TFMotionUpdaterCPU with a map); None -> plain update (TFMotionUpdaterGPU)."""
     poses = _tf(poses).reshape(-1).copy()
     attrs = np.ascontiguousarray(attrs).copy()
     T = _tf(T_bnew_bold)
-    lib().orc_pf_motion_update(C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(T), C.c_double(forget_rate))
+    lib().orc_pf_motion_update_collide(scene._h if scene is not None else None, C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(T), C.c_double(forget_rate))
     return poses, attrs
 
 

@@ -488,10 +488,12 @@ class PCDSensorUpdaterB200:
         _chk(lib.b2_pf_sensor_update_host(self._h, _p(poses), _p(attrs), C.c_uint32(len(poses)), _p(Tsb), _p(beams), C.c_uint32(len(beams)), C.byref(prm)))
         return attrs
 
-    def motionUpdate(self, particle_poses, particle_attrs, T_bnew_bold, forget_rate):
-        """TFMotionUpdaterGPU (rmcl_ros/src/rmcl/particle_motion.cu:11-46): in place on torch CUDA tensors."""
+    def motionUpdate(self, particle_poses, particle_attrs, T_bnew_bold, forget_rate, check_collision=False):
+        """TFMotionUpdaterGPU (rmcl_ros/src/rmcl/particle_motion.cu:11-46): in place on torch CUDA tensors.  check_collision adds the CPU
+        updater's wall check (TFMotionUpdaterCPU.cpp:17-50,205-216)."""
         n = particle_poses.numel() * particle_poses.element_size() // 32
-        _chk(load_library().b2_pf_motion_update(self._h, _devptr(particle_poses), _devptr(particle_attrs), C.c_uint32(n), _p(_tf(T_bnew_bold)), C.c_double(forget_rate)))
+        _chk(load_library().b2_pf_motion_update(self._h, _devptr(particle_poses), _devptr(particle_attrs), C.c_uint32(n), _p(_tf(T_bnew_bold)), C.c_double(forget_rate),
+                                                C.c_int(int(check_collision))))
 
     def likelihoodStats(self, particle_attrs, dist=None):
         """compute_stats (rmcl_ros/src/rmcl/resampling.cu:41-92) of the local particles; with `dist` (torch.distributed, particles sharded

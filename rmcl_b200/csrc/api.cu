@@ -1014,13 +1014,14 @@ extern "C" int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses, b2_
     return B2_OK;
 }
 
-extern "C" int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* T, double forget_rate)
+extern "C" int b2_pf_motion_update(b2_pf* h, b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* T, double forget_rate, int check_collision)
 {
     NOTNULL(h); NOTNULL(T);
     if (n == 0) return B2_OK;
     NOTNULL(poses_dev); NOTNULL(attrs_dev);
     CU(cudaSetDevice(h->map->device));
-    k_pf_motion<<<(n + 255) / 256, 256, 0, h->stream>>>(poses_dev, attrs_dev, n, *T, forget_rate);
+    if (check_collision) k_pf_motion<true><<<(n + 127) / 128, 128, 0, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *T, forget_rate);
+    else                 k_pf_motion<false><<<(n + 127) / 128, 128, 0, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *T, forget_rate);
     LAUNCHED();
     return B2_OK;
 }

@@ -1127,14 +1127,37 @@ __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const
 // rest of the PF cycle
 // ---------------------------------------------------------------------------------------------------------------------
 // particle_move_and_forget_kernel (rmcl_ros/src/rmcl/particle_motion.cu:11-34): HBM stream, 2 x (32 + 36) B per particle
-__global__ void k_pf_motion(b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n, b2_transform T_val, double forget_rate)
+// With COLLIDE the wall check of the CPU updater (TFMotionUpdaterCPU.cpp:17-50,205-216) rides along: one ray from the old to the new
+// position, tfar = their distance; a hit pins the likelihood to {0, 0, MAX_N_MEAS}.
+B2_DEV void pf_motion_one(const BvhView* bvh, b2_transform* pose_io, b2_particle_attr* attr_io, Tf T, double forget_rate)
+{
+    const Tf pose_old = tf_load(pose_io);
+    const Tf pose_new = tf_mul(pose_old, T);
+    b2_gaussian1d lk = attr_io->likelihood;
+    lk.n_meas = (uint32_t)((double)lk.n_meas - forget_rate * (double)lk.n_meas);
+    if (bvh) {
+        const V3 vec = v_sub(pose_new.t, pose_old.t);
+        const float length = v_l2norm(vec);
+        if (!(length < 0.00001f)) {
+            const RaySetup r = ray_setup(pose_old.t, mk3(dvd(vec.x, length), dvd(vec.y, length), dvd(vec.z, length)), *bvh);
+            HitRec h = trace_init(length);
+            uint32_t nn = 0, nt = 0;
+            trace_closest<false>(*bvh, r, h, nn, nt);
+            if (h.face != B2_NOFACE) { lk.mean = 0.0f; lk.sigma = 0.0f; lk.n_meas = 10000u; }
+        }
+    }
+    tf_store(pose_io, pose_new);
+    attr_io->likelihood = lk;
+}
+#ifdef __CUDACC__
+template <bool COLLIDE>
+__global__ void __launch_bounds__(128) k_pf_motion(BvhView bvh, b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n, b2_transform T_val, double forget_rate)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    tf_store(poses + i, tf_mul(tf_load(poses + i), tf_from_pod(T_val)));
-    const uint32_t nm = attrs[i].likelihood.n_meas;
-    attrs[i].likelihood.n_meas = (uint32_t)((double)nm - forget_rate * (double)nm);
+    pf_motion_one(COLLIDE ? &bvh : nullptr, poses + i, attrs + i, tf_from_pod(T_val), forget_rate);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Gladiator resampling (rmcl_ros/src/rmcl/resampling.cu:108-199).  Draws: Philox4x32-10 (Salmon et al., SC'11), counter =

@@ -119,6 +119,12 @@ __attribute__((visibility("default"))) void emul_segment(uint32_t n, const float
     *n_scan = a; *n_map = b;
 }
 
+__attribute__((visibility("default"))) void emul_pf_motion(void* sc, uint32_t n, b2_transform* poses, b2_particle_attr* attrs, const b2_transform* T, double forget_rate, int collide)
+{
+    const BvhView bvh = view(sc);
+    for (uint32_t i = 0; i < n; i++) pf_motion_one(collide ? &bvh : nullptr, poses + i, attrs + i, tf_from_pod(*T), forget_rate);
+}
+
 // sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
 __attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
                                                                   const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)

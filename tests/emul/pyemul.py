@@ -111,6 +111,12 @@ class Scene:
                                 _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm), C.c_int(int(fast_tail)))
         return Tn, Td, Cm
 
+    def pf_motion(self, poses, attrs, T, forget_rate, collide):
+        poses, attrs = np.ascontiguousarray(poses).copy(), np.ascontiguousarray(attrs).copy()
+        T = np.ascontiguousarray(T)
+        lib().emul_pf_motion(self._h, C.c_uint32(len(poses)), _p(poses), _p(attrs), _p(T), C.c_double(forget_rate), C.c_int(int(collide)))
+        return poses, attrs
+
     def pf_update(self, poses, attrs, Tsb, beams, params):
         poses = np.ascontiguousarray(poses)
         attrs = np.ascontiguousarray(attrs).copy()

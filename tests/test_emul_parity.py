@@ -210,3 +210,13 @@ def test_random_soup_bit_exact(pe, po, seed):
     a, b = osc.cpc_find(I, I, q, 0.1 * scale, brute=True), esc.cpc_find(I, I, q, 0.1 * scale)
     for k in ("points", "hits", "face_ids", "dists"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_motion_update_collision_bit_exact(pe, po, synth):
+    from test_oracle import _motion_case
+    osc, esc = oracle_scene("cube29"), emul_scene("cube29")
+    P, A, T = _motion_case(synth)
+    for collide in (False, True):
+        a = po.pf_motion_update(P, A, T, 0.03, scene=osc if collide else None)
+        b = esc.pf_motion(P, A, T, 0.03, collide)
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()

@@ -580,3 +580,24 @@ def test_bvh_blob_roundtrip_gpu(synth):
         rmcl_b200.Map.from_blob(blob[: len(blob) // 2])
     with pytest.raises(rmcl_b200.B2Error):
         rmcl_b200.Map.from_blob(np.zeros(100, np.uint8))
+
+
+def test_motion_update_collision_gpu(po, synth):
+    """motion update with the wall check (collision ray through our tracer), bit-exact vs the oracle."""
+    import torch
+    import rmcl_b200
+    from test_oracle import _motion_case
+    osc = oracle_scene("cube29")
+    P, A, T = _motion_case(synth, 50000)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map("cube29"))
+    for collide in (False, True):
+        ref_P, ref_A = po.pf_motion_update(P, A, T, 0.03, scene=osc if collide else None)
+        Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+        Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+        up.motionUpdate(Pd, Ad, T, 0.03, check_collision=collide)
+        torch.cuda.synchronize()
+        gP = Pd.cpu().numpy().view(P.dtype).reshape(-1)
+        gA = Ad.cpu().numpy().view(A.dtype).reshape(-1)
+        assert np.array_equal(gP["R"], ref_P["R"]) and np.array_equal(gP["t"], ref_P["t"])
+        assert gA.tobytes() == ref_A.tobytes()
+    assert (gA["likelihood"]["n_meas"] == 10000).mean() > 0.02

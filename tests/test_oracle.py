@@ -409,3 +409,31 @@ def test_segmentation_oracle(po, synth):
     assert np.allclose(a, preal[lab == 1], atol=1e-5)                     # raster order
     far = (lab == 2) & rv
     assert np.allclose(b[(lab == 2).nonzero()[0].searchsorted(far.nonzero()[0])], pint[far], atol=1e-5)
+
+
+def _motion_case(synth, n=4000):
+    """Particles inside the 20 m cube; a 1.5 m forward step pushes those facing a nearby wall through it."""
+    rng = np.random.default_rng(8)
+    P, A = synth.pf_particles(n, footprint=(19.0, 19.0), z=0.0, margin=0.0)
+    P["t"][:, :2] -= 9.5
+    A["likelihood"]["mean"] = rng.uniform(0.01, 0.2, n).astype(np.float32)
+    A["likelihood"]["sigma"] = 0.5
+    A["likelihood"]["n_meas"] = rng.integers(1, 10001, n).astype(np.uint32)
+    return P, A, synth.make_transform((1.5, 0.0, 0.0), (0, 0, 0.05))
+
+
+def test_motion_update_collision_oracle(po, synth):
+    """TFMotionUpdaterCPU wall check (TFMotionUpdaterCPU.cpp:17-50,205-216): crossing a cube face <=> the new position is outside."""
+    sc = oracle_scene("cube29")
+    P, A, T = _motion_case(synth)
+    P2, A2 = po.pf_motion_update(P, A, T, 0.03, scene=sc)
+    P0, A0 = po.pf_motion_update(P, A, T, 0.03)
+    assert P2.tobytes() == P0.tobytes()
+    outside = np.abs(P2["t"][:, :2]).max(1) > 10.0
+    assert 0.02 < outside.mean() < 0.5
+    hit = (A2["likelihood"]["mean"] == 0) & (A2["likelihood"]["sigma"] == 0) & (A2["likelihood"]["n_meas"] == 10000)
+    assert np.array_equal(hit, outside)
+    assert A2[~hit].tobytes() == A0[~hit].tobytes()
+    # no motion -> no ray (length < 1e-5)
+    P3, A3 = po.pf_motion_update(P, A, synth.make_transform(), 0.0, scene=sc)
+    assert A3.tobytes() == A.tobytes()
