@@ -96,6 +96,10 @@ B2_API int b2_mesh_create_from_file(const char* path, int device, int build_mode
 /* the import step alone (host only, no device needed): malloc'ed vertex / face arrays, released with b2_mesh_file_free */
 B2_API int b2_mesh_file_load(const char* path, float** verts_xyz, uint32_t* nv, uint32_t** faces_ijk, uint32_t* nf);
 B2_API void b2_mesh_file_free(float* verts_xyz, uint32_t* faces_ijk);
+/* Dynamic maps: the vertices moved, faces unchanged -> refit the resident BVH instead of rebuilding it (the reference
+ * re-commits its Embree scene and flags dependants `outdated`, Correspondences.hpp:26-31).  Maps built with B2_BUILD_DEVICE_LBVH only; the call
+ * synchronises the device first, so no handle may be tracing concurrently from another thread.  Results afterwards equal a fresh build's. */
+B2_API int b2_mesh_refit(b2_mesh* m, const float* verts_xyz, uint32_t nv, int src_is_device);
 /* BVH blob: the built map as one host buffer (header + nodes + leaf triangle records), so that a map is built once and
  * shipped to the other ranks (broadcast) or cached on disk; b2_mesh_create_from_blob validates the header and every index before uploading. */
 B2_API int b2_mesh_blob_size(const b2_mesh* m, uint64_t* bytes);

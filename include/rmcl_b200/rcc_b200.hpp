@@ -35,6 +35,8 @@ public:
     { b2_check(b2_mesh_create_from_file(mesh_file.c_str(), device, build_mode, &m_), "B200Map"); }
     ~B200Map() { b2_mesh_destroy(m_); }
     B200Map(const B200Map&) = delete; B200Map& operator=(const B200Map&) = delete;
+    // the map's vertices moved (same faces): refit the resident BVH; dependants set their `outdated` flag like Correspondences.hpp:26-31
+    void refit(const float* verts_xyz, uint32_t n_vertices, bool on_device = false) { b2_check(b2_mesh_refit(m_, verts_xyz, n_vertices, on_device ? 1 : 0), "B200Map::refit"); }
     b2_mesh* handle() const { return m_; }
     b2_mesh_info info() const { b2_mesh_info i; b2_check(b2_mesh_get_info(m_, &i), "B200Map::info"); return i; }
 private:

@@ -73,7 +73,7 @@ EXPORTS = [
     "b2_rcc_find", "b2_rcc_cross_statistics", "b2_rcc_model_view", "b2_rcc_dataset_view", "b2_rcc_download_model", "b2_rcc_download_dataset",
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
-    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob",
+    "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
 ]
 
 
@@ -173,6 +173,11 @@ class Map:
         _chk(lib.b2_mesh_create_from_file(os.fsencode(path), C.c_int(device), C.c_int(build_mode), C.byref(h)))
         self._h, self.device = h, device
         return self
+
+    def refit(self, verts):
+        """Vertices moved, same faces: refit the resident BVH.  Device-built maps only."""
+        verts = _f32(verts).reshape(-1, 3)
+        _chk(load_library().b2_mesh_refit(self._h, _p(verts), C.c_uint32(len(verts)), C.c_int(0)))
 
     def export_blob(self):
         """The built BVH as bytes (numpy uint8): build once, broadcast / cache, `Map.from_blob` on the receiving side."""

@@ -41,6 +41,8 @@ struct b2_mesh {
     B2Node8* d_nodes = nullptr; B2Tri* d_tris = nullptr;
     uint32_t n_nodes = 0, n_tris = 0, n_faces = 0, n_verts = 0, max_depth = 0;
     float build_ms = 0.f, sah = 0.f, abs_max[3] = {0.f, 0.f, 0.f};
+    std::vector<uint32_t> level_begin;          // device-built maps: node index ranges per tree level (for b2_mesh_refit)
+    uint32_t* d_faces = nullptr;                // device-built maps keep the face list for b2_mesh_refit (12 B per face)
     BvhView view() const
     {
         BvhView v; v.nodes = reinterpret_cast<const float4*>(d_nodes); v.tris = reinterpret_cast<const float4*>(d_tris);
@@ -84,9 +86,10 @@ extern "C" int b2_mesh_create(const float* verts, uint32_t nv, const uint32_t* f
         b2_mesh* m = new (std::nothrow) b2_mesh();
         if (!m) { cudaFree(d_v); cudaFree(d_f); return fail(B2_ERR_OOM, "out of host memory"); }
         const char* err = "";
-        const int rc = lbvh_build_device(d_v, nv, d_f, nf, &m->d_nodes, &m->n_nodes, &m->d_tris, &m->n_tris, &m->max_depth, m->abs_max, &err);
+        const int rc = lbvh_build_device(d_v, nv, d_f, nf, &m->d_nodes, &m->n_nodes, &m->d_tris, &m->n_tris, &m->max_depth, m->abs_max, &err, &m->level_begin);
         g_launches.fetch_add(5 + m->max_depth);
-        cudaFree(d_v); cudaFree(d_f);
+        cudaFree(d_v);
+        if (rc == 0) m->d_faces = d_f; else cudaFree(d_f);
         if (rc != 0) { delete m; return fail(rc == -5 ? B2_ERR_INVALID : B2_ERR_CUDA, "BVH build failed: %s (%s)", err, cudaGetErrorString(cudaGetLastError())); }
         m->device = device; m->build_mode = build_mode; m->n_faces = nf; m->n_verts = nv; m->sah = 0.f;
         m->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -137,6 +140,44 @@ extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_
     const int rc = b2_load_mesh_file(path, V, F, &err);
     if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : B2_ERR_INVALID, "mesh import of '%s' failed: %s", path, err);
     return b2_mesh_create(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), device, build_mode, out);
+}
+
+// Embree / OptiX scene re-commit after the vertices moved (the reference flags dependants with `outdated`,
+// Correspondences.hpp:26-31): refit of the resident tree, no rebuild.  Only for device-built maps (they keep their level ranges and faces).
+extern "C" int b2_mesh_refit(b2_mesh* m, const float* verts, uint32_t nv, int src_is_device)
+{
+    NOTNULL(m); NOTNULL(verts);
+    if (m->level_begin.size() < 2 || !m->d_faces) return fail(B2_ERR_UNSUPPORTED, "refit needs a map built with B2_BUILD_DEVICE_LBVH");
+    if (nv != m->n_verts) return fail(B2_ERR_INVALID, "refit keeps the topology: %u vertices given, the map has %u", nv, m->n_verts);
+    CU(cudaSetDevice(m->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!src_is_device) for (size_t i = 0; i < 3 * (size_t)nv; i++) if (!std::isfinite(verts[i])) return fail(B2_ERR_INVALID, "refit: non-finite vertex");
+    DevBuf<float> d_v; DevBuf<unsigned int> d_bits;
+    const float* vp = verts;
+    if (!src_is_device) {
+        RES(d_v.reserve(3 * (size_t)nv));
+        cudaError_t e = cudaMemcpy(d_v.p, verts, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { d_v.release(); return fail(B2_ERR_CUDA, "refit upload failed: %s", cudaGetErrorString(e)); }
+        vp = d_v.p;
+    }
+    int rc = d_bits.reserve(3);
+    if (rc == B2_OK && cudaMemset(d_bits.p, 0, 3 * sizeof(unsigned int)) != cudaSuccess) rc = fail(B2_ERR_CUDA, "refit: memset failed");
+    if (rc == B2_OK) {
+        cudaDeviceSynchronize();                                            // no trace of any handle may be in flight on the old boxes
+        for (size_t l = m->level_begin.size() - 1; l-- > 0;) {
+            const uint32_t b = m->level_begin[l], e = m->level_begin[l + 1];
+            if (e > b) { k_bvh8_refit_level<<<(e - b + 127) / 128, 128>>>(b, e, m->d_nodes, m->d_tris, vp, m->d_faces); g_launches.fetch_add(1); }
+        }
+        k_abs_max<<<296, 256>>>(vp, nv, d_bits.p); g_launches.fetch_add(1);
+        unsigned int bits[3] = {0, 0, 0};
+        cudaError_t e = cudaMemcpy(bits, d_bits.p, sizeof(bits), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(B2_ERR_CUDA, "refit failed: %s", cudaGetErrorString(e));
+        else for (int k = 0; k < 3; k++) memcpy(&m->abs_max[k], &bits[k], 4);
+    }
+    d_v.release(); d_bits.release();
+    if (rc == B2_OK) m->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 // ---- BVH blob: build once, ship to the other ranks / to disk (b2_mesh_bvh_blob for broadcast) ---------------------------
@@ -222,6 +263,7 @@ static void mesh_unref(b2_mesh* m)
     cudaSetDevice(m->device);
     if (m->d_nodes) cudaFree(m->d_nodes);
     if (m->d_tris) cudaFree(m->d_tris);
+    if (m->d_faces) cudaFree(m->d_faces);
     delete m;
     (void)cudaGetLastError();
 }

@@ -16,6 +16,7 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 
+#include <vector>
 #include "bvh8.h"
 
 struct LbvhBox { float lo[3], hi[3]; };
@@ -210,7 +211,7 @@ __global__ void k_lbvh_collapse(uint32_t level_begin, uint32_t level_end, uint32
 
 // host driver.  verts/faces are DEVICE pointers.  On success *nodes_out / *tris_out are exact-size device buffers owned by the caller.
 static int lbvh_build_device(const float* d_verts, uint32_t nv, const uint32_t* d_faces, uint32_t nf, B2Node8** nodes_out, uint32_t* n_nodes_out, B2Tri** tris_out,
-                             uint32_t* n_tris_out, uint32_t* depth_out, float abs_max_out[3], const char** err)
+                             uint32_t* n_tris_out, uint32_t* depth_out, float abs_max_out[3], const char** err, std::vector<uint32_t>* level_begin = nullptr)
 {
     (void)nv;
     static const char* e_cuda = "CUDA error in the device BVH build";
@@ -254,12 +255,14 @@ static int lbvh_build_device(const float* d_verts, uint32_t nv, const uint32_t* 
     LB(cudaMemcpy(counters, h_counters, 8, cudaMemcpyHostToDevice));
     uint32_t begin = 0, end = 1, depth = 0;
     while (begin < end) {
+        if (level_begin) level_begin->push_back(begin);       // nodes of one level are contiguous: [level_begin[l], level_begin[l+1])
         depth++;
         if (depth > B2_TRAVERSAL_STACK - 4) { *err = e_depth; rc = -5; freeall(); cudaFree(nodes8); cudaFree(tris8); return rc; }
         k_lbvh_collapse<<<(end - begin + 127) / 128, 128>>>(begin, end, root_of, n, left, right, first, last, nbox, ids_s, d_verts, d_faces, nodes8, tris8, counters);
         LB(cudaMemcpy(h_counters, counters, 8, cudaMemcpyDeviceToHost));
         begin = end; end = h_counters[0];
     }
+    if (level_begin) level_begin->push_back(end);
     LB(cudaGetLastError());
     unsigned int hb[9];
     LB(cudaMemcpy(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost));
@@ -276,4 +279,56 @@ static int lbvh_build_device(const float* d_verts, uint32_t nv, const uint32_t* 
 #undef LB
     *nodes_out = nodes_exact; *n_nodes_out = nn; *tris_out = tris_exact; *n_tris_out = nt; *depth_out = depth;
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Refit for dynamic maps: the vertices moved, the topology (faces, tree) stays.  Bottom-up over the levels of the wide
+// tree: a leaf child's box is the exact float AABB of its re-fetched triangles, an inner child's box the union of that child node's own
+// child boxes (already refitted: deeper level).  Boxes stay exact AABBs of the triangles below, so the hit definition -- and with it
+// every result -- is that of a freshly built map; only the tree's quality degrades as the mesh deforms.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bvh8_refit_level(uint32_t begin, uint32_t end, B2Node8* __restrict__ nodes, B2Tri* __restrict__ tris, const float* __restrict__ verts,
+                                                          const uint32_t* __restrict__ faces)
+{
+    const uint32_t t = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= end) return;
+    B2Node8& nd = nodes[t];
+    const float inf = __int_as_float(0x7f800000);
+    for (int s = 0; s < 8; s++) {
+        const uint32_t meta = nd.meta[s];
+        float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+        if ((nd.imask >> s) & 1u) {
+            const B2Node8& ch = nodes[nd.child_base + __popc(nd.imask & ((1u << s) - 1u))];
+            for (int c = 0; c < 8; c++) {
+                if (!ch.meta[c]) continue;
+                for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], ch.lo[k][c]); hi[k] = fmaxf(hi[k], ch.hi[k][c]); }
+            }
+        } else if (meta) {
+            const uint32_t cnt = (meta >> 5) == 7u ? 3u : ((meta >> 5) == 3u ? 2u : 1u), first = nd.tri_base + (meta & 0x1fu);
+            for (uint32_t j = 0; j < cnt; j++) {
+                B2Tri& tr = tris[first + j];
+                const uint32_t f = tr.face_id;
+                const float* a = verts + 3 * (size_t)faces[3 * (size_t)f + 0];
+                const float* b = verts + 3 * (size_t)faces[3 * (size_t)f + 1];
+                const float* c = verts + 3 * (size_t)faces[3 * (size_t)f + 2];
+                for (int k = 0; k < 3; k++) {
+                    tr.v0[k] = a[k]; tr.v1[k] = b[k]; tr.v2[k] = c[k];
+                    lo[k] = fminf(lo[k], fminf(fminf(a[k], b[k]), c[k])); hi[k] = fmaxf(hi[k], fmaxf(fmaxf(a[k], b[k]), c[k]));
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) { nd.lo[k][s] = lo[k]; nd.hi[k][s] = hi[k]; }
+    }
+}
+// max |coordinate| per axis (slack constant of the box test); bits[k] must be zeroed by the caller
+__global__ void k_abs_max(const float* __restrict__ verts, uint32_t nv, unsigned int* __restrict__ bits)
+{
+    float m[3] = {0.f, 0.f, 0.f};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+        for (int k = 0; k < 3; k++) m[k] = fmaxf(m[k], fabsf(verts[3 * (size_t)i + k]));
+    for (int k = 0; k < 3; k++) {
+        for (int o = 16; o > 0; o >>= 1) m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+        if ((threadIdx.x & 31) == 0) atomicMax(bits + k, __float_as_uint(m[k]));          // non-negative floats order like their bit patterns
+    }
 }

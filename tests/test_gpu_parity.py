@@ -601,3 +601,38 @@ def test_motion_update_collision_gpu(po, synth):
         assert np.array_equal(gP["R"], ref_P["R"]) and np.array_equal(gP["t"], ref_P["t"])
         assert gA.tobytes() == ref_A.tobytes()
     assert (gA["likelihood"]["n_meas"] == 10000).mean() > 0.02
+
+
+def test_refit_dynamic_map_gpu(po, synth):
+    """vertices move, faces stay -> refit instead of rebuild; every result equals the oracle on the moved mesh (the hit definition
+    does not depend on the tree), also through a handle that was created before the refit."""
+    import rmcl_b200
+    V, F = mesh("building:200000")
+    m = rmcl_b200.Map(V, F)
+    sensor = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 31, 32, -np.pi, 2 * np.pi / 256, 256, 0.5, 120.0)
+    h = rmcl_b200.RCCB200Spherical(m)
+    h.setTsb(synth.scenario_tsb()); h.setModel(sensor)
+    rng = np.random.default_rng(12)
+    V2 = (V + rng.normal(0, 0.02, V.shape)).astype(np.float32)               # every vertex moved by centimetres
+    V2[:, 0] += (0.3 * np.sin(V[:, 1] * 0.2)).astype(np.float32)             # plus a smooth bend of the whole building
+    m.refit(V2)
+    osc2 = po.Scene(V2, F)
+    o, d = random_rays(50000, 1.0, 2.9, seed=13)
+    o[:, 0] *= 20; o[:, 1] *= 13
+    t1, f1, n1, h1 = osc2.intersect(o, d)
+    t2, f2, n2, h2 = m.intersect(o, d)
+    assert np.array_equal(h1, h2) and np.array_equal(f1, f2) and np.array_equal(t1, t2) and np.array_equal(n1, n2)
+    oo, dd = po.model_rays(sensor)
+    ref = osc2.simulate(synth.building_gt_pose(), synth.scenario_tsb(), oo, dd, sensor.range_max)
+    h.find(synth.building_gt_pose())
+    mv = h.modelView()
+    assert all(np.array_equal(mv[k], ref[k], equal_nan=True) for k in ref)
+    q = rng.uniform([1, 1, 0.2], [59, 39, 2.8], (20000, 3)).astype(np.float32)
+    hc = rmcl_b200.CPCB200(m)
+    hc.setParams(1.0, 0.15); hc.setDataset(q); hc.find(synth.make_transform())
+    a, b = hc.modelView(), osc2.cpc_find(synth.make_transform(), synth.make_transform(), q, 1.0)
+    assert np.array_equal(a["face_ids"], b["face_ids"]) and np.array_equal(a["ranges"], b["dists"])
+    with pytest.raises(rmcl_b200.B2Error):
+        m.refit(V2[:-1])                                                     # topology must stay
+    with pytest.raises(rmcl_b200.B2Error):
+        rmcl_b200.Map(V, F, build_mode=0).refit(V2)                          # host-built maps keep no refit data
