@@ -623,6 +623,41 @@ __global__ void __launch_bounds__(B2_FIND_BLOCK) k_cpc_find(BvhView bvh, uint32_
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------------
+// refit of ONE node of the wide tree (b2_mesh_refit, lbvh.cuh:k_bvh8_refit_level): leaf children re-fetch their triangles, inner children
+// take the union of the (already refitted) child node's boxes
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV void bvh8_refit_node(uint32_t t, B2Node8* nodes, B2Tri* tris, const float* verts, const uint32_t* faces)
+{
+    B2Node8& nd = nodes[t];
+    const float inf = u2f(0x7f800000u);
+    for (int s = 0; s < 8; s++) {
+        const uint32_t meta = nd.meta[s];
+        float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+        if ((nd.imask >> s) & 1u) {
+            const B2Node8& ch = nodes[nd.child_base + popc32(nd.imask & ((1u << s) - 1u))];
+            for (int c = 0; c < 8; c++) {
+                if (!ch.meta[c]) continue;
+                for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], ch.lo[k][c]); hi[k] = fmaxf(hi[k], ch.hi[k][c]); }
+            }
+        } else if (meta) {
+            const uint32_t cnt = (meta >> 5) == 7u ? 3u : ((meta >> 5) == 3u ? 2u : 1u), first = nd.tri_base + (meta & 0x1fu);
+            for (uint32_t j = 0; j < cnt; j++) {
+                B2Tri& tr = tris[first + j];
+                const uint32_t f = tr.face_id;
+                const float* a = verts + 3 * (size_t)faces[3 * (size_t)f + 0];
+                const float* b = verts + 3 * (size_t)faces[3 * (size_t)f + 1];
+                const float* c = verts + 3 * (size_t)faces[3 * (size_t)f + 2];
+                for (int k = 0; k < 3; k++) {
+                    tr.v0[k] = a[k]; tr.v1[k] = b[k]; tr.v2[k] = c[k];
+                    lo[k] = fminf(lo[k], fminf(fminf(a[k], b[k]), c[k])); hi[k] = fmaxf(hi[k], fmaxf(fmaxf(a[k], b[k]), c[k]));
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) { nd.lo[k][s] = lo[k]; nd.hi[k][s] = hi[k]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // scan-vs-map segmentation: classification loop of ScanMapSegmentationEmbreeNode
 // (rmcl_ros/src/nodes/filter/scan_map_segmentation_embree.cpp:110-187) on the model buffers left by find() and the real ranges.
 // label 0: neither cloud, 1: outlier_scan (point = preal), 2: outlier_map (point = pint)

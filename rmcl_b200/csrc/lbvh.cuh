@@ -293,33 +293,7 @@ __global__ void __launch_bounds__(128) k_bvh8_refit_level(uint32_t begin, uint32
 {
     const uint32_t t = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= end) return;
-    B2Node8& nd = nodes[t];
-    const float inf = __int_as_float(0x7f800000);
-    for (int s = 0; s < 8; s++) {
-        const uint32_t meta = nd.meta[s];
-        float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-        if ((nd.imask >> s) & 1u) {
-            const B2Node8& ch = nodes[nd.child_base + __popc(nd.imask & ((1u << s) - 1u))];
-            for (int c = 0; c < 8; c++) {
-                if (!ch.meta[c]) continue;
-                for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], ch.lo[k][c]); hi[k] = fmaxf(hi[k], ch.hi[k][c]); }
-            }
-        } else if (meta) {
-            const uint32_t cnt = (meta >> 5) == 7u ? 3u : ((meta >> 5) == 3u ? 2u : 1u), first = nd.tri_base + (meta & 0x1fu);
-            for (uint32_t j = 0; j < cnt; j++) {
-                B2Tri& tr = tris[first + j];
-                const uint32_t f = tr.face_id;
-                const float* a = verts + 3 * (size_t)faces[3 * (size_t)f + 0];
-                const float* b = verts + 3 * (size_t)faces[3 * (size_t)f + 1];
-                const float* c = verts + 3 * (size_t)faces[3 * (size_t)f + 2];
-                for (int k = 0; k < 3; k++) {
-                    tr.v0[k] = a[k]; tr.v1[k] = b[k]; tr.v2[k] = c[k];
-                    lo[k] = fminf(lo[k], fminf(fminf(a[k], b[k]), c[k])); hi[k] = fmaxf(hi[k], fmaxf(fmaxf(a[k], b[k]), c[k]));
-                }
-            }
-        }
-        for (int k = 0; k < 3; k++) { nd.lo[k][s] = lo[k]; nd.hi[k][s] = hi[k]; }
-    }
+    bvh8_refit_node(t, nodes, tris, verts, faces);
 }
 // max |coordinate| per axis (slack constant of the box test); bits[k] must be zeroed by the caller
 __global__ void k_abs_max(const float* __restrict__ verts, uint32_t nv, unsigned int* __restrict__ bits)

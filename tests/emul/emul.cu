@@ -125,6 +125,17 @@ __attribute__((visibility("default"))) void emul_pf_motion(void* sc, uint32_t n,
     for (uint32_t i = 0; i < n; i++) pf_motion_one(collide ? &bvh : nullptr, poses + i, attrs + i, tf_from_pod(*T), forget_rate);
 }
 
+// refit of the whole host-built tree with the product's per-node function: nodes in decreasing index order (children of a node have
+// larger indices in both builders' layouts; returns -1 if that does not hold)
+__attribute__((visibility("default"))) int emul_refit(void* p, const float* verts, uint32_t nv, const uint32_t* faces)
+{
+    EmulScene* s = (EmulScene*)p;
+    for (uint32_t t = 0; t < s->bvh.n_nodes; t++) if (s->bvh.nodes[t].imask && s->bvh.nodes[t].child_base <= t) return -1;
+    for (uint32_t t = s->bvh.n_nodes; t-- > 0;) bvh8_refit_node(t, s->bvh.nodes, s->bvh.tris, verts, faces);
+    for (int k = 0; k < 3; k++) { float m = 0.f; for (uint32_t i = 0; i < nv; i++) m = fmaxf(m, fabsf(verts[3 * (size_t)i + k])); s->bvh.abs_max[k] = m; }
+    return 0;
+}
+
 // sequential stand-in for k_p2l_reduce (same per-element math, FP64 sum form)
 __attribute__((visibility("default"))) void emul_cross_statistics(const b2_transform* Tpre, uint32_t n, const float* dpts, const uint8_t* dmask, const float* mpts,
                                                                   const float* mnrm, const uint8_t* mmask, float max_dist, b2_cross_stats* out)

@@ -111,6 +111,12 @@ class Scene:
                                 _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm), C.c_int(int(fast_tail)))
         return Tn, Td, Cm
 
+    def refit(self, verts, faces):
+        verts, faces = _f32(verts).reshape(-1, 3), np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        lib().emul_refit.restype = C.c_int
+        rc = lib().emul_refit(self._h, _p(verts), C.c_uint32(len(verts)), _p(faces))
+        assert rc == 0, "tree layout: a child index is not larger than its parent's"
+
     def pf_motion(self, poses, attrs, T, forget_rate, collide):
         poses, attrs = np.ascontiguousarray(poses).copy(), np.ascontiguousarray(attrs).copy()
         T = np.ascontiguousarray(T)

@@ -220,3 +220,25 @@ def test_motion_update_collision_bit_exact(pe, po, synth):
         a = po.pf_motion_update(P, A, T, 0.03, scene=osc if collide else None)
         b = esc.pf_motion(P, A, T, 0.03, collide)
         assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+
+
+def test_refit_bit_exact(pe, po, synth):
+    """b2_mesh_refit's per-node code on the CPU: after the vertices moved, rays and closest points on the refitted tree equal the oracle
+    on the moved mesh."""
+    import pyemul
+    V, F = mesh("building:60000")
+    esc = pyemul.Scene(V, F)
+    rng = np.random.default_rng(21)
+    V2 = (V + rng.normal(0, 0.02, V.shape)).astype(np.float32)
+    V2[:, 0] += (0.3 * np.sin(V[:, 1] * 0.2)).astype(np.float32)
+    esc.refit(V2, F)
+    osc2 = po.Scene(V2, F)
+    o, d = random_rays(20000, 1.0, 2.9, seed=22)
+    o[:, 0] *= 20; o[:, 1] *= 13
+    t1, f1, n1, h1 = osc2.intersect(o, d)
+    t2, f2, n2, h2, _ = esc.intersect(o, d)
+    assert np.array_equal(h1, h2) and np.array_equal(f1, f2) and np.array_equal(t1, t2) and np.array_equal(n1, n2)
+    I = np.zeros((), pyemul.TRANSFORM); I["R"][3] = 1.0
+    q = rng.uniform([1, 1, 0.2], [59, 39, 2.8], (5000, 3)).astype(np.float32)
+    a, b = osc2.cpc_find(I, I, q, 1.0), esc.cpc_find(I, I, q, 1.0)
+    assert np.array_equal(a["face_ids"], b["face_ids"]) and np.array_equal(a["dists"], b["dists"])
