@@ -362,6 +362,31 @@ struct b2_rcc {
 
 static b2_transform tf_identity_pod() { b2_transform T; memset(&T, 0, sizeof(T)); T.R.w = 1.0f; return T; }
 
+extern "C" int b2_rcc_destroy(b2_rcc* h);
+
+// device resources of a fresh handle; any failure leaves the handle in a state b2_rcc_destroy can clean up
+static int rcc_init(b2_rcc* h)
+{
+    b2_mesh* map = h->map;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, map->device));
+    h->red_grid = prop.multiProcessorCount;
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, map->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop<true>, B2_ICP_BLOCK, 0) == cudaSuccess && per_sm > 0)
+            h->fused_grid = prop.multiProcessorCount;      // one block per SM
+        (void)cudaGetLastError();
+    }
+    RES(h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)); RES(h->d_ticket.reserve(1)); RES(h->d_stats.reserve(1)); RES(h->d_icp.reserve(1)); RES(h->d_bar.reserve(2));
+    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
+    CU(cudaMemset(h->d_bar.p, 0, 2 * sizeof(unsigned int)));
+    CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
+    memset((void*)h->pin, 0, sizeof(HostPin));
+    CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+    return B2_OK;
+}
+
 extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
 {
     NOTNULL(out); *out = nullptr;
@@ -370,24 +395,9 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     b2_rcc* h = new (std::nothrow) b2_rcc();
     if (!h) return fail(B2_ERR_OOM, "out of host memory");
     h->map = map; h->Tsb = tf_identity_pod();
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, map->device));
-    h->red_grid = prop.multiProcessorCount;
-    {
-        int coop = 0, per_sm = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, map->device);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop<true>, B2_ICP_BLOCK, 0) == cudaSuccess && per_sm > 0)
-            h->fused_grid = prop.multiProcessorCount;      // one block per SM
-    }
-    int rc;
-    if ((rc = h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)) || (rc = h->d_ticket.reserve(1)) || (rc = h->d_stats.reserve(1)) || (rc = h->d_icp.reserve(1))) { delete h; return rc; }
-    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
-    if ((rc = h->d_bar.reserve(2))) { delete h; return rc; }
-    CU(cudaMemset(h->d_bar.p, 0, 2 * sizeof(unsigned int)));
-    CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
-    memset((void*)h->pin, 0, sizeof(HostPin));
-    CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
     map->refs.fetch_add(1);             // released in b2_rcc_destroy
+    const int rc = rcc_init(h);
+    if (rc != B2_OK) { b2_rcc_destroy(h); return rc; }      // the error text of the failing call stays in b2_last_error
     *out = h;
     return B2_OK;
 }
@@ -949,6 +959,22 @@ struct b2_pf {
     int smem_optin = 0;
 };
 
+extern "C" int b2_pf_destroy(b2_pf* h);
+
+static int pf_init(b2_pf* h)
+{
+    b2_mesh* map = h->map;
+    CU(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device));
+    h->smem_optin -= 1024;              // room for the kernel's static shared memory
+    CU(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, map->device));
+    RES(h->d_part.reserve(2 * (size_t)h->n_sm * 4)); RES(h->d_ticket.reserve(1)); RES(h->d_out.reserve(2));
+    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
+    CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
+    CU(cudaFuncSetAttribute(k_pf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    return B2_OK;
+}
+
 extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
 {
     NOTNULL(out); *out = nullptr;
@@ -957,15 +983,9 @@ extern "C" int b2_pf_create(b2_mesh* map, b2_pf** out)
     b2_pf* h = new (std::nothrow) b2_pf();
     if (!h) return fail(B2_ERR_OOM, "out of host memory");
     h->map = map;
-    CU(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device));
-    h->smem_optin -= 1024;              // room for the kernel's static shared memory
-    CU(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, map->device));
-    { int rc2; if ((rc2 = h->d_part.reserve(2 * (size_t)h->n_sm * 4)) || (rc2 = h->d_ticket.reserve(1)) || (rc2 = h->d_out.reserve(2))) { delete h; return rc2; } }
-    CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
-    CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
-    CU(cudaFuncSetAttribute(k_pf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-    CU(cudaFuncSetAttribute(k_pf_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     map->refs.fetch_add(1);             // released in b2_pf_destroy
+    const int rc = pf_init(h);
+    if (rc != B2_OK) { b2_pf_destroy(h); return rc; }
     *out = h;
     return B2_OK;
 }
