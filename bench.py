@@ -35,7 +35,7 @@ MAX_DIST, ADAPTIVE_MIN = 1.0, 0.15
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)      # ~0.1 s per timed region: long enough for several nvidia-smi samples inside it
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C3 particle filter, v1 batched correct)")
