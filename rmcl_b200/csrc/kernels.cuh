@@ -140,14 +140,16 @@ B2_DEV float b2_rsqrt_approx(float x) { return 1.0f / std::sqrt(x); }
 // FP64 on the one thread that executes it), then one unscaled FP64 step that makes the result orthogonal to double precision.
 // Accuracy: FP32 rounding of the iterates perturbs the rotation by ~1e-7 rad (the reference's own rmagine SVD is FP32 as well); the
 // translation inherits ~1e-7 * |mean| -- two orders below the 1e-5 tolerance on dT.
-__host__ __device__ __noinline__ bool polar_newton3(const double A[3][3], double Q[3][3])
+__host__ __device__ __noinline__ bool polar_newton3(const float A[3][3], double Q[3][3])
 {
-    double fro = 0.0;
+    // scale to unit Frobenius norm so that the iteration starts in its well-behaved range; the polar factor does not depend on the scale,
+    // so the approximate reciprocal square root is as good as the exact one here
+    float fro = 0.0f;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) fro += A[i][j] * A[i][j];
-    if (!(fro > 0.0)) return false;
-    const double inv_n = 1.0 / sqrt(fro);
+    if (!(fro > 1e-30f)) return false;
+    const float inv_n = b2_rsqrt_approx(fro);
     float X[3][3];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) X[i][j] = (float)(A[i][j] * inv_n);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) X[i][j] = A[i][j] * inv_n;
     bool conv = false;
     for (int it = 0; it < 40 && !conv; it++) {
         float Cf[3][3];                                           // cofactor matrix = det * X^-T
@@ -198,14 +200,15 @@ __host__ __device__ __noinline__ Tf umeyama_dev(const CStats& s)
 {
     Tf out = tf_identity();
     if (s.n == 0) return out;
-    double C[3][3], R[3][3];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r][c] = (double)s.C[c * 3 + r];
+    float Cf[3][3]; double R[3][3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Cf[r][c] = s.C[c * 3 + r];
     // Fast path: for det(C) > 0 the Umeyama rotation U S V^T (S = I) is the orthogonal polar factor of C, obtained with the scaled
     // Newton iteration X <- (g X + X^-T / g) / 2 (quadratically convergent, ~100 serial FP64 instructions per step instead of the
     // ~4000 of a Jacobi SVD -- this code runs on ONE thread between two reductions of the ICP loop, so its latency is the step's).
     // det(C) <= 0 (reflection case), a singular C or no convergence fall back to the SVD.
-    if (!polar_newton3(C, R)) {
-        double U[3][3], V[3][3], w[3];
+    if (!polar_newton3(Cf, R)) {
+        double C[3][3], U[3][3], V[3][3], w[3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r][c] = (double)Cf[r][c];
         svd3_dev(C, U, w, V);
         const double sgn = (det3d(U) * det3d(V) < 0.0) ? -1.0 : 1.0;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + sgn * U[i][2] * V[j][2];
