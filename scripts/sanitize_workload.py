@@ -23,6 +23,7 @@ for mode in (1, 0):
     Tom = synth.compose(Tgt, synth.scenario_pose_offset())
     h.correctOnce(Tom, I, 5, 0.0)
     h.correctOnce(Tom, I, 5, 0.3, ranges=ranges)
+    h.correctOnce(Tom, I, 5, 0.0, ranges=torch.from_numpy(ranges.copy()).pin_memory())      # zero-copy scan + programmatic launch
     h.find(Tom); h.computeCrossStatistics(I, 0.0); h.segment(0.15, 0.15)
     T = synth.transforms(7); T[:] = Tom
     h.correct(T)
@@ -38,11 +39,17 @@ for mode in (1, 0):
     Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
     Ad = torch.from_numpy(A1.view(np.float32).reshape(-1, 9).copy()).cuda()
     up.motionUpdate(Pd, Ad, synth.make_transform((0.02, 0, 0), (0, 0, 0.01)), 0.01)
+    up.motionUpdate(Pd, Ad, synth.make_transform((0.5, 0, 0), (0, 0, 0.01)), 0.01, check_collision=True)
     up.update(Pd, Ad, Tsb, beams)
     up.likelihoodStats(Ad)
     Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
     up.resample(Pd, Ad, Pn, An)
     rmcl_b200.umeyama_transform(h.computeCrossStatistics(I, 0.0).reshape(1))
     torch.cuda.synchronize()
-    del h, hc, up, gmap
+    g2 = rmcl_b200.Map.from_blob(gmap.export_blob())
+    g2.intersect(np.zeros((5, 3), np.float32) + [30, 20, 1], np.eye(3, dtype=np.float32)[[0, 1, 2, 0, 1]])
+    if mode == 1:
+        gmap.refit((V + 0.01).astype(np.float32))
+        h.find(Tom)
+    del h, hc, up, gmap, g2
 print("sanitize workload done", rmcl_b200.kernel_launch_count())
