@@ -105,3 +105,20 @@ def test_mesh_file_import(tmp_path):
             rmcl_b200.read_mesh_file(str(bp))
     with pytest.raises(rmcl_b200.B2Error):
         rmcl_b200.read_mesh_file(str(tmp_path / "missing.ply"))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints exactly one JSON line with the contract's keys; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--faces", "20000", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "ray-correspondences/sec" and d["unit"] == "rays/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
