@@ -350,7 +350,9 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 224, "tri_bytes": 48, "io_bytes_per_ray": b_io,
                 "kernel_ms": find_s * 1e3, "kernel_share_of_step": float(np.mean(find_ms)) / float(np.mean(find_ms) + np.mean(red_ms)),
-                "kernel_rays_per_s": m.size / find_s}
+                "kernel_rays_per_s": m.size / find_s,
+                "note": "frac > 1 is expected here: the 85 MB map stays resident in the 126 MB L2, so ~93 % of the algorithmic bytes are served by L2/L1 "
+                        "(DRAM traffic per launch = `traffic`); the kernel is bound by latency / instruction issue, see DESIGN.md section 4"}
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample ----
     cpu = None
