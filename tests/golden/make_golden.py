@@ -84,7 +84,32 @@ def main():
     for ng_mode in (0, 1):
         out[f"attrs_ng{ng_mode}"] = sc.pf_update(P, A, Tsb, beams, po.PFParams.defaults(ng_mode))
     np.savez_compressed(os.path.join(OUT, "pf_cube.npz"), poses=P, attrs0=A, beams=beams, Tsb=Tsb, **out)
+    widened(sc, sim, o, d, m, Tsb, Tgt, P, A)
     print("golden vectors written to", OUT)
+
+
+def widened(sc, sim, o, d, m, Tsb, Tgt, P, A):
+    """Regression vectors for the SURVEY 8(f) rows: closest-point find, PF with the closest-point error, motion update with the wall check,
+    Gladiator resampling (Philox draws), scan-vs-map segmentation.  Same cube, small sizes."""
+    rs = np.random.default_rng(17)
+    q = rs.uniform(-11, 11, (256, 3)).astype(np.float32)
+    cpc = sc.cpc_find(Tgt, Tsb, q, 0.8)
+    beams = synth.pf_beams(sim["points"], 24, seed=3)
+    A1 = sc.pf_update(P, A, Tsb, beams, po.PFParams.defaults(0, 1))
+    A1["likelihood"]["n_meas"] = rs.integers(1, 9000, len(A1)).astype(np.uint32)
+    Tmo = synth.make_transform((1.5, 0.0, 0.0), (0, 0, 0.05))
+    Pm, Am = po.pf_motion_update(P, A1, Tmo, 0.03, scene=sc)
+    cfg = po.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    raw, nrm = po.pf_gladiator_randoms(1234, 3, 0, len(Pm))
+    Pr, Ar = po.pf_gladiator_resample(Pm, Am, 0, len(Pm), raw, nrm, cfg)
+    real = sim["ranges"].copy()
+    k = rs.permutation(len(real))
+    real[k[:40]] *= 0.6; real[k[40:80]] *= 1.3; real[k[80:90]] = m.range_max + 1
+    seg_scan, seg_map, seg_lab = po.segment(o, d, m.range_min, m.range_max, real, sim["ranges"], sim["normals"], 0.15, 0.1)
+    np.savez_compressed(os.path.join(OUT, "f_rows.npz"), Tgt=Tgt, Tsb=Tsb, queries=q, cpc_points=cpc["points"], cpc_normals=cpc["normals"], cpc_hits=cpc["hits"],
+                        cpc_faces=cpc["face_ids"], cpc_dists=cpc["dists"], poses=P, attrs0=A, beams=beams, attrs_cpc=A1, T_motion=Tmo, poses_moved=Pm,
+                        attrs_moved=Am, glad_raw=raw, glad_normals=nrm, poses_resampled=Pr, attrs_resampled=Ar, real_ranges=real,
+                        seg_scan=seg_scan, seg_map=seg_map, seg_labels=seg_lab)
 
 
 if __name__ == "__main__":

@@ -636,3 +636,32 @@ def test_refit_dynamic_map_gpu(po, synth):
         m.refit(V2[:-1])                                                     # topology must stay
     with pytest.raises(rmcl_b200.B2Error):
         rmcl_b200.Map(V, F, build_mode=0).refit(V2)                          # host-built maps keep no refit data
+
+
+def test_widened_rows_golden_gpu(po, synth):
+    """The SURVEY 8(f) rows through the C ABI against the committed fixtures (tests/golden/f_rows.npz)."""
+    import torch
+    import rmcl_b200
+    g = np.load(os.path.join(GOLD, "f_rows.npz"))
+    gm = gpu_map("cube29")
+    hc = rmcl_b200.CPCB200(gm)
+    hc.setTsb(g["Tsb"]); hc.setParams(0.8, 0.15); hc.setDataset(g["queries"]); hc.find(g["Tgt"])
+    mv = hc.modelView()
+    assert np.array_equal(mv["face_ids"], g["cpc_faces"]) and np.array_equal(mv["ranges"], g["cpc_dists"]) and np.array_equal(mv["hits"], g["cpc_hits"])
+    assert np.array_equal(mv["points"], g["cpc_points"], equal_nan=True) and np.array_equal(mv["normals"], g["cpc_normals"], equal_nan=True)
+    up = rmcl_b200.PCDSensorUpdaterB200(gm)
+    A1 = up.update(g["poses"], g["attrs0"], g["Tsb"], g["beams"], rmcl_b200.PFParams.defaults(0, 1))
+    assert np.abs(A1["likelihood"]["mean"] - g["attrs_cpc"]["likelihood"]["mean"]).max() <= TOL_LIK
+    Pd = torch.from_numpy(g["poses"].view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(g["attrs_cpc"].view(np.float32).reshape(-1, 9).copy()).cuda()
+    up.motionUpdate(Pd, Ad, g["T_motion"], 0.03, check_collision=True)
+    torch.cuda.synchronize()
+    assert Pd.cpu().numpy().tobytes() == g["poses_moved"].view(np.float32).tobytes() and Ad.cpu().numpy().tobytes() == g["attrs_moved"].view(np.float32).tobytes()
+    raw, nrm = up.gladiatorRandoms(1234, 3, 0, len(g["poses"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(raw.cpu().numpy().view(np.uint32), g["glad_raw"]) and np.abs(nrm.cpu().numpy() - g["glad_normals"]).max() <= 4e-6
+    m = synth.c1_sensor()
+    h = _rcc(synth, "cube29", m, g["Tsb"])
+    h.setRanges(g["real_ranges"]); h.find(g["Tgt"])
+    a, b, lab = h.segment(0.15, 0.1)
+    assert np.array_equal(lab, g["seg_labels"]) and np.array_equal(a, g["seg_scan"]) and np.array_equal(b, g["seg_map"])

@@ -437,3 +437,26 @@ def test_motion_update_collision_oracle(po, synth):
     # no motion -> no ray (length < 1e-5)
     P3, A3 = po.pf_motion_update(P, A, synth.make_transform(), 0.0, scene=sc)
     assert A3.tobytes() == A.tobytes()
+
+
+def test_widened_rows_golden(po, synth):
+    """Regression fixtures of the SURVEY 8(f) rows (tests/golden/f_rows.npz, generator tests/golden/make_golden.py:widened)."""
+    g = np.load(os.path.join(GOLD, "f_rows.npz"))
+    sc = oracle_scene("cube29")
+    m = synth.c1_sensor()
+    o, d = po.model_rays(m)
+    cpc = sc.cpc_find(g["Tgt"], g["Tsb"], g["queries"], 0.8)
+    assert np.array_equal(cpc["face_ids"], g["cpc_faces"]) and np.array_equal(cpc["dists"], g["cpc_dists"]) and np.array_equal(cpc["hits"], g["cpc_hits"])
+    assert np.array_equal(cpc["points"], g["cpc_points"], equal_nan=True) and np.array_equal(cpc["normals"], g["cpc_normals"], equal_nan=True)
+    A1 = sc.pf_update(g["poses"], g["attrs0"], g["Tsb"], g["beams"], po.PFParams.defaults(0, 1))
+    assert np.array_equal(A1["likelihood"]["mean"], g["attrs_cpc"]["likelihood"]["mean"])
+    Pm, Am = po.pf_motion_update(g["poses"], g["attrs_cpc"], g["T_motion"], 0.03, scene=sc)
+    assert Pm.tobytes() == g["poses_moved"].tobytes() and Am.tobytes() == g["attrs_moved"].tobytes()
+    raw, nrm = po.pf_gladiator_randoms(1234, 3, 0, len(Pm))
+    assert np.array_equal(raw, g["glad_raw"]) and np.array_equal(nrm, g["glad_normals"])
+    cfg = po.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    Pr, Ar = po.pf_gladiator_resample(Pm, Am, 0, len(Pm), raw, nrm, cfg)
+    assert Pr.tobytes() == g["poses_resampled"].tobytes() and Ar.tobytes() == g["attrs_resampled"].tobytes()
+    sim = sc.simulate(g["Tgt"], g["Tsb"], o, d, m.range_max)
+    a, b, lab = po.segment(o, d, m.range_min, m.range_max, g["real_ranges"], sim["ranges"], sim["normals"], 0.15, 0.1)
+    assert np.array_equal(lab, g["seg_labels"]) and np.array_equal(a, g["seg_scan"]) and np.array_equal(b, g["seg_map"])
