@@ -170,6 +170,26 @@ B2_API int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges_host, uint3
                                       uint32_t iterations, double convergence_progress, b2_transform* Tom_new, b2_transform* T_onew_oold,
                                       b2_cross_stats* Cmerged_o);
 
+/* The same step split into enqueue / collect: _async launches the kernels on the handle's stream and returns at once, _wait blocks until the
+ * result has landed (mapped pinned memory, no stream synchronise) and hands it out.  One call may be pending per handle.  Lets a caller keep
+ * the GPU queue full (bench.py's device-timed loop) or overlap its own host work with the correction. */
+B2_API int b2_rcc_correct_once_async(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double convergence_progress);
+B2_API int b2_rcc_correct_once_wait(b2_rcc* h, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
+/* MICPLocalizationNode::correctOnce over ALL sensors of the node (rmcl_ros/src/nodes/micp_localization.cpp:899-984): per sensor k
+ * find(Tom * Tbo[k]) (:900-908), then `iterations` x { per sensor: P2L cross statistics under T_bnew_bold = ~Tbo[k] * T_onew_oold * Tbo[k] (:926-929),
+ * Cs_o = Tbo[k] * Cs_b (:931), weighted copy n_meas *= merge_weights[k] (u32 *= double, :933-934), Cmerged_o += Cs_o, Cmerged_weighted_o +=
+ * Cs_weighted_o (:936-937) } -> umeyama(Cmerged_weighted_o) -> compose (:952-963).  1..4 sensors (RCC or CPC handles on one device); all inner
+ * iterations of all sensors run in one kernel.  merge_weights NULL = all 1.0 (MICPSensor.hpp:103); ranges_host NULL or per-sensor NULL = use the
+ * resident dataset, else that sensor's scan is uploaded / read zero-copy inside the call.  Outputs to HOST (may be NULL). */
+B2_API int b2_micp_correct_once(b2_rcc* const* sensors, const b2_transform* Tbo, const double* merge_weights, const float* const* ranges_host, uint32_t n_sensors,
+                                const b2_transform* Tom, uint32_t iterations, double convergence_progress,
+                                b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
+/* How b2_rcc_correct_once* runs the inner iterations: 2 (default) one kernel with a software grid barrier, launched programmatically behind
+ * find; 1 the same kernel through a cooperative launch; 0 one reduction launch per inner iteration in the reference's own frame-algebra order
+ * (MICPSensor.hpp:178-182).  Results agree within float rounding.  The environment variable B2_FUSED sets the default of new handles.  A
+ * software barrier that cannot get its blocks co-resident falls back to the cooperative launch by itself. */
+B2_API int b2_rcc_set_exec_mode(b2_rcc* h, int mode);
+
 /* v1 {Sphere,Pinhole,O1Dn}Corrector{Embree,Optix}::correct(Tbm[N]) -> {Tdelta[N], Ncorr[N]}
  * (shape: rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:86-133, ..._optix_benchmark.cpp:85-155):
  * fused trace -> P2L gate -> per-pose cross statistics -> batched Umeyama, one launch sequence for all poses.

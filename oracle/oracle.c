@@ -769,6 +769,52 @@ void orc_micp_correct_once(const orc_scene* s,
     free(mp); free(mn); free(mh);
 }
 
+/* MICPLocalizationNode::correctOnce over ALL sensors of the node (micp_localization.cpp:899-984), statement by statement. */
+void orc_micp_correct_once_multi(const orc_scene* s, uint32_t n_sensors, const orc_micp_sensor* sen, const orc_transform* Tom,
+                                 uint32_t optimization_iterations, double convergence_progress, int f64_accum,
+                                 orc_transform* Tom_new, orc_transform* T_onew_oold_out, orc_cross_stats* Cmerged_out)
+{
+    float** mp = (float**)malloc(sizeof(float*) * n_sensors); float** mn = (float**)malloc(sizeof(float*) * n_sensors);
+    uint8_t** mh = (uint8_t**)malloc(sizeof(uint8_t*) * n_sensors);
+    for (uint32_t k = 0; k < n_sensors; k++) {                               /* :900-908 setTom + findCorrespondences */
+        const orc_micp_sensor* S = &sen[k];
+        mp[k] = (float*)malloc(sizeof(float) * 3 * (size_t)(S->n ? S->n : 1)); mn[k] = (float*)malloc(sizeof(float) * 3 * (size_t)(S->n ? S->n : 1));
+        mh[k] = (uint8_t*)malloc((size_t)(S->n ? S->n : 1));
+        const orc_transform Tbm = T_mul(*Tom, S->Tbo);                       /* MICPSensor.hpp:148 */
+        if (S->dirs_s) orc_simulate(s, &Tbm, &S->Tsb, S->n, S->origs_s, S->n_origs, S->dirs_s, S->range_max, mp[k], mn[k], mh[k], NULL, NULL);
+        else           orc_cpc_find(s, &Tbm, &S->Tsb, S->n, S->dataset_pts, S->max_dist, 0, mp[k], mn[k], mh[k], NULL, NULL);
+    }
+    orc_transform T_onew_oold = T_identity();                                /* :910 */
+    orc_cross_stats Cmerged, Cmerged_w; orc_cross_stats_identity(&Cmerged); orc_cross_stats_identity(&Cmerged_w);
+    for (uint32_t it = 0; it < optimization_iterations; it++) {              /* :915 */
+        orc_cross_stats_identity(&Cmerged); orc_cross_stats_identity(&Cmerged_w);   /* :918-919 */
+        for (uint32_t k = 0; k < n_sensors; k++) {                           /* :923 */
+            const orc_micp_sensor* S = &sen[k];
+            const orc_transform T_bnew_bold = T_mul(T_mul(T_inv(S->Tbo), T_onew_oold), S->Tbo);      /* :926 */
+            const orc_transform T_snew_sold = T_mul(T_mul(T_inv(S->Tsb), T_bnew_bold), S->Tsb);      /* MICPSensor.hpp:178 */
+            const float md = orc_adaptive_max_dist(S->max_dist, S->adaptive_max_dist_min, convergence_progress);   /* CorrespondencesCPU.cpp:21-23 */
+            orc_cross_stats stats_s, Cs_b, Cs_o, Cs_w, tmp;
+            if (f64_accum) orc_statistics_p2l_f64(&T_snew_sold, S->n, S->dataset_pts, S->dataset_mask, mp[k], mn[k], mh[k], md, &stats_s);
+            else           orc_statistics_p2l(&T_snew_sold, S->n, S->dataset_pts, S->dataset_mask, mp[k], mn[k], mh[k], md, &stats_s);
+            orc_cross_stats_transform(&S->Tsb, &stats_s, &Cs_b);             /* MICPSensor.hpp:182 */
+            orc_cross_stats_transform(&S->Tbo, &Cs_b, &Cs_o);                /* :931 */
+            Cs_w = Cs_o;
+            Cs_w.n_meas = (uint32_t)((double)Cs_w.n_meas * S->merge_weight); /* :933-934: unsigned *= double */
+            orc_cross_stats_merge(&Cmerged, &Cs_o, &tmp); Cmerged = tmp;     /* :936 */
+            orc_cross_stats_merge(&Cmerged_w, &Cs_w, &tmp); Cmerged_w = tmp; /* :937 */
+        }
+        orc_transform T_inner; orc_umeyama(&Cmerged_w, &T_inner);            /* :952-953 */
+        T_onew_oold = T_mul(T_onew_oold, T_inner);                           /* :963 */
+    }
+    orc_transform Tn = T_mul(*Tom, T_onew_oold);                             /* :972 */
+    if (Cmerged.n_meas > 0) Tn.R = q_normalize(Tn.R); else Tn = *Tom;        /* :974-984 */
+    *Tom_new = Tn;
+    if (T_onew_oold_out) *T_onew_oold_out = T_onew_oold;
+    if (Cmerged_out) *Cmerged_out = Cmerged;
+    for (uint32_t k = 0; k < n_sensors; k++) { free(mp[k]); free(mn[k]); free(mh[k]); }
+    free(mp); free(mn); free(mh);
+}
+
 void orc_correct_batch(const orc_scene* s, uint32_t n_poses, const orc_transform* Tbm, const orc_transform* Tsb,
                        uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max,
                        const float* ranges, float max_dist, int f64_accum,

@@ -111,6 +111,20 @@ void orc_micp_correct_once(const orc_scene* s,
                            double convergence_progress, int f64_accum /* 0: FP32 sequential, 1: FP64 sums, 2: FP32 OpenMP chunks */,
                            orc_transform* Tom_new, orc_transform* T_onew_oold, orc_cross_stats* Cmerged_o);
 
+/* The same over ALL sensors of the node (micp_localization.cpp:899-984): per sensor find, then per inner iteration the per-sensor statistics are
+ * moved to the odom frame, merged un-weighted (Cmerged_o, :936) and weighted (n_meas *= merge_weight as u32 *= double, :933-937); Umeyama runs on the
+ * weighted merge.  dirs_s == NULL selects closest-point correspondences for that sensor. */
+typedef struct {
+    uint32_t n; uint32_t n_origs;
+    const float* origs_s; const float* dirs_s; const float* dataset_pts; const uint8_t* dataset_mask;
+    orc_transform Tbo, Tsb;
+    float range_max, max_dist, adaptive_max_dist_min, pad_;
+    double merge_weight;
+} orc_micp_sensor;
+void orc_micp_correct_once_multi(const orc_scene* s, uint32_t n_sensors, const orc_micp_sensor* sensors, const orc_transform* Tom,
+                                 uint32_t optimization_iterations, double convergence_progress, int f64_accum,
+                                 orc_transform* Tom_new, orc_transform* T_onew_oold, orc_cross_stats* Cmerged_o);
+
 /* v1 SphereCorrectorEmbree::correct(Tbm[N]) shape (rmcl_ros/src/benchmarks/lidar_corrector_embree_benchmark.cpp:117-133):
  * per pose: simulate at Tbm[p], P2L against the dataset built from `ranges`, one Umeyama step; Tdelta is in the BASE frame. */
 void orc_correct_batch(const orc_scene* s, uint32_t n_poses, const orc_transform* Tbm, const orc_transform* Tsb,

@@ -31,6 +31,17 @@ class PFParams(C.Structure):
         return PFParams(2.0, 100.0, 100.0, 0.0, 0.05, 80.0, ng_mode, correspondence_type)
 
 
+class _Tf(C.Structure):
+    _fields_ = [("v", C.c_float * 7), ("stamp", C.c_uint32)]
+
+
+class _MicpSensor(C.Structure):
+    """orc_micp_sensor (oracle.h)"""
+    _fields_ = [("n", C.c_uint32), ("n_origs", C.c_uint32), ("origs_s", C.c_void_p), ("dirs_s", C.c_void_p), ("dataset_pts", C.c_void_p), ("dataset_mask", C.c_void_p),
+                ("Tbo", _Tf), ("Tsb", _Tf), ("range_max", C.c_float), ("max_dist", C.c_float), ("adaptive_max_dist_min", C.c_float), ("pad_", C.c_float),
+                ("merge_weight", C.c_double)]
+
+
 def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
             os.path.getmtime(os.path.join(_HERE, "oracle.c")), os.path.getmtime(os.path.join(_HERE, "oracle.h"))):
@@ -137,6 +148,32 @@ class Scene:
                                     _p(dp), _p(dm), _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist),
                                     C.c_float(adaptive_max_dist_min), C.c_double(convergence_progress), C.c_int(int(f64_accum)),   # 0 seq f32, 1 f64, 2 parallel f32
                                     _p(Tn), _p(Td), _p(Cm))
+        return Tn, Td, Cm
+
+    def micp_correct_once_multi(self, sensors, Tom, iterations=5, convergence_progress=0.0, f64_accum=True):
+        """sensors: list of dicts(origs, dirs (None = closest point), range_max, dataset_points, dataset_mask, Tbo, Tsb, max_dist, adaptive_max_dist_min, weight)"""
+        arr = (_MicpSensor * len(sensors))()
+        keep = []
+        for k, sd in enumerate(sensors):
+            dp = _f32(sd["dataset_points"]).reshape(-1, 3)
+            dm = np.ascontiguousarray(sd["dataset_mask"], np.uint8)
+            if sd.get("dirs") is None:
+                o, d, n = np.zeros((1, 3), np.float32), None, dp.shape[0]
+            else:
+                o, d = _f32(sd["origs"]).reshape(-1, 3), _f32(sd["dirs"]).reshape(-1, 3)
+                n = d.shape[0]
+            keep += [dp, dm, o, d]
+            a = arr[k]
+            a.n, a.n_origs = n, o.shape[0]
+            a.origs_s, a.dirs_s = o.ctypes.data, (d.ctypes.data if d is not None else None)
+            a.dataset_pts, a.dataset_mask = dp.ctypes.data, dm.ctypes.data
+            C.memmove(C.byref(a, _MicpSensor.Tbo.offset), _tf(sd["Tbo"]).ctypes.data, 32)
+            C.memmove(C.byref(a, _MicpSensor.Tsb.offset), _tf(sd["Tsb"]).ctypes.data, 32)
+            a.range_max, a.max_dist, a.adaptive_max_dist_min = sd.get("range_max", 0.0), sd.get("max_dist", 1.0), sd.get("adaptive_max_dist_min", 0.15)
+            a.merge_weight = sd.get("weight", 1.0)
+        Tn, Td, Cm = np.zeros((), TRANSFORM), np.zeros((), TRANSFORM), np.zeros((), CROSS_STATS)
+        lib().orc_micp_correct_once_multi(self._h, C.c_uint32(len(sensors)), arr, _p(_tf(Tom)), C.c_uint32(iterations), C.c_double(convergence_progress),
+                                          C.c_int(int(f64_accum)), _p(Tn), _p(Td), _p(Cm))
         return Tn, Td, Cm
 
     def correct_batch(self, Tbm, Tsb, origs_s, dirs_s, range_min, range_max, ranges, max_dist, f64_accum=False):

@@ -6,9 +6,9 @@ v1 correct(), ParticleUpdater::update).  There is no CPU fallback: importing wor
 the CUDA library and a GPU and raises otherwise.
 """
 from .api import (B2Error, Map, RCCB200, RCCB200Spherical, RCCB200Pinhole, RCCB200O1Dn, RCCB200OnDn, CPCB200, SphereCorrectorB200, PinholeCorrectorB200,
-                  O1DnCorrectorB200, OnDnCorrectorB200, PCDSensorUpdaterB200, PFParams, GladiatorConfig, umeyama_transform, read_mesh_file, kernel_launch_count, lib_path, load_library)
+                  O1DnCorrectorB200, OnDnCorrectorB200, PCDSensorUpdaterB200, PFParams, GladiatorConfig, umeyama_transform, micp_correct_once, read_mesh_file, kernel_launch_count, lib_path, load_library)
 from . import synth
 
 __all__ = ["B2Error", "Map", "RCCB200", "RCCB200Spherical", "RCCB200Pinhole", "RCCB200O1Dn", "RCCB200OnDn", "CPCB200", "SphereCorrectorB200",
-           "PinholeCorrectorB200", "O1DnCorrectorB200", "OnDnCorrectorB200", "PCDSensorUpdaterB200", "PFParams", "GladiatorConfig", "umeyama_transform", "read_mesh_file",
+           "PinholeCorrectorB200", "O1DnCorrectorB200", "OnDnCorrectorB200", "PCDSensorUpdaterB200", "PFParams", "GladiatorConfig", "umeyama_transform", "micp_correct_once", "read_mesh_file",
            "kernel_launch_count", "lib_path", "load_library", "synth"]

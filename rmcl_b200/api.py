@@ -74,6 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode",
 ]
 
 
@@ -360,6 +361,9 @@ class RCCB200:
             lib = load_library()
             lib.b2_rcc_correct_once.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
             lib.b2_rcc_correct_once_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.b2_rcc_correct_once_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double]
+            lib.b2_rcc_correct_once_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            self._co_async, self._co_wait = lib.b2_rcc_correct_once_async, lib.b2_rcc_correct_once_wait
             sc = self._co = (buf, memoryview(buf).cast("B"), base, lib.b2_rcc_correct_once, lib.b2_rcc_correct_once_ranges)
         return sc
 
@@ -381,6 +385,28 @@ class RCCB200:
                 ranges = _f32(ranges).reshape(-1)
                 rp, rn = ranges.ctypes.data, len(ranges)
             rc = f_ranges(self._h, rp, rn, base, base + 32, iterations, convergence_progress, base + 64, base + 96, base + 128)
+        if rc != 0:
+            _chk(rc)
+        self.outdated = False
+        out = np.frombuffer(bytearray(mv[64:192]), self._CO_OUT)
+        return out["Tn"][0], out["Td"][0], out["Cm"][0]
+
+    def setExecMode(self, mode):
+        """2 (default): one kernel, software grid barrier, programmatic launch; 1: cooperative launch; 0: one reduction launch per inner iteration."""
+        _chk(load_library().b2_rcc_set_exec_mode(self._h, C.c_int(int(mode))))
+
+    def correctOnceAsync(self, Tom, Tbo, iterations=5, convergence_progress=0.0):
+        """Enqueue one correctOnce on the handle's stream and return; collect with correctOnceWait()."""
+        buf, mv, base, _, _ = self._co_scratch()
+        mv[0:32] = np.asarray(Tom).tobytes()
+        mv[32:64] = np.asarray(Tbo).tobytes()
+        rc = self._co_async(self._h, base, base + 32, iterations, convergence_progress)
+        if rc != 0:
+            _chk(rc)
+
+    def correctOnceWait(self):
+        buf, mv, base, _, _ = self._co_scratch()
+        rc = self._co_wait(self._h, base + 64, base + 96, base + 128)
         if rc != 0:
             _chk(rc)
         self.outdated = False
@@ -440,6 +466,34 @@ SphereCorrectorB200 = RCCB200Spherical
 PinholeCorrectorB200 = RCCB200Pinhole
 O1DnCorrectorB200 = RCCB200O1Dn
 OnDnCorrectorB200 = RCCB200OnDn
+
+
+def micp_correct_once(sensors, Tbo, Tom, iterations=5, convergence_progress=0.0, merge_weights=None, ranges=None):
+    """MICPLocalizationNode::correctOnce over all sensors (micp_localization.cpp:899-984): `sensors` RCCB200 / CPCB200 handles on one device,
+    `Tbo` one Transform per sensor, `merge_weights` the sensors' merge_weight_multiplier (MICPSensor.hpp:103), `ranges` optional per-sensor
+    host scans (None entries keep the resident dataset).  -> (Tom_new, T_onew_oold, Cmerged_o)."""
+    n = len(sensors)
+    hs = (C.c_void_p * n)(*[s._h for s in sensors])
+    Tb = np.ascontiguousarray(np.asarray(Tbo, TRANSFORM_DTYPE).reshape(n))
+    w = None if merge_weights is None else np.ascontiguousarray(merge_weights, np.float64).reshape(n)
+    keep, rp = [], None
+    if ranges is not None:
+        rp = (C.c_void_p * n)()
+        for k, r in enumerate(ranges):
+            if r is None:
+                rp[k] = None
+            elif hasattr(r, "data_ptr"):
+                rp[k] = r.data_ptr()
+            else:
+                r = _f32(r).reshape(-1)
+                keep.append(r)
+                rp[k] = r.ctypes.data
+    Tn, Td, Cm = np.zeros((), TRANSFORM_DTYPE), np.zeros((), TRANSFORM_DTYPE), np.zeros((), CROSS_STATS_DTYPE)
+    _chk(load_library().b2_micp_correct_once(hs, _p(Tb), _p(w), rp, C.c_uint32(n), _p(_tf(Tom)), C.c_uint32(iterations), C.c_double(convergence_progress),
+                                             _p(Tn), _p(Td), _p(Cm)))
+    for s in sensors:
+        s.outdated = False
+    return Tn, Td, Cm
 
 
 def umeyama_transform(stats, device=0):

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -333,7 +334,20 @@ extern "C" int b2_mesh_intersect_stats(const b2_mesh* m, const float* origs, con
 // RCC handle
 // ---------------------------------------------------------------------------------------------------------------------
 struct HostPin {            // pinned (mapped) staging for small results
-    b2_transform T[3]; b2_cross_stats S[2]; IcpState icp; IcpState icp_out; volatile unsigned int flag; unsigned int pad[3];
+    b2_transform T[3]; b2_cross_stats S[2]; IcpState icp;
+    uint4 chunks[B2_ICP_RESULT_CHUNKS + 1];        // result of k_icp_loop: 16-byte chunks {3 payload words, sequence number} written by the kernel
+    IcpResult res;                                  // D2H staging of the non-spin path
+    unsigned long long dbg[8];
+};
+
+// What is still to be collected from an enqueued correctOnce (b2_rcc_correct_once_async .. _wait)
+struct PendingCall {
+    bool active = false;
+    int kind = 0;                       // 0: result already in `res`, 1: spin on the mapped chunks, 2: D2H copy of d_res enqueued (stream sync), 3: D2H copy of d_icp (multi-launch chain)
+    unsigned int seq = 0;
+    bool barrier_used = false;
+    IcpLaunch launch{}; size_t smem = 0; int grid = 0;      // kept for the cooperative re-run after a barrier abort
+    IcpResult res{};
 };
 
 struct b2_rcc {
@@ -345,20 +359,31 @@ struct b2_rcc {
     DevBuf<float> d_dpts; DevBuf<uint8_t> d_dmask; uint32_t n_dataset = 0; DevBuf<float> d_ranges_in;
     DevBuf<float> d_mpts, d_mnrm, d_mranges; DevBuf<uint8_t> d_mhits; DevBuf<uint32_t> d_mfaces; uint32_t n_model = 0; bool found = false;
     DevBuf<double> d_partials; DevBuf<unsigned int> d_ticket; DevBuf<b2_cross_stats> d_stats; DevBuf<IcpState> d_icp;
+    DevBuf<IcpResult> d_res; DevBuf<unsigned long long> d_dbg;
     DevBuf<b2_transform> d_poses, d_tdelta; DevBuf<uint32_t> d_ncorr; DevBuf<b2_cross_stats> d_bstats;
-    HostPin* pin = nullptr;
+    HostPin* pin = nullptr; uint4* pin_chunks_dev = nullptr;
     int red_grid = 0;
     int fused_grid = 0;                 // blocks of k_icp_loop, one per SM (0: a whole-grid barrier is not available on this device)
+    int smem_u_cap = 0;                 // pairs per thread k_icp_loop can keep in shared memory (beyond the two in registers)
+    int exec_mode = 2;                  // b2_rcc_set_exec_mode: 2 software grid barrier + programmatic launch (default), 1 cooperative launch, 0 one launch per reduction
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
     DevBuf<unsigned int> d_bar; unsigned int bar_base = 0;      // arrival counter + abort word of the software grid barrier; counter value at the next launch
-    unsigned int seq = 0;               // completion sequence number written by k_icp_loop into pin->flag
+    unsigned int seq = 0;               // sequence number of the last k_icp_loop launch (carried by every result chunk)
+    PendingCall pending;
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
+    cudaEvent_t ev_join = nullptr;      // multi-sensor correctOnce: orders this handle's stream against the lead handle's
     uint32_t n_ranges_in = 0;           // real ranges resident in d_ranges_in (set_ranges / correct_once_ranges), needed by b2_rcc_segment
     DevBuf<uint32_t> d_seg_counts, d_seg_offsets, d_seg_totals; DevBuf<float> d_seg_scan, d_seg_map; DevBuf<uint8_t> d_seg_labels;
     int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
     uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
 };
+
+// Per device: k_icp_loop launches with the software grid barrier must never overlap each other (two partially resident grids would wait
+// for each other's SMs).  Handles on different streams are therefore chained through one event per device; a single handle on a single
+// stream -- the common case -- pays nothing (stream order already serialises its launches).
+struct DeviceCtx { std::mutex m; cudaEvent_t loop_done = nullptr; bool recorded = false, multi = false; int n_handles = 0; b2_rcc* last = nullptr; cudaStream_t last_stream = nullptr; };
+static DeviceCtx g_dev[64];
 
 static b2_transform tf_identity_pod() { b2_transform T; memset(&T, 0, sizeof(T)); T.R.w = 1.0f; return T; }
 
@@ -371,19 +396,34 @@ static int rcc_init(b2_rcc* h)
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, map->device));
     h->red_grid = prop.multiProcessorCount;
     {
-        int coop = 0, per_sm = 0;
+        // k_icp_loop: one 512-thread block per SM; the shared memory the block does not need statically holds pairs (18 KB per pair-per-thread)
+        int coop = 0, per_sm = 0, optin = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, map->device);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop<true>, B2_ICP_BLOCK, 0) == cudaSuccess && per_sm > 0)
-            h->fused_grid = prop.multiProcessorCount;      // one block per SM
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device);
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, k_icp_loop<false>) == cudaSuccess) {
+            const int room = optin - (int)fa.sharedSizeBytes - 1024;
+            h->smem_u_cap = std::max(0, room / (9 * B2_ICP_BLOCK * 4));
+            const int dyn = h->smem_u_cap * 9 * B2_ICP_BLOCK * 4;
+            if (dyn > 0 && (cudaFuncSetAttribute(k_icp_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess ||
+                            cudaFuncSetAttribute(k_icp_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess)) h->smem_u_cap = 0;
+        }
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop<true>, B2_ICP_BLOCK, (size_t)h->smem_u_cap * 9 * B2_ICP_BLOCK * 4) == cudaSuccess && per_sm > 0)
+            h->fused_grid = std::min(prop.multiProcessorCount, B2_ICP_MAX_GRID);      // one block per SM
         (void)cudaGetLastError();
     }
-    RES(h->d_partials.reserve((size_t)(B2_NACC + 1) * h->red_grid)); RES(h->d_ticket.reserve(1)); RES(h->d_stats.reserve(1)); RES(h->d_icp.reserve(1)); RES(h->d_bar.reserve(2));
+    { const char* e = getenv("B2_FUSED"); h->exec_mode = e ? atoi(e) : 2; if (h->exec_mode < 0 || h->exec_mode > 2) h->exec_mode = 2; }
+    RES(h->d_partials.reserve((size_t)(B2_NACC + 1) * std::max(h->red_grid, 2 * B2_ICP_MAX_GRID))); RES(h->d_ticket.reserve(1)); RES(h->d_stats.reserve(1)); RES(h->d_icp.reserve(1));
+    RES(h->d_bar.reserve(2)); RES(h->d_res.reserve(1)); RES(h->d_dbg.reserve(8));
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
     CU(cudaMemset(h->d_bar.p, 0, 2 * sizeof(unsigned int)));
+    CU(cudaMemset(h->d_dbg.p, 0, 8 * sizeof(unsigned long long)));
     CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
     memset((void*)h->pin, 0, sizeof(HostPin));
+    CU(cudaHostGetDevicePointer((void**)&h->pin_chunks_dev, (void*)h->pin->chunks, 0));
     CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return B2_OK;
 }
 
@@ -396,6 +436,7 @@ extern "C" int b2_rcc_create(b2_mesh* map, b2_rcc** out)
     if (!h) return fail(B2_ERR_OOM, "out of host memory");
     h->map = map; h->Tsb = tf_identity_pod();
     map->refs.fetch_add(1);             // released in b2_rcc_destroy
+    { DeviceCtx& dc = g_dev[map->device & 63]; std::lock_guard<std::mutex> lk(dc.m); if (++dc.n_handles > 1) dc.multi = true; }
     const int rc = rcc_init(h);
     if (rc != B2_OK) { b2_rcc_destroy(h); return rc; }      // the error text of the failing call stays in b2_last_error
     *out = h;
@@ -409,11 +450,13 @@ extern "C" int b2_rcc_destroy(b2_rcc* h)
     cudaStreamSynchronize(h->stream);
     h->d_dirs.release(); h->d_origs.release(); h->d_dpts.release(); h->d_dmask.release(); h->d_ranges_in.release();
     h->d_mpts.release(); h->d_mnrm.release(); h->d_mranges.release(); h->d_mhits.release(); h->d_mfaces.release();
-    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release();
+    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release(); h->d_res.release(); h->d_dbg.release();
+    { DeviceCtx& dc = g_dev[h->map->device & 63]; std::lock_guard<std::mutex> lk(dc.m); dc.n_handles--; if (dc.last == h) { dc.last = nullptr; dc.recorded = false; } }
     h->d_poses.release(); h->d_tdelta.release(); h->d_ncorr.release(); h->d_bstats.release();
     if (h->pin) cudaFreeHost(h->pin);
     if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     h->d_seg_counts.release(); h->d_seg_offsets.release(); h->d_seg_totals.release(); h->d_seg_scan.release(); h->d_seg_map.release(); h->d_seg_labels.release();
     b2_mesh* map = h->map;
@@ -447,7 +490,9 @@ extern "C" int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms)
 extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc* h, unsigned long long* out8)
 {
     NOTNULL(h); NOTNULL(out8);
-    for (int i = 0; i < 8; i++) out8[i] = h->pin->icp.dbg[i];
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out8, h->d_dbg.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 
@@ -731,141 +776,277 @@ extern "C" int b2_rcc_download_dataset(b2_rcc* h, float* p, uint8_t* m)
     return B2_OK;
 }
 
-static int correct_once_impl(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double cp,
-                             b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged, const float* ranges_host = nullptr, uint32_t n_ranges = 0)
+// ---------------------------------------------------------------------------------------------------------------------
+// correctOnce (micp_localization.cpp:899-984) for 1..B2_MAX_SENSORS sensors.  sc[0].h is the LEAD handle: its stream carries the launches,
+// its buffers hold the partial sums / the barrier / the result.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SensorCall { b2_rcc* h; b2_transform Tbo; double weight; const float* ranges_host; uint32_t n_ranges; };
+
+static void fill_sensor_frames(IcpSensor& S, const b2_transform& Tbo, const b2_transform& Tsb)
 {
-    bool aux_used = false;
-    const bool cpc = h->corr_type == B2_CORR_CPC;
-    if (ranges_host && cpc) return fail(B2_ERR_INVALID, "correctOnce(ranges) needs ray-casting correspondences (the handle is in closest-point mode)");
-    static const int use_coop = [] { const char* e = getenv("B2_FUSED"); return e ? atoi(e) : 2; }();
+    const Tf Tos = tf_mul(tf_from_pod(Tbo), tf_from_pod(Tsb));
+    memset(&S.Tos, 0, sizeof(S.Tos)); memset(&S.Tso, 0, sizeof(S.Tso));
+    tf_store(&S.Tos, Tos); tf_store(&S.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, S.Ros);
+}
+
+static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem, int mode, bool pdl)
+{
+    double* parts = H->d_partials.p; IcpResult* res_dev = H->d_res.p; uint4* host_out = H->pin_chunks_dev;
+    unsigned int* bar = H->d_bar.p; unsigned int bar_base = H->bar_base; unsigned int* bar_abort = H->d_bar.p + 1; unsigned long long* dbg = H->d_dbg.p;
+    if (mode == 1) {
+        IcpLaunch Lc = L;
+        void* args[] = {&Lc, &parts, &res_dev, &host_out, &bar, &bar_base, &bar_abort, &dbg};
+        CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop<true>, dim3((unsigned)grid), dim3(B2_ICP_BLOCK), args, smem, H->stream));
+    } else {
+        // One software-barrier loop at a time per device: launches of different handles / streams are chained through the device's event
+        DeviceCtx& dc = g_dev[H->map->device & 63];
+        std::lock_guard<std::mutex> lk(dc.m);
+        if (!dc.loop_done) CU(cudaEventCreateWithFlags(&dc.loop_done, cudaEventDisableTiming));
+        const bool foreign = dc.last && (dc.last != H || dc.last_stream != H->stream);
+        if (foreign) {
+            dc.multi = true;
+            if (dc.recorded) CU(cudaStreamWaitEvent(H->stream, dc.loop_done, 0));
+            else CU(cudaDeviceSynchronize());            // the previous launch left no marker (first change of handle / stream): drain once
+            pdl = false;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(B2_ICP_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = H->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, L, parts, res_dev, host_out, bar, bar_base, bar_abort, dbg));
+        H->bar_base += L.iterations * (unsigned int)grid;
+        dc.recorded = false;
+        if (dc.multi) { CU(cudaEventRecord(dc.loop_done, H->stream)); dc.recorded = true; }     // the marker the next foreign launch waits on
+        dc.last = H; dc.last_stream = H->stream;
+    }
+    LAUNCHED();
+    return B2_OK;
+}
+
+static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, uint32_t iterations, double cp)
+{
+    b2_rcc* H = sc[0].h;
+    if (H->pending.active) return fail(B2_ERR_INVALID, "correctOnce: the previous asynchronous call has not been collected (b2_rcc_correct_once_wait)");
     static const int use_zc = [] { const char* e = getenv("B2_ZEROCOPY"); return e ? atoi(e) : 1; }();
-    // Zero-copy scan: when the caller's buffer is pinned host memory the ICP-loop kernel reads it directly (and unpacks it) instead of
-    // memcpy + unpack kernel + cross-stream event.  Needs the register-cached loop (<= 2 pairs per thread) and the fused path.
-    const float* zc_ranges = nullptr;
-    if (ranges_host) {
-        if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
-        if (n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n_ranges, h->n);
-        if (use_zc && use_coop && h->fused_grid > 0 && iterations > 0 && h->n > 0 && h->n <= 2u * (uint32_t)h->fused_grid * B2_ICP_BLOCK) {
-            // asked on every call (about a microsecond): an address can change from pinned to pageable between calls
-            cudaPointerAttributes pa;
-            if (cudaPointerGetAttributes(&pa, ranges_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) zc_ranges = (const float*)pa.devicePointer;
-            (void)cudaGetLastError();
-        }
-        if (h->n > 0) {
-            RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n));
-            if (!zc_ranges) {
-                CU(cudaEventRecord(h->ev_aux, h->stream));                // the side stream starts after whatever the main stream had in flight BEFORE this call
-                CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
-            }
-        }
-        h->n_dataset = h->n; h->n_ranges_in = h->n;
-    }
-    // the find kernel does not read the dataset: the scan is uploaded + unpacked on the side stream WHILE it runs (and the host-side
-    // cost of issuing the copy is hidden behind the already launched find)
-    auto upload_scan = [&]() -> int {
-        if (!ranges_host || h->n == 0 || zc_ranges) return B2_OK;
-        CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
-        k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max,
-                                                                      h->d_dpts.p, h->d_dmask.p);
-        LAUNCHED();
-        CU(cudaEventRecord(h->ev_aux, h->aux));
-        aux_used = true;
-        return B2_OK;
-    };
-    if (!cpc && !h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
-    const uint32_t nw = h->work_n();
-    if (h->n_dataset != nw) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
-    IcpState& st = h->pin->icp;
-    memset(&st, 0, sizeof(st));
-    st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = h->Tsb; st.max_dist = adaptive_max_dist(h, cp);
-    st.T_onew_oold = tf_identity_pod(); st.Tom_new = *Tom;
-    // pre-transform of the first reduction, evaluated on the host with the same inline functions the kernels use (individually
-    // rounded ops on both sides -> identical bits); saves a launch
-    tf_store(&st.T_snew_sold, icp_pretransform(tf_from_pod(*Tbo), tf_from_pod(h->Tsb), tf_identity()));
-    {
-        const Tf Tos = tf_mul(tf_from_pod(*Tbo), tf_from_pod(h->Tsb));
-        tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros);
-    }
-    bool barrier_used = false;
     static const int use_spin = [] { const char* e = getenv("B2_SPIN"); return e ? atoi(e) : 1; }();
-    bool waited = false;
-    if (nw > 0 && use_coop && h->fused_grid > 0 && iterations > 0) {
-        // find, then ALL inner iterations in one cooperative kernel; state in by kernel parameter, result out through mapped pinned memory
-        if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
-        b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
-        tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(*Tbo)));        // MICPSensor.hpp:148, same inline ops as the kernels
-        static const int use_pdl = [] { const char* e = getenv("B2_PDL"); return e ? atoi(e) : 1; }();
-        h->pdl_next = use_coop == 2 && use_pdl && !h->timing && h->corr_type == B2_CORR_RCC && (!ranges_host || zc_ranges);      // event records between the two kernels would serialise them anyway
-        const int rc_find = launch_find(h, &Tbm_host, nullptr);
-        h->pdl_next = false;
-        RES(rc_find);
-        if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
-        RES(upload_scan());
-        if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
-        int grid = std::min<int>(h->fused_grid, (int)((nw + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK));
-        if (grid < 1) grid = 1;
-        RES(h->d_partials.reserve((size_t)2 * grid * (B2_NACC + 1)));
-        const float* dp = h->d_dpts.p; const uint8_t* dmk = h->d_dmask.p; const float* mp = h->d_mpts.p; const float* mn = h->d_mnrm.p; const uint8_t* mh = h->d_mhits.p;
-        uint32_t nel = nw; IcpState* icp_dev = h->d_icp.p; uint32_t its = iterations; double* parts = h->d_partials.p;
-        IcpState* host_out = use_spin ? &h->pin->icp_out : nullptr; volatile unsigned int* host_flag = use_spin ? &h->pin->flag : nullptr;
-        unsigned int seq = ++h->seq; if (seq == 0) seq = ++h->seq;
-        // B2_FUSED=2 (default): ordinary launch + software grid barrier (one block per SM, all resident) -- measured ~10 us less launch
-        // overhead per step than the cooperative launch (B2_FUSED=1), which stays available
-        unsigned int* bar = h->d_bar.p; unsigned int bar_base = h->bar_base; unsigned int* bar_abort = h->d_bar.p + 1;
-        RayModel zc_model = ray_model(h); float* zc_dpts = h->d_dpts.p; uint8_t* zc_dmask = h->d_dmask.p; float* zc_rin = h->d_ranges_in.p;
-        if (use_coop == 1) {
-            void* args[] = {&dp, &dmk, &mp, &mn, &mh, &nel, &icp_dev, &its, &parts, &st, &host_out, &host_flag, &seq, &bar, &bar_base, &bar_abort, &zc_ranges, &zc_model, &zc_dpts, &zc_dmask, &zc_rin};
-            CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop<true>, dim3(grid), dim3(B2_ICP_BLOCK), args, 0, h->stream));
-        } else {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(B2_ICP_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = (h->pdl_armed && !aux_used) ? 1 : 0;      // with a scan upload in flight the kernel also waits on the side stream's event
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, dp, dmk, mp, mn, mh, nel, icp_dev, its, parts, st, host_out, host_flag, seq, bar, bar_base, bar_abort, zc_ranges, zc_model, zc_dpts, zc_dmask, zc_rin));
-            h->bar_base += its * (unsigned int)grid;
-            barrier_used = true;
+    static const int use_pdl = [] { const char* e = getenv("B2_PDL"); return e ? atoi(e) : 1; }();
+    int mode = H->exec_mode;
+    if (H->fused_grid <= 0) mode = 0;
+    if (ns > 1 && mode == 0) mode = H->fused_grid > 0 ? 1 : 0;
+    if (ns > 1 && mode == 0) return fail(B2_ERR_UNSUPPORTED, "multi-sensor correctOnce needs a device with cooperative launch");
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < ns; k++) {
+        b2_rcc* h = sc[k].h;
+        if (h->map->device != H->map->device) return fail(B2_ERR_INVALID, "correctOnce: all sensors must live on the same device");
+        const bool cpc = h->corr_type == B2_CORR_CPC;
+        if (sc[k].ranges_host && cpc) return fail(B2_ERR_INVALID, "correctOnce(ranges) needs ray-casting correspondences (the handle is in closest-point mode)");
+        if (!cpc && !h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
+        if (sc[k].ranges_host) {
+            if (sc[k].n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", sc[k].n_ranges, h->n);
+            h->n_dataset = h->n; h->n_ranges_in = h->n;
+            if (h->n > 0) { RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n)); }
         }
-        LAUNCHED();
-        if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
-        if (use_spin) {
-            // spin on the completion flag the kernel writes into mapped host memory (a stream synchronise costs several microseconds more)
-            const auto t_start = std::chrono::steady_clock::now();
-            unsigned long long spins = 0;
-            while (h->pin->flag != seq) {
-                if ((++spins & 0xfffffull) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 5.0) break;
-            }
-            if (h->pin->flag == seq) { memcpy(&st, (const void*)&h->pin->icp_out, sizeof(IcpState)); waited = true; }
+        if (h->n_dataset != h->work_n()) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
+        total += h->work_n();
+    }
+    PendingCall& pc = H->pending;
+    pc = PendingCall();
+    // ---- nothing to do on the device: identity update (micp_localization.cpp:974: Tom stays when n_meas == 0) ----
+    if (total == 0 || iterations == 0) {
+        memset(&pc.res, 0, sizeof(pc.res));
+        pc.res.Tom_new = *Tom; pc.res.T_onew_oold = tf_identity_pod();
+        if (total > 0) for (uint32_t k = 0; k < ns; k++) {          // iterations == 0: the reference still runs findCorrespondences (:900-908)
+            b2_transform Tbm; memset(&Tbm, 0, sizeof(Tbm)); tf_store(&Tbm, tf_mul(tf_from_pod(*Tom), tf_from_pod(sc[k].Tbo)));
+            if (sc[k].ranges_host && sc[k].h->n) { RES(ranges_to_dataset(sc[k].h, sc[k].ranges_host, sc[k].n_ranges, 0)); CU(cudaStreamSynchronize(sc[k].h->stream)); }
+            RES(launch_find(sc[k].h, &Tbm, nullptr));
         }
-    } else if (nw > 0) {
-        RES(upload_scan());
-        if (aux_used) CU(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
+        pc.active = true; pc.kind = 0;
+        return B2_OK;
+    }
+    // ---- the multi-launch chain (exec mode 0): find + one k_p2l_reduce per inner iteration, state in device memory ----
+    if (mode == 0) {
+        b2_rcc* h = H;
+        if (sc[0].ranges_host && h->n) RES(ranges_to_dataset(h, sc[0].ranges_host, sc[0].n_ranges, 0));
+        IcpState& st = h->pin->icp;
+        memset(&st, 0, sizeof(st));
+        st.Tom = *Tom; st.Tbo = sc[0].Tbo; st.Tsb = h->Tsb; st.max_dist = (float)(h->max_dist * (1.0 - cp) + h->adaptive_max_dist_min * cp);
+        st.T_onew_oold = tf_identity_pod(); st.Tom_new = *Tom;
+        tf_store(&st.T_snew_sold, icp_pretransform(tf_from_pod(sc[0].Tbo), tf_from_pod(h->Tsb), tf_identity()));
         CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
         if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
         RES(launch_find(h, nullptr, h->d_icp.p));
         if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
         for (uint32_t it = 0; it < iterations; it++) RES(launch_reduce(h, nullptr, 0.f, h->d_icp.p, nullptr));
         if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
-    } else {
-        CU(cudaMemcpyAsync(h->d_icp.p, &st, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
-    }
-    if (!waited) {
         CU(cudaMemcpyAsync(&st, h->d_icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        if (barrier_used) {
-            // the completion flag never arrived: either the spin is switched off, or the grid barrier gave up (blocks not co-resident)
-            unsigned int bar_state[2] = {0u, 0u};
-            CU(cudaMemcpy(bar_state, h->d_bar.p, sizeof(bar_state), cudaMemcpyDeviceToHost));
-            if (bar_state[1] != 0u) {
-                CU(cudaMemset(h->d_bar.p, 0, 2 * sizeof(unsigned int))); h->bar_base = 0;
-                return fail(B2_ERR_CUDA, "correctOnce: the grid barrier of the ICP loop timed out (blocks not co-resident); set B2_FUSED=1 or 0");
-            }
+        pc.active = true; pc.kind = 3;
+        return B2_OK;
+    }
+    // ---- fused path: find per sensor, then ALL inner iterations of ALL sensors in one k_icp_loop ----
+    IcpLaunch& L = pc.launch;
+    memset(&L, 0, sizeof(L));
+    L.Tom = *Tom; L.n_sensors = ns; L.iterations = iterations;
+    int grid = std::min<int>(H->fused_grid, (int)std::max<uint64_t>((total + B2_ICP_BLOCK - 1) / B2_ICP_BLOCK, ns));
+    // blocks per sensor in proportion to the pairs, at least one each
+    uint32_t nblk[B2_MAX_SENSORS]; int assigned = 0;
+    for (uint32_t k = 0; k < ns; k++) { nblk[k] = std::max<uint32_t>(1u, (uint32_t)((uint64_t)grid * sc[k].h->work_n() / total)); assigned += (int)nblk[k]; }
+    while (assigned > grid) { uint32_t big = 0; for (uint32_t k = 1; k < ns; k++) if (nblk[k] > nblk[big]) big = k; nblk[big]--; assigned--; }
+    while (assigned < grid) { uint32_t best = 0; double load = -1.0; for (uint32_t k = 0; k < ns; k++) { const double l = (double)sc[k].h->work_n() / nblk[k]; if (l > load) { load = l; best = k; } } nblk[best]++; assigned++; }
+    bool aux_any = false;
+    uint32_t blk0 = 0, smem_u_max = 0;
+    if (H->timing) CU(cudaEventRecord(H->ev[0], H->stream));
+    for (uint32_t k = 0; k < ns; k++) {
+        b2_rcc* h = sc[k].h;
+        IcpSensor& S = L.s[k];
+        const uint32_t nw = h->work_n();
+        S.n = nw; S.blk0 = blk0; S.nblk = nblk[k]; blk0 += nblk[k];
+        const uint32_t stride = S.nblk * B2_ICP_BLOCK;
+        const uint32_t per_thread = (nw + stride - 1) / stride;
+        S.smem_u = per_thread > B2_ICP_REG_PAIRS ? std::min<uint32_t>(per_thread - B2_ICP_REG_PAIRS, (uint32_t)H->smem_u_cap) : 0u;
+        smem_u_max = std::max(smem_u_max, S.smem_u);
+        S.max_dist = (float)(h->max_dist * (1.0 - cp) + h->adaptive_max_dist_min * cp);       // CorrespondencesCPU.cpp:21-23
+        S.merge_weight = sc[k].weight; S.range_min = h->range_min; S.range_max = h->range_max;
+        fill_sensor_frames(S, sc[k].Tbo, h->Tsb);
+        // Zero-copy scan: when the caller's buffer is pinned host memory the loop kernel reads it directly (and unpacks it) instead of
+        // memcpy + unpack kernel + cross-stream event.  Needs every pair of the sensor resident in registers / shared memory.
+        const float* zc = nullptr;
+        if (sc[k].ranges_host && nw > 0 && use_zc && per_thread <= B2_ICP_REG_PAIRS + S.smem_u) {
+            cudaPointerAttributes pa;      // asked on every call (about a microsecond): an address can change from pinned to pageable between calls
+            if (cudaPointerGetAttributes(&pa, sc[k].ranges_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) zc = (const float*)pa.devicePointer;
+            (void)cudaGetLastError();
+        }
+        const bool need_upload = sc[k].ranges_host && nw > 0 && !zc;
+        if (need_upload) {      // the side stream starts after whatever this sensor's stream had in flight BEFORE this call
+            CU(cudaEventRecord(h->ev_aux, h == H ? H->stream : h->stream));
+            CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+        }
+        if (h != H) {           // order the lead stream behind this sensor's own stream (pending set_ranges / set_dataset copies)
+            CU(cudaEventRecord(h->ev_join, h->stream));
+            CU(cudaStreamWaitEvent(H->stream, h->ev_join, 0));
+        }
+        b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
+        tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(sc[k].Tbo)));          // MICPSensor.hpp:148, same inline ops as the kernels
+        // the loop kernel may start early behind the LAST find only (event records / other kernels in between would serialise them anyway)
+        const cudaStream_t own = h->stream;
+        h->stream = H->stream;                                                        // all launches of this call ride the lead stream
+        h->pdl_next = (k + 1 == ns) && mode == 2 && use_pdl && !H->timing && h->corr_type == B2_CORR_RCC && !need_upload && !aux_any;
+        const int rc_find = launch_find(h, &Tbm_host, nullptr);
+        h->pdl_next = false; h->stream = own;
+        RES(rc_find);
+        if (need_upload) {
+            // the find kernel does not read the dataset: the scan is uploaded + unpacked on the side stream WHILE it runs
+            CU(cudaMemcpyAsync(h->d_ranges_in.p, sc[k].ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
+            k_dataset_from_ranges<<<(h->n + 255) / 256, 256, 0, h->aux>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, h->n, h->range_min, h->range_max, h->d_dpts.p, h->d_dmask.p);
+            LAUNCHED();
+            CU(cudaEventRecord(h->ev_aux, h->aux));
+            CU(cudaStreamWaitEvent(H->stream, h->ev_aux, 0));
+            aux_any = true;
+        }
+        S.dpts = h->d_dpts.p; S.dmask = h->d_dmask.p; S.mpts = h->d_mpts.p; S.mnrm = h->d_mnrm.p; S.mmask = h->d_mhits.p;
+        S.zc_ranges = zc; S.zc_dirs = h->d_dirs.p; S.zc_origs = h->d_origs.p; S.zc_n_origs = h->n_origs;
+        S.dpts_out = h->d_dpts.p; S.dmask_out = h->d_dmask.p; S.ranges_out = h->d_ranges_in.p;
+    }
+    if (H->timing) CU(cudaEventRecord(H->ev[1], H->stream));
+    L.smem_u_max = smem_u_max;
+    unsigned int seq = ++H->seq; if (seq == 0) seq = ++H->seq;
+    L.seq = seq;
+    const size_t smem = (size_t)smem_u_max * 9 * B2_ICP_BLOCK * sizeof(float);
+    const bool pdl = mode == 2 && sc[ns - 1].h->pdl_armed && !aux_any;
+    sc[ns - 1].h->pdl_armed = false;
+    RES(launch_icp_loop(H, L, grid, smem, mode, pdl));
+    if (H->timing) { CU(cudaEventRecord(H->ev[2], H->stream)); H->timing_valid = true; }
+    for (uint32_t k = 1; k < ns; k++) {        // later work on the other sensors' own streams sees the model buffers this call wrote
+        CU(cudaEventRecord(sc[k].h->ev_join, H->stream));
+        CU(cudaStreamWaitEvent(sc[k].h->stream, sc[k].h->ev_join, 0));
+    }
+    pc.active = true; pc.seq = seq; pc.grid = grid; pc.smem = smem; pc.barrier_used = mode == 2;
+    if (use_spin) pc.kind = 1;
+    else { CU(cudaMemcpyAsync(&H->pin->res, H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream)); pc.kind = 2; }
+    return B2_OK;
+}
+
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
+
+// every chunk of the mapped result carries this call's sequence number?
+static bool chunks_ready(const HostPin* pin, unsigned int seq)
+{
+    const volatile uint4* c = pin->chunks;
+    for (int i = 0; i < B2_ICP_RESULT_CHUNKS; i++) if (c[i].w != seq) return false;
+    return true;
+}
+
+static int micp_collect(b2_rcc* H, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    PendingCall& pc = H->pending;
+    if (!pc.active) return fail(B2_ERR_INVALID, "correctOnce: nothing to wait for");
+    pc.active = false;
+    bool have = pc.kind == 0;
+    if (pc.kind == 1) {
+        // spin on the chunks the kernel writes into mapped host memory (a stream synchronise costs several microseconds more)
+        const auto t_start = std::chrono::steady_clock::now();
+        unsigned long long spins = 0;
+        while (!chunks_ready(H->pin, pc.seq)) {
+            cpu_relax();
+            if ((++spins & 0xfffffull) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 5.0) break;
+        }
+        if (chunks_ready(H->pin, pc.seq)) {
+            std::atomic_thread_fence(std::memory_order_acquire);          // payload reads stay behind the sequence-number reads (aarch64 hosts)
+            uint32_t w[3 * B2_ICP_RESULT_CHUNKS];
+            for (int i = 0; i < B2_ICP_RESULT_CHUNKS; i++) { const volatile uint4* c = &H->pin->chunks[i]; w[3 * i] = c->x; w[3 * i + 1] = c->y; w[3 * i + 2] = c->z; }
+            memcpy(&pc.res, w, sizeof(IcpResult));
+            have = true;
         }
     }
-    if (Tom_new) *Tom_new = st.Tom_new;
-    if (T_onew_oold) *T_onew_oold = st.T_onew_oold;
-    if (Cmerged) *Cmerged = st.Cmerged_o;
+    if (!have) {
+        const cudaError_t e = cudaStreamSynchronize(H->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(B2_ERR_CUDA, "correctOnce: %s", cudaGetErrorString(e)); }
+        if (pc.kind == 3) {
+            const IcpState& st = H->pin->icp;
+            pc.res.Tom_new = st.Tom_new; pc.res.T_onew_oold = st.T_onew_oold; pc.res.Cmerged_o = st.Cmerged_o;
+            have = true;
+        } else {
+            bool aborted = false;
+            if (pc.barrier_used) {
+                unsigned int bar_state[2] = {0u, 0u};
+                CU(cudaMemcpy(bar_state, H->d_bar.p, sizeof(bar_state), cudaMemcpyDeviceToHost));
+                aborted = bar_state[1] != 0u;
+            }
+            if (aborted) {
+                // The software grid barrier gave up (its blocks were not co-resident: SMs held by something that itself waits).  That is a
+                // scheduling condition, not an error: reset the barrier and run the same iterations again through the cooperative launch,
+                // whose co-residency the driver guarantees.  The find results are already in the model buffers.
+                CU(cudaMemset(H->d_bar.p, 0, 2 * sizeof(unsigned int))); H->bar_base = 0;
+                unsigned int seq = ++H->seq; if (seq == 0) seq = ++H->seq;
+                pc.launch.seq = seq;
+                RES(launch_icp_loop(H, pc.launch, pc.grid, pc.smem, 1, false));
+            }
+            if (aborted || pc.kind == 1) {
+                CU(cudaMemcpyAsync(&H->pin->res, H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream));
+                CU(cudaStreamSynchronize(H->stream));
+            }
+            memcpy(&pc.res, (const void*)&H->pin->res, sizeof(IcpResult));
+        }
+    }
+    if (Tom_new) *Tom_new = pc.res.Tom_new;
+    if (T_onew_oold) *T_onew_oold = pc.res.T_onew_oold;
+    if (Cmerged) *Cmerged = pc.res.Cmerged_o;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_exec_mode(b2_rcc* h, int mode)
+{
+    NOTNULL(h);
+    if (mode < 0 || mode > 2) return fail(B2_ERR_INVALID, "unknown exec mode %d", mode);
+    h->exec_mode = mode;
     return B2_OK;
 }
 
@@ -874,7 +1055,9 @@ extern "C" int b2_rcc_correct_once(b2_rcc* h, const b2_transform* Tom, const b2_
 {
     NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
     CU(cudaSetDevice(h->map->device));
-    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged);
+    SensorCall sc{h, *Tbo, 1.0, nullptr, 0};
+    RES(micp_enqueue(&sc, 1, Tom, iterations, cp));
+    return micp_collect(h, Tom_new, T_onew_oold, Cmerged);
 }
 
 extern "C" int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges, uint32_t n, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations,
@@ -883,7 +1066,43 @@ extern "C" int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges, uint32
     NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
     CU(cudaSetDevice(h->map->device));
     if (n) NOTNULL(ranges);
-    return correct_once_impl(h, Tom, Tbo, iterations, cp, Tom_new, T_onew_oold, Cmerged, ranges, n);
+    if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
+    SensorCall sc{h, *Tbo, 1.0, n ? ranges : nullptr, n};
+    if (n == 0 && h->n != 0) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n, h->n);
+    RES(micp_enqueue(&sc, 1, Tom, iterations, cp));
+    return micp_collect(h, Tom_new, T_onew_oold, Cmerged);
+}
+
+extern "C" int b2_rcc_correct_once_async(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double cp)
+{
+    NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
+    CU(cudaSetDevice(h->map->device));
+    SensorCall sc{h, *Tbo, 1.0, nullptr, 0};
+    return micp_enqueue(&sc, 1, Tom, iterations, cp);
+}
+
+extern "C" int b2_rcc_correct_once_wait(b2_rcc* h, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    NOTNULL(h);
+    CU(cudaSetDevice(h->map->device));
+    return micp_collect(h, Tom_new, T_onew_oold, Cmerged);
+}
+
+extern "C" int b2_micp_correct_once(b2_rcc* const* sensors, const b2_transform* Tbo, const double* merge_weights, const float* const* ranges_host, uint32_t n_sensors,
+                                    const b2_transform* Tom, uint32_t iterations, double cp, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    NOTNULL(sensors); NOTNULL(Tbo); NOTNULL(Tom);
+    if (n_sensors == 0 || n_sensors > B2_MAX_SENSORS) return fail(B2_ERR_INVALID, "correctOnce: %u sensors (1..%d supported per call)", n_sensors, B2_MAX_SENSORS);
+    SensorCall sc[B2_MAX_SENSORS];
+    for (uint32_t k = 0; k < n_sensors; k++) {
+        NOTNULL(sensors[k]);
+        for (uint32_t j = 0; j < k; j++) if (sensors[j] == sensors[k]) return fail(B2_ERR_INVALID, "correctOnce: sensor %u given twice", k);
+        sc[k].h = sensors[k]; sc[k].Tbo = Tbo[k]; sc[k].weight = merge_weights ? merge_weights[k] : 1.0;
+        sc[k].ranges_host = ranges_host ? ranges_host[k] : nullptr; sc[k].n_ranges = sc[k].ranges_host ? sensors[k]->n : 0;
+    }
+    CU(cudaSetDevice(sc[0].h->map->device));
+    RES(micp_enqueue(sc, n_sensors, Tom, iterations, cp));
+    return micp_collect(sc[0].h, Tom_new, T_onew_oold, Cmerged);
 }
 
 extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t n_poses, int poses_on_device,

@@ -1,0 +1,419 @@
+// icp_loop.cuh -- the inner iterations of MICPLocalizationNode::correctOnce (rmcl_ros/src/nodes/micp_localization.cpp:915-964) for up to
+// B2_MAX_SENSORS sensors in ONE kernel (included at the end of kernels.cuh).
+//
+//   per iteration (reference, per sensor s):  T_bnew_bold = ~Tbo_s * T_onew_oold * Tbo_s                    :926
+//                                             Cs_b = sensor.computeCrossStatistics(T_bnew_bold, cp)          :928  (MICPSensor.hpp:158-184)
+//                                             Cs_o = Tbo_s * Cs_b;  weighted copy n_meas *= merge_weight     :931-934 (u32 *= double truncates, quirk D3)
+//                                             Cmerged_o += Cs_o;  Cmerged_weighted_o += Cs_weighted_o        :936-937
+//                                           T_inner = umeyama_transform(Cmerged_weighted_o)                  :952-953
+//                                           T_onew_oold = T_onew_oold * T_inner                              :963
+//
+// Shape on the B200: one 512-thread block per SM; the blocks are split among the sensors in proportion to their pair counts.  Every thread
+// owns a fixed set of (dataset, model) pairs for the whole kernel -- two in registers, the next ones in shared memory, anything beyond
+// streamed from L2 -- so that after the first pass an iteration touches no global memory except 128 bytes of partial sums per block.
+// Per iteration:  P2L pass (FP32 per-pair math identical to the oracle, FP64 sums) -> reduce-scatter warp reduction -> block partial ->
+// software grid barrier (or cooperative grid sync) -> EVERY block re-sums the partials in the same fixed order and runs the serial tail
+// redundantly (no broadcast hop).  The result leaves through mapped pinned host memory in 16-byte chunks that each carry the sequence
+// number of the call, so the host needs no separate completion flag and the kernel no system-wide fence.
+#pragma once
+
+#define B2_MAX_SENSORS 4
+#define B2_ICP_BLOCK 512
+#define B2_ICP_REG_PAIRS 2                     // pairs per thread kept in registers
+#define B2_ICP_MAX_GRID 160                    // re-sum: 32 groups x 5 predicated loads
+
+struct IcpSensor {
+    const float* dpts; const uint8_t* dmask;                   // dataset (sensor frame)
+    const float* mpts; const float* mnrm; const uint8_t* mmask; // model buffers written by find (sensor frame)
+    const float* zc_ranges;                                     // != nullptr: the scan is read from the caller's pinned host buffer and unpacked here
+    const float* zc_dirs; const float* zc_origs;                //   (MICPSphericalSensorCPU.cpp:181-233), results mirrored into the handle's buffers:
+    float* dpts_out; uint8_t* dmask_out; float* ranges_out;
+    double merge_weight;                                        // MICPSensor.hpp:103, applied at micp_localization.cpp:934
+    b2_transform Tos, Tso;                                      // Tos = Tbo * Tsb (sensor -> odom), Tso = ~Tos, composed once on the host
+    float Ros[9];                                               // rotation matrix of Tos, row-major
+    float max_dist, range_min, range_max;
+    uint32_t n, blk0, nblk, zc_n_origs, smem_u;                 // pairs; blocks [blk0, blk0+nblk); pairs per thread kept in shared memory
+    uint32_t pad_;
+};
+struct IcpLaunch {
+    IcpSensor s[B2_MAX_SENSORS];
+    b2_transform Tom;
+    uint32_t n_sensors, iterations, seq, smem_u_max;
+};
+struct IcpResult { b2_transform Tom_new, T_onew_oold; b2_cross_stats Cmerged_o; };                  // 128 bytes
+static_assert(sizeof(IcpResult) == 128, "IcpResult must be 128 bytes");
+#define B2_ICP_RESULT_CHUNKS 11                // 32 payload words, 3 per 16-byte chunk + the sequence number
+
+// ---------------------------------------------------------------------------------------------------------------------
+// serial tail of one inner iteration (one thread; host+device so that tests/emul runs the same code)
+// ---------------------------------------------------------------------------------------------------------------------
+B2_DEV double b2_rcp_u32(uint32_t n)
+{
+    const double d = (double)n;
+    double x = (double)b2_rcp_approx((float)n);
+    x = x * (2.0 - d * x); x = x * (2.0 - d * x);              // two Newton steps: full double precision without the software division
+    return x;
+}
+
+// sums (n, S_d, S_m, S_md^T in FP64) -> CrossStatistics in FP32, like acc_finalize but without the FP64 division
+B2_DEV CStats icp_finalize(const double* v)
+{
+    CStats s = cs_identity();
+    const uint32_t n = (uint32_t)(v[B2_NACC] + 0.5);
+    if (n == 0) return s;
+    const double inv = b2_rcp_u32(n);
+    double dm[3], mm[3];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) { dm[k] = v[k] * inv; mm[k] = v[3 + k] * inv; }
+    s.dm = mk3((float)dm[0], (float)dm[1], (float)dm[2]);
+    s.mm = mk3((float)mm[0], (float)mm[1], (float)mm[2]);
+    #pragma unroll
+    for (int c = 0; c < 3; c++)
+        #pragma unroll
+        for (int r = 0; r < 3; r++) s.C[c * 3 + r] = (float)(v[6 + c * 3 + r] * inv - mm[r] * dm[c]);
+    s.n = n;
+    return s;
+}
+
+// Tos * stats in rotation-matrix form (means as points, C -> R C R^T), explicit FMAs
+B2_DEV CStats icp_to_odom(const float* R, V3 t, const CStats& s)
+{
+    CStats o; o.n = s.n;
+    o.dm = mk3(fma_rn(R[2], s.dm.z, fma_rn(R[1], s.dm.y, fma_rn(R[0], s.dm.x, t.x))), fma_rn(R[5], s.dm.z, fma_rn(R[4], s.dm.y, fma_rn(R[3], s.dm.x, t.y))),
+               fma_rn(R[8], s.dm.z, fma_rn(R[7], s.dm.y, fma_rn(R[6], s.dm.x, t.z))));
+    o.mm = mk3(fma_rn(R[2], s.mm.z, fma_rn(R[1], s.mm.y, fma_rn(R[0], s.mm.x, t.x))), fma_rn(R[5], s.mm.z, fma_rn(R[4], s.mm.y, fma_rn(R[3], s.mm.x, t.y))),
+               fma_rn(R[8], s.mm.z, fma_rn(R[7], s.mm.y, fma_rn(R[6], s.mm.x, t.z))));
+    float RC[9];
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) RC[i * 3 + j] = fma_rn(R[i * 3 + 2], s.C[j * 3 + 2], fma_rn(R[i * 3 + 1], s.C[j * 3 + 1], mul(R[i * 3 + 0], s.C[j * 3 + 0])));
+    #pragma unroll
+    for (int i = 0; i < 3; i++)
+        #pragma unroll
+        for (int j = 0; j < 3; j++) o.C[j * 3 + i] = fma_rn(RC[i * 3 + 2], R[j * 3 + 2], fma_rn(RC[i * 3 + 1], R[j * 3 + 1], mul(RC[i * 3 + 0], R[j * 3 + 0])));
+    return o;
+}
+
+// Orthogonal polar factor of C (det > 0) by the Frobenius-scaled Newton iteration, everything in registers: FP32 iterations, one FP64
+// polishing step whose 1/det is a Newton reciprocal around 1.  Returns false for reflections / singular / non-converged input (the caller
+// then takes the Jacobi SVD).  Same mathematics as polar_newton3, minus the call, the stack frame and the software divisions.
+B2_DEV bool icp_polar(const float* C /* column-major, like CStats::C */, float* Rf /* row-major */)
+{
+    float X[9];
+    #pragma unroll
+    for (int r = 0; r < 3; r++)
+        #pragma unroll
+        for (int c = 0; c < 3; c++) X[r * 3 + c] = C[c * 3 + r];
+    float fro = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 9; i++) fro = fma_rn(X[i], X[i], fro);
+    if (!(fro > 1e-30f)) return false;
+    const float inv_n = b2_rsqrt_approx(fro);
+    #pragma unroll
+    for (int i = 0; i < 9; i++) X[i] = mul(X[i], inv_n);
+    bool conv = false;
+    for (int it = 0; it < 40 && !conv; it++) {
+        float Cf[9];
+        Cf[0] = fma_rn(X[4], X[8], -mul(X[5], X[7])); Cf[1] = fma_rn(X[5], X[6], -mul(X[3], X[8])); Cf[2] = fma_rn(X[3], X[7], -mul(X[4], X[6]));
+        Cf[3] = fma_rn(X[2], X[7], -mul(X[1], X[8])); Cf[4] = fma_rn(X[0], X[8], -mul(X[2], X[6])); Cf[5] = fma_rn(X[1], X[6], -mul(X[0], X[7]));
+        Cf[6] = fma_rn(X[1], X[5], -mul(X[2], X[4])); Cf[7] = fma_rn(X[2], X[3], -mul(X[0], X[5])); Cf[8] = fma_rn(X[0], X[4], -mul(X[1], X[3]));
+        const float det = fma_rn(X[2], Cf[2], fma_rn(X[1], Cf[1], mul(X[0], Cf[0])));
+        if (!(det > 1e-12f)) return false;
+        float a, b;
+        if (it < 3) {
+            // two short FMA chains per norm instead of one of nine
+            const float nx = add(fma_rn(X[4], X[4], fma_rn(X[3], X[3], fma_rn(X[2], X[2], fma_rn(X[1], X[1], mul(X[0], X[0]))))), fma_rn(X[8], X[8], fma_rn(X[7], X[7], fma_rn(X[6], X[6], mul(X[5], X[5])))));
+            const float nc = add(fma_rn(Cf[4], Cf[4], fma_rn(Cf[3], Cf[3], fma_rn(Cf[2], Cf[2], fma_rn(Cf[1], Cf[1], mul(Cf[0], Cf[0]))))), fma_rn(Cf[8], Cf[8], fma_rn(Cf[7], Cf[7], fma_rn(Cf[6], Cf[6], mul(Cf[5], Cf[5])))));
+            const float rdet = b2_rcp_approx(det);
+            const float q = mul(nc, b2_rcp_approx(nx));
+            const float g2 = mul(mul(q, b2_rsqrt_approx(q)), rdet);
+            const float rg = b2_rsqrt_approx(g2);
+            a = mul(mul(0.5f, g2), rg); b = mul(mul(0.5f, rg), rdet);
+        } else { a = 0.5f; b = mul(0.5f, b2_rcp_approx(det)); }
+        float diff = 0.f;
+        #pragma unroll
+        for (int i = 0; i < 9; i++) { const float y = fma_rn(b, Cf[i], mul(a, X[i])); const float d = sub(y, X[i]); diff = fma_rn(d, d, diff); X[i] = y; }
+        conv = (it >= 3) && diff < 1e-10f;
+    }
+    if (!conv) return false;
+    double Y[9];
+    #pragma unroll
+    for (int i = 0; i < 9; i++) Y[i] = (double)X[i];
+    double Cf[9];
+    Cf[0] = Y[4] * Y[8] - Y[5] * Y[7]; Cf[1] = Y[5] * Y[6] - Y[3] * Y[8]; Cf[2] = Y[3] * Y[7] - Y[4] * Y[6];
+    Cf[3] = Y[2] * Y[7] - Y[1] * Y[8]; Cf[4] = Y[0] * Y[8] - Y[2] * Y[6]; Cf[5] = Y[1] * Y[6] - Y[0] * Y[7];
+    Cf[6] = Y[1] * Y[5] - Y[2] * Y[4]; Cf[7] = Y[2] * Y[3] - Y[0] * Y[5]; Cf[8] = Y[0] * Y[4] - Y[1] * Y[3];
+    const double det = Y[0] * Cf[0] + Y[1] * Cf[1] + Y[2] * Cf[2];
+    const double e = 1.0 - det;                                   // |e| ~ 1e-6 after the FP32 iterations: 1/det = 1 + e + e^2 + O(e^3)
+    const double b = 0.5 * (1.0 + e + e * e);
+    #pragma unroll
+    for (int i = 0; i < 9; i++) Rf[i] = (float)(0.5 * Y[i] + b * Cf[i]);
+    return true;
+}
+
+// rotation matrix (row-major, orthogonal) -> unit quaternion; same branches and rounding as the tail of umeyama_dev
+B2_DEV Q4 icp_mat_to_quat(const float* R)
+{
+    float q[4];
+    const float tr = R[0] + R[4] + R[8];
+    if (tr > 0.0f) {
+        const float sc = sqrt_rn(tr + 1.0f) * 2.0f; q[3] = 0.25f * sc;
+        q[0] = dvd(R[7] - R[5], sc); q[1] = dvd(R[2] - R[6], sc); q[2] = dvd(R[3] - R[1], sc);
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        const float sc = sqrt_rn(1.0f + R[0] - R[4] - R[8]) * 2.0f; q[3] = dvd(R[7] - R[5], sc);
+        q[0] = 0.25f * sc; q[1] = dvd(R[1] + R[3], sc); q[2] = dvd(R[2] + R[6], sc);
+    } else if (R[4] > R[8]) {
+        const float sc = sqrt_rn(1.0f + R[4] - R[0] - R[8]) * 2.0f; q[3] = dvd(R[2] - R[6], sc);
+        q[0] = dvd(R[1] + R[3], sc); q[1] = 0.25f * sc; q[2] = dvd(R[5] + R[7], sc);
+    } else {
+        const float sc = sqrt_rn(1.0f + R[8] - R[0] - R[4]) * 2.0f; q[3] = dvd(R[3] - R[1], sc);
+        q[0] = dvd(R[2] + R[6], sc); q[1] = dvd(R[5] + R[7], sc); q[2] = 0.25f * sc;
+    }
+    Q4 qq; qq.x = q[0]; qq.y = q[1]; qq.z = q[2]; qq.w = q[3];
+    return q_normalize(qq);
+}
+
+// rm::umeyama_transform on the critical path of the loop: polar fast path inline, SVD fallback out of line
+B2_DEV Tf icp_umeyama(const CStats& s)
+{
+    if (s.n == 0) return tf_identity();
+    float Rf[9];
+    if (!icp_polar(s.C, Rf)) return umeyama_dev(s);
+    Tf out;
+    out.R = icp_mat_to_quat(Rf);
+    out.t = v_sub(s.mm, q_rot(out.R, s.dm));
+    return out;
+}
+
+// One inner iteration after the reduction delivered the per-sensor sums.  T_onew_oold is updated in place, Tpre_out[s] receives the
+// pre-transform of sensor s for the NEXT pass (T_snew_sold = Tso * T_onew_oold * Tos: MICPSensor.hpp:178 with the constant frame chain
+// pre-composed), `res` is filled after the last iteration (micp_localization.cpp:972-984).
+B2_DEV void icp_tail(const IcpLaunch& L, const double (*sums)[B2_NACC + 1], Tf& T_onew_oold, Tf* Tpre_out, bool last, IcpResult* res)
+{
+    CStats merged = cs_identity(), merged_w = cs_identity();
+    for (uint32_t k = 0; k < L.n_sensors; k++) {
+        const IcpSensor& S = L.s[k];
+        const CStats ss = icp_finalize(sums[k]);
+        const CStats o = icp_to_odom(S.Ros, mk3(S.Tos.t.x, S.Tos.t.y, S.Tos.t.z), ss);                 // Cs_o = Tbo * (Tsb * stats_s)
+        CStats w = o; w.n = (uint32_t)((double)o.n * S.merge_weight);                                 // :933-934
+        if (L.n_sensors == 1) { merged = o; merged_w = w; }                                           // merging with the empty identity is an exact no-op
+        else { merged = cs_merge(merged, o); merged_w = cs_merge(merged_w, w); }                      // :936-937
+    }
+    const Tf T_inner = icp_umeyama(merged_w);                                                         // :952-953
+    T_onew_oold = tf_mul(T_onew_oold, T_inner);                                                       // :963
+    for (uint32_t k = 0; k < L.n_sensors; k++) Tpre_out[k] = tf_mul(tf_mul(tf_from_pod(L.s[k].Tso), T_onew_oold), tf_from_pod(L.s[k].Tos));
+    if (last) {
+        const Tf Tom = tf_from_pod(L.Tom);
+        Tf Tn = tf_mul(Tom, T_onew_oold);                                                             // :972
+        if (merged.n > 0) Tn.R = q_normalize(Tn.R); else Tn = Tom;                                    // :974-984
+        tf_store(&res->Tom_new, Tn); tf_store(&res->T_onew_oold, T_onew_oold); cs_store(&res->Cmerged_o, merged);
+    }
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------------------
+// Grid barrier without a cooperative launch: a monotonically increasing arrival counter; barrier k of a launch is passed when the counter
+// reaches base + k * gridDim.x.  Needs all blocks co-resident: one block per SM, and the host never lets two such kernels overlap on a
+// device (api.cu: per-device ordering of the loop launches); blocks of ordinary kernels only delay residency.  A block that waits longer
+// than ~2 s raises the abort word: a scheduling surprise ends in a re-run through the cooperative launch, never in a hung GPU.
+// Called by warp 0 only, after its lanes stored the block's partial sums; the caller's __syncthreads releases the other warps.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_barrier_warp0(unsigned int* counter, unsigned int target, unsigned int* abort_word)
+{
+    __syncwarp();                                                  // orders the partial stores of lanes 0..15 before lane 0's release
+    unsigned int ok = 1u;
+    if ((threadIdx.x & 31u) == 0u) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        const long long t0 = clock64();
+        unsigned int spins = 0, v;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if ((++spins & 0x3ffu) == 0u && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile unsigned int*>(abort_word) != 0u)) { ok = 0u; atomicExch(abort_word, 1u); break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0u;
+}
+
+// reduce-scatter warp reduction + cross-warp sum; lanes 0..15 of warp 0 end up with value index `lane` (15 = count) and store it to dst
+template <int BLOCK>
+__device__ __forceinline__ void block_reduce_to_global(P2LAcc& a, double* smem, double* __restrict__ dst)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = BLOCK / 32;
+    double v[16];
+    #pragma unroll
+    for (int i = 0; i < B2_NACC; i++) v[i] = a.v[i];
+    v[15] = (double)a.n;                                           // counts <= 2^32 are exact in FP64
+    rs_step<8>(v, 16, (lane & 16) != 0);
+    rs_step<4>(v, 8, (lane & 8) != 0);
+    rs_step<2>(v, 4, (lane & 4) != 0);
+    rs_step<1>(v, 2, (lane & 2) != 0);
+    const double tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if ((lane & 1) == 0) smem[vidx * NW + warp] = tot;
+    __syncthreads();
+    if (warp == 0 && lane < 16) {
+        double x = 0.0;
+        #pragma unroll
+        for (int w = 0; w < NW; w++) x += smem[lane * NW + w];     // fixed order
+        dst[lane] = x;
+    }
+}
+
+// The kernel.  COOP: cooperative launch + cg grid sync (fallback when co-residency cannot be guaranteed); otherwise an ordinary launch,
+// normally with programmatic stream serialization behind the last find kernel.
+template <bool COOP>
+__global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant__ IcpLaunch L, double* __restrict__ partials, IcpResult* __restrict__ res_dev,
+                                                          uint4* host_out, unsigned int* bar_counter, unsigned int bar_base, unsigned int* bar_abort,
+                                                          unsigned long long* __restrict__ dbg)
+{
+    namespace cg = cooperative_groups;
+    extern __shared__ float s_pairs[];                             // [smem_u][9][B2_ICP_BLOCK]
+    __shared__ double smem[16 * (B2_ICP_BLOCK / 32)];
+    __shared__ double s_part[B2_MAX_SENSORS][B2_ICP_BLOCK / 32][B2_NACC + 1];
+    __shared__ double s_sum[B2_MAX_SENSORS][B2_NACC + 1];
+    __shared__ Tf s_Tpre[B2_MAX_SENSORS];
+    __shared__ Tf s_T;                                             // T_onew_oold
+    __shared__ IcpResult s_res;
+    __shared__ unsigned int s_ok;
+    const long long k0 = clock64();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t si = 0;
+    for (uint32_t k = 1; k < L.n_sensors; k++) if (blockIdx.x >= L.s[k].blk0) si = k;
+    const IcpSensor& S = L.s[si];
+    const uint32_t stride = S.nblk * B2_ICP_BLOCK, lid = (blockIdx.x - S.blk0) * B2_ICP_BLOCK + tid, n = S.n, smem_u = S.smem_u;
+    const uint32_t n_cached = B2_ICP_REG_PAIRS + smem_u;           // pairs per thread that never touch global memory again
+    if (tid < L.n_sensors) {
+        // pre-transform of the first pass: T_onew_oold = I  ->  Tso * I * Tos with the same individually rounded ops as later iterations
+        s_Tpre[tid] = tf_mul(tf_mul(tf_from_pod(L.s[tid].Tso), tf_identity()), tf_from_pod(L.s[tid].Tos));
+        if (tid == 0) s_T = tf_identity();
+    }
+    const float qnan = u2f(0x7fc00000u);
+    V3 c_d[B2_ICP_REG_PAIRS], c_I[B2_ICP_REG_PAIRS], c_N[B2_ICP_REG_PAIRS];
+    // ---- everything that does not depend on the find kernel: with the programmatic launch this overlaps find's tail ----
+    if (S.zc_ranges) {
+        for (uint32_t u = 0; u < n_cached; u++) {
+            const uint32_t i = lid + u * stride;
+            const bool in = i < n;
+            const uint32_t j = in ? i : 0u, oj = S.zc_n_origs == 1 ? 0u : j;
+            const float r = __ldcs(S.zc_ranges + j);
+            const V3 dir = mk3(S.zc_dirs[3 * j], S.zc_dirs[3 * j + 1], S.zc_dirs[3 * j + 2]), org = mk3(S.zc_origs[3 * oj], S.zc_origs[3 * oj + 1], S.zc_origs[3 * oj + 2]);
+            V3 d = mk3(add(mul(dir.x, r), org.x), add(mul(dir.y, r), org.y), add(mul(dir.z, r), org.z));
+            const bool valid = !(r < S.range_min || r > S.range_max);
+            if (in) {      // keep the handle's dataset / scan buffers coherent for datasetView(), computeCrossStatistics(), segment()
+                S.dpts_out[3 * j] = d.x; S.dpts_out[3 * j + 1] = d.y; S.dpts_out[3 * j + 2] = d.z;
+                S.dmask_out[j] = valid ? 1 : 0; S.ranges_out[j] = r;
+            }
+            if (!(in && valid)) d.x = qnan;
+            if (u < B2_ICP_REG_PAIRS) { if (u == 0) c_d[0] = d; else c_d[1] = d; }
+            else { float* p = s_pairs + (size_t)(u - B2_ICP_REG_PAIRS) * 9 * B2_ICP_BLOCK + tid; p[0] = d.x; p[B2_ICP_BLOCK] = d.y; p[2 * B2_ICP_BLOCK] = d.z; }
+        }
+    }
+    if (!COOP) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ---- load this thread's pairs once: validity is folded into the dataset point (NaN fails the P2L gate like a masked pair) ----
+    for (uint32_t u = 0; u < n_cached; u++) {
+        const uint32_t i = lid + u * stride;
+        const bool in = i < n;
+        const uint32_t j = in ? i : 0u;
+        V3 d;
+        if (S.zc_ranges) {
+            if (u < B2_ICP_REG_PAIRS) d = (u == 0) ? c_d[0] : c_d[1];
+            else { const float* p = s_pairs + (size_t)(u - B2_ICP_REG_PAIRS) * 9 * B2_ICP_BLOCK + tid; d = mk3(p[0], p[B2_ICP_BLOCK], p[2 * B2_ICP_BLOCK]); }
+            if (!(S.mmask[j] > 0)) d.x = qnan;
+        } else {
+            d = mk3(S.dpts[3 * j], S.dpts[3 * j + 1], S.dpts[3 * j + 2]);
+            if (!(in && (S.dmask[j] > 0) && (S.mmask[j] > 0))) d.x = qnan;
+        }
+        const V3 I = mk3(S.mpts[3 * j], S.mpts[3 * j + 1], S.mpts[3 * j + 2]), N = mk3(S.mnrm[3 * j], S.mnrm[3 * j + 1], S.mnrm[3 * j + 2]);
+        if (u < B2_ICP_REG_PAIRS) { if (u == 0) { c_d[0] = d; c_I[0] = I; c_N[0] = N; } else { c_d[1] = d; c_I[1] = I; c_N[1] = N; } }
+        else {
+            float* p = s_pairs + (size_t)(u - B2_ICP_REG_PAIRS) * 9 * B2_ICP_BLOCK + tid;
+            p[0] = d.x; p[B2_ICP_BLOCK] = d.y; p[2 * B2_ICP_BLOCK] = d.z;
+            p[3 * B2_ICP_BLOCK] = I.x; p[4 * B2_ICP_BLOCK] = I.y; p[5 * B2_ICP_BLOCK] = I.z;
+            p[6 * B2_ICP_BLOCK] = N.x; p[7 * B2_ICP_BLOCK] = N.y; p[8 * B2_ICP_BLOCK] = N.z;
+        }
+    }
+    __syncthreads();
+    const long long k1 = clock64();
+    for (uint32_t it = 0; it < L.iterations; it++) {
+        const long long c0 = clock64();
+        const Tf Tpre = s_Tpre[si];
+        const float max_dist = S.max_dist;
+        P2LAcc acc; acc_zero(acc);
+        #pragma unroll
+        for (int u = 0; u < B2_ICP_REG_PAIRS; u++) {
+            V3 D, M;
+            if (p2l_pair(Tpre, c_d[u], c_I[u], c_N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
+        }
+        for (uint32_t u = 0; u < smem_u; u++) {
+            const float* p = s_pairs + (size_t)u * 9 * B2_ICP_BLOCK + tid;
+            V3 D, M;
+            if (p2l_pair(Tpre, mk3(p[0], p[B2_ICP_BLOCK], p[2 * B2_ICP_BLOCK]), mk3(p[3 * B2_ICP_BLOCK], p[4 * B2_ICP_BLOCK], p[5 * B2_ICP_BLOCK]),
+                         mk3(p[6 * B2_ICP_BLOCK], p[7 * B2_ICP_BLOCK], p[8 * B2_ICP_BLOCK]), max_dist, D, M)) acc_add_pair(acc, D, M);
+        }
+        for (uint32_t i = lid + n_cached * stride; i < n; i += stride) {        // beyond registers + shared memory: streamed from L2 every iteration
+            const uint8_t dm = S.dmask[i], mm = S.mmask[i];
+            const V3 d = mk3(S.dpts[3 * i], S.dpts[3 * i + 1], S.dpts[3 * i + 2]);
+            const V3 I = mk3(S.mpts[3 * i], S.mpts[3 * i + 1], S.mpts[3 * i + 2]), N = mk3(S.mnrm[3 * i], S.mnrm[3 * i + 1], S.mnrm[3 * i + 2]);
+            V3 D, M;
+            if ((dm > 0) && (mm > 0) && p2l_pair(Tpre, d, I, N, max_dist, D, M)) acc_add_pair(acc, D, M);
+        }
+        double* part = partials + (size_t)(it & 1u) * B2_ICP_MAX_GRID * (B2_NACC + 1);
+        block_reduce_to_global<B2_ICP_BLOCK>(acc, smem, part + (size_t)blockIdx.x * (B2_NACC + 1));
+        const long long c1 = clock64();
+        if (COOP) { __threadfence(); cg::this_grid().sync(); }
+        else {
+            if (warp == 0) { const bool ok = grid_barrier_warp0(bar_counter, bar_base + (it + 1u) * gridDim.x, bar_abort); if (lane == 0) s_ok = ok ? 1u : 0u; }
+            __syncthreads();
+            if (!s_ok) return;                                     // gave up: the host finds the abort word set and re-runs the step cooperatively
+        }
+        const long long c2 = clock64();
+        // every block: sum the block partials of each sensor in the same fixed order.  thread = (group g of 32, value i of 16)
+        {
+            const uint32_t i = tid & 15u, g = tid >> 4;
+            for (uint32_t k = 0; k < L.n_sensors; k++) {
+                const uint32_t b0 = L.s[k].blk0, b1 = b0 + L.s[k].nblk;
+                double a[5];
+                #pragma unroll
+                for (int q = 0; q < 5; q++) { const uint32_t b = b0 + g + 32u * q; a[q] = b < b1 ? __ldcg(part + (size_t)b * (B2_NACC + 1) + i) : 0.0; }
+                double x = ((a[0] + a[1]) + (a[2] + a[3])) + a[4];
+                x += __shfl_xor_sync(0xffffffffu, x, 16);          // the warp's two groups
+                if (lane < 16) s_part[k][warp][lane] = x;
+            }
+        }
+        __syncthreads();
+        if (tid < 16u * L.n_sensors) {
+            const uint32_t k = tid >> 4, i = tid & 15u;
+            double x = 0.0;
+            #pragma unroll
+            for (int w = 0; w < B2_ICP_BLOCK / 32; w++) x += s_part[k][w][i];
+            s_sum[k][i] = x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long c3 = clock64();
+            Tf T = s_T;
+            icp_tail(L, s_sum, T, s_Tpre, it + 1 == L.iterations, &s_res);
+            s_T = T;
+            if (it == 1 && blockIdx.x == 0 && dbg) {
+                const long long c4 = clock64();
+                dbg[0] = (unsigned long long)(c1 - c0); dbg[1] = (unsigned long long)(c2 - c1); dbg[2] = (unsigned long long)(c3 - c2); dbg[3] = (unsigned long long)(c4 - c3);
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        // result: device copy + (spin path) mapped pinned host memory, 16-byte chunks {3 payload words, sequence number}: each chunk is one
+        // store, the host accepts the result when every chunk carries this call's sequence number -- no flag, no system-wide fence
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_res);
+        if (tid < 32u) reinterpret_cast<uint32_t*>(res_dev)[tid] = w[tid];
+        if (host_out && tid < B2_ICP_RESULT_CHUNKS) {
+            uint4 c; c.x = w[3 * tid]; c.y = 3 * tid + 1 < 32u ? w[3 * tid + 1] : 0u; c.z = 3 * tid + 2 < 32u ? w[3 * tid + 2] : 0u; c.w = L.seq;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(host_out + tid), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+        }
+        if (tid == 0 && dbg) { dbg[4] = (unsigned long long)(k1 - k0); dbg[5] = (unsigned long long)(clock64() - k0); }
+    }
+}
+#endif

@@ -361,42 +361,6 @@ B2_DEV void quat_to_mat(Q4 q, float R[9])
     R[6] = mul(2.0f, sub(mul(x, z), mul(y, w))); R[7] = mul(2.0f, add(mul(y, z), mul(x, w))); R[8] = sub(1.0f, mul(2.0f, add(mul(x, x), mul(y, y))));
 }
 
-// Lean inner-iteration tail for the cooperative ICP loop.  Same mathematics as icp_step (micp_localization.cpp:926-963) with the
-// constant frame chain pre-composed: Cs_o = Tos * stats_s in one step (rotation-matrix form), the merge with the empty identity
-// statistics dropped (exact no-op), T_snew_sold = Tso * T_onew_oold * Tos, and Tom_new only after the last iteration.  Rounding
-// differs from the two-step chain at the 1e-7 level (covered by the 1e-5 tolerance on dT; n_meas may differ by a unit when a pair
-// sits within an ulp of max_dist).
-B2_DEV void icp_step_fast(IcpState* st, const CStats& s, bool last)
-{
-    const float* R = st->Ros;
-    const V3 t = mk3(st->Tos.t.x, st->Tos.t.y, st->Tos.t.z);
-    CStats o; o.n = s.n;
-    o.dm = mk3(R[0] * s.dm.x + R[1] * s.dm.y + R[2] * s.dm.z + t.x, R[3] * s.dm.x + R[4] * s.dm.y + R[5] * s.dm.z + t.y, R[6] * s.dm.x + R[7] * s.dm.y + R[8] * s.dm.z + t.z);
-    o.mm = mk3(R[0] * s.mm.x + R[1] * s.mm.y + R[2] * s.mm.z + t.x, R[3] * s.mm.x + R[4] * s.mm.y + R[5] * s.mm.z + t.y, R[6] * s.mm.x + R[7] * s.mm.y + R[8] * s.mm.z + t.z);
-    float RC[9];
-    #pragma unroll
-    for (int i = 0; i < 3; i++)
-        #pragma unroll
-        for (int j = 0; j < 3; j++) RC[i * 3 + j] = R[i * 3 + 0] * s.C[j * 3 + 0] + R[i * 3 + 1] * s.C[j * 3 + 1] + R[i * 3 + 2] * s.C[j * 3 + 2];
-    #pragma unroll
-    for (int i = 0; i < 3; i++)
-        #pragma unroll
-        for (int j = 0; j < 3; j++) o.C[j * 3 + i] = RC[i * 3 + 0] * R[j * 3 + 0] + RC[i * 3 + 1] * R[j * 3 + 1] + RC[i * 3 + 2] * R[j * 3 + 2];
-    const Tf T_inner = umeyama_dev(o);
-    const Tf T_onew_oold = tf_mul(tf_load(&st->T_onew_oold), T_inner);
-    tf_store(&st->T_onew_oold, T_onew_oold);
-    tf_store(&st->T_snew_sold, tf_mul(tf_mul(tf_load(&st->Tso), T_onew_oold), tf_load(&st->Tos)));
-    if (last) {
-        const Tf Tom = tf_load(&st->Tom);
-        Tf Tn = tf_mul(Tom, T_onew_oold);
-        if (o.n > 0) Tn.R = q_normalize(Tn.R); else Tn = Tom;
-        tf_store(&st->Tom_new, Tn);
-        cs_store(&st->Cmerged_o, o);
-        cs_store(&st->stats_s, s);
-    }
-    st->iter++;
-}
-
 static_assert(offsetof(IcpState, Tos) % 16 == 0 && offsetof(IcpState, Tso) % 16 == 0 && offsetof(IcpState, Cmerged_o) % 16 == 0 && sizeof(IcpState) % 16 == 0, "IcpState alignment");
 
 B2_DEV Tf icp_pretransform(Tf Tbo, Tf Tsb, Tf T_onew_oold)
@@ -814,191 +778,6 @@ __global__ void __launch_bounds__(B2_RED_BLOCK) k_p2l_reduce(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The `optimization_iterations` inner iterations of correctOnce (micp_localization.cpp:915-964) as ONE cooperative kernel: per
-// iteration a P2L pass over the n pairs (model buffers are L2-hot after find) -> FP64 block partials -> grid sync -> EVERY block sums
-// the partials in the same fixed order and runs the serial tail redundantly on its shared-memory copy of the ICP state.  One block
-// per SM; 5 iterations cost 5 grid syncs instead of 5 launches + 5 "last block" rounds.  Partials are double-buffered by parity.
-// ---------------------------------------------------------------------------------------------------------------------
-#define B2_ICP_BLOCK 512
-// Grid barrier without a cooperative launch: a monotonically increasing arrival counter in global memory; barrier number k (1-based,
-// counted from the launch) is passed when the counter reaches base + k * gridDim.x.  Needs all blocks co-resident, which the host
-// guarantees by launching at most one block per SM on an otherwise drained stream (blocks of an unrelated kernel only delay residency,
-// they never wait on us).  A block that waits longer than ~2 s gives up and raises the abort word so that a scheduling surprise ends in
-// an error code, never in a hung GPU.
-__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int target, unsigned int* abort_word)
-{
-    __shared__ bool s_ok;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // arrive with release, poll with acquire (gpu scope): no stand-alone fences on the critical path
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        bool ok = true;
-        const long long t0 = clock64();
-        unsigned int spins = 0, v;
-        while (true) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if ((int)(v - target) >= 0) break;
-            if ((++spins & 0x3ffu) == 0u && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile unsigned int*>(abort_word) != 0u)) { ok = false; atomicExch(abort_word, 1u); break; }
-        }
-        s_ok = ok;
-    }
-    __syncthreads();
-    return s_ok;
-}
-
-template <bool COOP>
-__global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, const float* __restrict__ mpts,
-                                                          const float* __restrict__ mnrm, const uint8_t* __restrict__ mmask, uint32_t n, IcpState* __restrict__ icp_g,
-                                                          uint32_t iterations, double* __restrict__ partials, const __grid_constant__ IcpState init,
-                                                          IcpState* host_out, volatile unsigned int* host_flag, unsigned int seq,
-                                                          unsigned int* bar_counter, unsigned int bar_base, unsigned int* bar_abort,
-                                                          const float* __restrict__ zc_ranges, RayModel zc_model, float* __restrict__ dpts_out, uint8_t* __restrict__ dmask_out,
-                                                          float* __restrict__ ranges_out)
-{
-    namespace cg = cooperative_groups;
-    const long long k0 = clock64();
-    const unsigned long long g0 = globaltimer_ns();
-    __shared__ double smem[(B2_NACC + 1) * (B2_ICP_BLOCK / 32)];
-    __shared__ double s_part[B2_ICP_BLOCK / 16][B2_NACC + 1];
-    __shared__ __align__(16) IcpState s_icp;
-    // the initial state arrives as a kernel parameter (no H2D copy in front of the launch)
-    for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) reinterpret_cast<uint32_t*>(&s_icp)[w] = reinterpret_cast<const uint32_t*>(&init)[w];
-    __syncthreads();
-    const uint32_t stride = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
-    // With at most two pairs per thread (C2: 131 072 pairs on 148 x 512 threads) the pairs are loaded ONCE and stay in registers for
-    // all iterations: only the pre-transform changes between passes, so later passes touch no memory at all.
-    const bool cached = n <= 2u * stride;
-    // End-to-end entry (zc_ranges != nullptr, host passes it only in the cached case): the scan is read straight from the caller's pinned
-    // host buffer (zero copy over PCIe / C2C) and unpacked here exactly like k_dataset_from_ranges does (MICPSphericalSensorCPU.cpp:181-233).
-    // None of this depends on the find kernel, so with the programmatic launch it overlaps find's tail; no H2D copy, no unpack launch,
-    // no cross-stream event on the host's critical path.
-    float zr[2] = {0.f, 0.f}; V3 zdir[2], zorg[2];
-    if (zc_ranges) {
-        #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const uint32_t i = gid + (uint32_t)u * stride;
-            const uint32_t j = i < n ? i : 0u, oj = zc_model.n_origs == 1 ? 0u : j;
-            zr[u] = __ldcs(zc_ranges + j);
-            zdir[u] = mk3(zc_model.dirs[3 * j], zc_model.dirs[3 * j + 1], zc_model.dirs[3 * j + 2]);
-            zorg[u] = mk3(zc_model.origs[3 * oj], zc_model.origs[3 * oj + 1], zc_model.origs[3 * oj + 2]);
-        }
-    }
-    // Launched with programmatic stream serialization (see api.cu): the blocks may become resident while the find kernel is still
-    // draining; everything above overlapped with its tail, everything below reads its output.
-    if (!COOP) asm volatile("griddepcontrol.wait;" ::: "memory");
-    bool c_ok[2] = {false, false}; V3 c_d[2], c_I[2], c_N[2];
-    if (cached) {
-        #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const uint32_t i = gid + (uint32_t)u * stride;
-            const bool in = i < n;
-            const uint32_t j = in ? i : 0u;
-            if (zc_ranges) {
-                const float r = zr[u];
-                c_d[u] = mk3(add(mul(zdir[u].x, r), zorg[u].x), add(mul(zdir[u].y, r), zorg[u].y), add(mul(zdir[u].z, r), zorg[u].z));
-                const bool valid = !(r < zc_model.range_min || r > zc_model.range_max);
-                c_ok[u] = in && valid && (mmask[j] > 0);
-                if (in) {          // keep the handle's dataset / scan buffers coherent for datasetView(), computeCrossStatistics(), segment()
-                    dpts_out[3 * j] = c_d[u].x; dpts_out[3 * j + 1] = c_d[u].y; dpts_out[3 * j + 2] = c_d[u].z;
-                    dmask_out[j] = valid ? 1 : 0; ranges_out[j] = r;
-                }
-                c_I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
-                c_N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
-                continue;
-            }
-            c_ok[u] = in && (dmask[j] > 0) && (mmask[j] > 0);
-            c_d[u] = mk3(dpts[3 * j], dpts[3 * j + 1], dpts[3 * j + 2]);
-            c_I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
-            c_N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
-        }
-    }
-    const long long k1 = clock64();
-    for (uint32_t it = 0; it < iterations; it++) {
-        const long long c0 = clock64();
-        const Tf Tpre = tf_load(&s_icp.T_snew_sold);
-        const float max_dist = s_icp.max_dist;
-        P2LAcc acc; acc_zero(acc);
-        if (cached) {
-            #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                V3 D, M;
-                if (c_ok[u] && p2l_pair(Tpre, c_d[u], c_I[u], c_N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
-            }
-        } else
-        for (uint32_t base = gid; base < n; base += 2u * stride) {
-            // up to 2 pairs per trip with all their loads issued before the first use
-            uint8_t dm[2], mm[2]; V3 d[2], I[2], N[2];
-            #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const uint32_t i = base + (uint32_t)u * stride;
-                const bool in = i < n;
-                const uint32_t j = in ? i : base;
-                dm[u] = in ? dmask[j] : (uint8_t)0; mm[u] = mmask[j];
-                d[u] = mk3(dpts[3 * j], dpts[3 * j + 1], dpts[3 * j + 2]);
-                I[u] = mk3(mpts[3 * j], mpts[3 * j + 1], mpts[3 * j + 2]);
-                N[u] = mk3(mnrm[3 * j], mnrm[3 * j + 1], mnrm[3 * j + 2]);
-            }
-            #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                V3 D, M;
-                if ((dm[u] > 0) && (mm[u] > 0) && p2l_pair(Tpre, d[u], I[u], N[u], max_dist, D, M)) acc_add_pair(acc, D, M);
-            }
-        }
-        block_reduce_acc<B2_ICP_BLOCK>(acc, smem);
-        double* part = partials + (size_t)(it & 1u) * gridDim.x * (B2_NACC + 1);
-        if (threadIdx.x == 0) {
-            double* p = part + (size_t)blockIdx.x * (B2_NACC + 1);
-            for (int i = 0; i < B2_NACC; i++) p[i] = acc.v[i];
-            p[B2_NACC] = (double)acc.n;
-            __threadfence();
-        }
-        const long long c1 = clock64();
-        if (COOP) cg::this_grid().sync();
-        else if (!grid_barrier(bar_counter, bar_base + (it + 1u) * gridDim.x, bar_abort)) return;       // gave up: the host sees no completion flag and reports the error
-        const long long c2 = clock64();
-        {
-            constexpr uint32_t NG = B2_ICP_BLOCK / 16;               // thread (g, i) adds value i of blocks g, g+NG, ...
-            const uint32_t i = threadIdx.x & 15u, g = threadIdx.x >> 4;
-            double a = 0.0;
-            for (uint32_t b = g; b < gridDim.x; b += NG) a += __ldcg(part + (size_t)b * (B2_NACC + 1) + i);
-            s_part[g][i] = a;
-        }
-        __syncthreads();
-        if (threadIdx.x < B2_NACC + 1) {
-            double a = 0.0;
-            #pragma unroll
-            for (int g = 0; g < B2_ICP_BLOCK / 16; g++) a += s_part[g][threadIdx.x];
-            s_part[0][threadIdx.x] = a;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long c3 = clock64();
-            icp_step_fast(&s_icp, acc_finalize(&s_part[0][0], (uint32_t)(s_part[0][B2_NACC] + 0.5)), it + 1 == iterations);
-            if (it == 1) {
-                const long long c4 = clock64();
-                s_icp.dbg[0] = (unsigned long long)(c1 - c0); s_icp.dbg[1] = (unsigned long long)(c2 - c1);
-                s_icp.dbg[2] = (unsigned long long)(c3 - c2); s_icp.dbg[3] = (unsigned long long)(c4 - c3);
-            }
-        }
-        __syncthreads();
-    }
-    if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) { s_icp.dbg[4] = (unsigned long long)(k1 - k0); s_icp.dbg[5] = (unsigned long long)(clock64() - k0); s_icp.dbg[6] = g0; s_icp.dbg[7] = globaltimer_ns(); }
-        __syncthreads();
-        for (uint32_t w = threadIdx.x; w < sizeof(IcpState) / 4; w += blockDim.x) {
-            const uint32_t x = reinterpret_cast<const uint32_t*>(&s_icp)[w];
-            reinterpret_cast<uint32_t*>(icp_g)[w] = x;
-            if (host_out) reinterpret_cast<volatile uint32_t*>(host_out)[w] = x;      // mapped pinned host memory: result lands without a D2H copy
-        }
-        if (host_flag) {
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) { *host_flag = seq; __threadfence_system(); }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // v1 batched correct(): fused trace -> P2L gate -> per-block partial statistics (no model buffers written)
 // grid = n_poses * blocks_per_pose; each block handles `rays_per_block` consecutive rays of one pose
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1334,3 +1113,5 @@ __global__ void __launch_bounds__(256) k_pf_stats(const b2_particle_attr* __rest
         *ticket = 0u;
     }
 }
+
+#include "icp_loop.cuh"

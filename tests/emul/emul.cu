@@ -155,11 +155,62 @@ __attribute__((visibility("default"))) void emul_umeyama(const b2_cross_stats* s
 __attribute__((visibility("default"))) void emul_cs_merge(const b2_cross_stats* a, const b2_cross_stats* b, b2_cross_stats* out) { cs_store(out, cs_merge(cs_load(a), cs_load(b))); }
 __attribute__((visibility("default"))) void emul_cs_transform(const b2_transform* T, const b2_cross_stats* s, b2_cross_stats* out) { cs_store(out, cs_transform(tf_from_pod(*T), cs_load(s))); }
 
-// whole correctOnce with the device functions (find_one + sequential reduce + icp_step)
+// The fused loop of the product (icp_loop.cuh: icp_tail with pre-composed frames, weighted multi-sensor merge) run sequentially on the CPU.
+struct EmulSensor {
+    uint32_t n, n_origs; const float* origs; const float* dirs; const float* dpts; const uint8_t* dmask;
+    b2_transform Tbo, Tsb; float range_max, max_dist, pad0, pad1; double merge_weight;
+};
+__attribute__((visibility("default"))) void emul_micp_multi(void* sc, uint32_t ns, const EmulSensor* sen, const b2_transform* Tom, uint32_t iterations,
+                                                            b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
+{
+    IcpLaunch L; memset(&L, 0, sizeof(L));
+    L.Tom = *Tom; L.n_sensors = ns; L.iterations = iterations;
+    std::vector<std::vector<float>> mp(ns), mn(ns), mr(ns); std::vector<std::vector<uint8_t>> mh(ns); std::vector<std::vector<uint32_t>> mf(ns);
+    for (uint32_t k = 0; k < ns; k++) {
+        const EmulSensor& E = sen[k];
+        IcpSensor& S = L.s[k];
+        S.n = E.n; S.max_dist = E.max_dist; S.merge_weight = E.merge_weight;
+        const Tf Tos = tf_mul(tf_from_pod(E.Tbo), tf_from_pod(E.Tsb));
+        tf_store(&S.Tos, Tos); tf_store(&S.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, S.Ros);
+        mp[k].resize(3 * (size_t)E.n); mn[k].resize(3 * (size_t)E.n); mr[k].resize(E.n); mh[k].resize(E.n); mf[k].resize(E.n);
+        b2_transform Tbm; memset(&Tbm, 0, sizeof(Tbm)); tf_store(&Tbm, tf_mul(tf_from_pod(*Tom), tf_from_pod(E.Tbo)));
+        emul_find(sc, &Tbm, &E.Tsb, E.n, E.origs, E.n_origs, E.dirs, E.range_max, mp[k].data(), mn[k].data(), mh[k].data(), mf[k].data(), mr[k].data());
+    }
+    Tf T = tf_identity(); Tf Tpre[B2_MAX_SENSORS];
+    for (uint32_t k = 0; k < ns; k++) Tpre[k] = tf_mul(tf_mul(tf_from_pod(L.s[k].Tso), tf_identity()), tf_from_pod(L.s[k].Tos));
+    IcpResult res; memset(&res, 0, sizeof(res));
+    res.Tom_new = *Tom; tf_store(&res.T_onew_oold, tf_identity());
+    for (uint32_t it = 0; it < iterations; it++) {
+        double sums[B2_MAX_SENSORS][B2_NACC + 1];
+        for (uint32_t k = 0; k < ns; k++) {
+            const EmulSensor& E = sen[k];
+            P2LAcc acc; acc_zero(acc);
+            for (uint32_t i = 0; i < E.n; i++) {
+                if (!(E.dmask[i] > 0) || !(mh[k][i] > 0)) continue;
+                V3 D, M;
+                if (p2l_pair(Tpre[k], mk3(E.dpts[3 * i], E.dpts[3 * i + 1], E.dpts[3 * i + 2]), mk3(mp[k][3 * i], mp[k][3 * i + 1], mp[k][3 * i + 2]),
+                             mk3(mn[k][3 * i], mn[k][3 * i + 1], mn[k][3 * i + 2]), E.max_dist, D, M)) acc_add_pair(acc, D, M);
+            }
+            for (int i = 0; i < B2_NACC; i++) sums[k][i] = acc.v[i];
+            sums[k][B2_NACC] = (double)acc.n;
+        }
+        icp_tail(L, sums, T, Tpre, it + 1 == iterations, &res);
+    }
+    *Tom_new = res.Tom_new; *T_onew_oold = res.T_onew_oold; *Cmerged = res.Cmerged_o;
+}
+
+// whole correctOnce with the device functions: find_one + sequential reduce + icp_step (the reference's frame-algebra order, exec mode 0), or
+// -- fast_tail -- the fused loop's icp_tail
 __attribute__((visibility("default"))) void emul_correct_once(void* sc, uint32_t n, const float* origs, uint32_t n_origs, const float* dirs, float range_max,
                                                               const float* dpts, const uint8_t* dmask, const b2_transform* Tom, const b2_transform* Tbo, const b2_transform* Tsb,
                                                               uint32_t iterations, float max_dist, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged, int fast_tail)
 {
+    if (fast_tail) {
+        EmulSensor E; memset(&E, 0, sizeof(E));
+        E.n = n; E.n_origs = n_origs; E.origs = origs; E.dirs = dirs; E.dpts = dpts; E.dmask = dmask; E.Tbo = *Tbo; E.Tsb = *Tsb; E.range_max = range_max; E.max_dist = max_dist; E.merge_weight = 1.0;
+        emul_micp_multi(sc, 1, &E, Tom, iterations, Tom_new, T_onew_oold, Cmerged);
+        return;
+    }
     std::vector<float> mp(3 * (size_t)n), mn(3 * (size_t)n), mr(n); std::vector<uint8_t> mh(n); std::vector<uint32_t> mf(n);
     IcpState st; memset(&st, 0, sizeof(st));
     st.Tom = *Tom; st.Tbo = *Tbo; st.Tsb = *Tsb; st.max_dist = max_dist;
@@ -167,13 +218,12 @@ __attribute__((visibility("default"))) void emul_correct_once(void* sc, uint32_t
     tf_store(&st.T_onew_oold, I);
     tf_store(&st.T_snew_sold, icp_pretransform(tf_load(&st.Tbo), tf_load(&st.Tsb), I));
     tf_store(&st.Tom_new, tf_load(&st.Tom));
-    { const Tf Tos = tf_mul(tf_load(&st.Tbo), tf_load(&st.Tsb)); tf_store(&st.Tos, Tos); tf_store(&st.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, st.Ros); }
     b2_transform Tbm; memset(&Tbm, 0, sizeof(Tbm)); tf_store(&Tbm, tf_mul(tf_load(&st.Tom), tf_load(&st.Tbo)));
     emul_find(sc, &Tbm, Tsb, n, origs, n_origs, dirs, range_max, mp.data(), mn.data(), mh.data(), mf.data(), mr.data());
     for (uint32_t it = 0; it < iterations; it++) {
         b2_cross_stats ss;
         emul_cross_statistics(&st.T_snew_sold, n, dpts, dmask, mp.data(), mn.data(), mh.data(), max_dist, &ss);
-        if (fast_tail) icp_step_fast(&st, cs_load(&ss), it + 1 == iterations); else icp_step(&st, cs_load(&ss));
+        icp_step(&st, cs_load(&ss));
     }
     *Tom_new = st.Tom_new; *T_onew_oold = st.T_onew_oold; *Cmerged = st.Cmerged_o;
 }

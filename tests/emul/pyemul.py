@@ -14,6 +14,16 @@ TRANSFORM = np.dtype([("R", np.float32, 4), ("t", np.float32, 3), ("stamp", np.u
 CROSS_STATS = np.dtype([("dataset_mean", np.float32, 3), ("model_mean", np.float32, 3), ("covariance", np.float32, 9), ("n_meas", np.uint32)])
 
 
+class _EmulTf(C.Structure):
+    _fields_ = [("v", C.c_float * 7), ("stamp", C.c_uint32)]
+
+
+class _EmulSensor(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("n_origs", C.c_uint32), ("origs", C.c_void_p), ("dirs", C.c_void_p), ("dpts", C.c_void_p), ("dmask", C.c_void_p),
+                ("Tbo", _EmulTf), ("Tsb", _EmulTf), ("range_max", C.c_float), ("max_dist", C.c_float), ("pad0", C.c_float), ("pad1", C.c_float),
+                ("merge_weight", C.c_double)]
+
+
 class PFParams(C.Structure):
     _fields_ = [("dist_sigma", C.c_float), ("real_hit_sim_miss_error", C.c_float), ("real_miss_sim_hit_error", C.c_float),
                 ("real_miss_sim_miss_error", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("ng_mode", C.c_int),
@@ -109,6 +119,25 @@ class Scene:
         Tom, Tbo, Tsb = np.ascontiguousarray(Tom), np.ascontiguousarray(Tbo), np.ascontiguousarray(Tsb)
         lib().emul_correct_once(self._h, C.c_uint32(len(dirs_s)), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_max), _p(dpts), _p(dmask),
                                 _p(Tom), _p(Tbo), _p(Tsb), C.c_uint32(iterations), C.c_float(max_dist), _p(Tn), _p(Td), _p(Cm), C.c_int(int(fast_tail)))
+        return Tn, Td, Cm
+
+    def micp_multi(self, sensors, Tom, iterations=5):
+        """the fused loop of the product (icp_tail, weighted multi-sensor merge) on the CPU; sensors: list of dicts like pyoracle.micp_correct_once_multi
+        (ray-casting sensors only; `max_dist` is the effective gate)"""
+        arr = (_EmulSensor * len(sensors))()
+        keep = []
+        for k, sd in enumerate(sensors):
+            dp, dm = _f32(sd["dataset_points"]).reshape(-1, 3), np.ascontiguousarray(sd["dataset_mask"], np.uint8)
+            o, d = _f32(sd["origs"]).reshape(-1, 3), _f32(sd["dirs"]).reshape(-1, 3)
+            keep += [dp, dm, o, d]
+            a = arr[k]
+            a.n, a.n_origs, a.origs, a.dirs, a.dpts, a.dmask = len(d), len(o), o.ctypes.data, d.ctypes.data, dp.ctypes.data, dm.ctypes.data
+            C.memmove(C.byref(a, _EmulSensor.Tbo.offset), np.ascontiguousarray(sd["Tbo"]).ctypes.data, 32)
+            C.memmove(C.byref(a, _EmulSensor.Tsb.offset), np.ascontiguousarray(sd["Tsb"]).ctypes.data, 32)
+            a.range_max, a.max_dist, a.merge_weight = sd["range_max"], sd.get("max_dist", 1.0), sd.get("weight", 1.0)
+        Tn, Td, Cm = np.zeros((), TRANSFORM), np.zeros((), TRANSFORM), np.zeros((), CROSS_STATS)
+        Tom = np.ascontiguousarray(Tom)
+        lib().emul_micp_multi(self._h, C.c_uint32(len(sensors)), arr, _p(Tom), C.c_uint32(iterations), _p(Tn), _p(Td), _p(Cm))
         return Tn, Td, Cm
 
     def refit(self, verts, faces):

@@ -84,6 +84,49 @@ def test_icp_chain_parity(pe, po, synth):
     assert np.abs(a[1]["t"] - c[1]["t"]).max() <= 2e-6 and np.abs(a[1]["R"] - c[1]["R"]).max() <= 2e-6
 
 
+def _two_sensor_case(po, synth, osc, scale=1):
+    """spherical LiDAR + pinhole camera on one robot (different Tsb / Tbo / weights), scans taken at T_gt"""
+    Tgt = synth.building_gt_pose()
+    m1 = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 15, 16 * scale, -np.pi, 2 * np.pi / (128 * scale), 128 * scale, 0.5, 120.0)
+    m2 = synth.PinholeModel(64 * scale, 48 * scale, 52.5 * scale, 52.5 * scale, 31.5 * scale, 23.5 * scale, 0.3, 30.0)
+    Tsb1, Tsb2 = synth.scenario_tsb(), synth.make_transform((0.3, 0.1, 0.4), (0.0, 0.1, -0.4))
+    Tbo1, Tbo2 = synth.make_transform((0.05, 0.02, 0.0), (0, 0, 0.1)), synth.make_transform((0.04, 0.03, 0.0), (0, 0, 0.09))
+    sensors = []
+    for m, Tsb, Tbo, w, seed in ((m1, Tsb1, Tbo1, 1.0, 3), (m2, Tsb2, Tbo2, 0.35, 4)):
+        o, d = po.model_rays(m)
+        # the scan is what the sensor sees from the TRUE base pose: Tbm_gt = T_gt (map <- base)
+        r = synth.noisy_ranges(osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max, seed=seed)
+        dp, dm, _ = po.dataset_from_ranges(o, d, r, m.range_min, m.range_max)
+        sensors.append(dict(model=m, origs=o, dirs=d, range_max=m.range_max, dataset_points=dp, dataset_mask=dm, Tbo=Tbo, Tsb=Tsb, max_dist=1.0,
+                            adaptive_max_dist_min=0.15, weight=w, ranges=r))
+    # Tom such that Tom * Tbo1 = T_gt o offset
+    Tom = synth.compose(synth.compose(Tgt, synth.scenario_pose_offset()), synth.inverse(Tbo1))
+    return sensors, Tom
+
+
+def test_multi_sensor_loop_parity(pe, po, synth):
+    """micp_localization.cpp:915-964 over two sensors: the product's fused loop (icp_tail: pre-composed frames, weighted merge with the
+    u32 *= double truncation) against the oracle's statement-by-statement restatement."""
+    osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
+    sensors, Tom = _two_sensor_case(po, synth, osc)
+    a = osc.micp_correct_once_multi(sensors, Tom, 5, 0.0, f64_accum=True)
+    b = esc.micp_multi(sensors, Tom, 5)
+    assert a[2]["n_meas"] > 2000 and abs(int(a[2]["n_meas"]) - int(b[2]["n_meas"])) <= 2
+    for i in (0, 1):
+        assert np.abs(a[i]["t"] - b[i]["t"]).max() <= 2e-6 and min(np.abs(a[i]["R"] - b[i]["R"]).max(), np.abs(a[i]["R"] + b[i]["R"]).max()) <= 2e-6
+    # the weights matter: a different camera weight changes the update
+    sensors[1]["weight"] = 3.0
+    c = osc.micp_correct_once_multi(sensors, Tom, 5, 0.0, f64_accum=True)
+    d = esc.micp_multi(sensors, Tom, 5)
+    assert np.abs(c[1]["t"] - a[1]["t"]).max() > 1e-5
+    assert np.abs(c[1]["t"] - d[1]["t"]).max() <= 2e-6
+    # one sensor through the multi path == the single-sensor call
+    e = osc.micp_correct_once_multi(sensors[:1], Tom, 5, 0.0, f64_accum=True)
+    s0 = sensors[0]
+    f = osc.micp_correct_once(s0["origs"], s0["dirs"], s0["range_max"], s0["dataset_points"], s0["dataset_mask"], Tom, s0["Tbo"], s0["Tsb"], 5, 1.0, 0.15, 0.0, f64_accum=True)
+    assert e[0].tobytes() == f[0].tobytes() and e[2].tobytes() == f[2].tobytes()
+
+
 def test_pf_bit_exact(pe, po, synth):
     osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
     m = synth.c1_sensor()
