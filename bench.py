@@ -127,8 +127,9 @@ def host_threads():
     return max(1, int(env)) if env else n
 
 
-def cpu_reference_leg(args, steps, warmup):
-    """The reference's CPU path restated (oracle port) on the host cores: same step, same inputs."""
+def cpu_reference_leg(args, steps, warmup, budget_s=150.0):
+    """The reference's CPU path restated (oracle port) on the host cores: same step, same inputs.  K timed steps after W warm-up steps as asked;
+    when that would not finish within `budget_s`, every step processes a bounded SAMPLE of the scan (its first rows), and says so."""
     from oracle import pyoracle as po
     from rmcl_b200 import synth
     po.set_num_threads(host_threads())
@@ -140,13 +141,25 @@ def cpu_reference_leg(args, steps, warmup):
     ranges = synth.noisy_ranges(sc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"], m.range_max)
     dp, dm, _ = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
     Tom = rank_pose(synth, 0)
-    for _ in range(warmup):
-        sc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
+
+    def step(nr):
+        sc.micp_correct_once(o, d[:nr], m.range_max, dp[:nr], dm[:nr], Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
+
+    t0 = time.perf_counter()
+    step(m.size)                                  # calibration (also the first warm-up step)
+    t_full = time.perf_counter() - t0
+    rows = m.phi_size
+    if t_full * (steps + warmup) > budget_s:
+        rows = max(1, int(m.phi_size * budget_s / (t_full * (steps + warmup))))
+    nr = rows * m.theta_size
+    for _ in range(max(0, warmup - 1)):
+        step(nr)
     t0 = time.perf_counter()
     for _ in range(steps):
-        sc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, I, Tsb, ITERATIONS, MAX_DIST, ADAPTIVE_MIN, 0.0, f64_accum=2)
+        step(nr)
     dt = (time.perf_counter() - t0) / steps
-    return m.size / dt, dt, host_threads(), m.size
+    sample = f"{steps} steps x {nr} of the {m.size} rays of the C2 scan ({rows} of {m.phi_size} rows) + 5 reductions each"
+    return nr / dt, dt, host_threads(), nr, sample
 
 
 _JSON_OUT = None
@@ -192,13 +205,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-        val, dt, cores, n = cpu_reference_leg(args, steps, warmup)
+        steps, warmup = max(1, args.steps), max(1, args.warmup)
+        val, dt, cores, n, sample = cpu_reference_leg(args, steps, warmup)
         line = {"impl": "reference", "metric": "ray-correspondences/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "micp_iters_per_s": 1.0 / dt,
                 "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                                 "sample": f"{steps} full C2 correctOnce steps (131072 rays + 5 reductions each) on the CPU oracle, OpenMP over rays and over reduction chunks, threads = min(CPU affinity, cgroup CPU quota); Embree/rmagine not buildable here",
+                                 "sample": sample + " on the CPU oracle port, OpenMP over rays and over reduction chunks, threads = min(CPU affinity, cgroup CPU quota); Embree/rmagine not buildable here",
                                  "host_logical_cpus": os.cpu_count()},
                 "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -246,6 +259,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident steps ----
+    # The step is enqueued asynchronously (b2_rcc_correct_once_async) and collected up to QUEUE steps later, so the GPU always has the next
+    # steps queued: the CUDA-event interval of a step then contains its kernels only, no host launch / poll latency (with 8 ranks and a clock
+    # sampler sharing one host, a single descheduled rank thread used to add milliseconds to one of 20 steps).  Every step is still a complete
+    # correctOnce whose result lands in host memory; the synchronous call is what `e2e` times below.
+    QUEUE = 4
     for _ in range(args.warmup):
         flush.fill_(1)
         h.correctOnce(Tom, I, ITERATIONS, 0.0)
@@ -254,14 +272,23 @@ def main():
     if sampler:
         sampler.mark()
     launches0 = rmcl_b200.kernel_launch_count()
+    inflight = 0
     for a, b in ev:
         flush.fill_(2)                      # untimed L2 flush
         a.record(stream)
-        Tn, Td, Cm = h.correctOnce(Tom, I, ITERATIONS, 0.0)      # the production path: no instrumentation inside the call
+        h.correctOnceAsync(Tom, I, ITERATIONS, 0.0)              # the production kernels: no instrumentation inside the call
         b.record(stream)
+        inflight += 1
+        if inflight == QUEUE:
+            Tn, Td, Cm = h.correctOnceWait()
+            inflight -= 1
+    while inflight:
+        Tn, Td, Cm = h.correctOnceWait()
+        inflight -= 1
     launches = rmcl_b200.kernel_launch_count() - launches0
     barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev], np.float64)
+    dev_ms = float(step_ms.sum())
 
     # ---- the same steps once more with the library's CUDA events around each kernel (stage split; the event records between the two
     #      kernels cost ~3 us per step and keep the second kernel from launching early, hence not inside the timed region above) ----
@@ -293,13 +320,24 @@ def main():
     for _ in range(max(3, args.warmup // 4)):
         h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
     barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
+    e2e_ms = np.zeros(args.steps)
+    for k in range(args.steps):
         flush.fill_(3)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         Tn2, Td2, Cm2 = h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
-        e2e_s += time.perf_counter() - t0
+        e2e_ms[k] = (time.perf_counter() - t0) * 1e3
+    e2e_s = float(e2e_ms.sum()) * 1e-3
+    barrier()
+    # the same call with a PAGEABLE host scan (cudaMemcpyAsync + unpack kernel on a side stream instead of the zero-copy read)
+    pg_ms = np.zeros(min(args.steps, 100))
+    for k in range(len(pg_ms) + 3):
+        flush.fill_(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges)
+        if k >= 3:
+            pg_ms[k - 3] = (time.perf_counter() - t0) * 1e3
     barrier()
     clocks = sampler.stop() if sampler else None
 
@@ -307,6 +345,14 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    # per-rank distribution of the per-step device times (p50 / p99 / max per rank): a stall on one rank is visible here, not averaged away
+    mine = torch.tensor([np.percentile(step_ms, 50), np.percentile(step_ms, 99), step_ms.max(), step_ms.sum(), np.percentile(e2e_ms, 50), e2e_ms.max()], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": r, "p50_ms": float(x[0]), "p99_ms": float(x[1]), "max_ms": float(x[2]), "sum_ms": float(x[3]), "e2e_p50_ms": float(x[4]), "e2e_max_ms": float(x[5])} for r, x in enumerate(allr)]
     rays_total = float(m.size) * args.steps * world
     value = rays_total / (dev_ms_max * 1e-3)
     e2e_value = rays_total / (e2e_ms_max * 1e-3)
@@ -315,7 +361,7 @@ def main():
     extra = {}
     if not args.no_extra:
         try:
-            extra = extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank)
+            extra = extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank, args)
         except Exception as e:                     # never lose the headline because a secondary workload failed
             extra = {"error": repr(e)}
 
@@ -324,43 +370,67 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_rcc_find): algorithmic bytes per launch / CUDA-event duration ----
+    # ---- roofline of the dominant kernel (k_rcc_find).  Live: the kernel's duration (CUDA events, L2 flushed), the L2 / HBM read bandwidth of
+    #      this box (the library's micro-benchmark), the SM clock under load.  From the committed ncu capture of the same kernel on the same
+    #      input (profiles/counters.json): warp instructions, L1 wavefronts, L2 and DRAM bytes per launch.  Every roof is a time the kernel
+    #      cannot beat; frac = that time / measured time; the largest one is the binding roof. ----
     q = np.asarray(synth.compose(Tom, Tsb)["R"], np.float64)
     tsm = np.asarray(synth.compose(Tom, Tsb)["t"], np.float32)
-    from rmcl_b200.api import _SphericalModel  # noqa: F401
     dirs_s = spherical_dirs_np(m)
     dirs_m = synth._qrot(q[None, :], dirs_s.astype(np.float64)).astype(np.float32)
     vn, vt = gmap.traversal_stats(np.tile(tsm, (len(dirs_m), 1)), dirs_m, m.range_max)
     b_io = 12 + 33                                   # direction table in, point+normal+hit+face+range out
     bytes_per_ray = vn * 224.0 + vt * 48.0 + b_io
     find_s = float(np.mean(find_alone)) * 1e-3
-    achieved = bytes_per_ray * m.size / find_s / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    f_sm = ((clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))) * 1e6
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_rcc_find_dram_bytes_per_launch")
+        l2_gbs = rmcl_b200.api.read_bandwidth(32 << 20, 40, local_rank)          # 32 MiB working set: L2-resident
+        hbm_read_gbs = rmcl_b200.api.read_bandwidth(4 << 30, 4, local_rank)       # 4 GiB working set: HBM
+    except Exception:
+        l2_gbs, hbm_read_gbs = None, None
+    counters = {}
+    try:
+        counters = json.load(open(os.path.join(ROOT, "profiles", "counters.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_rcc_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 224, "tri_bytes": 48, "io_bytes_per_ray": b_io,
-                "kernel_ms": find_s * 1e3, "kernel_share_of_step": float(np.mean(find_ms)) / float(np.mean(find_ms) + np.mean(red_ms)),
-                "kernel_rays_per_s": m.size / find_s,
-                "note": "frac > 1 is expected here: the 85 MB map stays resident in the 126 MB L2, so ~93 % of the algorithmic bytes are served by L2/L1 "
-                        "(DRAM traffic per launch = `traffic`); the kernel is bound by latency / instruction issue, see DESIGN.md section 4"}
+    roofline = kernel_roofs("k_rcc_find", f"k_rcc_find#{(m.size + 63) // 64}", find_s, counters, n_sm, f_sm, l2_gbs, hbm_peak, algorithmic_bytes=bytes_per_ray * m.size)
+    roofline.update({"peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "bytes_per_ray": bytes_per_ray, "nodes_per_ray": vn, "tris_per_ray": vt, "node_bytes": 224, "tri_bytes": 48, "io_bytes_per_ray": b_io,
+                     "kernel_ms": find_s * 1e3, "kernel_share_of_step": float(np.mean(find_ms)) / float(np.mean(find_ms) + np.mean(red_ms)),
+                     "kernel_rays_per_s": m.size / find_s, "l2_read_gbs_measured": l2_gbs, "hbm_read_gbs_measured": hbm_read_gbs, "sm_mhz_used": f_sm / 1e6,
+                     "note": "the 85 MB map stays resident in the 126 MB L2, so HBM does not bind this kernel: `frac_hbm_dram` is the DRAM side, `frac_hbm_algorithmic` the "
+                             "contract's algorithmic-bytes figure (can exceed 1 because the bytes come from L1/L2); the binding roof is named in `bound`"})
+    loop_s = float(np.mean(red_ms)) * 1e-3
+    roof_loop = kernel_roofs("k_icp_loop", f"k_icp_loop<0>#{min(n_sm, (m.size + 511) // 512)}", loop_s, counters, n_sm, f_sm, l2_gbs, hbm_peak, algorithmic_bytes=m.size * 38.0)
+    roof_loop["note"] = "five serial grid-wide reductions: latency-bound by construction; algorithmic bytes = one pass over the 38-byte pairs (later passes read registers)"
+
+    def roofs_for(prefix, seconds, alg_bytes):
+        keys = [k for k in (counters.get("kernels") or {}) if k.startswith(prefix + "#")]
+        key = max(keys, key=lambda k: counters["kernels"][k].get("warp_instructions", 0)) if keys else prefix
+        return kernel_roofs(prefix, key, seconds, counters, n_sm, f_sm, l2_gbs, hbm_peak, algorithmic_bytes=alg_bytes)
+    if isinstance(extra.get("c3_pf"), dict):
+        extra["c3_pf"]["roofline"] = roofs_for("k_pf_update<0>", extra["c3_pf"]["ms_per_step"] * 1e-3, None)
+    if isinstance(extra.get("v1_batch"), dict):
+        extra["v1_batch"]["roofline"] = roofs_for("k_rcc_fused_batch", extra["v1_batch"]["ms_per_step"] * 1e-3, None)
+    if isinstance(extra.get("c4_pinhole"), dict):
+        c4 = extra["c4_pinhole"]
+        c4["roofline_find"] = kernel_roofs("k_rcc_find", f"k_rcc_find#{(640 * 480 + 63) // 64}", c4["find_alone_ms"] * 1e-3, counters, n_sm, f_sm, l2_gbs, hbm_peak,
+                                           algorithmic_bytes=c4["bytes_per_ray"] * 640 * 480)
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample ----
     cpu = None
     if world == 1 or rank == 0:
         try:
-            val, dt, cores, _ = cpu_reference_leg(args, 10, 1)
+            val, dt, cores, _, sample = cpu_reference_leg(args, 10, 1, budget_s=30.0)
             cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": "10 full C2 correctOnce steps on the CPU oracle (FP32 merges, OpenMP over rays and reduction chunks); Embree/rmagine unavailable",
+                   "sample": sample + " on the CPU oracle port (FP32 merges, OpenMP over rays and reduction chunks); Embree/rmagine unavailable",
                    "ms_per_step": dt * 1e3}
         except Exception as e:
             cpu = {"error": repr(e)}
@@ -368,9 +438,11 @@ def main():
     line = {"metric": "ray-correspondences/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config, "micp_iters_per_s": args.steps * world / (dev_ms_max * 1e-3),
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(ranges.nbytes + 416), "d2h_bytes_per_step": 416,
-                    "ms_per_step": e2e_ms_max / args.steps, "timer": "host wall clock around the synchronous C-ABI call"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(ranges.nbytes + 1216), "d2h_bytes_per_step": 176,
+                    "ms_per_step": e2e_ms_max / args.steps, "timer": "host wall clock around the synchronous C-ABI call, pinned host scan (read zero-copy by the kernel)",
+                    "pageable_scan_ms_per_step": float(np.mean(pg_ms)), "pageable_scan_rays_per_s": m.size / (float(np.mean(pg_ms)) * 1e-3)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_icp_loop": roof_loop, "cpu_baseline": cpu,
+            "step_ms_per_rank": per_rank, "queue_depth": QUEUE,
             "stage_ms": {"fused_kernel_or_find": float(np.mean(find_ms)), "separate_reduce_launches": float(np.mean(red_ms)), "find_alone": find_s * 1e3},
             "map": {"n_nodes": info["n_nodes"], "bvh_mb": info["bvh_bytes"] / 1e6, "build_ms": info["build_ms"], "max_depth": info["max_depth"], "build_mode": info["build_mode"]},
             "result_check": {"n_meas": int(Cm["n_meas"]), "dt_norm": float(np.linalg.norm(Td["t"]))},
@@ -378,6 +450,35 @@ def main():
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def kernel_roofs(name, key, seconds, counters, n_sm, f_sm, l2_gbs, hbm_gbs, algorithmic_bytes=None):
+    """Lower bounds of a kernel's duration from its per-launch counters (profiles/counters.json, ncu) against this box's peaks, as fractions of
+    the measured duration.  Returns the contract's roofline object for the binding roof plus every individual roof under `roofs`."""
+    c = (counters.get("kernels") or {}).get(key)
+    roofs = {}
+    if c:
+        if c.get("warp_instructions"):
+            roofs["issue"] = {"achieved": c["warp_instructions"] / seconds / 1e9, "peak": n_sm * 4 * f_sm / 1e9, "unit": "G warp-inst/s", "per_launch": c["warp_instructions"]}
+        if c.get("l1_lsu_wavefronts"):
+            roofs["l1_wavefronts"] = {"achieved": c["l1_lsu_wavefronts"] / seconds / 1e9, "peak": n_sm * f_sm / 1e9, "unit": "G wavefronts/s", "per_launch": c["l1_lsu_wavefronts"]}
+        if c.get("l2_bytes") and l2_gbs:
+            roofs["l2"] = {"achieved": c["l2_bytes"] / seconds / 1e9, "peak": l2_gbs, "unit": "GB/s", "per_launch": c["l2_bytes"]}
+        if c.get("dram_bytes") is not None:
+            roofs["hbm_dram"] = {"achieved": c["dram_bytes"] / seconds / 1e9, "peak": hbm_gbs, "unit": "GB/s", "per_launch": c["dram_bytes"]}
+    if algorithmic_bytes:
+        roofs["hbm_algorithmic"] = {"achieved": algorithmic_bytes / seconds / 1e9, "peak": hbm_gbs, "unit": "GB/s", "per_launch": algorithmic_bytes}
+    for r in roofs.values():
+        r["frac"] = r["achieved"] / r["peak"]
+    binding = [k for k in ("issue", "l1_wavefronts", "l2", "hbm_dram") if k in roofs]
+    bound = max(binding, key=lambda k: roofs[k]["frac"]) if binding else "hbm_algorithmic"
+    top = roofs.get(bound, {"achieved": None, "peak": None, "unit": None, "frac": None})
+    out = {"bound": bound, "kernel": name, "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+           "traffic": (c or {}).get("dram_bytes"), "roofs": roofs, "counters_key": key, "counters_found": bool(c),
+           "frac_hbm_dram": roofs.get("hbm_dram", {}).get("frac"), "frac_hbm_algorithmic": roofs.get("hbm_algorithmic", {}).get("frac"),
+           "lanes_active_per_instruction": (c or {}).get("lanes_active_per_instruction"), "duration_us": seconds * 1e6,
+           "duration_us_under_ncu": (c or {}).get("duration_us_under_ncu")}
+    return out
 
 
 def spherical_dirs_np(m):
@@ -388,7 +489,7 @@ def spherical_dirs_np(m):
     return d.reshape(-1, 3).astype(np.float32)
 
 
-def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank):
+def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush, dist, world, rank, args=None):
     """C3: particle filter 100k particles x 180 beams per GPU (particles sharded across ranks); v1: batched correct(), 1000 poses x vlp16_900."""
     out = {}
 
@@ -514,6 +615,65 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     ms = maxr(tot) / steps
     out["v1_batch"] = {"workload": "v1 correct(): 1000 poses x vlp16_900 (14400 rays) per GPU, fused trace+P2L+Umeyama", "rays_per_s": n_poses * world * mv.size / (ms * 1e-3),
                        "ms_per_step": ms, "reference_numbers": "Embree 0.201 s, OptiX 0.0169 s per correct() on a 1M-face sphere (BASELINE.md)"}
+    # ---- C4 (BASELINE.json configs[3]): PinholeCorrector, 640 x 480 depth camera on the 500k-triangle indoor mesh ----
+    if rank == 0 or world > 1:
+        V4, F4 = synth.indoor(500_000)
+        map4 = rmcl_b200.Map(V4, F4, device=torch.cuda.current_device())
+        m4 = synth.c4_sensor()
+        h4 = rmcl_b200.RCCB200Pinhole(map4)
+        h4.setStream(stream.cuda_stream)
+        h4.setTsb(Tsb); h4.setModel(m4); h4.setParams(1.0, 0.15)
+        T4 = synth.indoor_gt_pose()
+        h4.find(T4)
+        r4 = synth.noisy_ranges(h4.modelView()["ranges"], m4.range_max)
+        h4.setRanges(r4)
+        r4_pinned = torch.from_numpy(r4.copy()).pin_memory()
+        Tom4 = synth.compose(T4, synth.scenario_pose_offset())
+        I4 = synth.make_transform()
+        n4, warm4 = 40, 5
+        for _ in range(warm4):
+            flush.fill_(7); h4.correctOnce(Tom4, I4, ITERATIONS, 0.0)
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n4)]
+        infl = 0
+        for a, bb in ev4:
+            flush.fill_(7)
+            a.record(stream); h4.correctOnceAsync(Tom4, I4, ITERATIONS, 0.0); bb.record(stream)
+            infl += 1
+            if infl == 4:
+                out4 = h4.correctOnceWait(); infl -= 1
+        while infl:
+            out4 = h4.correctOnceWait(); infl -= 1
+        torch.cuda.synchronize()
+        ms4 = maxr(sum(a.elapsed_time(bb) for a, bb in ev4)) / n4
+        f4 = []
+        for i in range(13):
+            flush.fill_(7)
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); h4.find(synth.compose(Tom4, I4)); bb.record(stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                f4.append(a.elapsed_time(bb))
+        e4 = 0.0
+        for i in range(n4 + 3):
+            flush.fill_(7); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            h4.correctOnce(Tom4, I4, ITERATIONS, 0.0, ranges=r4_pinned)
+            if i >= 3:
+                e4 += time.perf_counter() - t0
+        e4 = maxr(e4) / n4
+        from rmcl_b200.api import _PinholeModel  # noqa: F401
+        px = ((np.arange(m4.width, dtype=np.float32) - np.float32(m4.cx)) / np.float32(m4.fx))[None, :].repeat(m4.height, 0)
+        py = ((np.arange(m4.height, dtype=np.float32) - np.float32(m4.cy)) / np.float32(m4.fy))[:, None].repeat(m4.width, 1)
+        nrm = np.sqrt(px * px + py * py + 1.0)
+        d4 = np.stack([1.0 / nrm, -px / nrm, -py / nrm], -1).reshape(-1, 3).astype(np.float32)
+        Tsm4 = synth.compose(Tom4, Tsb)
+        d4m = synth._qrot(np.asarray(Tsm4["R"], np.float64)[None, :], d4.astype(np.float64)).astype(np.float32)
+        vn4, vt4 = map4.traversal_stats(np.tile(np.asarray(Tsm4["t"], np.float32), (len(d4m), 1)), d4m, m4.range_max)
+        out["c4_pinhole"] = {"workload": "C4: PinholeCorrector correctOnce, 1 pose x 640x480 depth image, 500k-triangle indoor mesh (find + 5 inner iterations)",
+                             "rays_per_s": m4.size * world / (ms4 * 1e-3), "ms_per_step": ms4, "find_alone_ms": float(np.mean(f4)), "find_rays_per_s": m4.size / (float(np.mean(f4)) * 1e-3),
+                             "e2e_rays_per_s": m4.size * world / e4, "e2e_ms_per_step": e4 * 1e3, "h2d_bytes_per_step": int(r4.nbytes + 1216), "d2h_bytes_per_step": 176,
+                             "nodes_per_ray": vn4, "tris_per_ray": vt4, "bytes_per_ray": vn4 * 224.0 + vt4 * 48.0 + 45, "n_meas": int(out4[2]["n_meas"]),
+                             "pairs_per_loop_thread": "2 in registers + 3 in shared memory (307 200 pairs on 148 x 512 threads)"}
     return out
 
 

@@ -171,8 +171,9 @@ B2_API int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges_host, uint3
                                       b2_cross_stats* Cmerged_o);
 
 /* The same step split into enqueue / collect: _async launches the kernels on the handle's stream and returns at once, _wait blocks until the
- * result has landed (mapped pinned memory, no stream synchronise) and hands it out.  One call may be pending per handle.  Lets a caller keep
- * the GPU queue full (bench.py's device-timed loop) or overlap its own host work with the correction. */
+ * result of the OLDEST call in flight has landed (mapped pinned memory, no stream synchronise) and hands it out.  Up to 8 calls may be in flight
+ * per handle (exec mode 0: one); the synchronous entry points refuse to run while any is.  Lets a caller keep the GPU queue full (bench.py's
+ * device-timed loop) or overlap its own host work with the correction.  The dataset must not be changed while calls are in flight. */
 B2_API int b2_rcc_correct_once_async(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations, double convergence_progress);
 B2_API int b2_rcc_correct_once_wait(b2_rcc* h, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
 /* MICPLocalizationNode::correctOnce over ALL sensors of the node (rmcl_ros/src/nodes/micp_localization.cpp:899-984): per sensor k
@@ -245,6 +246,9 @@ B2_API int b2_rcc_enable_timing(b2_rcc* h, int enable);
 B2_API int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms);
 /* the calling thread's pending CUDA runtime error as text ("" if none), without clearing it: no entry point of this library leaves one behind */
 B2_API const char* b2_peek_cuda_error(void);
+/* memory-system micro-benchmark for bench.py's roofline denominators: read bandwidth (GB/s) of a `bytes` working set, 128-bit loads from all SMs,
+ * `iters` timed launches after a warm-up.  Below the L2 capacity it measures the L2, far above it the HBM. */
+B2_API int b2_debug_read_bandwidth(int device, uint64_t bytes, int iters, double* gbytes_per_s);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 B2_API uint64_t b2_kernel_launch_count(void);
 

@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth",
 ]
 
 
@@ -102,6 +102,13 @@ def load_library():
 def _chk(rc):
     if rc != 0:
         raise B2Error(rc, load_library().b2_last_error().decode("utf-8", "replace"))
+
+
+def read_bandwidth(nbytes, iters=20, device=0):
+    """GB/s of the library's read micro-benchmark over a working set of `nbytes` (L2 below its capacity, HBM far above)."""
+    out = C.c_double()
+    _chk(load_library().b2_debug_read_bandwidth(C.c_int(device), C.c_uint64(int(nbytes)), C.c_int(int(iters)), C.byref(out)))
+    return out.value
 
 
 def kernel_launch_count():

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -333,20 +334,21 @@ extern "C" int b2_mesh_intersect_stats(const b2_mesh* m, const float* origs, con
 // ---------------------------------------------------------------------------------------------------------------------
 // RCC handle
 // ---------------------------------------------------------------------------------------------------------------------
+#define B2_RING 8                // correctOnce calls that may be in flight per handle (b2_rcc_correct_once_async)
 struct HostPin {            // pinned (mapped) staging for small results
     b2_transform T[3]; b2_cross_stats S[2]; IcpState icp;
-    uint4 chunks[B2_ICP_RESULT_CHUNKS + 1];        // result of k_icp_loop: 16-byte chunks {3 payload words, sequence number} written by the kernel
-    IcpResult res;                                  // D2H staging of the non-spin path
+    uint4 chunks[B2_RING][B2_ICP_RESULT_CHUNKS + 1];   // results of k_icp_loop: 16-byte chunks {3 payload words, sequence number} written by the kernel
+    IcpResult res[B2_RING];                         // D2H staging of the non-spin path
     unsigned long long dbg[8];
 };
 
 // What is still to be collected from an enqueued correctOnce (b2_rcc_correct_once_async .. _wait)
 struct PendingCall {
-    bool active = false;
     int kind = 0;                       // 0: result already in `res`, 1: spin on the mapped chunks, 2: D2H copy of d_res enqueued (stream sync), 3: D2H copy of d_icp (multi-launch chain)
-    unsigned int seq = 0;
-    bool barrier_used = false;
-    IcpLaunch launch{}; size_t smem = 0; int grid = 0;      // kept for the cooperative re-run after a barrier abort
+    unsigned int seq = 0; int slot = 0;
+    bool barrier_used = false, rerun = false;
+    IcpLaunch launch{}; size_t smem = 0; int grid = 0;      // kept for the cooperative re-run after a barrier abort:
+    b2_rcc* sensors[B2_MAX_SENSORS] = {nullptr, nullptr, nullptr, nullptr}; b2_transform Tbm[B2_MAX_SENSORS];   //   the finds are repeated as well (later calls overwrote the model buffers)
     IcpResult res{};
 };
 
@@ -369,7 +371,8 @@ struct b2_rcc {
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
     DevBuf<unsigned int> d_bar; unsigned int bar_base = 0;      // arrival counter + abort word of the software grid barrier; counter value at the next launch
     unsigned int seq = 0;               // sequence number of the last k_icp_loop launch (carried by every result chunk)
-    PendingCall pending;
+    std::deque<PendingCall> pending;    // enqueued, not yet collected (oldest first), at most B2_RING
+    unsigned int slot_counter = 0;
     bool timing = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool timing_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_aux = nullptr;     // side stream: scan upload + unpack overlap the find kernel
     cudaEvent_t ev_join = nullptr;      // multi-sensor correctOnce: orders this handle's stream against the lead handle's
@@ -420,7 +423,7 @@ static int rcc_init(b2_rcc* h)
     CU(cudaMemset(h->d_dbg.p, 0, 8 * sizeof(unsigned long long)));
     CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
     memset((void*)h->pin, 0, sizeof(HostPin));
-    CU(cudaHostGetDevicePointer((void**)&h->pin_chunks_dev, (void*)h->pin->chunks, 0));
+    CU(cudaHostGetDevicePointer((void**)&h->pin_chunks_dev, (void*)&h->pin->chunks[0][0], 0));
     CU(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -789,9 +792,9 @@ static void fill_sensor_frames(IcpSensor& S, const b2_transform& Tbo, const b2_t
     tf_store(&S.Tos, Tos); tf_store(&S.Tso, tf_inv(Tos)); quat_to_mat(Tos.R, S.Ros);
 }
 
-static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem, int mode, bool pdl)
+static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem, int mode, bool pdl, int slot)
 {
-    double* parts = H->d_partials.p; IcpResult* res_dev = H->d_res.p; uint4* host_out = H->pin_chunks_dev;
+    double* parts = H->d_partials.p; IcpResult* res_dev = H->d_res.p; uint4* host_out = H->pin_chunks_dev + (size_t)slot * (B2_ICP_RESULT_CHUNKS + 1);
     unsigned int* bar = H->d_bar.p; unsigned int bar_base = H->bar_base; unsigned int* bar_abort = H->d_bar.p + 1; unsigned long long* dbg = H->d_dbg.p;
     if (mode == 1) {
         IcpLaunch Lc = L;
@@ -828,7 +831,7 @@ static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem,
 static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, uint32_t iterations, double cp)
 {
     b2_rcc* H = sc[0].h;
-    if (H->pending.active) return fail(B2_ERR_INVALID, "correctOnce: the previous asynchronous call has not been collected (b2_rcc_correct_once_wait)");
+    if (H->pending.size() >= B2_RING) return fail(B2_ERR_INVALID, "correctOnce: %d asynchronous calls are in flight already, collect one first (b2_rcc_correct_once_wait)", B2_RING);
     static const int use_zc = [] { const char* e = getenv("B2_ZEROCOPY"); return e ? atoi(e) : 1; }();
     static const int use_spin = [] { const char* e = getenv("B2_SPIN"); return e ? atoi(e) : 1; }();
     static const int use_pdl = [] { const char* e = getenv("B2_PDL"); return e ? atoi(e) : 1; }();
@@ -851,8 +854,11 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
         if (h->n_dataset != h->work_n()) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
         total += h->work_n();
     }
-    PendingCall& pc = H->pending;
-    pc = PendingCall();
+    if (mode == 0 && !H->pending.empty()) return fail(B2_ERR_INVALID, "correctOnce: exec mode 0 keeps its state in one staging block: collect the pending call first");
+    for (const PendingCall& q : H->pending) if (q.kind == 3) return fail(B2_ERR_INVALID, "correctOnce: an exec-mode-0 call is pending: collect it first");
+    H->pending.emplace_back();
+    PendingCall& pc = H->pending.back();
+    struct Guard { b2_rcc* H; bool ok = false; ~Guard() { if (!ok) H->pending.pop_back(); } } guard{H};
     // ---- nothing to do on the device: identity update (micp_localization.cpp:974: Tom stays when n_meas == 0) ----
     if (total == 0 || iterations == 0) {
         memset(&pc.res, 0, sizeof(pc.res));
@@ -862,7 +868,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
             if (sc[k].ranges_host && sc[k].h->n) { RES(ranges_to_dataset(sc[k].h, sc[k].ranges_host, sc[k].n_ranges, 0)); CU(cudaStreamSynchronize(sc[k].h->stream)); }
             RES(launch_find(sc[k].h, &Tbm, nullptr));
         }
-        pc.active = true; pc.kind = 0;
+        pc.kind = 0; guard.ok = true;
         return B2_OK;
     }
     // ---- the multi-launch chain (exec mode 0): find + one k_p2l_reduce per inner iteration, state in device memory ----
@@ -881,7 +887,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
         for (uint32_t it = 0; it < iterations; it++) RES(launch_reduce(h, nullptr, 0.f, h->d_icp.p, nullptr));
         if (h->timing) { CU(cudaEventRecord(h->ev[2], h->stream)); h->timing_valid = true; }
         CU(cudaMemcpyAsync(&st, h->d_icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
-        pc.active = true; pc.kind = 3;
+        pc.kind = 3; guard.ok = true;
         return B2_OK;
     }
     // ---- fused path: find per sensor, then ALL inner iterations of ALL sensors in one k_icp_loop ----
@@ -928,6 +934,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
         }
         b2_transform Tbm_host; memset(&Tbm_host, 0, sizeof(Tbm_host));
         tf_store(&Tbm_host, tf_mul(tf_from_pod(*Tom), tf_from_pod(sc[k].Tbo)));          // MICPSensor.hpp:148, same inline ops as the kernels
+        pc.sensors[k] = h; pc.Tbm[k] = Tbm_host;
         // the loop kernel may start early behind the LAST find only (event records / other kernels in between would serialise them anyway)
         const cudaStream_t own = h->stream;
         h->stream = H->stream;                                                        // all launches of this call ride the lead stream
@@ -955,15 +962,17 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
     const size_t smem = (size_t)smem_u_max * 9 * B2_ICP_BLOCK * sizeof(float);
     const bool pdl = mode == 2 && sc[ns - 1].h->pdl_armed && !aux_any;
     sc[ns - 1].h->pdl_armed = false;
-    RES(launch_icp_loop(H, L, grid, smem, mode, pdl));
+    pc.slot = (int)(H->slot_counter++ % B2_RING);
+    RES(launch_icp_loop(H, L, grid, smem, mode, pdl, pc.slot));
     if (H->timing) { CU(cudaEventRecord(H->ev[2], H->stream)); H->timing_valid = true; }
     for (uint32_t k = 1; k < ns; k++) {        // later work on the other sensors' own streams sees the model buffers this call wrote
         CU(cudaEventRecord(sc[k].h->ev_join, H->stream));
         CU(cudaStreamWaitEvent(sc[k].h->stream, sc[k].h->ev_join, 0));
     }
-    pc.active = true; pc.seq = seq; pc.grid = grid; pc.smem = smem; pc.barrier_used = mode == 2;
+    pc.seq = seq; pc.grid = grid; pc.smem = smem; pc.barrier_used = mode == 2;
     if (use_spin) pc.kind = 1;
-    else { CU(cudaMemcpyAsync(&H->pin->res, H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream)); pc.kind = 2; }
+    else { CU(cudaMemcpyAsync(&H->pin->res[pc.slot], H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream)); pc.kind = 2; }
+    guard.ok = true;
     return B2_OK;
 }
 
@@ -977,34 +986,35 @@ static inline void cpu_relax()
 }
 
 // every chunk of the mapped result carries this call's sequence number?
-static bool chunks_ready(const HostPin* pin, unsigned int seq)
+static bool chunks_ready(const HostPin* pin, int slot, unsigned int seq)
 {
-    const volatile uint4* c = pin->chunks;
+    const volatile uint4* c = pin->chunks[slot];
     for (int i = 0; i < B2_ICP_RESULT_CHUNKS; i++) if (c[i].w != seq) return false;
     return true;
+}
+static void chunks_read(const HostPin* pin, int slot, IcpResult* out)
+{
+    std::atomic_thread_fence(std::memory_order_acquire);          // payload reads stay behind the sequence-number reads (aarch64 hosts)
+    uint32_t w[3 * B2_ICP_RESULT_CHUNKS];
+    for (int i = 0; i < B2_ICP_RESULT_CHUNKS; i++) { const volatile uint4* c = &pin->chunks[slot][i]; w[3 * i] = c->x; w[3 * i + 1] = c->y; w[3 * i + 2] = c->z; }
+    memcpy(out, w, sizeof(IcpResult));
 }
 
 static int micp_collect(b2_rcc* H, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged)
 {
-    PendingCall& pc = H->pending;
-    if (!pc.active) return fail(B2_ERR_INVALID, "correctOnce: nothing to wait for");
-    pc.active = false;
+    if (H->pending.empty()) return fail(B2_ERR_INVALID, "correctOnce: nothing to wait for");
+    PendingCall pc = H->pending.front();
+    H->pending.pop_front();
     bool have = pc.kind == 0;
-    if (pc.kind == 1) {
+    if (pc.kind == 1 && !pc.rerun) {
         // spin on the chunks the kernel writes into mapped host memory (a stream synchronise costs several microseconds more)
         const auto t_start = std::chrono::steady_clock::now();
         unsigned long long spins = 0;
-        while (!chunks_ready(H->pin, pc.seq)) {
+        while (!chunks_ready(H->pin, pc.slot, pc.seq)) {
             cpu_relax();
             if ((++spins & 0xfffffull) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 5.0) break;
         }
-        if (chunks_ready(H->pin, pc.seq)) {
-            std::atomic_thread_fence(std::memory_order_acquire);          // payload reads stay behind the sequence-number reads (aarch64 hosts)
-            uint32_t w[3 * B2_ICP_RESULT_CHUNKS];
-            for (int i = 0; i < B2_ICP_RESULT_CHUNKS; i++) { const volatile uint4* c = &H->pin->chunks[i]; w[3 * i] = c->x; w[3 * i + 1] = c->y; w[3 * i + 2] = c->z; }
-            memcpy(&pc.res, w, sizeof(IcpResult));
-            have = true;
-        }
+        if (chunks_ready(H->pin, pc.slot, pc.seq)) { chunks_read(H->pin, pc.slot, &pc.res); have = true; }
     }
     if (!have) {
         const cudaError_t e = cudaStreamSynchronize(H->stream);
@@ -1012,28 +1022,38 @@ static int micp_collect(b2_rcc* H, b2_transform* Tom_new, b2_transform* T_onew_o
         if (pc.kind == 3) {
             const IcpState& st = H->pin->icp;
             pc.res.Tom_new = st.Tom_new; pc.res.T_onew_oold = st.T_onew_oold; pc.res.Cmerged_o = st.Cmerged_o;
-            have = true;
         } else {
-            bool aborted = false;
-            if (pc.barrier_used) {
+            if (pc.barrier_used && !pc.rerun) {
                 unsigned int bar_state[2] = {0u, 0u};
                 CU(cudaMemcpy(bar_state, H->d_bar.p, sizeof(bar_state), cudaMemcpyDeviceToHost));
-                aborted = bar_state[1] != 0u;
+                if (bar_state[1] != 0u) {
+                    // The software grid barrier gave up (its blocks were not co-resident: SMs held by something that itself waits).  That is a
+                    // scheduling condition, not an error: reset the barrier; this call and every later call already in flight (their kernels
+                    // saw the abort word and left) run again through the cooperative launch, whose co-residency the driver guarantees.
+                    CU(cudaMemset(H->d_bar.p, 0, 2 * sizeof(unsigned int))); H->bar_base = 0;
+                    pc.rerun = true;
+                    for (PendingCall& q : H->pending) if (q.barrier_used) q.rerun = true;
+                }
             }
-            if (aborted) {
-                // The software grid barrier gave up (its blocks were not co-resident: SMs held by something that itself waits).  That is a
-                // scheduling condition, not an error: reset the barrier and run the same iterations again through the cooperative launch,
-                // whose co-residency the driver guarantees.  The find results are already in the model buffers.
-                CU(cudaMemset(H->d_bar.p, 0, 2 * sizeof(unsigned int))); H->bar_base = 0;
+            if (pc.rerun) {
+                for (uint32_t k = 0; k < pc.launch.n_sensors; k++) {
+                    b2_rcc* h = pc.sensors[k];
+                    const cudaStream_t own = h->stream; h->stream = H->stream; h->pdl_next = false;
+                    const int rc = launch_find(h, &pc.Tbm[k], nullptr);
+                    h->stream = own;
+                    RES(rc);
+                }
                 unsigned int seq = ++H->seq; if (seq == 0) seq = ++H->seq;
-                pc.launch.seq = seq;
-                RES(launch_icp_loop(H, pc.launch, pc.grid, pc.smem, 1, false));
-            }
-            if (aborted || pc.kind == 1) {
-                CU(cudaMemcpyAsync(&H->pin->res, H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream));
+                pc.launch.seq = seq; pc.seq = seq;
+                RES(launch_icp_loop(H, pc.launch, pc.grid, pc.smem, 1, false, pc.slot));
+                CU(cudaMemcpyAsync(&H->pin->res[pc.slot], H->d_res.p, sizeof(IcpResult), cudaMemcpyDeviceToHost, H->stream));
                 CU(cudaStreamSynchronize(H->stream));
-            }
-            memcpy(&pc.res, (const void*)&H->pin->res, sizeof(IcpResult));
+                memcpy(&pc.res, (const void*)&H->pin->res[pc.slot], sizeof(IcpResult));
+            } else if (pc.kind == 1) {
+                // spin timed out without an abort: the stream has drained meanwhile, the chunks must be there now
+                if (!chunks_ready(H->pin, pc.slot, pc.seq)) return fail(B2_ERR_CUDA, "correctOnce: the result of the ICP loop never arrived");
+                chunks_read(H->pin, pc.slot, &pc.res);
+            } else memcpy(&pc.res, (const void*)&H->pin->res[pc.slot], sizeof(IcpResult));
         }
     }
     if (Tom_new) *Tom_new = pc.res.Tom_new;
@@ -1055,6 +1075,7 @@ extern "C" int b2_rcc_correct_once(b2_rcc* h, const b2_transform* Tom, const b2_
 {
     NOTNULL(h); NOTNULL(Tom); NOTNULL(Tbo);
     CU(cudaSetDevice(h->map->device));
+    if (!h->pending.empty()) return fail(B2_ERR_INVALID, "correctOnce: asynchronous calls are still in flight on this handle, collect them first");
     SensorCall sc{h, *Tbo, 1.0, nullptr, 0};
     RES(micp_enqueue(&sc, 1, Tom, iterations, cp));
     return micp_collect(h, Tom_new, T_onew_oold, Cmerged);
@@ -1069,6 +1090,7 @@ extern "C" int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges, uint32
     if (!h->has_model) return fail(B2_ERR_INVALID, "set_ranges before setModel");
     SensorCall sc{h, *Tbo, 1.0, n ? ranges : nullptr, n};
     if (n == 0 && h->n != 0) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n, h->n);
+    if (!h->pending.empty()) return fail(B2_ERR_INVALID, "correctOnce: asynchronous calls are still in flight on this handle, collect them first");
     RES(micp_enqueue(&sc, 1, Tom, iterations, cp));
     return micp_collect(h, Tom_new, T_onew_oold, Cmerged);
 }
@@ -1101,6 +1123,7 @@ extern "C" int b2_micp_correct_once(b2_rcc* const* sensors, const b2_transform* 
         sc[k].ranges_host = ranges_host ? ranges_host[k] : nullptr; sc[k].n_ranges = sc[k].ranges_host ? sensors[k]->n : 0;
     }
     CU(cudaSetDevice(sc[0].h->map->device));
+    if (!sc[0].h->pending.empty()) return fail(B2_ERR_INVALID, "correctOnce: asynchronous calls are still in flight on the lead handle, collect them first");
     RES(micp_enqueue(sc, n_sensors, Tom, iterations, cp));
     return micp_collect(sc[0].h, Tom_new, T_onew_oold, Cmerged);
 }
@@ -1164,6 +1187,55 @@ extern "C" int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_tran
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     ds.release(); dt.release();
     if (e != cudaSuccess) return fail(B2_ERR_CUDA, "b2_umeyama_batch: %s", cudaGetErrorString(e));
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Memory-system micro-benchmark (bench.py's roofline denominators): read `bytes` with 128-bit loads from all SMs, `iters` launches timed with
+// CUDA events after one warm-up pass.  A working set below the L2 capacity measures the L2 read bandwidth, a large one the HBM read bandwidth.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) k_read_bw(const uint4* __restrict__ p, size_t n16, unsigned int* __restrict__ sink)
+{
+    unsigned int acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        const uint4 a = __ldcg(p + i), b = __ldcg(p + i + stride), c = __ldcg(p + i + 2 * stride), d = __ldcg(p + i + 3 * stride);
+        acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    }
+    for (; i < n16; i += stride) { const uint4 a = __ldcg(p + i); acc ^= a.x ^ a.y ^ a.z ^ a.w; }
+    if (acc == 0x12345678u) *sink = acc;            // never true in practice; keeps the loads alive
+}
+extern "C" int b2_debug_read_bandwidth(int device, uint64_t bytes, int iters, double* gbytes_per_s)
+{
+    NOTNULL(gbytes_per_s);
+    if (bytes < 4096 || iters < 1) return fail(B2_ERR_INVALID, "b2_debug_read_bandwidth: bad arguments");
+    CU(cudaSetDevice(device));
+    int n_sm = 0; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    DevBuf<uint4> buf; DevBuf<unsigned int> sink;
+    const size_t n16 = bytes / 16;
+    int rc = buf.reserve(n16); if (rc == B2_OK) rc = sink.reserve(1);
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t e = rc == B2_OK ? cudaMemset(buf.p, 1, n16 * 16) : cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaEventCreate(&a);
+    if (e == cudaSuccess) e = cudaEventCreate(&b);
+    float ms = 0.f;
+    if (e == cudaSuccess) {
+        k_read_bw<<<n_sm * 4, 512>>>(buf.p, n16, sink.p);
+        k_read_bw<<<n_sm * 4, 512>>>(buf.p, n16, sink.p);
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) k_read_bw<<<n_sm * 4, 512>>>(buf.p, n16, sink.p);
+        cudaEventRecord(b);
+        g_launches.fetch_add(iters + 2);
+        e = cudaEventSynchronize(b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b);
+    buf.release(); sink.release();
+    if (rc != B2_OK) return rc;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(B2_ERR_CUDA, "b2_debug_read_bandwidth: %s", cudaGetErrorString(e)); }
+    *gbytes_per_s = (double)(n16 * 16) * iters / (ms * 1e-3) / 1e9;
     return B2_OK;
 }
 

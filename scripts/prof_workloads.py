@@ -54,4 +54,16 @@ up.likelihoodStats(Ad)
 Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
 up.resample(Pd, Ad, Pn, An)
 torch.cuda.synchronize()
+# C4 (BASELINE config 4): pinhole 640 x 480 on the 500k-triangle indoor mesh -- k_rcc_find#4800 and the ICP loop with pairs in shared memory
+V4, F4 = synth.indoor(500_000)
+map4 = rmcl_b200.Map(V4, F4)
+m4 = synth.c4_sensor()
+h4 = rmcl_b200.RCCB200Pinhole(map4)
+h4.setTsb(Tsb); h4.setModel(m4); h4.setParams(1.0, 0.15)
+T4 = synth.indoor_gt_pose()
+h4.find(T4)
+h4.setRanges(synth.noisy_ranges(h4.modelView()["ranges"], m4.range_max))
+for _ in range(2):
+    h4.correctOnce(synth.compose(T4, synth.scenario_pose_offset()), I, 5, 0.0)
+torch.cuda.synchronize()
 print("done", rmcl_b200.kernel_launch_count())

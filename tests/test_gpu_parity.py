@@ -905,10 +905,21 @@ def test_correct_once_async(po, synth):
         want = h.correctOnce(Tom, Tbo, 5, 0.0)
         h.correctOnceAsync(Tom, Tbo, 5, 0.0)
         with pytest.raises(rmcl_b200.B2Error):
-            h.correctOnceAsync(Tom, Tbo, 5, 0.0)                       # still pending
+            h.correctOnce(Tom, Tbo, 5, 0.0)                            # synchronous entry refuses while a call is in flight
         x = torch.ones(1 << 20, device="cuda").sum().item()              # unrelated work while the step runs
         got = h.correctOnceWait()
         assert x == float(1 << 20) and got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes()
         with pytest.raises(rmcl_b200.B2Error):
             h.correctOnceWait()                                        # nothing pending
     assert np.abs(sync[0]["t"] - want[0]["t"]).max() <= 2e-6
+    # a queue of calls with different poses: results come back in order; the 9th in flight is refused
+    h.setExecMode(2)
+    Toms = [synth.compose(Tom, synth.make_transform((0.01 * k, 0, 0), (0, 0, 0.001 * k))) for k in range(8)]
+    wants = [h.correctOnce(T, Tbo, 5, 0.0) for T in Toms]
+    for T in Toms:
+        h.correctOnceAsync(T, Tbo, 5, 0.0)
+    with pytest.raises(rmcl_b200.B2Error):
+        h.correctOnceAsync(Tom, Tbo, 5, 0.0)
+    for w in wants:
+        g = h.correctOnceWait()
+        assert g[0].tobytes() == w[0].tobytes() and g[2].tobytes() == w[2].tobytes()
