@@ -90,8 +90,8 @@ B2_API int         b2_device_count(int* n);
 B2_API int b2_mesh_create(const float* verts_xyz, uint32_t n_vertices, const uint32_t* faces_ijk, uint32_t n_faces,
                           int device, int build_mode, b2_mesh** out);
 /* rm::import_embree_map(file) (rmcl_ros/src/nodes/micp_localization.cpp:188, rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:158): mesh file ->
- * map.  Self-contained readers for Stanford PLY (ascii / binary_little_endian) and Wavefront OBJ; polygons are fan-triangulated.
- * COLLADA (.dae) needs assimp and is refused with B2_ERR_INVALID. */
+ * map.  Self-contained readers (no assimp) for Stanford PLY (ascii / binary_little_endian), Wavefront OBJ and COLLADA .dae (geometry library +
+ * visual-scene node transforms; the format of the reference's example maps, docs/MICPL.md:46-49); polygons are fan-triangulated. */
 B2_API int b2_mesh_create_from_file(const char* path, int device, int build_mode, b2_mesh** out);
 /* the import step alone (host only, no device needed): malloc'ed vertex / face arrays, released with b2_mesh_file_free */
 B2_API int b2_mesh_file_load(const char* path, float** verts_xyz, uint32_t* nv, uint32_t** faces_ijk, uint32_t* nf);

@@ -126,7 +126,7 @@ extern "C" int b2_mesh_file_load(const char* path, float** verts, uint32_t* nv, 
     *verts = nullptr; *faces = nullptr; *nv = 0; *nf = 0;
     std::vector<float> V; std::vector<uint32_t> F; const char* err = "";
     const int rc = b2_load_mesh_file(path, V, F, &err);
-    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : B2_ERR_INVALID, "mesh import of '%s' failed: %s", path, err);
+    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : (rc == -4 ? B2_ERR_OOM : B2_ERR_INVALID), "mesh import of '%s' failed: %s", path, err);
     float* v = (float*)malloc(sizeof(float) * V.size()); uint32_t* f = (uint32_t*)malloc(sizeof(uint32_t) * F.size());
     if (!v || !f) { free(v); free(f); return fail(B2_ERR_OOM, "out of host memory"); }
     memcpy(v, V.data(), sizeof(float) * V.size()); memcpy(f, F.data(), sizeof(uint32_t) * F.size());
@@ -140,7 +140,7 @@ extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_
     NOTNULL(out); *out = nullptr; NOTNULL(path);
     std::vector<float> V; std::vector<uint32_t> F; const char* err = "";
     const int rc = b2_load_mesh_file(path, V, F, &err);
-    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : B2_ERR_INVALID, "mesh import of '%s' failed: %s", path, err);
+    if (rc != 0) return fail(rc == -3 ? B2_ERR_NO_MAP : (rc == -4 ? B2_ERR_OOM : B2_ERR_INVALID), "mesh import of '%s' failed: %s", path, err);
     return b2_mesh_create(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), device, build_mode, out);
 }
 
@@ -149,7 +149,9 @@ extern "C" int b2_mesh_create_from_file(const char* path, int device, int build_
 extern "C" int b2_mesh_refit(b2_mesh* m, const float* verts, uint32_t nv, int src_is_device)
 {
     NOTNULL(m); NOTNULL(verts);
-    if (m->level_begin.size() < 2 || !m->d_faces) return fail(B2_ERR_UNSUPPORTED, "refit needs a map built with B2_BUILD_DEVICE_LBVH");
+    if (m->level_begin.size() < 2 || !m->d_faces)
+        return fail(B2_ERR_UNSUPPORTED, "refit is not available for this map: it needs the level ranges and face list only b2_mesh_create(..., B2_BUILD_DEVICE_LBVH) keeps "
+                                        "(host-SAH maps and maps imported from a blob do not have them)");
     if (nv != m->n_verts) return fail(B2_ERR_INVALID, "refit keeps the topology: %u vertices given, the map has %u", nv, m->n_verts);
     CU(cudaSetDevice(m->device));
     const auto t0 = std::chrono::steady_clock::now();
@@ -239,6 +241,20 @@ extern "C" int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, i
         }
         if ((n_inner && (uint64_t)nodes[i].child_base + n_inner > hd.n_nodes) || (tri_end && (uint64_t)nodes[i].tri_base + tri_end > hd.n_tris))
             return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u points outside the arrays", i);
+        // children sit strictly behind their parent (breadth-first layout): makes the structure acyclic, so the depth below is well defined
+        if (n_inner && nodes[i].child_base <= i) return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u has a child at or before itself", i);
+    }
+    {
+        // the real depth, not the header's claim: the traversal stack has B2_TRAVERSAL_STACK entries
+        std::vector<uint8_t> depth;
+        try { depth.assign(hd.n_nodes, 0); } catch (const std::exception&) { return fail(B2_ERR_OOM, "out of host memory"); }
+        uint32_t max_depth = 0;
+        for (uint32_t i = 0; i < hd.n_nodes; i++) {            // parents precede children: one forward pass
+            uint32_t n_inner = 0;
+            for (int sl = 0; sl < 8; sl++) if ((nodes[i].imask >> sl) & 1u) n_inner++;
+            for (uint32_t c = 0; c < n_inner; c++) { const uint32_t d = (uint32_t)depth[i] + 1u; if (d > 250u) return fail(B2_ERR_INVALID, "BVH blob corrupt: tree too deep"); depth[nodes[i].child_base + c] = (uint8_t)std::max<uint32_t>(depth[nodes[i].child_base + c], d); max_depth = std::max(max_depth, d); }
+        }
+        if (max_depth + 1 > B2_TRAVERSAL_STACK - 4) return fail(B2_ERR_INVALID, "BVH blob: tree depth %u exceeds the traversal stack", max_depth + 1);
     }
     int ndev = 0; CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
@@ -535,7 +551,9 @@ extern "C" int b2_rcc_set_model_spherical(b2_rcc* h, const b2_spherical_model* m
 {
     NOTNULL(h); NOTNULL(m);
     const size_t n = (size_t)m->phi_size * m->theta_size;
-    std::vector<float> dirs(3 * n);
+    if (n > 0xffffffffu / 4) return fail(B2_ERR_INVALID, "model too large");
+    std::vector<float> dirs;
+    try { dirs.resize(3 * n); } catch (const std::exception&) { return fail(B2_ERR_OOM, "out of host memory (%zu rays)", n); }
     for (uint32_t vid = 0; vid < m->phi_size; vid++) {
         const float phi = m->phi_min + (float)vid * m->phi_inc;
         const float cp = cosf(phi), sp = sinf(phi);
@@ -553,7 +571,9 @@ extern "C" int b2_rcc_set_model_pinhole(b2_rcc* h, const b2_pinhole_model* m)
 {
     NOTNULL(h); NOTNULL(m);
     const size_t n = (size_t)m->width * m->height;
-    std::vector<float> dirs(3 * n);
+    if (n > 0xffffffffu / 4) return fail(B2_ERR_INVALID, "model too large");
+    std::vector<float> dirs;
+    try { dirs.resize(3 * n); } catch (const std::exception&) { return fail(B2_ERR_OOM, "out of host memory (%zu rays)", n); }
     for (uint32_t vid = 0; vid < m->height; vid++)
         for (uint32_t hid = 0; hid < m->width; hid++) {
             const float px = ((float)hid - m->cx) / m->fx, py = ((float)vid - m->cy) / m->fy;
@@ -1317,7 +1337,8 @@ static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_a
     }
     RES(h->d_beams.reserve(n_beams));
     CU(cudaStreamSynchronize(h->stream));                 // previous launch may still read the staging buffer's device copy
-    std::vector<std::pair<uint32_t, uint32_t>> order(n_beams);
+    std::vector<std::pair<uint32_t, uint32_t>> order;
+    try { order.resize(n_beams); } catch (const std::exception&) { return fail(B2_ERR_OOM, "out of host memory (%u beams)", n_beams); }
     for (uint32_t i = 0; i < n_beams; i++) order[i] = {dir_sort_key(beams[i]), i};
     std::sort(order.begin(), order.end());
     for (uint32_t j = 0; j < n_beams; j++) {

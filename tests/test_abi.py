@@ -97,7 +97,7 @@ def test_mesh_file_import(tmp_path):
         f.write(f"f {t[0] - len(V)} {t[1] - len(V)} {t[2] - len(V)}\n")               # negative (relative) indices
     Vo, Fo = rmcl_b200.read_mesh_file(o)
     assert np.array_equal(Vo, V) and np.array_equal(Fo, F)
-    for bad, txt in (("x.dae", "<COLLADA/>"), ("empty.ply", "ply\nformat ascii 1.0\nelement vertex 0\nproperty float x\nproperty float y\nproperty float z\nend_header\n"),
+    for bad, txt in (("x.dae", "<COLLADA/>"), ("x.stl", "solid"), ("empty.ply", "ply\nformat ascii 1.0\nelement vertex 0\nproperty float x\nproperty float y\nproperty float z\nend_header\n"),
                      ("oob.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")):
         bp = tmp_path / bad
         bp.write_text(txt)
@@ -105,6 +105,75 @@ def test_mesh_file_import(tmp_path):
             rmcl_b200.read_mesh_file(str(bp))
     with pytest.raises(rmcl_b200.B2Error):
         rmcl_b200.read_mesh_file(str(tmp_path / "missing.ply"))
+
+
+def _dae(geoms, scene_nodes, up="Z_UP"):
+    """COLLADA 1.4.1 document: geoms = {id: (positions (n,3), primitive xml)}, scene_nodes = xml of the <visual_scene> body"""
+    lib = ""
+    for gid, (P, prim) in geoms.items():
+        fa = " ".join(repr(float(x)) for x in np.asarray(P, np.float64).reshape(-1))
+        lib += (f'<geometry id="{gid}" name="{gid}"><mesh><source id="{gid}-pos"><float_array id="{gid}-arr" count="{len(P) * 3}">{fa}</float_array>'
+                f'<technique_common><accessor source="#{gid}-arr" count="{len(P)}" stride="3"><param name="X" type="float"/><param name="Y" type="float"/>'
+                f'<param name="Z" type="float"/></accessor></technique_common></source>'
+                f'<source id="{gid}-nrm"><float_array id="{gid}-narr" count="3">0 0 1</float_array></source>'
+                f'<vertices id="{gid}-vtx"><input semantic="POSITION" source="#{gid}-pos"/></vertices>{prim.format(g=gid)}</mesh></geometry>')
+    return (f'<?xml version="1.0" encoding="utf-8"?>\n<!-- test map -->\n<COLLADA xmlns="http://www.collada.org/2005/11/COLLADASchema" version="1.4.1">'
+            f'<asset><unit name="meter" meter="1"/><up_axis>{up}</up_axis></asset><library_geometries>{lib}</library_geometries>'
+            f'<library_visual_scenes><visual_scene id="Scene">{scene_nodes}</visual_scene></library_visual_scenes>'
+            f'<scene><instance_visual_scene url="#Scene"/></scene></COLLADA>')
+
+
+def test_collada_import(tmp_path):
+    """SURVEY 8f4: the reference's example maps are COLLADA (docs/MICPL.md:46-49, loaded through assimp by rm::import_embree_map,
+    micp_localization.cpp:188).  <triangles> / <polylist> / <polygons> with interleaved inputs, node transforms (matrix, translate, rotate,
+    scale, nesting), two instances of one geometry, up_axis left alone."""
+    import rmcl_b200
+    from rmcl_b200 import synth
+    V, F = synth.cube(2)
+    tri = '<triangles count="%d"><input semantic="VERTEX" source="#{g}-vtx" offset="0"/><input semantic="NORMAL" source="#{g}-nrm" offset="1"/><p>%s</p></triangles>' % (
+        len(F), " ".join(f"{i} 0" for i in F.reshape(-1)))
+    quad = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0.5, 2, 0)]
+    plist = '<polylist count="2"><input semantic="VERTEX" source="#{g}-vtx" offset="0"/><vcount>4 3</vcount><p>0 1 2 3 3 2 4</p></polylist>'
+    pgons = '<polygons count="1"><input semantic="VERTEX" source="#{g}-vtx" offset="0"/><p>0 1 2 3</p></polygons>'
+    nodes = ('<node id="a"><matrix>1 0 0 5  0 1 0 -2  0 0 1 0.5  0 0 0 1</matrix><instance_geometry url="#cube"/></node>'
+             '<node id="b"><translate>10 0 0</translate><rotate>0 0 1 90</rotate><scale>2 2 2</scale><instance_geometry url="#quad"/>'
+             '<node id="c"><translate>0 0 1</translate><instance_geometry url="#pg"/></node></node>'
+             '<node id="d"><instance_geometry url="#cube"/></node>')
+    p = tmp_path / "map.dae"
+    p.write_text(_dae({"cube": (V, tri), "quad": (quad, plist), "pg": (quad[:4], pgons)}, nodes))
+    V2, F2 = rmcl_b200.read_mesh_file(str(p))
+    nv, nf = len(V), len(F)
+    assert len(V2) == 2 * nv + 5 + 4 and len(F2) == 2 * nf + 3 + 2
+    assert np.allclose(V2[:nv], V + np.float32([5, -2, 0.5])) and np.array_equal(F2[:nf], F)                    # <matrix>
+    q = np.float32(quad)
+    want = np.stack([-2 * q[:, 1] + 10, 2 * q[:, 0], 2 * q[:, 2]], 1)                                                # T * Rz(90) * S(2)
+    assert np.allclose(V2[nv:nv + 5], want, atol=1e-5) and F2[nf:nf + 3].tolist() == [[nv, nv + 1, nv + 2], [nv, nv + 2, nv + 3], [nv + 3, nv + 2, nv + 4]]
+    qq = q[:4] + np.float32([0, 0, 1])                                                                              # nested: parent * translate
+    want = np.stack([-2 * qq[:, 1] + 10, 2 * qq[:, 0], 2 * qq[:, 2]], 1)
+    assert np.allclose(V2[nv + 5:nv + 9], want, atol=1e-5)
+    assert np.allclose(V2[nv + 9:], V) and np.array_equal(F2[nf + 5:] - (nv + 9), F)                               # second instance, identity
+    # no scene graph: geometries are taken as they are
+    p2 = tmp_path / "bare.dae"
+    p2.write_text(_dae({"cube": (V, tri)}, ""))
+    V3, F3 = rmcl_b200.read_mesh_file(str(p2))
+    assert np.allclose(V3, V) and np.array_equal(F3, F)
+    for bad in ('<COLLADA><library_geometries><geometry id="g"><mesh><triangles count="1"><p>0 1 2</p></triangles></mesh></geometry></library_geometries></COLLADA>',
+                "<COLLADA><asset>", "<html/>"):
+        bp = tmp_path / "bad.dae"
+        bp.write_text(bad)
+        with pytest.raises(rmcl_b200.B2Error):
+            rmcl_b200.read_mesh_file(str(bp))
+
+
+def test_ply_header_cannot_force_huge_allocation(tmp_path):
+    """a header announcing billions of vertices in a tiny file is refused before anything is reserved"""
+    import rmcl_b200
+    p = tmp_path / "huge.ply"
+    p.write_text("ply\nformat binary_little_endian 1.0\nelement vertex 4000000000\nproperty float x\nproperty float y\nproperty float z\nelement face 1\n"
+                 "property list uchar int vertex_indices\nend_header\n")
+    with pytest.raises(rmcl_b200.B2Error) as e:
+        rmcl_b200.read_mesh_file(str(p))
+    assert "more" in str(e.value)
 
 
 def test_bench_reference_arm_contract():
