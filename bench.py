@@ -65,7 +65,7 @@ class ClockSampler:
         """ONE sampler process (rank 0) for all GPUs of the job, started well before the timed region: nvidia-smi start-up takes NVML /
         driver locks for ~a second and would otherwise stall the first launches of every rank."""
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpus}", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpus}", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("B2_SAMPLER_MS", "20")],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None

@@ -138,6 +138,10 @@ B2_API int b2_rcc_set_dataset(b2_rcc* h, const float* points_xyz, const uint8_t*
 B2_API int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device);
 /* RCC..::find(Tbm_est), rmcl/src/rmcl/registration/RCCEmbree.cpp:26-36,58-68,89-99,121-131 */
 B2_API int b2_rcc_find(b2_rcc* h, const b2_transform* Tbm_est);
+/* The three semantics of rm::*SimulatorEmbree::simulate that SURVEY.md Appendix A.3 cannot settle without rmagine's source, as switches (all 0 = the
+ * defaults stated there): tfar_mode 1: rays are traced to +inf instead of model.range.max; min_mode 1: a closest hit nearer than model.range.min is
+ * reported as a miss; miss_fill 1: points / normals of a miss are zeros instead of NaN.  Affects b2_rcc_find, correct_once and correct_batch. */
+B2_API int b2_rcc_set_sim_options(b2_rcc* h, int tfar_mode, int min_mode, int miss_fill);
 /* CPCEmbree (rmcl/include/rmcl/registration/CPCEmbree.hpp:20-54, find at rmcl/src/rmcl/registration/CPCEmbree.cpp:17-43): with
  * B2_CORR_CPC, b2_rcc_find runs one closest-point query per DATASET point (mask not consulted, as in the reference) instead of tracing
  * the sensor model: Pm = Tsm*d_i; cp = map.closestPoint(Pm); hits = cp.d <= max_dist; points = Tms*cp.p; normals = Tms.R*cp.n.

@@ -427,12 +427,15 @@ void orc_pinhole_dirs(uint32_t width, uint32_t height, float fx, float fy, float
 /* ------------------------------------------------------------------------------------------------ */
 static inline void put3(float* dst, size_t i, orc_vec3 v) { if (dst) { dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; } }
 
-void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb,
-                  uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_max,
-                  float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges)
+void orc_simulate_opt(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb,
+                      uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max, const orc_sim_options* opt,
+                      float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges)
 {
     const orc_transform Tsm = T_mul(*Tbm, *Tsb);
     const orc_transform Tms = T_inv(Tsm);
+    const float tfar = (opt && opt->tfar_mode == 1) ? INFINITY : range_max;                 /* tfar = range.max (default) vs +inf */
+    const int cull_min = opt && opt->min_mode == 1;                                          /*             hits with t < range.min kept (default) vs dropped */
+    const float fill = (opt && opt->miss_fill == 1) ? 0.0f : NAN;                            /*             miss fill NaN (default) vs zeros */
     #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         const float* op = origs_s + 3 * (size_t)(n_origs == 1 ? 0 : i);
@@ -443,7 +446,9 @@ void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transf
         float o[3] = {orig_m.x, orig_m.y, orig_m.z}, d[3] = {dir_m.x, dir_m.y, dir_m.z};
         ray_t r; ray_setup(&r, o, d);
         float t; uint32_t f;
-        if (closest_hit(s, &r, range_max, 0, &t, &f)) {
+        int hit = closest_hit(s, &r, tfar, 0, &t, &f);
+        if (hit && cull_min && t < range_min) hit = 0;          /* the CLOSEST hit is below range.min: the ray reports a miss (nothing behind it is searched) */
+        if (hit) {
             float ng[3]; tri_ng(s, f, ng);
             orc_vec3 p = v3_add(v3_scale(dir_s, t), orig_s);
             orc_vec3 nm = v3_normalize(v3(ng[0], ng[1], ng[2]));
@@ -455,13 +460,20 @@ void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transf
             if (face_ids) face_ids[i] = f;
             if (ranges) ranges[i] = t;
         } else {
-            orc_vec3 nanv = v3(NAN, NAN, NAN);
-            put3(points, (size_t)i, nanv); put3(normals, (size_t)i, nanv);
+            orc_vec3 fv = v3(fill, fill, fill);
+            put3(points, (size_t)i, fv); put3(normals, (size_t)i, fv);
             if (hits) hits[i] = 0;
             if (face_ids) face_ids[i] = ORC_NOFACE;
             if (ranges) ranges[i] = range_max + 1.0f;
         }
     }
+}
+
+void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb,
+                  uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_max,
+                  float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges)
+{
+    orc_simulate_opt(s, Tbm, Tsb, n, origs_s, n_origs, dirs_s, 0.0f, range_max, NULL, points, normals, hits, face_ids, ranges);
 }
 
 void orc_dataset_from_ranges(uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, const float* ranges,

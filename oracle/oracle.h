@@ -78,6 +78,16 @@ void orc_simulate(const orc_scene* s, const orc_transform* Tbm, const orc_transf
                   uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_max,
                   float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges);
 
+/* The three rmagine semantics SURVEY.md Appendix A.3 leaves open (rmagine's source is not in the tree), as switches; 0 = the stated default. */
+typedef struct {
+    int tfar_mode;     /* 0: ray.tfar = model.range.max (hits beyond it are misses); 1: tfar = +inf (every hit is reported, like PCDSensorUpdaterEmbree.cpp:38) */
+    int min_mode;      /* 0: a closest hit with t < model.range.min is a hit; 1: it is a miss (sim_hit needs t > range.min at PCDSensorUpdaterEmbree.cpp:47) */
+    int miss_fill;     /* 0: points / normals of a miss are NaN; 1: zeros */
+} orc_sim_options;
+void orc_simulate_opt(const orc_scene* s, const orc_transform* Tbm, const orc_transform* Tsb,
+                      uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, float range_min, float range_max, const orc_sim_options* opt,
+                      float* points, float* normals, uint8_t* hits, uint32_t* face_ids, float* ranges);
+
 /* MICP*Sensor*::unpackMessage (rmcl_ros/src/micpl/MICPSphericalSensorCPU.cpp:181-233): dataset point = dir*range (+orig), mask = range in [min,max] */
 void orc_dataset_from_ranges(uint32_t n, const float* origs_s, uint32_t n_origs, const float* dirs_s, const float* ranges,
                              float range_min, float range_max, float* points, uint8_t* mask, uint32_t* n_valid);

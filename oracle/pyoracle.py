@@ -119,15 +119,17 @@ class Scene:
         return t, face, ng, hit
 
     # ---- find -------------------------------------------------------------------------------
-    def simulate(self, Tbm, Tsb, origs_s, dirs_s, range_max):
+    def simulate(self, Tbm, Tsb, origs_s, dirs_s, range_max, range_min=0.0, tfar_mode=0, min_mode=0, miss_fill=0):
+        """tfar_mode / min_mode / miss_fill: the open rmagine semantics of SURVEY.md A.3 (orc_sim_options); all 0 = the stated defaults"""
         origs_s = _f32(origs_s).reshape(-1, 3)
         dirs_s = _f32(dirs_s).reshape(-1, 3)
         n = dirs_s.shape[0]
         out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
                    face_ids=np.empty(n, np.uint32), ranges=np.empty(n, np.float32))
         Tbm, Tsb = _tf(Tbm), _tf(Tsb)
-        lib().orc_simulate(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(origs_s), C.c_uint32(origs_s.shape[0]), _p(dirs_s), C.c_float(range_max),
-                           _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
+        opt = (C.c_int * 3)(int(tfar_mode), int(min_mode), int(miss_fill))
+        lib().orc_simulate_opt(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(origs_s), C.c_uint32(origs_s.shape[0]), _p(dirs_s), C.c_float(range_min), C.c_float(range_max),
+                               opt, _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
         return out
 
     def micp_correct_once(self, origs_s, dirs_s, range_max, dataset_pts, dataset_mask, Tom, Tbo, Tsb, iterations=5, max_dist=1.0,

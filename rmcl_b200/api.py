@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options",
 ]
 
 
@@ -397,6 +397,10 @@ class RCCB200:
         self.outdated = False
         out = np.frombuffer(bytearray(mv[64:192]), self._CO_OUT)
         return out["Tn"][0], out["Td"][0], out["Cm"][0]
+
+    def setSimOptions(self, tfar_mode=0, min_mode=0, miss_fill=0):
+        """the open rmagine simulate() semantics of SURVEY.md A.3: tfar = +inf, closest hit below range.min = miss, misses filled with zeros"""
+        _chk(load_library().b2_rcc_set_sim_options(self._h, C.c_int(tfar_mode), C.c_int(min_mode), C.c_int(miss_fill)))
 
     def setExecMode(self, mode):
         """2 (default): one kernel, software grid barrier, programmatic launch; 1: cooperative launch; 0: one reduction launch per inner iteration."""

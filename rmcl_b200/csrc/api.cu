@@ -394,6 +394,7 @@ struct b2_rcc {
     cudaEvent_t ev_join = nullptr;      // multi-sensor correctOnce: orders this handle's stream against the lead handle's
     uint32_t n_ranges_in = 0;           // real ranges resident in d_ranges_in (set_ranges / correct_once_ranges), needed by b2_rcc_segment
     DevBuf<uint32_t> d_seg_counts, d_seg_offsets, d_seg_totals; DevBuf<float> d_seg_scan, d_seg_map; DevBuf<uint8_t> d_seg_labels;
+    uint32_t sim_opts = 0;              // b2_rcc_set_sim_options
     int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
     uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
 };
@@ -647,7 +648,7 @@ static int reserve_model(b2_rcc* h, size_t n)
 static RayModel ray_model(const b2_rcc* h)
 {
     RayModel m; m.dirs = h->d_dirs.p; m.origs = h->d_origs.p; m.n_origs = h->n_origs; m.n = h->n; m.range_min = h->range_min; m.range_max = h->range_max;
-    m.width = h->width; m.height = h->height; return m;
+    m.width = h->width; m.height = h->height; m.sim_opts = h->sim_opts; return m;
 }
 static ModelBuffers model_buffers(const b2_rcc* h)
 {
@@ -680,6 +681,14 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h), early);
     LAUNCHED();
     h->n_model = h->n; h->found = true;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_set_sim_options(b2_rcc* h, int tfar_mode, int min_mode, int miss_fill)
+{
+    NOTNULL(h);
+    if ((tfar_mode | min_mode | miss_fill) & ~1) return fail(B2_ERR_INVALID, "sim options are 0 or 1");
+    h->sim_opts = (uint32_t)(tfar_mode | (min_mode << 1) | (miss_fill << 2)); h->found = false;
     return B2_OK;
 }
 

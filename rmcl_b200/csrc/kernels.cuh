@@ -445,7 +445,10 @@ struct RayModel {
     uint32_t n;             // rays per pose
     float range_min, range_max;
     uint32_t width, height; // scan raster (buffer id = vid*width + hid); used for the coherent tile order
+    uint32_t sim_opts;      // b2_rcc_set_sim_options: bit 0 tfar = +inf instead of range.max; bit 1 a closest hit below range.min is a miss; bit 2 misses filled with zeros instead of NaN
 };
+B2_DEV float sim_tfar(const RayModel& m) { return (m.sim_opts & 1u) ? u2f(0x7f800000u) : m.range_max; }
+B2_DEV bool sim_is_hit(const RayModel& m, const HitRec& h) { return h.face != B2_NOFACE && !((m.sim_opts & 2u) && h.t < m.range_min); }
 
 // Rays are traced in 8x4 raster tiles (one tile per warp) instead of 32-long row segments: neighbouring rows/columns of a
 // LiDAR / depth raster stay inside the same BVH subtrees, which shortens the warp's union of traversal paths.  Results are
@@ -482,16 +485,16 @@ B2_DEV void find_one(const BvhView& bvh, Tf Tsm, const RayModel& model, uint32_t
     const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
     const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
     const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s), bvh);
-    HitRec h = trace_init(model.range_max);
+    HitRec h = trace_init(sim_tfar(model));
     uint32_t nn = 0, nt = 0;
     trace_closest<false>(bvh, r, h, nn, nt);
-    if (h.face != B2_NOFACE) {
+    if (sim_is_hit(model, h)) {
         V3 p, ns; hit_to_sensor(bvh, h, Rms, dir_s, orig_s, p, ns);
         out.pts[3 * o] = p.x; out.pts[3 * o + 1] = p.y; out.pts[3 * o + 2] = p.z;
         out.nrm[3 * o] = ns.x; out.nrm[3 * o + 1] = ns.y; out.nrm[3 * o + 2] = ns.z;
         out.hits[o] = 1; out.faces[o] = h.face; out.ranges[o] = h.t;
     } else {
-        const float qnan = u2f(0x7fc00000u);
+        const float qnan = (model.sim_opts & 4u) ? 0.0f : u2f(0x7fc00000u);
         out.pts[3 * o] = qnan; out.pts[3 * o + 1] = qnan; out.pts[3 * o + 2] = qnan;
         out.nrm[3 * o] = qnan; out.nrm[3 * o + 1] = qnan; out.nrm[3 * o + 2] = qnan;
         out.hits[o] = 0; out.faces[o] = B2_NOFACE; out.ranges[o] = add(model.range_max, 1.0f);
@@ -802,10 +805,10 @@ __global__ void __launch_bounds__(B2_FUSED_BLOCK, 6) k_rcc_fused_batch(BvhView b
         const V3 orig_s = mk3(model.origs[3 * oi], model.origs[3 * oi + 1], model.origs[3 * oi + 2]);
         const V3 dir_s = mk3(model.dirs[3 * i], model.dirs[3 * i + 1], model.dirs[3 * i + 2]);
         const RaySetup r = ray_setup(tf_apply(Tsm, orig_s), q_rot(Tsm.R, dir_s), bvh);
-        HitRec h = trace_init(model.range_max);
+        HitRec h = trace_init(sim_tfar(model));
         uint32_t nn = 0, nt = 0;
         trace_closest<false>(bvh, r, h, nn, nt);
-        if (h.face == B2_NOFACE) continue;
+        if (!sim_is_hit(model, h)) continue;
         V3 p, ns; hit_to_sensor(bvh, h, Rms, dir_s, orig_s, p, ns);
         V3 D, M;
         if (p2l_pair(I, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), p, ns, max_dist, D, M)) acc_add_pair(acc, D, M);

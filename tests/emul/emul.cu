@@ -55,11 +55,18 @@ __attribute__((visibility("default"))) void emul_intersect(void* sc, const float
     if (mean_tris) *mean_tris = (double)tt / (double)(n ? n : 1);
 }
 
+__attribute__((visibility("default"))) void emul_find_opt(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* origs, uint32_t n_origs,
+                                                          const float* dirs, float range_min, float range_max, uint32_t sim_opts, float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* ranges);
 __attribute__((visibility("default"))) void emul_find(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* origs, uint32_t n_origs,
                                                       const float* dirs, float range_max, float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* ranges)
 {
+    emul_find_opt(sc, Tbm, Tsb, n, origs, n_origs, dirs, 0.f, range_max, 0u, pts, nrm, hits, faces, ranges);
+}
+__attribute__((visibility("default"))) void emul_find_opt(void* sc, const b2_transform* Tbm, const b2_transform* Tsb, uint32_t n, const float* origs, uint32_t n_origs,
+                                                          const float* dirs, float range_min, float range_max, uint32_t sim_opts, float* pts, float* nrm, uint8_t* hits, uint32_t* faces, float* ranges)
+{
     const BvhView bvh = view(sc);
-    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = 0.f; m.range_max = range_max;
+    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = range_min; m.range_max = range_max; m.sim_opts = sim_opts;
     ModelBuffers out; out.pts = pts; out.nrm = nrm; out.hits = hits; out.faces = faces; out.ranges = ranges;
     const Tf Tsm = tf_mul(tf_from_pod(*Tbm), tf_from_pod(*Tsb));
     #pragma omp parallel for schedule(dynamic, 256)
@@ -107,7 +114,7 @@ __attribute__((visibility("default"))) void emul_segment(uint32_t n, const float
                                                          const float* rs, const float* nsim, float min_scan, float min_map, float* out_scan, uint32_t* n_scan, float* out_map,
                                                          uint32_t* n_map, uint8_t* labels)
 {
-    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = range_min; m.range_max = range_max; m.width = n; m.height = 1;
+    RayModel m; m.dirs = dirs; m.origs = origs; m.n_origs = n_origs; m.n = n; m.range_min = range_min; m.range_max = range_max; m.width = n; m.height = 1; m.sim_opts = 0;
     uint32_t a = 0, b = 0;
     for (uint32_t i = 0; i < n; i++) {
         V3 p;

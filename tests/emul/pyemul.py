@@ -88,14 +88,14 @@ class Scene:
             return t, f, ng, h, (mn.value, mt.value), pn, pt
         return t, f, ng, h, (mn.value, mt.value)
 
-    def find(self, Tbm, Tsb, origs_s, dirs_s, range_max):
+    def find(self, Tbm, Tsb, origs_s, dirs_s, range_max, range_min=0.0, sim_opts=0):
         origs_s, dirs_s = _f32(origs_s).reshape(-1, 3), _f32(dirs_s).reshape(-1, 3)
         n = len(dirs_s)
         out = dict(points=np.empty((n, 3), np.float32), normals=np.empty((n, 3), np.float32), hits=np.empty(n, np.uint8),
                    face_ids=np.empty(n, np.uint32), ranges=np.empty(n, np.float32))
         Tbm, Tsb = np.ascontiguousarray(Tbm), np.ascontiguousarray(Tsb)
-        lib().emul_find(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_max),
-                        _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
+        lib().emul_find_opt(self._h, _p(Tbm), _p(Tsb), C.c_uint32(n), _p(origs_s), C.c_uint32(len(origs_s)), _p(dirs_s), C.c_float(range_min), C.c_float(range_max),
+                            C.c_uint32(sim_opts), _p(out["points"]), _p(out["normals"]), _p(out["hits"]), _p(out["face_ids"]), _p(out["ranges"]))
         return out
 
     def cpc_find(self, Tbm, Tsb, dataset_pts, max_dist):

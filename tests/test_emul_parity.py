@@ -61,6 +61,32 @@ def test_find_all_models_bit_exact(pe, po, synth):
         assert 0.3 < r1["hits"].mean() <= 1.0
 
 
+def test_sim_options_parity(pe, po, synth):
+    """SURVEY.md A.3 leaves three rmagine simulate() semantics open (tfar = range.max vs inf, closest hit below range.min, miss fill): both
+    settings of each exist as a switch in the oracle and in the product's find_one; every combination agrees bit for bit, and each switch
+    changes what it should."""
+    osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
+    m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 15, 16, -np.pi, 2 * np.pi / 256, 256, 2.0, 6.0)      # short range: both limits bite
+    o, d = po.model_rays(m)
+    Tbm, Tsb = synth.building_gt_pose(), synth.scenario_tsb()
+    base = osc.simulate(Tbm, Tsb, o, d, m.range_max, m.range_min)
+    seen = {}
+    for opts in range(8):
+        tf, mn, fill = opts & 1, (opts >> 1) & 1, (opts >> 2) & 1
+        a = osc.simulate(Tbm, Tsb, o, d, m.range_max, m.range_min, tfar_mode=tf, min_mode=mn, miss_fill=fill)
+        b = esc.find(Tbm, Tsb, o, d, m.range_max, m.range_min, sim_opts=opts)
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), (opts, k)
+        seen[opts] = a
+    assert seen[0]["hits"].tobytes() == base["hits"].tobytes()
+    assert seen[1]["hits"].sum() > seen[0]["hits"].sum() and (seen[1]["ranges"][seen[1]["hits"] > 0] > m.range_max).any()       # tfar = inf: far hits appear
+    near = (seen[0]["hits"] > 0) & (seen[0]["ranges"] < m.range_min)
+    assert near.any() and (seen[2]["hits"][near] == 0).all() and (seen[2]["hits"][~near] == seen[0]["hits"][~near]).all()       # hits below range.min become misses
+    miss = seen[4]["hits"] == 0
+    assert miss.any() and (seen[4]["points"][miss] == 0).all() and np.isnan(seen[0]["points"][miss]).all()                      # zero fill vs NaN fill
+    assert (seen[4]["ranges"][miss] == np.float32(m.range_max + 1)).all()
+
+
 def test_icp_chain_parity(pe, po, synth):
     osc, esc = oracle_scene("building:60000"), emul_scene("building:60000")
     m = synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 31, 32, -np.pi, 2 * np.pi / 256, 256, 0.5, 120.0)
