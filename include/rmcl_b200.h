@@ -133,6 +133,13 @@ B2_API int b2_rcc_set_model_ondn(b2_rcc* h, uint32_t width, uint32_t height, con
 B2_API int b2_rcc_set_params(b2_rcc* h, float max_dist, float adaptive_max_dist_min);
 /* public field dataset (points + mask), Correspondences.hpp:24; src_is_device != 0: pointers are device addresses */
 B2_API int b2_rcc_set_dataset(b2_rcc* h, const float* points_xyz, const uint8_t* mask, uint32_t n, int src_is_device);
+/* The same two members as CALLER-OWNED device memory, nothing copied: a subclass of rmcl::Correspondences_<rm::VRAM_CUDA> keeps the reference's public
+ * `dataset` (rm::PointCloud_<VRAM_CUDA>, Correspondences.hpp:24) and protected `model_buffers_` (Correspondences.hpp:81-85) and binds their device
+ * pointers here; find() then writes points / normals / hits straight into the bound buffers (capacity entries; grow and re-bind like
+ * RCCOptix.cpp:36-40), the reductions read the bound dataset.  b2_rcc_set_dataset / set_ranges / correct_once_ranges switch back to the handle's
+ * own dataset buffers; binding with capacity 0 unbinds the model buffers. */
+B2_API int b2_rcc_bind_dataset(b2_rcc* h, const float* points_xyz_dev, const uint8_t* mask_dev, uint32_t n);
+B2_API int b2_rcc_bind_model_buffers(b2_rcc* h, float* points_xyz_dev, float* normals_xyz_dev, uint8_t* hits_dev, uint32_t capacity);
 /* MICP..Sensor..::unpackMessage (rmcl_ros/src/micpl/MICPSphericalSensorCPU.cpp:181-233) on the device: dataset = dir*range (+orig),
  * mask = range in [range.min, range.max].  Also the v1 setInputData(ranges) (lidar_corrector_embree_benchmark.cpp:118). */
 B2_API int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int src_is_device);

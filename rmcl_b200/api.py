@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers",
 ]
 
 
@@ -397,6 +397,22 @@ class RCCB200:
         self.outdated = False
         out = np.frombuffer(bytearray(mv[64:192]), self._CO_OUT)
         return out["Tn"][0], out["Td"][0], out["Cm"][0]
+
+    def bindDataset(self, points, mask):
+        """use caller-owned CUDA tensors as the dataset (no copy): the reference's public `dataset` member in VRAM (Correspondences.hpp:24)"""
+        n = points.numel() // 3
+        _chk(load_library().b2_rcc_bind_dataset(self._h, _devptr(points), _devptr(mask), C.c_uint32(n)))
+        self._bound = (points, mask)
+        self.outdated = True
+
+    def bindModelBuffers(self, points, normals, hits):
+        """find() writes into these caller-owned CUDA tensors: the reference's protected `model_buffers_` (Correspondences.hpp:81-85); None unbinds"""
+        if points is None:
+            _chk(load_library().b2_rcc_bind_model_buffers(self._h, None, None, None, C.c_uint32(0)))
+            self._bound_model = None
+            return
+        _chk(load_library().b2_rcc_bind_model_buffers(self._h, _devptr(points), _devptr(normals), _devptr(hits), C.c_uint32(hits.numel())))
+        self._bound_model = (points, normals, hits)
 
     def setSimOptions(self, tfar_mode=0, min_mode=0, miss_fill=0):
         """the open rmagine simulate() semantics of SURVEY.md A.3: tfar = +inf, closest hit below range.min = miss, misses filled with zeros"""

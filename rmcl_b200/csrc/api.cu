@@ -394,6 +394,15 @@ struct b2_rcc {
     cudaEvent_t ev_join = nullptr;      // multi-sensor correctOnce: orders this handle's stream against the lead handle's
     uint32_t n_ranges_in = 0;           // real ranges resident in d_ranges_in (set_ranges / correct_once_ranges), needed by b2_rcc_segment
     DevBuf<uint32_t> d_seg_counts, d_seg_offsets, d_seg_totals; DevBuf<float> d_seg_scan, d_seg_map; DevBuf<uint8_t> d_seg_labels;
+    // caller-owned device memory (b2_rcc_bind_dataset / b2_rcc_bind_model_buffers): the reference's public `dataset` member and protected
+    // `model_buffers_` (Correspondences.hpp:24,81-85) live in rm::Memory<.., VRAM_CUDA>; a subclass binds them so that nothing is copied
+    const float* b_dpts = nullptr; const uint8_t* b_dmask = nullptr;        // borrowed dataset (read only)
+    float* b_mpts = nullptr; float* b_mnrm = nullptr; uint8_t* b_mhits = nullptr; uint32_t b_mcap = 0;
+    const float* dpts() const { return b_dpts ? b_dpts : d_dpts.p; }
+    const uint8_t* dmask() const { return b_dpts ? b_dmask : d_dmask.p; }
+    float* mpts() const { return b_mpts ? b_mpts : d_mpts.p; }
+    float* mnrm() const { return b_mpts ? b_mnrm : d_mnrm.p; }
+    uint8_t* mhits() const { return b_mpts ? b_mhits : d_mhits.p; }
     uint32_t sim_opts = 0;              // b2_rcc_set_sim_options
     int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
     uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
@@ -603,6 +612,7 @@ extern "C" int b2_rcc_set_dataset(b2_rcc* h, const float* pts, const uint8_t* ma
     NOTNULL(h);
     CU(cudaSetDevice(h->map->device));
     if (n) { NOTNULL(pts); }
+    h->b_dpts = nullptr; h->b_dmask = nullptr;                                        // own buffers from now on
     RES(h->d_dpts.reserve(3 * (size_t)std::max(n, 1u))); RES(h->d_dmask.reserve(std::max(n, 1u)));
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n) {
@@ -621,6 +631,7 @@ static int ranges_to_dataset(b2_rcc* h, const float* ranges, uint32_t n, int src
     if (n != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", n, h->n);
     if (n == 0) { h->n_dataset = 0; return B2_OK; }
     NOTNULL(ranges);
+    h->b_dpts = nullptr; h->b_dmask = nullptr;
     RES(h->d_dpts.reserve(3 * (size_t)n)); RES(h->d_dmask.reserve(n)); RES(h->d_ranges_in.reserve(n));
     CU(cudaMemcpyAsync(h->d_ranges_in.p, ranges, sizeof(float) * n, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     k_dataset_from_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_ranges_in.p, h->d_dirs.p, h->d_origs.p, h->n_origs, n, h->range_min, h->range_max, h->d_dpts.p, h->d_dmask.p);
@@ -641,7 +652,8 @@ extern "C" int b2_rcc_set_ranges(b2_rcc* h, const float* ranges, uint32_t n, int
 static int reserve_model(b2_rcc* h, size_t n)
 {
     // buffers only ever grow (RCCEmbree.cpp:28-33)
-    RES(h->d_mpts.reserve(3 * n)); RES(h->d_mnrm.reserve(3 * n)); RES(h->d_mranges.reserve(n)); RES(h->d_mhits.reserve(n)); RES(h->d_mfaces.reserve(n));
+    if (h->b_mpts && n > h->b_mcap) return fail(B2_ERR_INVALID, "bound model buffers hold %u entries, find needs %zu (resize them and bind again, RCCOptix.cpp:36-40)", h->b_mcap, n);
+    RES(h->d_mpts.reserve(h->b_mpts ? 1 : 3 * n)); RES(h->d_mnrm.reserve(h->b_mpts ? 1 : 3 * n)); RES(h->d_mranges.reserve(n)); RES(h->d_mhits.reserve(h->b_mpts ? 1 : n)); RES(h->d_mfaces.reserve(n));
     return B2_OK;
 }
 
@@ -652,7 +664,7 @@ static RayModel ray_model(const b2_rcc* h)
 }
 static ModelBuffers model_buffers(const b2_rcc* h)
 {
-    ModelBuffers b; b.pts = h->d_mpts.p; b.nrm = h->d_mnrm.p; b.hits = h->d_mhits.p; b.faces = h->d_mfaces.p; b.ranges = h->d_mranges.p; return b;
+    ModelBuffers b; b.pts = h->mpts(); b.nrm = h->mnrm(); b.hits = h->mhits(); b.faces = h->d_mfaces.p; b.ranges = h->d_mranges.p; return b;
 }
 
 static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* icp_dev)
@@ -664,7 +676,7 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
         if (n == 0) { h->n_model = 0; h->found = true; return B2_OK; }
         RES(reserve_model(h, n));
         k_cpc_find<<<(n + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode_cp, icp_dev,
-                                                                                             Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, h->d_dpts.p, n, h->max_dist, model_buffers(h));
+                                                                                             Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, h->dpts(), n, h->max_dist, model_buffers(h));
         LAUNCHED();
         h->n_model = n; h->found = true;
         return B2_OK;
@@ -681,6 +693,24 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h), early);
     LAUNCHED();
     h->n_model = h->n; h->found = true;
+    return B2_OK;
+}
+
+extern "C" int b2_rcc_bind_dataset(b2_rcc* h, const float* points_dev, const uint8_t* mask_dev, uint32_t n)
+{
+    NOTNULL(h);
+    if (n) { NOTNULL(points_dev); NOTNULL(mask_dev); }
+    if (!h->pending.empty()) return fail(B2_ERR_INVALID, "bind_dataset while correctOnce calls are in flight");
+    h->b_dpts = n ? points_dev : nullptr; h->b_dmask = n ? mask_dev : nullptr; h->n_dataset = n;
+    return B2_OK;
+}
+extern "C" int b2_rcc_bind_model_buffers(b2_rcc* h, float* points_dev, float* normals_dev, uint8_t* hits_dev, uint32_t capacity)
+{
+    NOTNULL(h);
+    if (!h->pending.empty()) return fail(B2_ERR_INVALID, "bind_model_buffers while correctOnce calls are in flight");
+    if (capacity == 0 || !points_dev) { h->b_mpts = nullptr; h->b_mnrm = nullptr; h->b_mhits = nullptr; h->b_mcap = 0; h->found = false; return B2_OK; }
+    NOTNULL(normals_dev); NOTNULL(hits_dev);
+    h->b_mpts = points_dev; h->b_mnrm = normals_dev; h->b_mhits = hits_dev; h->b_mcap = capacity; h->found = false;
     return B2_OK;
 }
 
@@ -712,7 +742,7 @@ static int launch_reduce(b2_rcc* h, const b2_transform* Tpre_host, float max_dis
     const uint32_t n = std::min(h->n_dataset, h->n_model);
     int grid = (int)std::min<uint32_t>((uint32_t)h->red_grid, (n + B2_RED_BLOCK - 1) / B2_RED_BLOCK);
     if (grid < 1) grid = 1;
-    k_p2l_reduce<<<grid, B2_RED_BLOCK, 0, h->stream>>>(h->d_dpts.p, h->d_dmask.p, h->d_mpts.p, h->d_mnrm.p, h->d_mhits.p, n,
+    k_p2l_reduce<<<grid, B2_RED_BLOCK, 0, h->stream>>>(h->dpts(), h->dmask(), h->mpts(), h->mnrm(), h->mhits(), n,
                                                        Tpre_host ? *Tpre_host : tf_identity_pod(), max_dist, icp_dev, h->d_partials.p, h->d_ticket.p, out_dev);
     LAUNCHED();
     return B2_OK;
@@ -752,11 +782,11 @@ extern "C" int b2_rcc_segment(b2_rcc* h, float min_dist_outlier_scan, float min_
     RES(h->d_seg_counts.reserve(2 * (size_t)blocks)); RES(h->d_seg_offsets.reserve(2 * (size_t)blocks)); RES(h->d_seg_totals.reserve(2));
     RES(h->d_seg_scan.reserve(3 * (size_t)n)); RES(h->d_seg_map.reserve(3 * (size_t)n)); RES(h->d_seg_labels.reserve(n));
     const RayModel m = ray_model(h);
-    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->d_mnrm.p, min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, nullptr, nullptr, nullptr, nullptr);
+    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->mnrm(), min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, nullptr, nullptr, nullptr, nullptr);
     LAUNCHED();
     k_segment_scan<<<1, 1024, 0, h->stream>>>(h->d_seg_counts.p, blocks, h->d_seg_offsets.p, h->d_seg_totals.p);
     LAUNCHED();
-    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->d_mnrm.p, min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, h->d_seg_offsets.p,
+    k_segment<<<blocks, B2_SEG_BLOCK, 0, h->stream>>>(m, h->d_ranges_in.p, h->d_mranges.p, h->mnrm(), min_dist_outlier_scan, min_dist_outlier_map, h->d_seg_counts.p, h->d_seg_offsets.p,
                                                       h->d_seg_scan.p, h->d_seg_map.p, h->d_seg_labels.p);
     LAUNCHED();
     uint32_t tot[2] = {0, 0};
@@ -773,13 +803,13 @@ extern "C" int b2_rcc_segment(b2_rcc* h, float min_dist_outlier_scan, float min_
 extern "C" int b2_rcc_model_view(b2_rcc* h, float** p, float** nr, uint8_t** hi, uint32_t** f, float** r, uint32_t* n)
 {
     NOTNULL(h);
-    if (p) *p = h->d_mpts.p; if (nr) *nr = h->d_mnrm.p; if (hi) *hi = h->d_mhits.p; if (f) *f = h->d_mfaces.p; if (r) *r = h->d_mranges.p; if (n) *n = h->n_model;
+    if (p) *p = h->mpts(); if (nr) *nr = h->mnrm(); if (hi) *hi = h->mhits(); if (f) *f = h->d_mfaces.p; if (r) *r = h->d_mranges.p; if (n) *n = h->n_model;
     return B2_OK;
 }
 extern "C" int b2_rcc_dataset_view(b2_rcc* h, float** p, uint8_t** m, uint32_t* n)
 {
     NOTNULL(h);
-    if (p) *p = h->d_dpts.p; if (m) *m = h->d_dmask.p; if (n) *n = h->n_dataset;
+    if (p) *p = const_cast<float*>(h->dpts()); if (m) *m = const_cast<uint8_t*>(h->dmask()); if (n) *n = h->n_dataset;
     return B2_OK;
 }
 extern "C" int b2_rcc_download_model(b2_rcc* h, float* p, float* nr, uint8_t* hi, uint32_t* f, float* r)
@@ -789,9 +819,9 @@ extern "C" int b2_rcc_download_model(b2_rcc* h, float* p, float* nr, uint8_t* hi
     const size_t n = h->n_model;
     CU(cudaStreamSynchronize(h->stream));
     if (n == 0) return B2_OK;
-    if (p) CU(cudaMemcpy(p, h->d_mpts.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
-    if (nr) CU(cudaMemcpy(nr, h->d_mnrm.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
-    if (hi) CU(cudaMemcpy(hi, h->d_mhits.p, n, cudaMemcpyDeviceToHost));
+    if (p) CU(cudaMemcpy(p, h->mpts(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (nr) CU(cudaMemcpy(nr, h->mnrm(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (hi) CU(cudaMemcpy(hi, h->mhits(), n, cudaMemcpyDeviceToHost));
     if (f) CU(cudaMemcpy(f, h->d_mfaces.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
     if (r) CU(cudaMemcpy(r, h->d_mranges.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
     return B2_OK;
@@ -803,8 +833,8 @@ extern "C" int b2_rcc_download_dataset(b2_rcc* h, float* p, uint8_t* m)
     const size_t n = h->n_dataset;
     CU(cudaStreamSynchronize(h->stream));
     if (n == 0) return B2_OK;
-    if (p) CU(cudaMemcpy(p, h->d_dpts.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
-    if (m) CU(cudaMemcpy(m, h->d_dmask.p, n, cudaMemcpyDeviceToHost));
+    if (p) CU(cudaMemcpy(p, h->dpts(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (m) CU(cudaMemcpy(m, h->dmask(), n, cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 
@@ -877,7 +907,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
         if (!cpc && !h->has_model) return fail(B2_ERR_INVALID, "correctOnce before setModel");
         if (sc[k].ranges_host) {
             if (sc[k].n_ranges != h->n) return fail(B2_ERR_INVALID, "ranges size %u != model size %u", sc[k].n_ranges, h->n);
-            h->n_dataset = h->n; h->n_ranges_in = h->n;
+            h->n_dataset = h->n; h->n_ranges_in = h->n; h->b_dpts = nullptr; h->b_dmask = nullptr;
             if (h->n > 0) { RES(h->d_dpts.reserve(3 * (size_t)h->n)); RES(h->d_dmask.reserve(h->n)); RES(h->d_ranges_in.reserve(h->n)); }
         }
         if (h->n_dataset != h->work_n()) return fail(B2_ERR_INVALID, "dataset size %u != model size %u", h->n_dataset, h->n);
@@ -980,7 +1010,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
             CU(cudaStreamWaitEvent(H->stream, h->ev_aux, 0));
             aux_any = true;
         }
-        S.dpts = h->d_dpts.p; S.dmask = h->d_dmask.p; S.mpts = h->d_mpts.p; S.mnrm = h->d_mnrm.p; S.mmask = h->d_mhits.p;
+        S.dpts = h->dpts(); S.dmask = h->dmask(); S.mpts = h->mpts(); S.mnrm = h->mnrm(); S.mmask = h->mhits();
         S.zc_ranges = zc; S.zc_dirs = h->d_dirs.p; S.zc_origs = h->d_origs.p; S.zc_n_origs = h->n_origs;
         S.dpts_out = h->d_dpts.p; S.dmask_out = h->d_dmask.p; S.ranges_out = h->d_ranges_in.p;
     }
@@ -1177,7 +1207,7 @@ extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t
     const uint64_t grid = (uint64_t)bpp * n_poses;
     if (grid > 0x7fffffffull) return fail(B2_ERR_INVALID, "too many poses");
     RES(h->d_partials.reserve((size_t)std::max<uint64_t>(grid, (uint64_t)h->red_grid) * (B2_NACC + 1)));
-    k_rcc_fused_batch<<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->d_dpts.p, h->d_dmask.p, h->max_dist,
+    k_rcc_fused_batch<<<(uint32_t)grid, B2_FUSED_BLOCK, 0, h->stream>>>(h->map->view(), poses_dev, h->Tsb, ray_model(h), h->dpts(), h->dmask(), h->max_dist,
                                                                        bpp, rays_per_block, h->d_partials.p);
     LAUNCHED();
     b2_transform* td = Tdelta; uint32_t* nc = ncorr; b2_cross_stats* sb = stats_b;
