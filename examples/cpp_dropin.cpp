@@ -9,8 +9,20 @@
 #include <vector>
 
 #include <rmcl_b200/rcc_b200.hpp>
+#include <rmcl_b200/rmcl_msgs_adapters.hpp>
 
 namespace rm = rmagine;
+
+// plain stand-ins for the rosidl-generated rmcl_msgs structs (same field names as rmcl_msgs/msg/*.msg): the adapters are duck-typed
+namespace mock_msgs {
+struct ScanInfo { float phi_min, phi_inc; uint32_t phi_n; float theta_min, theta_inc; uint32_t theta_n; float range_min, range_max; };
+struct RangeData { std::vector<float> ranges; std::vector<bool> mask; };
+struct Scan { ScanInfo info; RangeData data; };
+struct Point32 { float x, y, z; };
+struct O1DnInfo { uint32_t width, height; float range_min, range_max; Point32 orig; std::vector<Point32> dirs; };
+struct O1Dn { O1DnInfo info; RangeData data; };
+struct MICPSensorStats { uint32_t total_measurements, valid_measurements, valid_matches; float cov_trace; };
+}
 
 static void make_sphere(unsigned A, unsigned B, float radius, std::vector<float>& V, std::vector<uint32_t>& F)
 {
@@ -84,6 +96,34 @@ int main(int argc, char** argv)
         const rm::CrossStatistics cs = correct.computeCrossStatistics(rm::Transform::Identity());
         const rm::Transform Tu = rmcl::umeyama_transform(cs);
         printf("V2 n_meas %u cov_trace %.9g tz %.9g\n", cs.n_meas, cs.covariance.trace(), Tu.t.z);
+
+        // the same v2 round fed from rmcl_msgs-shaped messages (rmcl_msgs_adapters.hpp): Scan for the spherical sensor, O1Dn with the same rays
+        {
+            mock_msgs::Scan msg;
+            msg.info = {model.phi.min, model.phi.inc, model.phi.size, model.theta.min, model.theta.inc, model.theta.size, model.range.min, model.range.max};
+            msg.data.ranges = ranges;
+            rmcl::RCCB200Spherical rcc(map);
+            rcc.setTsb(rm::Transform::Identity()); rcc.params.max_dist = 1.0f;
+            rmcl::b200::unpackMessage(rcc, msg);
+            rcc.find(Tg);
+            const rm::CrossStatistics c1 = rcc.computeCrossStatistics(rm::Transform::Identity());
+            mock_msgs::O1Dn omsg;
+            omsg.info.width = model.theta.size; omsg.info.height = model.phi.size; omsg.info.range_min = model.range.min; omsg.info.range_max = model.range.max; omsg.info.orig = {0.f, 0.f, 0.f};
+            for (uint32_t vid = 0; vid < model.phi.size; vid++)
+                for (uint32_t hid = 0; hid < model.theta.size; hid++) {
+                    const float ph = model.phi.min + (float)vid * model.phi.inc, th = model.theta.min + (float)hid * model.theta.inc;
+                    omsg.info.dirs.push_back({cosf(ph) * cosf(th), cosf(ph) * sinf(th), sinf(ph)});
+                }
+            omsg.data.ranges = ranges;
+            rmcl::RCCB200O1Dn orcc(map);
+            orcc.setTsb(rm::Transform::Identity()); orcc.params.max_dist = 1.0f;
+            rmcl::b200::unpackMessage(orcc, omsg);
+            orcc.find(Tg);
+            const rm::CrossStatistics c2 = orcc.computeCrossStatistics(rm::Transform::Identity());
+            mock_msgs::MICPSensorStats st{};
+            rmcl::b200::fillSensorStats(st, c1, (uint32_t)ranges.size(), (uint32_t)ranges.size());
+            printf("MSG n_meas %u cov_trace %.9g o1dn_n_meas %u o1dn_cov_trace %.9g stats_matches %u\n", c1.n_meas, c1.covariance.trace(), c2.n_meas, c2.covariance.trace(), st.valid_matches);
+        }
 
         // particle update with a handful of beams
         rmcl::PCDSensorUpdaterB200 up(map);

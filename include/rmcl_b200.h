@@ -208,6 +208,9 @@ B2_API int b2_rcc_set_exec_mode(b2_rcc* h, int mode);
  * poses_on_device / out_on_device select HOST or DEVICE pointers. Outputs may be NULL. */
 B2_API int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t n_poses, int poses_on_device,
                                 b2_transform* Tdelta, uint32_t* ncorr, b2_cross_stats* stats_b, int out_on_device);
+/* v1 corrector.benchmark(Tbm, Nruns) -> {sim, red, svd} seconds (rmcl_ros/src/benchmarks/lidar_corrector_optix_benchmark.cpp:143-155): the stages of
+ * correct() run unfused (trace of all poses -> P2L reduction -> Umeyama) and timed separately with CUDA events, summed over n_runs.  Poses on the HOST. */
+B2_API int b2_rcc_benchmark_batch(b2_rcc* h, const b2_transform* Tbm_host, uint32_t n_poses, uint32_t n_runs, double* sim_s, double* red_s, double* svd_s);
 /* rm::umeyama_transform for n statistics (rmcl_ros/src/nodes/micp_localization.cpp:952-953) */
 B2_API int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_transform* out, int on_device, int device, void* cuda_stream);
 

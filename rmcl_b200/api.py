@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers", "b2_rcc_benchmark_batch",
 ]
 
 
@@ -439,6 +439,13 @@ class RCCB200:
         self.outdated = False
         out = np.frombuffer(bytearray(mv[64:192]), self._CO_OUT)
         return out["Tn"][0], out["Td"][0], out["Cm"][0]
+
+    def benchmark(self, Tbm, n_runs=10):
+        """v1 corrector.benchmark(T, Nruns) -> dict(sim, red, svd) seconds (lidar_corrector_optix_benchmark.cpp:143-155): stages run unfused"""
+        Tbm = _tf(Tbm).reshape(-1)
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _chk(load_library().b2_rcc_benchmark_batch(self._h, _p(Tbm), C.c_uint32(len(Tbm)), C.c_uint32(n_runs), C.byref(a), C.byref(b), C.byref(c)))
+        return dict(sim=a.value, red=b.value, svd=c.value)
 
     def correct(self, Tbm):
         """v1 {Sphere,Pinhole,O1Dn}Corrector::correct(Tbm[N]) -> (Tdelta[N], Ncorr[N], stats_b[N])

@@ -1226,6 +1226,50 @@ extern "C" int b2_rcc_correct_batch(b2_rcc* h, const b2_transform* Tbm, uint32_t
     return B2_OK;
 }
 
+// v1 corrector.benchmark(Tbm, Nruns) -> {sim, red, svd} (rmcl_ros/src/benchmarks/lidar_corrector_optix_benchmark.cpp:143-155): the three stages
+// of correct() run UNFUSED and timed separately with CUDA events (trace of all poses into pose-major model buffers, P2L reduction, Umeyama),
+// summed over n_runs.  The production call b2_rcc_correct_batch fuses trace + reduction; this entry exists for the stage split only.
+extern "C" int b2_rcc_benchmark_batch(b2_rcc* h, const b2_transform* Tbm_host, uint32_t n_poses, uint32_t n_runs, double* sim_s, double* red_s, double* svd_s)
+{
+    NOTNULL(h); NOTNULL(Tbm_host);
+    CU(cudaSetDevice(h->map->device));
+    if (!h->has_model || h->n == 0 || n_poses == 0 || n_runs == 0) return fail(B2_ERR_INVALID, "benchmark needs a model, poses and runs");
+    if (h->n_dataset != h->n) return fail(B2_ERR_INVALID, "benchmark before setInputData (dataset %u != model %u)", h->n_dataset, h->n);
+    const uint64_t total = (uint64_t)h->n * n_poses;
+    if (total > 0x7fffffffull) return fail(B2_ERR_INVALID, "too many rays for the unfused benchmark (%llu)", (unsigned long long)total);
+    DevBuf<float> pts, nrm, rng; DevBuf<uint8_t> hits; DevBuf<uint32_t> faces;
+    auto cleanup = [&]() { pts.release(); nrm.release(); rng.release(); hits.release(); faces.release(); };
+    int rc = B2_OK;
+    if ((rc = pts.reserve(3 * total)) || (rc = nrm.reserve(3 * total)) || (rc = rng.reserve(total)) || (rc = hits.reserve(total)) || (rc = faces.reserve(total)) ||
+        (rc = h->d_poses.reserve(n_poses)) || (rc = h->d_tdelta.reserve(n_poses)) || (rc = h->d_ncorr.reserve(n_poses)) || (rc = h->d_bstats.reserve(n_poses))) { cleanup(); return rc; }
+    const uint32_t rays_per_block = B2_FUSED_BLOCK * 8, bpp = (h->n + rays_per_block - 1) / rays_per_block;
+    if ((rc = h->d_partials.reserve((size_t)std::max<uint64_t>((uint64_t)bpp * n_poses, (uint64_t)std::max(h->red_grid, 2 * B2_ICP_MAX_GRID)) * (B2_NACC + 1)))) { cleanup(); return rc; }
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaMemcpyAsync(h->d_poses.p, Tbm_host, sizeof(b2_transform) * (size_t)n_poses, cudaMemcpyHostToDevice, h->stream);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
+    double acc[3] = {0, 0, 0};
+    ModelBuffers out; out.pts = pts.p; out.nrm = nrm.p; out.hits = hits.p; out.faces = faces.p; out.ranges = rng.p;
+    for (uint32_t r = 0; r < n_runs && e == cudaSuccess; r++) {
+        cudaEventRecord(ev[0], h->stream);
+        k_rcc_find<<<(uint32_t)((total + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK), B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, 0, h->d_poses.p, nullptr,
+                                                                                                        tf_identity_pod(), h->Tsb, ray_model(h), n_poses, out, 0);
+        cudaEventRecord(ev[1], h->stream);
+        k_p2l_batch<<<bpp * n_poses, B2_FUSED_BLOCK, 0, h->stream>>>(pts.p, nrm.p, hits.p, h->n, h->dpts(), h->dmask(), h->max_dist, bpp, rays_per_block, h->d_partials.p);
+        cudaEventRecord(ev[2], h->stream);
+        k_umeyama_from_partials<<<(n_poses + 63) / 64, 64, 0, h->stream>>>(h->d_partials.p, bpp, n_poses, h->Tsb, h->d_tdelta.p, h->d_ncorr.p, h->d_bstats.p);
+        cudaEventRecord(ev[3], h->stream);
+        g_launches.fetch_add(3);
+        e = cudaEventSynchronize(ev[3]);
+        for (int i = 0; i < 3 && e == cudaSuccess; i++) { float ms = 0.f; e = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e-3; }
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    cleanup();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(B2_ERR_CUDA, "b2_rcc_benchmark_batch: %s", cudaGetErrorString(e)); }
+    if (sim_s) *sim_s = acc[0]; if (red_s) *red_s = acc[1]; if (svd_s) *svd_s = acc[2];
+    return B2_OK;
+}
+
 extern "C" int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_transform* out, int on_device, int device, void* stream_)
 {
     if (n == 0) return B2_OK;

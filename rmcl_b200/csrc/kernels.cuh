@@ -821,6 +821,32 @@ __global__ void __launch_bounds__(B2_FUSED_BLOCK, 6) k_rcc_fused_batch(BvhView b
     }
 }
 
+// stage-split twin of k_rcc_fused_batch for the v1 benchmark() call ({sim, red, svd} seconds, lidar_corrector_optix_benchmark.cpp:143-155):
+// the reduction alone over model buffers that k_rcc_find wrote for ALL poses (pose-major), same partial layout as the fused kernel
+__global__ void __launch_bounds__(B2_FUSED_BLOCK) k_p2l_batch(const float* __restrict__ mpts, const float* __restrict__ mnrm, const uint8_t* __restrict__ mhits, uint32_t n,
+                                                             const float* __restrict__ dpts, const uint8_t* __restrict__ dmask, float max_dist,
+                                                             uint32_t blocks_per_pose, uint32_t rays_per_block, double* __restrict__ partials)
+{
+    __shared__ double smem[(B2_NACC + 1) * (B2_FUSED_BLOCK / 32)];
+    const uint32_t pose = blockIdx.x / blocks_per_pose, chunk = blockIdx.x % blocks_per_pose;
+    const Tf I = tf_identity();
+    P2LAcc acc; acc_zero(acc);
+    const uint32_t begin = chunk * rays_per_block, end = min(begin + rays_per_block, n);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        const size_t o = (size_t)pose * n + i;
+        if (!(dmask[i] > 0) || !(mhits[o] > 0)) continue;
+        V3 D, M;
+        if (p2l_pair(I, mk3(dpts[3 * i], dpts[3 * i + 1], dpts[3 * i + 2]), mk3(mpts[3 * o], mpts[3 * o + 1], mpts[3 * o + 2]), mk3(mnrm[3 * o], mnrm[3 * o + 1], mnrm[3 * o + 2]), max_dist, D, M))
+            acc_add_pair(acc, D, M);
+    }
+    block_reduce_acc<B2_FUSED_BLOCK>(acc, smem);
+    if (threadIdx.x == 0) {
+        double* p = partials + (size_t)blockIdx.x * (B2_NACC + 1);
+        for (int i = 0; i < B2_NACC; i++) p[i] = acc.v[i];
+        p[B2_NACC] = (double)acc.n;
+    }
+}
+
 // per pose: sum the block partials in order -> stats_s -> stats_b = Tsb * stats_s -> Umeyama
 __global__ void k_umeyama_from_partials(const double* __restrict__ partials, uint32_t blocks_per_pose, uint32_t n_poses, b2_transform Tsb_val,
                                         b2_transform* __restrict__ Tdelta, uint32_t* __restrict__ ncorr, b2_cross_stats* __restrict__ stats_b_out)
