@@ -210,7 +210,7 @@ extern "C" int b2_mesh_export_blob(const b2_mesh* m, void* dst_host, uint64_t ca
     CU(cudaSetDevice(m->device));
     B2BlobHeader hd; memset(&hd, 0, sizeof(hd));
     memcpy(hd.magic, kBlobMagic, 8);
-    hd.version = 1; hd.node_bytes = sizeof(B2Node8); hd.tri_bytes = sizeof(B2Tri); hd.n_nodes = m->n_nodes; hd.n_tris = m->n_tris; hd.n_faces = m->n_faces;
+    hd.version = 2; hd.node_bytes = sizeof(B2Node8); hd.tri_bytes = sizeof(B2Tri); hd.n_nodes = m->n_nodes; hd.n_tris = m->n_tris; hd.n_faces = m->n_faces;
     hd.n_verts = m->n_verts; hd.max_depth = m->max_depth; hd.build_mode = m->build_mode; hd.sah = m->sah;
     for (int k = 0; k < 3; k++) hd.abs_max[k] = m->abs_max[k];
     char* p = static_cast<char*>(dst_host);
@@ -225,7 +225,7 @@ extern "C" int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, i
     NOTNULL(out); *out = nullptr; NOTNULL(blob_host);
     if (bytes < sizeof(B2BlobHeader)) return fail(B2_ERR_INVALID, "BVH blob truncated (%llu bytes)", (unsigned long long)bytes);
     B2BlobHeader hd; memcpy(&hd, blob_host, sizeof(hd));
-    if (memcmp(hd.magic, kBlobMagic, 8) != 0 || hd.version != 1 || hd.node_bytes != sizeof(B2Node8) || hd.tri_bytes != sizeof(B2Tri))
+    if (memcmp(hd.magic, kBlobMagic, 8) != 0 || hd.version != 2 || hd.node_bytes != sizeof(B2Node8) || hd.tri_bytes != sizeof(B2Tri))
         return fail(B2_ERR_INVALID, "not a BVH blob of this library version");
     const uint64_t need = sizeof(hd) + (uint64_t)hd.n_nodes * sizeof(B2Node8) + (uint64_t)hd.n_tris * sizeof(B2Tri);
     if (hd.n_nodes == 0 || hd.n_tris == 0) return fail(B2_ERR_NO_MAP, "EMPTY MAP in BVH blob");
@@ -236,11 +236,12 @@ extern "C" int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, i
         uint32_t n_inner = 0, tri_end = 0;
         for (int sl = 0; sl < 8; sl++) {
             const uint8_t meta = nodes[i].meta[sl];
-            if ((nodes[i].imask >> sl) & 1u) n_inner++;
+            if ((nodes[i].imask() >> sl) & 1u) n_inner++;
             else if (meta) { const uint32_t cnt = (meta >> 5) == 7 ? 3 : ((meta >> 5) == 3 ? 2 : 1); tri_end = std::max(tri_end, (uint32_t)(meta & 0x1fu) + cnt); }
         }
         if ((n_inner && (uint64_t)nodes[i].child_base + n_inner > hd.n_nodes) || (tri_end && (uint64_t)nodes[i].tri_base + tri_end > hd.n_tris))
             return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u points outside the arrays", i);
+        if (nodes[i].masks != b2_masks_from_meta(nodes[i].meta)) return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u has inconsistent child masks", i);
         // children sit strictly behind their parent (breadth-first layout): makes the structure acyclic, so the depth below is well defined
         if (n_inner && nodes[i].child_base <= i) return fail(B2_ERR_INVALID, "BVH blob corrupt: node %u has a child at or before itself", i);
     }
@@ -251,7 +252,7 @@ extern "C" int b2_mesh_create_from_blob(const void* blob_host, uint64_t bytes, i
         uint32_t max_depth = 0;
         for (uint32_t i = 0; i < hd.n_nodes; i++) {            // parents precede children: one forward pass
             uint32_t n_inner = 0;
-            for (int sl = 0; sl < 8; sl++) if ((nodes[i].imask >> sl) & 1u) n_inner++;
+            for (int sl = 0; sl < 8; sl++) if ((nodes[i].imask() >> sl) & 1u) n_inner++;
             for (uint32_t c = 0; c < n_inner; c++) { const uint32_t d = (uint32_t)depth[i] + 1u; if (d > 250u) return fail(B2_ERR_INVALID, "BVH blob corrupt: tree too deep"); depth[nodes[i].child_base + c] = (uint8_t)std::max<uint32_t>(depth[nodes[i].child_base + c], d); max_depth = std::max(max_depth, d); }
         }
         if (max_depth + 1 > B2_TRAVERSAL_STACK - 4) return fail(B2_ERR_INVALID, "BVH blob: tree depth %u exceeds the traversal stack", max_depth + 1);
@@ -710,6 +711,7 @@ extern "C" int b2_rcc_bind_model_buffers(b2_rcc* h, float* points_dev, float* no
     if (!h->pending.empty()) return fail(B2_ERR_INVALID, "bind_model_buffers while correctOnce calls are in flight");
     if (capacity == 0 || !points_dev) { h->b_mpts = nullptr; h->b_mnrm = nullptr; h->b_mhits = nullptr; h->b_mcap = 0; h->found = false; return B2_OK; }
     NOTNULL(normals_dev); NOTNULL(hits_dev);
+    if (h->b_mpts == points_dev && h->b_mnrm == normals_dev && h->b_mhits == hits_dev && h->b_mcap == capacity) return B2_OK;      // bound already: the last find stays valid
     h->b_mpts = points_dev; h->b_mnrm = normals_dev; h->b_mhits = hits_dev; h->b_mcap = capacity; h->found = false;
     return B2_OK;
 }

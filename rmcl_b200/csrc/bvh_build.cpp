@@ -283,11 +283,11 @@ int b2_build_bvh8_host(const float* verts, uint32_t nv, const uint32_t* faces, u
                 sah += (double)cn.box.half_area() / rootA * kCPrim * cnt;
             } else {
                 nd8.meta[s] = (uint8_t)(0x20 | (24 + s));
-                nd8.imask |= (uint8_t)(1u << s);
                 queue.push_back({ch[c].node2, pe.depth + 1});
                 nodes8.emplace_back();
             }
         }
+        nd8.masks = b2_masks_from_meta(nd8.meta);
         nodes8[qi] = nd8;
     }
     free(n2);

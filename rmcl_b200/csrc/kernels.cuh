@@ -603,8 +603,8 @@ B2_DEV void bvh8_refit_node(uint32_t t, B2Node8* nodes, B2Tri* tris, const float
     for (int s = 0; s < 8; s++) {
         const uint32_t meta = nd.meta[s];
         float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-        if ((nd.imask >> s) & 1u) {
-            const B2Node8& ch = nodes[nd.child_base + popc32(nd.imask & ((1u << s) - 1u))];
+        if ((nd.imask() >> s) & 1u) {
+            const B2Node8& ch = nodes[nd.child_base + popc32(nd.imask() & ((1u << s) - 1u))];
             for (int c = 0; c < 8; c++) {
                 if (!ch.meta[c]) continue;
                 for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], ch.lo[k][c]); hi[k] = fmaxf(hi[k], ch.hi[k][c]); }

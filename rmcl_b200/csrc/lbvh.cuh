@@ -179,7 +179,7 @@ __global__ void k_lbvh_collapse(uint32_t level_begin, uint32_t level_end, uint32
     B2Node8 nd;
     for (int a = 0; a < 3; a++) for (int s = 0; s < 8; s++) { nd.lo[a][s] = __int_as_float(0x7f800000); nd.hi[a][s] = __int_as_float(0xff800000); }
     for (int s = 0; s < 8; s++) nd.meta[s] = 0;
-    nd.child_base = child_base; nd.tri_base = tri_base; nd.imask = 0; nd.pad[0] = nd.pad[1] = nd.pad[2] = 0;
+    nd.child_base = child_base; nd.tri_base = tri_base; nd.masks = 0; nd.pad0 = 0; nd.pad[0] = nd.pad[1] = 0;
     uint32_t ki = 0, toff = 0;
     for (int s = 0; s < 8; s++) {
         const int k = child_in_slot[s];
@@ -189,7 +189,7 @@ __global__ void k_lbvh_collapse(uint32_t level_begin, uint32_t level_end, uint32
         for (int a = 0; a < 3; a++) { nd.lo[a][s] = b.lo[a]; nd.hi[a][s] = b.hi[a]; }
         const uint32_t m = lbvh_count(id, n, first, last);
         if (m > B2_MAX_LEAF_TRIS) {
-            nd.meta[s] = (uint8_t)(0x20 | (24 + s)); nd.imask |= 1u << s;
+            nd.meta[s] = (uint8_t)(0x20 | (24 + s));
             root_of[child_base + ki] = id; ki++;
         } else {
             const uint32_t unary = m == 1 ? 1u : (m == 2 ? 3u : 7u);
@@ -206,6 +206,7 @@ __global__ void k_lbvh_collapse(uint32_t level_begin, uint32_t level_end, uint32
             toff += m;
         }
     }
+    nd.masks = b2_masks_from_meta(nd.meta);
     nodes8[t] = nd;
 }
 

@@ -119,28 +119,55 @@ B2_DEV RaySetup ray_setup(V3 o, V3 d, const BvhView& bvh)
     r.ncf = mk3(-(oix - dlx), -(oiy - dly), -(oiz - dlz));
     // node layout in float4 units: lo_x 0..1, lo_y 2..3, lo_z 4..5, hi_x 6..7, hi_y 8..9, hi_z 10..11
     r.onx = (r.oct & 1u) ? 0u : 6u; r.ony = (r.oct & 2u) ? 2u : 8u; r.onz = (r.oct & 4u) ? 4u : 10u;
+#if B2_ON_DEVICE
+    // Per-ray constants of the box test are made opaque to the optimiser: under the 72-register cap of the traversal kernels ptxas otherwise
+    // RE-DERIVES them from o / d in every node visit (octant, plane offsets, scaled slopes, slack constants: ~45 of ~190 instructions per visit in
+    // the round-1 SASS) instead of keeping -- or, at worst, spilling and reloading -- nine values.
+    asm volatile("" : "+f"(r.ncn.x), "+f"(r.ncn.y), "+f"(r.ncn.z), "+f"(r.idn.x), "+f"(r.idn.y), "+f"(r.idn.z));
+    asm volatile("" : "+r"(r.oct), "+r"(r.onx), "+r"(r.ony), "+r"(r.onz));
+#endif
     return r;
 }
 
-// Intersect the 8 children of one node; returns the hit mask: bits 31..24 inner children by priority (slot ^ oct), bits 23..0 leaf triangles.
-B2_DEV uint32_t node_test(const float4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& imask)
+// XOR-permutation of an 8-bit child mask: bit s moves to bit s ^ oct (three conditional swaps: nibbles, bit pairs, bits).  A ray visits the
+// inner children of a node in descending order of (slot ^ octant); with the hit bits permuted like this that order is "highest set bit first".
+B2_DEV uint32_t xor_permute8(uint32_t x, uint32_t oct)
+{
+    if (oct & 4u) x = ((x << 4) | (x >> 4)) & 0xffu;
+    if (oct & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (oct & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    return x;
+}
+// 8 child bits -> 24 slot-space triangle bits: bit s becomes bits 3s..3s+2
+B2_DEV uint32_t spread3x(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00f00fu;
+    x = (x | (x << 4)) & 0x0c30c3u;
+    x = (x | (x << 2)) & 0x249249u;
+    return x * 7u;
+}
+
+// Intersect the 8 children of one node.  Outputs: `inner` = (hit inner children in priority positions 31..24) | imask 7..0 -- the stack-entry
+// format; `tris` = pending leaf triangles in slot space (bit 3s+j = triangle j of leaf child s), `trimask` = the node's existing triangles in the
+// same space (record index of bit b = tri_base + popc(trimask & ((1 << b) - 1))).
+// 13 quads per visit (12 plane quads + one header quad); the masks come from the eight box-test bits with ~30 bit operations -- the first
+// version decoded one meta byte per child (~60 instructions, a third of the visit: profiles/r02 SASS histogram).
+B2_DEV void node_test(const float4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& inner, uint32_t& tris, uint32_t& trimask)
 {
     // near planes: the "lo" arrays for positive directions, the "hi" arrays otherwise; far planes: the other one (offset 6 quads apart)
     const float4 nxa = ldg(np + r.onx), nxb = ldg(np + r.onx + 1), fxa = ldg(np + (6u - r.onx)), fxb = ldg(np + (7u - r.onx));
     const float4 nya = ldg(np + r.ony), nyb = ldg(np + r.ony + 1), fya = ldg(np + (10u - r.ony)), fyb = ldg(np + (11u - r.ony));
     const float4 nza = ldg(np + r.onz), nzb = ldg(np + r.onz + 1), fza = ldg(np + (14u - r.onz)), fzb = ldg(np + (15u - r.onz));
-    const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
-    child_base = f2u(h0.x); tri_base = f2u(h0.y); imask = f2u(h1.x);
-    // octant permutation of the priority bits of all inner children at once: meta ^= oct where (meta & 0x18) == 0x18
-    const uint32_t w0 = f2u(h0.z), w1 = f2u(h0.w);
-    const uint32_t m0 = w0 ^ ((((w0 >> 3) & (w0 >> 4)) & 0x01010101u) * r.oct);
-    const uint32_t m1 = w1 ^ ((((w1 >> 3) & (w1 >> 4)) & 0x01010101u) * r.oct);
+    const float4 h = ldg(np + 12);
+    child_base = f2u(h.x); tri_base = f2u(h.y);
+    const uint32_t masks = f2u(h.z), imask = masks & 0xffu;
+    trimask = masks >> 8;
     const float tlim = tbest * B2_C1;
-    uint32_t hitmask = 0;
+    uint32_t hit8 = 0;
     // Two children per step: Blackwell's packed FP32 FMA (FFMA2, PTX fma.rn.f32x2) evaluates one plane of two neighbouring slots in ONE
     // issue slot -- the operand pair is the register pair the 128-bit node load delivered, slope and addend are scalar broadcasts.  Each
     // half is an ordinary round-to-nearest FMA, so the results are those of the scalar code (and of the CPU emulation) bit for bit.
-#define B2_PAIR(S, NX0, NX1, NY0, NY1, NZ0, NZ1, FX0, FX1, FY0, FY1, FZ0, FZ1, M)                                     \
+#define B2_PAIR(S, NX0, NX1, NY0, NY1, NZ0, NZ1, FX0, FX1, FY0, FY1, FZ0, FZ1)                                        \
     {                                                                                                                  \
         float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;                                              \
         fma2_bcast(NX0, NX1, r.idn.x, r.ncn.x, nx0, nx1); fma2_bcast(NY0, NY1, r.idn.y, r.ncn.y, ny0, ny1);            \
@@ -149,16 +176,16 @@ B2_DEV uint32_t node_test(const float4* __restrict__ np, const RaySetup& r, floa
         fma2_bcast(FZ0, FZ1, r.idir.z, r.ncf.z, fz0, fz1);                                                             \
         const float tn0 = fmaxf(fmaxf(nx0, ny0), fmaxf(nz0, 0.0f)), tn1 = fmaxf(fmaxf(nx1, ny1), fmaxf(nz1, 0.0f));    \
         const float tf0 = fminf(fminf(fx0, fy0), fminf(fz0, tlim)), tf1 = fminf(fminf(fx1, fy1), fminf(fz1, tlim));    \
-        const uint32_t meta0 = ((M) >> (8 * ((S) & 3))) & 0xffu, meta1 = ((M) >> (8 * (((S) + 1) & 3))) & 0xffu;       \
-        hitmask |= (tn0 <= tf0) ? ((meta0 >> 5) << (meta0 & 0x1fu)) : 0u;                                              \
-        hitmask |= (tn1 <= tf1) ? ((meta1 >> 5) << (meta1 & 0x1fu)) : 0u;                                              \
+        hit8 |= (tn0 <= tf0) ? (1u << (S)) : 0u;                                                                       \
+        hit8 |= (tn1 <= tf1) ? (2u << (S)) : 0u;                                                                       \
     }
-    B2_PAIR(0, nxa.x, nxa.y, nya.x, nya.y, nza.x, nza.y, fxa.x, fxa.y, fya.x, fya.y, fza.x, fza.y, m0)
-    B2_PAIR(2, nxa.z, nxa.w, nya.z, nya.w, nza.z, nza.w, fxa.z, fxa.w, fya.z, fya.w, fza.z, fza.w, m0)
-    B2_PAIR(4, nxb.x, nxb.y, nyb.x, nyb.y, nzb.x, nzb.y, fxb.x, fxb.y, fyb.x, fyb.y, fzb.x, fzb.y, m1)
-    B2_PAIR(6, nxb.z, nxb.w, nyb.z, nyb.w, nzb.z, nzb.w, fxb.z, fxb.w, fyb.z, fyb.w, fzb.z, fzb.w, m1)
+    B2_PAIR(0, nxa.x, nxa.y, nya.x, nya.y, nza.x, nza.y, fxa.x, fxa.y, fya.x, fya.y, fza.x, fza.y)
+    B2_PAIR(2, nxa.z, nxa.w, nya.z, nya.w, nza.z, nza.w, fxa.z, fxa.w, fya.z, fya.w, fza.z, fza.w)
+    B2_PAIR(4, nxb.x, nxb.y, nyb.x, nyb.y, nzb.x, nzb.y, fxb.x, fxb.y, fyb.x, fyb.y, fzb.x, fzb.y)
+    B2_PAIR(6, nxb.z, nxb.w, nyb.z, nyb.w, nzb.z, nzb.w, fxb.z, fxb.w, fyb.z, fyb.w, fzb.z, fzb.w)
 #undef B2_PAIR
-    return hitmask;
+    inner = (xor_permute8(hit8 & imask, r.oct) << 24) | imask;
+    tris = spread3x(hit8 & ~imask) & trimask;           // empty slots never pass the box test (lo = +inf, hi = -inf) and have no trimask bits
 }
 
 // Closest hit. best.t must be initialised to tfar, best.face to B2_NOFACE by the caller (see trace_init).
@@ -169,7 +196,8 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
     int sp = 0;
     // root group: slot 0 of a virtual parent -> priority bit 24 + (0 ^ oct), imask bit 0
     uint2 G = make_uint2(0u, (1u << (24 + r.oct)) | 1u);      // pending inner children: (child_base, hit bits 31..24 | imask 7..0)
-    uint2 Gt = make_uint2(0u, 0u);                             // pending leaf triangles of the last visited node: (tri_base, bits 23..0)
+    uint2 Gt = make_uint2(0u, 0u);                             // pending leaf triangles of the last visited node: (tri_base, slot-space bits 23..0)
+    uint32_t Gm = 0u;                                          //   and that node's trimask (slot-space bit -> record index)
     // Each trip does ONE unit of work per lane -- a triangle test if one is pending, otherwise a node visit -- instead of a node visit
     // followed by an inner loop over that node's triangles: a warp then never waits for the lane with the most triangles in a node
     // (profiles/r01: the max-over-lanes triangle loop dominated the slowest warps' instruction streams).  The closest hit under the
@@ -178,7 +206,7 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
         if (Gt.y) {
             const uint32_t i = 31u - (uint32_t)clz32(Gt.y);
             Gt.y &= ~(1u << i);
-            tri_test(bvh, r, Gt.x + i, best);
+            tri_test(bvh, r, Gt.x + (uint32_t)popc32(Gm & ((1u << i) - 1u)), best);
             if (STATS) n_tris++;
         }
         if (!Gt.y) {                                           // last pending triangle done (or none): visit a node in the same trip
@@ -192,11 +220,11 @@ B2_DEV void trace_closest(const BvhView& bvh, const RaySetup& r, HitRec& best, u
             const uint32_t rel = popc32(G.y & 0xffu & ((1u << slot) - 1u));
             const uint32_t node_idx = G.x + rel;
             if (G.y & 0xff000000u) stack[sp++] = G;
-            uint32_t child_base, tri_base, imask;
-            const uint32_t hm = node_test(bvh.nodes + B2_NODE_QUADS * (size_t)node_idx, r, best.t, child_base, tri_base, imask);
+            uint32_t child_base, tri_base, inner, tris;
+            node_test(bvh.nodes + B2_NODE_QUADS * (size_t)node_idx, r, best.t, child_base, tri_base, inner, tris, Gm);
             if (STATS) n_nodes++;
-            G = make_uint2(child_base, (hm & 0xff000000u) | imask);
-            Gt = make_uint2(tri_base, hm & 0x00ffffffu);
+            G = make_uint2(child_base, inner);
+            Gt = make_uint2(tri_base, tris);
         }
     }
 }
@@ -331,8 +359,8 @@ B2_DEV void closest_point(const BvhView& bvh, V3 q, CpBest& best, uint32_t& n_no
             const float4 lxa = ldg(np + 0), lxb = ldg(np + 1), lya = ldg(np + 2), lyb = ldg(np + 3), lza = ldg(np + 4), lzb = ldg(np + 5);
             const float4 hxa = ldg(np + 6), hxb = ldg(np + 7), hya = ldg(np + 8), hyb = ldg(np + 9), hza = ldg(np + 10), hzb = ldg(np + 11);
             const float4 h0 = ldg(np + 12), h1 = ldg(np + 13);
-            const uint32_t child_base = f2u(h0.x), imask = f2u(h1.x);
-            tri_base = f2u(h0.y); m0 = f2u(h0.z); m1 = f2u(h0.w);
+            const uint32_t child_base = f2u(h0.x), imask = f2u(h0.z) & 0xffu;
+            tri_base = f2u(h0.y); m0 = f2u(h1.x); m1 = f2u(h1.y);
             if (STATS) n_nodes++;
             b2[0] = cp_b2(cp_axis(lxa.x, hxa.x, q.x), cp_axis(lya.x, hya.x, q.y), cp_axis(lza.x, hza.x, q.z));
             b2[1] = cp_b2(cp_axis(lxa.y, hxa.y, q.x), cp_axis(lya.y, hya.y, q.y), cp_axis(lza.y, hza.y, q.z));

@@ -137,7 +137,7 @@ __attribute__((visibility("default"))) void emul_pf_motion(void* sc, uint32_t n,
 __attribute__((visibility("default"))) int emul_refit(void* p, const float* verts, uint32_t nv, const uint32_t* faces)
 {
     EmulScene* s = (EmulScene*)p;
-    for (uint32_t t = 0; t < s->bvh.n_nodes; t++) if (s->bvh.nodes[t].imask && s->bvh.nodes[t].child_base <= t) return -1;
+    for (uint32_t t = 0; t < s->bvh.n_nodes; t++) if (s->bvh.nodes[t].imask() && s->bvh.nodes[t].child_base <= t) return -1;
     for (uint32_t t = s->bvh.n_nodes; t-- > 0;) bvh8_refit_node(t, s->bvh.nodes, s->bvh.tris, verts, faces);
     for (int k = 0; k < 3; k++) { float m = 0.f; for (uint32_t i = 0; i < nv; i++) m = fmaxf(m, fabsf(verts[3 * (size_t)i + k])); s->bvh.abs_max[k] = m; }
     return 0;
