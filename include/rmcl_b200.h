@@ -250,6 +250,18 @@ typedef struct {
 B2_API int b2_pf_resample_gladiator(b2_pf* h, const b2_transform* poses_dev, const b2_particle_attr* attrs_dev, uint32_t n_all, uint32_t first, uint32_t n_local,
                                     b2_transform* poses_new_dev, b2_particle_attr* attrs_new_dev, const b2_gladiator_config* cfg, uint64_t seed, uint32_t step,
                                     const uint32_t* raw_dev, const float* normals_dev);
+/* The same resampling with the particles SHARDED over GPUs (one process per GPU) and no all-gather: every rank publishes its shard in a buffer
+ * the other ranks map over NVLink (CUDA IPC); a champion reads its opponent's 4-byte likelihood from the owner's HBM and fetches the 68-byte
+ * record only when the opponent wins (the reference draws opponents from all particles, resampling.cu:137).  Equal shard sizes; results equal the
+ * single-GPU resampling of the concatenated set bit for bit.  init -> (exchange the 128-byte handles of all ranks) -> connect; per step:
+ * publish, cross-rank barrier, resample_p2p, cross-rank barrier.  remote_bytes_out (may be NULL) receives the bytes read from other GPUs. */
+B2_API int b2_pf_p2p_init(b2_pf* h, uint32_t n_per_rank, void* handles_out_128_bytes);
+B2_API int b2_pf_p2p_connect(b2_pf* h, const void* all_handles_world_x_128, uint32_t world, uint32_t rank, uint32_t n_per_rank);
+B2_API int b2_pf_p2p_publish(b2_pf* h, const b2_transform* poses_dev, const b2_particle_attr* attrs_dev, uint32_t n_local);
+B2_API int b2_pf_resample_gladiator_p2p(b2_pf* h, b2_transform* poses_new_dev, b2_particle_attr* attrs_new_dev, const b2_gladiator_config* cfg, uint64_t seed, uint32_t step,
+                                        uint64_t* remote_bytes_out);
+/* test hook: several shards on one device (poses_all / attrs_all hold world * n_per_rank particles; this handle plays `rank`) */
+B2_API int b2_pf_p2p_connect_local(b2_pf* h, const b2_transform* poses_all_dev, const b2_particle_attr* attrs_all_dev, uint32_t world, uint32_t rank, uint32_t n_per_rank);
 /* the draws b2_pf_resample_gladiator would use (replaces init_curand / curand(), resampling.cu:13-30,134-143): raw u32 + 6 normals per particle */
 B2_API int b2_pf_gladiator_randoms(b2_pf* h, uint64_t seed, uint32_t step, uint32_t first, uint32_t n, uint32_t* raw_dev, float* normals_dev);
 

@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers", "b2_rcc_benchmark_batch",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers", "b2_rcc_benchmark_batch", "b2_pf_p2p_init", "b2_pf_p2p_connect", "b2_pf_p2p_publish", "b2_pf_resample_gladiator_p2p", "b2_pf_p2p_connect_local",
 ]
 
 
@@ -625,6 +625,51 @@ class PCDSensorUpdaterB200:
                                                      _devptr(particle_poses_new), _devptr(particle_attrs_new), C.byref(cfg), C.c_uint64(seed), C.c_uint32(step),
                                                      _devptr(raw) if raw is not None else None, _devptr(normals) if normals is not None else None))
         return particle_poses_new, particle_attrs_new
+
+    def p2pConnect(self, dist, n_per_rank):
+        """Map the other ranks' particle exchange buffers over NVLink (CUDA IPC): once per particle-set size.  Raises B2Error if the GPUs have no
+        peer access or CUDA IPC is unavailable (the caller then stays with resampleSharded's all-gather)."""
+        import torch
+        ws, rank = dist.get_world_size(), dist.get_rank()
+        mine = np.zeros(128, np.uint8)
+        _chk(load_library().b2_pf_p2p_init(self._h, C.c_uint32(n_per_rank), _p(mine)))
+        dev = torch.device("cuda", self.map.device) if dist.get_backend() == "nccl" else "cpu"
+        allh = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(ws)]
+        dist.all_gather(allh, torch.from_numpy(mine).to(dev))
+        table = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
+        _chk(load_library().b2_pf_p2p_connect(self._h, _p(table), C.c_uint32(ws), C.c_uint32(rank), C.c_uint32(n_per_rank)))
+        self._p2p = (ws, rank, n_per_rank)
+
+    def resampleShardedP2P(self, poses_local, attrs_local, dist, config=None, seed=1234, step=0, want_traffic=False):
+        """Gladiator resampling over peer memory (b2_pf_resample_gladiator_p2p): publish the shard, barrier, one kernel that reads opponents'
+        likelihoods (4 B) and winners' records (68 B) from the owners' HBM, barrier.  -> (poses_new, attrs_new[, remote bytes read])"""
+        import torch
+        cfg = config or GladiatorConfig.defaults()
+        n = poses_local.shape[0]
+        if getattr(self, "_p2p", None) is None or self._p2p[2] != n:
+            raise B2Error(-1, "resampleShardedP2P: call p2pConnect(dist, n_per_rank) first")
+        _chk(load_library().b2_pf_p2p_publish(self._h, _devptr(poses_local), _devptr(attrs_local), C.c_uint32(n)))
+        dist.barrier()
+        P_new, A_new = torch.empty_like(poses_local), torch.empty_like(attrs_local)
+        t = C.c_uint64()
+        _chk(load_library().b2_pf_resample_gladiator_p2p(self._h, _devptr(P_new), _devptr(A_new), C.byref(cfg), C.c_uint64(seed), C.c_uint32(step),
+                                                         C.byref(t) if want_traffic else None))
+        torch.cuda.synchronize(poses_local.device)
+        dist.barrier()                      # nobody overwrites a published shard while a peer may still read it
+        return (P_new, A_new, int(t.value)) if want_traffic else (P_new, A_new)
+
+    def resampleP2PLocalWorld(self, poses_all, attrs_all, world, rank, config=None, seed=1234, step=0):
+        """test hook: `world` equal shards on ONE device; this handle plays `rank`.  -> (poses_new, attrs_new, bytes read from "remote" shards)"""
+        import torch
+        cfg = config or GladiatorConfig.defaults()
+        n_all = poses_all.shape[0]
+        n = n_all // world
+        _chk(load_library().b2_pf_p2p_connect_local(self._h, _devptr(poses_all), _devptr(attrs_all), C.c_uint32(world), C.c_uint32(rank), C.c_uint32(n)))
+        P_new = torch.empty((n, 8), dtype=torch.float32, device=poses_all.device)
+        A_new = torch.empty((n, 9), dtype=torch.float32, device=poses_all.device)
+        t = C.c_uint64()
+        _chk(load_library().b2_pf_resample_gladiator_p2p(self._h, _devptr(P_new), _devptr(A_new), C.byref(cfg), C.c_uint64(seed), C.c_uint32(step), C.byref(t)))
+        return P_new, A_new, int(t.value)
 
     def resampleSharded(self, poses_local, attrs_local, dist, config=None, seed=1234, step=0):
         """Particles sharded over ranks (equal contiguous slices in rank order): all-gather the particle set (the exchange step of this

@@ -1353,6 +1353,9 @@ struct b2_pf {
     DevBuf<b2_transform> d_poses; DevBuf<b2_particle_attr> d_attrs;
     DevBuf<double> d_part; DevBuf<unsigned int> d_ticket; DevBuf<float> d_out; float* h_out = nullptr; int n_sm = 0;
     int smem_optin = 0;
+    // sharded resampling over NVLink peer memory (b2_pf_p2p_*): own exchange buffers (cudaMalloc: exportable through CUDA IPC) + the peers' mappings
+    b2_transform* x_poses = nullptr; b2_particle_attr* x_attrs = nullptr; uint32_t x_cap = 0;
+    PfPeers peers{}; bool peers_open = false; DevBuf<unsigned long long> d_traffic;
 };
 
 extern "C" int b2_pf_destroy(b2_pf* h);
@@ -1393,6 +1396,13 @@ extern "C" int b2_pf_destroy(b2_pf* h)
     h->d_beams.release(); h->d_poses.release(); h->d_attrs.release(); h->d_part.release(); h->d_ticket.release(); h->d_out.release();
     if (h->h_beams) cudaFreeHost(h->h_beams);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->peers_open) for (uint32_t r = 0; r < h->peers.world; r++) if (r != h->peers.rank) {
+        if (h->peers.poses[r]) cudaIpcCloseMemHandle((void*)h->peers.poses[r]);
+        if (h->peers.attrs[r]) cudaIpcCloseMemHandle((void*)h->peers.attrs[r]);
+    }
+    if (h->x_poses) cudaFree(h->x_poses);
+    if (h->x_attrs) cudaFree(h->x_attrs);
+    h->d_traffic.release();
     b2_mesh* map = h->map;
     delete h;
     (void)cudaGetLastError();
@@ -1499,6 +1509,99 @@ extern "C" int b2_pf_resample_gladiator(b2_pf* h, const b2_transform* poses_dev,
     CU(cudaSetDevice(h->map->device));
     k_pf_gladiator<<<(n_local + 255) / 256, 256, 0, h->stream>>>(poses_dev, attrs_dev, n_all, first, n_local, poses_new_dev, attrs_new_dev, *cfg, seed, step, raw_dev, normals_dev);
     LAUNCHED();
+    return B2_OK;
+}
+
+// ---- sharded Gladiator resampling over NVLink peer memory ------------------------------------------------------------------------------------
+// Life cycle (one process per GPU):  init -> exchange the 128-byte handles of all ranks (any transport: torch.distributed all_gather) -> connect;
+// then per resampling step: publish (device-to-device copy of the local particles into the exported buffers), a cross-rank barrier, resample_p2p,
+// a second barrier before the next publish.
+extern "C" int b2_pf_p2p_init(b2_pf* h, uint32_t n_per_rank, void* handles_out_128)
+{
+    NOTNULL(h); NOTNULL(handles_out_128);
+    if (n_per_rank == 0) return fail(B2_ERR_INVALID, "p2p: empty shard");
+    CU(cudaSetDevice(h->map->device));
+    if (h->peers_open) return fail(B2_ERR_INVALID, "p2p: already connected");
+    if (h->x_cap < n_per_rank) {
+        if (h->x_poses) cudaFree(h->x_poses); if (h->x_attrs) cudaFree(h->x_attrs);
+        h->x_poses = nullptr; h->x_attrs = nullptr; h->x_cap = 0;
+        CU(cudaMalloc((void**)&h->x_poses, sizeof(b2_transform) * (size_t)n_per_rank));
+        CU(cudaMalloc((void**)&h->x_attrs, sizeof(b2_particle_attr) * (size_t)n_per_rank));
+        h->x_cap = n_per_rank;
+    }
+    cudaIpcMemHandle_t hp, ha;
+    CU(cudaIpcGetMemHandle(&hp, h->x_poses)); CU(cudaIpcGetMemHandle(&ha, h->x_attrs));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handles_out_128, &hp, 64); memcpy(static_cast<char*>(handles_out_128) + 64, &ha, 64);
+    RES(h->d_traffic.reserve(1));
+    return B2_OK;
+}
+extern "C" int b2_pf_p2p_connect(b2_pf* h, const void* all_handles, uint32_t world, uint32_t rank, uint32_t n_per_rank)
+{
+    NOTNULL(h); NOTNULL(all_handles);
+    if (world == 0 || world > B2_MAX_PEERS || rank >= world) return fail(B2_ERR_INVALID, "p2p: world %u / rank %u (at most %d ranks)", world, rank, B2_MAX_PEERS);
+    if (!h->x_poses || n_per_rank > h->x_cap) return fail(B2_ERR_INVALID, "p2p: connect before init");
+    if (h->peers_open) return fail(B2_ERR_INVALID, "p2p: already connected");
+    CU(cudaSetDevice(h->map->device));
+    PfPeers P{}; P.world = world; P.rank = rank; P.n_per_rank = n_per_rank;
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank) { P.poses[r] = h->x_poses; P.attrs[r] = h->x_attrs; continue; }
+        cudaIpcMemHandle_t hp, ha;
+        memcpy(&hp, static_cast<const char*>(all_handles) + 128 * (size_t)r, 64); memcpy(&ha, static_cast<const char*>(all_handles) + 128 * (size_t)r + 64, 64);
+        void *pp = nullptr, *pa = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pa, ha, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (uint32_t q = 0; q < r; q++) if (q != rank) { cudaIpcCloseMemHandle((void*)P.poses[q]); cudaIpcCloseMemHandle((void*)P.attrs[q]); }
+            if (pp) cudaIpcCloseMemHandle(pp);
+            return fail(B2_ERR_CUDA, "p2p: cannot map the particle buffers of rank %u (%s): no peer access between the GPUs or CUDA IPC unavailable", r, cudaGetErrorString(e));
+        }
+        P.poses[r] = (const b2_transform*)pp; P.attrs[r] = (const b2_particle_attr*)pa;
+    }
+    h->peers = P; h->peers_open = true;
+    return B2_OK;
+}
+extern "C" int b2_pf_p2p_publish(b2_pf* h, const b2_transform* poses_dev, const b2_particle_attr* attrs_dev, uint32_t n_local)
+{
+    NOTNULL(h); NOTNULL(poses_dev); NOTNULL(attrs_dev);
+    if (!h->peers_open || n_local != h->peers.n_per_rank) return fail(B2_ERR_INVALID, "p2p: publish needs a connected handle and exactly n_per_rank particles");
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaMemcpyAsync(h->x_poses, poses_dev, sizeof(b2_transform) * (size_t)n_local, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->x_attrs, attrs_dev, sizeof(b2_particle_attr) * (size_t)n_local, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));            // the caller's cross-rank barrier follows: peers may read as soon as it is passed
+    return B2_OK;
+}
+extern "C" int b2_pf_resample_gladiator_p2p(b2_pf* h, b2_transform* poses_new_dev, b2_particle_attr* attrs_new_dev, const b2_gladiator_config* cfg, uint64_t seed, uint32_t step,
+                                            uint64_t* remote_bytes_out)
+{
+    NOTNULL(h); NOTNULL(cfg); NOTNULL(poses_new_dev); NOTNULL(attrs_new_dev);
+    if (!h->peers_open && h->peers.pad != 1u) return fail(B2_ERR_INVALID, "p2p: resample before connect");
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaMemsetAsync(h->d_traffic.p, 0, sizeof(unsigned long long), h->stream));
+    k_pf_gladiator_p2p<<<(h->peers.n_per_rank + 255) / 256, 256, 0, h->stream>>>(h->peers, poses_new_dev, attrs_new_dev, *cfg, seed, step, h->d_traffic.p);
+    LAUNCHED();
+    if (remote_bytes_out) {
+        unsigned long long t = 0;
+        CU(cudaMemcpyAsync(&t, h->d_traffic.p, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *remote_bytes_out = t;
+    }
+    return B2_OK;
+}
+// test hook: a "world" of several shards on ONE device (the peers are plain device buffers of this process), so that the indexing of the
+// p2p kernel can be checked on a single GPU; poses_all / attrs_all hold world * n_per_rank particles, this handle plays `rank`
+extern "C" int b2_pf_p2p_connect_local(b2_pf* h, const b2_transform* poses_all_dev, const b2_particle_attr* attrs_all_dev, uint32_t world, uint32_t rank, uint32_t n_per_rank)
+{
+    NOTNULL(h); NOTNULL(poses_all_dev); NOTNULL(attrs_all_dev);
+    if (world == 0 || world > B2_MAX_PEERS || rank >= world || n_per_rank == 0) return fail(B2_ERR_INVALID, "p2p: bad local world");
+    if (h->peers_open) return fail(B2_ERR_INVALID, "p2p: already connected");
+    CU(cudaSetDevice(h->map->device));
+    RES(h->d_traffic.reserve(1));
+    PfPeers P{}; P.world = world; P.rank = rank; P.n_per_rank = n_per_rank;
+    for (uint32_t r = 0; r < world; r++) { P.poses[r] = poses_all_dev + (size_t)r * n_per_rank; P.attrs[r] = attrs_all_dev + (size_t)r * n_per_rank; }
+    h->peers = P;                 // peers_open stays false: nothing to unmap, and publish is not needed
+    h->peers.pad = 1u;
     return B2_OK;
 }
 

@@ -1054,14 +1054,9 @@ B2_DEV Q4 euler_to_quat(float roll, float pitch, float yaw)
     q.z = sub(mul(mul(cr, cp), sy), mul(mul(sr, sp), cy));
     return q;
 }
-// one champion: poses/attrs are the n_all particles, champion = global index, outputs are written at out_p / out_a
-B2_DEV void gladiator_one(const b2_transform* poses, const b2_particle_attr* attrs, uint32_t n_all, uint32_t champion, uint32_t raw, const float N[6],
-                          const b2_gladiator_config& cfg, b2_transform* out_p, b2_particle_attr* out_a)
+// the opponent won (resampling.cu:150-192): the champion's slot receives a perturbed copy of the opponent whose n_meas is reduced by the forget rate
+B2_DEV void gladiator_take(b2_transform pn, b2_particle_attr an, const float N[6], const b2_gladiator_config& cfg, b2_transform* out_p, b2_particle_attr* out_a)
 {
-    const uint32_t enemy = raw % n_all;                                                    // :137
-    const float Lc = attrs[champion].likelihood.mean, Le = attrs[enemy].likelihood.mean;
-    if (!(Le > Lc)) { *out_p = poses[champion]; *out_a = attrs[champion]; return; }       // :150, :193-196
-    b2_transform pn = poses[enemy]; b2_particle_attr an = attrs[enemy];
     const Tf pose = tf_from_pod(pn);
     Tf pnew = pose;
     pnew.t = mk3(add(pose.t.x, mul(N[0], cfg.min_noise_tx)), add(pose.t.y, mul(N[1], cfg.min_noise_ty)), add(pose.t.z, mul(N[2], cfg.min_noise_tz)));   // :166-168
@@ -1077,6 +1072,15 @@ B2_DEV void gladiator_one(const b2_transform* poses, const b2_particle_attr* att
     an.likelihood.n_meas = (uint32_t)mul((float)an.likelihood.n_meas, remember);           // :187
     pn.R.x = pnew.R.x; pn.R.y = pnew.R.y; pn.R.z = pnew.R.z; pn.R.w = pnew.R.w; pn.t.x = pnew.t.x; pn.t.y = pnew.t.y; pn.t.z = pnew.t.z;   // stamp: the enemy's
     *out_p = pn; *out_a = an;
+}
+// one champion: poses/attrs are the n_all particles, champion = global index, outputs are written at out_p / out_a
+B2_DEV void gladiator_one(const b2_transform* poses, const b2_particle_attr* attrs, uint32_t n_all, uint32_t champion, uint32_t raw, const float N[6],
+                          const b2_gladiator_config& cfg, b2_transform* out_p, b2_particle_attr* out_a)
+{
+    const uint32_t enemy = raw % n_all;                                                    // :137
+    const float Lc = attrs[champion].likelihood.mean, Le = attrs[enemy].likelihood.mean;
+    if (!(Le > Lc)) { *out_p = poses[champion]; *out_a = attrs[champion]; return; }       // :150, :193-196
+    gladiator_take(poses[enemy], attrs[enemy], N, cfg, out_p, out_a);
 }
 
 #ifdef __CUDACC__
@@ -1100,6 +1104,48 @@ __global__ void k_pf_gladiator_randoms(uint64_t seed, uint32_t step, uint32_t fi
     gladiator_draws(seed, step, first + i, raw, N);
     raw_out[i] = raw;
     for (int k = 0; k < 6; k++) normals_out[6 * (size_t)i + k] = N[k];
+}
+#endif
+
+#ifdef __CUDACC__
+// Gladiator resampling with the particles SHARDED over GPUs and no all-gather: every rank publishes its particles in a buffer its peers map over
+// NVLink (CUDA IPC); a champion reads its opponent's 4-byte likelihood straight from the owner's HBM and fetches the 68-byte record only when
+// the opponent wins -- the reference draws opponents from ALL particles (resampling.cu:137), so this is the one stage of the cycle whose data
+// crosses GPUs.  Shards have equal size n_per_rank; global index = rank * n_per_rank + local index; draws are keyed by the global index, so
+// the concatenation over ranks equals the single-GPU result bit for bit.  `traffic` counts the bytes actually read from remote ranks.
+#define B2_MAX_PEERS 16
+struct PfPeers { const b2_transform* poses[B2_MAX_PEERS]; const b2_particle_attr* attrs[B2_MAX_PEERS]; uint32_t world, rank, n_per_rank, pad; };
+__global__ void __launch_bounds__(256) k_pf_gladiator_p2p(PfPeers peers, b2_transform* __restrict__ poses_new, b2_particle_attr* __restrict__ attrs_new, b2_gladiator_config cfg,
+                                                          uint64_t seed, uint32_t step, unsigned long long* __restrict__ traffic)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long remote = 0ull;
+    if (i < peers.n_per_rank) {
+        const uint32_t n_all = peers.n_per_rank * peers.world, champion = peers.rank * peers.n_per_rank + i;
+        uint32_t raw; float N[6];
+        gladiator_draws(seed, step, champion, raw, N);
+        const uint32_t enemy = raw % n_all, er = enemy / peers.n_per_rank, ei = enemy % peers.n_per_rank;      // resampling.cu:137
+        const b2_particle_attr* ea = peers.attrs[er] + ei;
+        const float Lc = peers.attrs[peers.rank][i].likelihood.mean;
+        const float Le = __ldcv(&ea->likelihood.mean);                                                       // peer memory: never from a stale cache line
+        if (er != peers.rank) remote += 4ull;
+        if (!(Le > Lc)) { poses_new[i] = peers.poses[peers.rank][i]; attrs_new[i] = peers.attrs[peers.rank][i]; }
+        else {
+            const b2_transform* ep = peers.poses[er] + ei;
+            b2_transform pn; b2_particle_attr an;
+            const uint4 p0 = __ldcv(reinterpret_cast<const uint4*>(ep)), p1 = __ldcv(reinterpret_cast<const uint4*>(ep) + 1);
+            memcpy(&pn, &p0, 16); memcpy(reinterpret_cast<char*>(&pn) + 16, &p1, 16);
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(ea);
+            uint32_t w[9];
+            #pragma unroll
+            for (int k = 0; k < 9; k++) w[k] = __ldcv(aw + k);
+            memcpy(&an, w, 36);
+            if (er != peers.rank) remote += 68ull;
+            gladiator_take(pn, an, N, cfg, poses_new + i, attrs_new + i);
+        }
+    }
+    remote = warp_sum_u64(remote);
+    if (traffic && (threadIdx.x & 31u) == 0u && remote) atomicAdd(traffic, remote);
 }
 #endif
 

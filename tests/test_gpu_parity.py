@@ -954,3 +954,38 @@ def test_sim_options_gpu(po, synth):
     h.setSimOptions(1, 0, 0)
     n1 = h.correct(T)[1]
     assert (n1 >= n0).all() and n1.sum() > n0.sum()
+
+
+def test_gladiator_p2p_local_world(po, synth):
+    """Sharded Gladiator resampling over peer memory (b2_pf_resample_gladiator_p2p) with four shards that all live on this one GPU: the
+    concatenated champions equal the single-GPU resampling bit for bit, and the byte counter equals what the draws imply (4 B per remote
+    opponent likelihood + 68 B per remote winner) -- the real multi-GPU run (bench.py --gpus N, scripts/check_multigpu.py) uses the same kernel
+    with CUDA-IPC peer pointers."""
+    import torch
+    import rmcl_b200
+    from test_oracle import _glad_particles
+    world, n = 4, 40000
+    P, A = _glad_particles(synth, world * n)
+    cfg = rmcl_b200.GladiatorConfig(0.03, 0.03, 0.01, 0.002, 0.002, 0.01, 0.3, 0.2)
+    up = rmcl_b200.PCDSensorUpdaterB200(gpu_map("cube29"))
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+    Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
+    up.resample(Pd, Ad, Pn, An, cfg, seed=77, step=3)
+    torch.cuda.synchronize()
+    raw, _ = up.gladiatorRandoms(77, 3, 0, world * n)
+    raw = raw.cpu().numpy().view(np.uint32).astype(np.int64)
+    L = A["likelihood"]["mean"]
+    enemy = raw % (world * n)
+    total = 0
+    for r in range(world):
+        pr, ar, traffic = up.resampleP2PLocalWorld(Pd, Ad, world, r, cfg, seed=77, step=3)
+        torch.cuda.synchronize()
+        assert torch.equal(pr, Pn[r * n:(r + 1) * n]) and torch.equal(ar, An[r * n:(r + 1) * n])
+        e = enemy[r * n:(r + 1) * n]
+        remote = (e // n) != r
+        wins = L[e] > L[r * n:(r + 1) * n]
+        assert traffic == 4 * int(remote.sum()) + 68 * int((remote & wins).sum())
+        total += traffic
+    allgather = world * (world - 1) * n * 68          # what the all-gather variant moves (every rank receives the other ranks' shards)
+    assert total < 0.6 * allgather
