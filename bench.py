@@ -562,6 +562,15 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     # resampling (all-gather of the particle set when sharded); particles never leave HBM
     glad = rmcl_b200.GladiatorConfig.defaults()
     Tmo = synth.make_transform((0.02, 0.0, 0.0), (0.0, 0.0, 0.01))
+    # sharded resampling: opponents over NVLink peer memory (CUDA IPC: 4-byte likelihood reads, 68-byte records for winners only); all-gather
+    # of the whole particle set as the fallback when the GPUs cannot map each other's memory
+    exchange, p2p_bytes, variants_equal = "none", None, None
+    if world > 1:
+        try:
+            up.p2pConnect(dist, n_part)
+            exchange = "p2p"
+        except Exception as ex:                      # noqa: BLE001
+            exchange = f"allgather (p2p unavailable: {ex})"
     Pc, Ac = Pd.clone(), A0.clone()
     tot = 0.0
     for i in range(warm + steps):
@@ -572,20 +581,31 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
         up.motionUpdate(Pc, Ac, Tmo, 0.01)
         up.update(Pc, Ac, Tsb, beams, prm)
         up.likelihoodStats(Ac, dist if world > 1 else None)
-        if world > 1:
+        if world > 1 and exchange == "p2p":
+            Pn, An, p2p_bytes = up.resampleShardedP2P(Pc, Ac, dist, glad, seed=1234, step=i, want_traffic=True)
+        elif world > 1:
             Pn, An = up.resampleSharded(Pc, Ac, dist, glad, seed=1234, step=i)
         else:
             Pn, An = torch.empty_like(Pc), torch.empty_like(Ac)
             up.resample(Pc, Ac, Pn, An, glad, seed=1234, step=i)
         bb.record(stream)
         torch.cuda.synchronize()
+        if i == warm + steps - 1 and world > 1 and exchange == "p2p":          # correctness on hardware: both exchange variants give the same particles
+            Pg, Ag = up.resampleSharded(Pc, Ac, dist, glad, seed=1234, step=i)
+            torch.cuda.synchronize()
+            ok = torch.tensor([int(torch.equal(Pg, Pn) and torch.equal(Ag, An))], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            variants_equal = bool(int(ok[0]))
         Pc, Ac = Pn, An
         if i >= warm:
             tot += a.elapsed_time(bb)
     ms_cycle = maxr(tot) / steps
     out["c3_pf_cycle"] = {"workload": f"C3 full cycle on the device: motion + sensor update ({n_part} particles x 180 beams per GPU) + stats + Gladiator resampling",
                           "rays_per_s": n_part * world * 180 / (ms_cycle * 1e-3), "ms_per_cycle": ms_cycle,
-                          "exchange": "none" if world == 1 else f"all-reduce 16 B + all-gather {n_part * world * 68} B per cycle (NCCL)"}
+                          "exchange": "none" if world == 1 else exchange,
+                          "exchange_bytes_per_rank_per_cycle": None if world == 1 else ({"p2p_read": p2p_bytes, "allgather_would_receive": (world - 1) * n_part * 68} if exchange == "p2p"
+                                                                                          else {"allgather_received": (world - 1) * n_part * 68}),
+                          "p2p_equals_allgather": variants_equal}
     # ---- v1 batched correct ----
     hv = rmcl_b200.SphereCorrectorB200(gmap)
     hv.setStream(stream.cuda_stream)

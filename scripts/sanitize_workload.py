@@ -46,6 +46,35 @@ for mode in (1, 0):
     up.resample(Pd, Ad, Pn, An)
     rmcl_b200.umeyama_transform(h.computeCrossStatistics(I, 0.0).reshape(1))
     torch.cuda.synchronize()
+    # round 2: exec modes, queued asynchronous calls, a scan with pairs in shared memory and beyond (streamed), simulate switches, bound caller
+    # buffers, two sensors in one loop, v1 benchmark stage split, peer-memory resampling on a one-device world
+    for em in (1, 0, 2):
+        h.setExecMode(em); h.correctOnce(Tom, I, 5, 0.0)
+    for k in range(4):
+        h.correctOnceAsync(Tom, I, 5, 0.0)
+    for k in range(4):
+        h.correctOnceWait()
+    mb = synth.SphericalModel(np.radians(-30.0), np.radians(60.0) / 383, 384, -np.pi, 2 * np.pi / 1024, 1024, 0.5, 120.0)      # 393 216 rays: registers + shared memory
+    hb = rmcl_b200.RCCB200Spherical(gmap)
+    hb.setTsb(Tsb); hb.setModel(mb); hb.setParams(1.0, 0.15)
+    hb.find(Tgt); rb = synth.noisy_ranges(hb.modelView()["ranges"], mb.range_max)
+    hb.setRanges(rb); hb.correctOnce(Tom, I, 3, 0.0); hb.correctOnce(Tom, I, 3, 0.0, ranges=torch.from_numpy(rb.copy()).pin_memory())
+    mh = synth.SphericalModel(np.radians(-30.0), np.radians(60.0) / 1023, 1024, -np.pi, 2 * np.pi / 1024, 1024, 0.5, 120.0)    # 1 048 576 rays: the tail of each thread's list streams from L2
+    hb.setModel(mh); hb.find(Tgt); hb.setRanges(synth.noisy_ranges(hb.modelView()["ranges"], mh.range_max)); hb.correctOnce(Tom, I, 2, 0.0)
+    h.setSimOptions(1, 1, 1); h.find(Tom); h.setSimOptions(0, 0, 0)
+    dsd = torch.from_numpy(ds["points"]).cuda(); dmd = torch.from_numpy(ds["mask"]).cuda()
+    bp, bn, bh = torch.empty((m.size, 3), device="cuda"), torch.empty((m.size, 3), device="cuda"), torch.empty(m.size, dtype=torch.uint8, device="cuda")
+    h.bindDataset(dsd, dmd); h.bindModelBuffers(bp, bn, bh); h.find(Tom); h.computeCrossStatistics(I, 0.0); h.correctOnce(Tom, I, 3, 0.0)
+    h.bindModelBuffers(None, None, None); h.setRanges(ranges)
+    mp = synth.PinholeModel(64, 48, 52.5, 52.5, 31.5, 23.5, 0.3, 30.0)
+    hp = rmcl_b200.RCCB200Pinhole(gmap); hp.setTsb(Tsb); hp.setModel(mp); hp.setParams(1.0, 0.15)
+    hp.find(Tgt); hp.setRanges(hp.modelView()["ranges"])
+    rmcl_b200.micp_correct_once([h, hp], np.stack([I, I]), Tom, 5, 0.0, merge_weights=[1.0, 0.4])
+    h.benchmark(T, 2)
+    Pall = torch.cat([Pd, Pd]); Aall = torch.cat([Ad, Ad])
+    up.resampleP2PLocalWorld(Pall, Aall, 2, 1)
+    torch.cuda.synchronize()
+    del hb, hp
     g2 = rmcl_b200.Map.from_blob(gmap.export_blob())
     g2.intersect(np.zeros((5, 3), np.float32) + [30, 20, 1], np.eye(3, dtype=np.float32)[[0, 1, 2, 0, 1]])
     if mode == 1:
