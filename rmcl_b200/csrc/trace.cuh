@@ -44,7 +44,8 @@ struct RaySetup {
     V3 o, d, idir;
     V3 idn, ncn, ncf;       // near-plane slope (idir*C3'), NEGATED near / far constants of the box test (see header): the FMA addends
     uint32_t oct;           // bit k set iff idir_k >= 0
-    uint32_t onx, ony, onz; // float4 offsets of the near planes inside a node (lo arrays for positive directions, hi arrays otherwise)
+    uint32_t noff;          // float4 offsets of the near planes inside a node, one byte per axis (lo arrays for positive directions, hi arrays
+                            // otherwise); the far planes sit at 6 - onx, 10 - ony, 14 - onz
 };
 
 #define B2_C3P 0.99951171875f          // 1 - 2^-11
@@ -118,13 +119,14 @@ B2_DEV RaySetup ray_setup(V3 o, V3 d, const BvhView& bvh)
     r.ncn = mk3(-((oix + dlx) * B2_C3P), -((oiy + dly) * B2_C3P), -((oiz + dlz) * B2_C3P));
     r.ncf = mk3(-(oix - dlx), -(oiy - dly), -(oiz - dlz));
     // node layout in float4 units: lo_x 0..1, lo_y 2..3, lo_z 4..5, hi_x 6..7, hi_y 8..9, hi_z 10..11
-    r.onx = (r.oct & 1u) ? 0u : 6u; r.ony = (r.oct & 2u) ? 2u : 8u; r.onz = (r.oct & 4u) ? 4u : 10u;
+    r.noff = ((r.oct & 1u) ? 0u : 6u) | (((r.oct & 2u) ? 2u : 8u) << 8) | (((r.oct & 4u) ? 4u : 10u) << 16);
 #if B2_ON_DEVICE
-    // Per-ray constants of the box test are made opaque to the optimiser: under the 72-register cap of the traversal kernels ptxas otherwise
-    // RE-DERIVES them from o / d in every node visit (octant, plane offsets, scaled slopes, slack constants: ~45 of ~190 instructions per visit in
-    // the round-1 SASS) instead of keeping -- or, at worst, spilling and reloading -- nine values.
-    asm volatile("" : "+f"(r.ncn.x), "+f"(r.ncn.y), "+f"(r.ncn.z), "+f"(r.idn.x), "+f"(r.idn.y), "+f"(r.idn.z));
-    asm volatile("" : "+r"(r.oct), "+r"(r.onx), "+r"(r.ony), "+r"(r.onz));
+    // Per-ray constants of the box test are made opaque to the optimiser: under the 72-register cap of the traversal kernels it otherwise
+    // RE-DERIVES them from o / d in every node visit (octant, plane offsets, slack constants: ~45 of ~190 instructions per visit in the round-1
+    // SASS).  Kept small on purpose -- 3 + 3 + 3 slopes / addends, the octant and ONE word of plane offsets; what is cheap to derive (the
+    // near-plane slope idir * C3', the six plane offsets) is derived inside node_test from these.
+    asm volatile("" : "+f"(r.ncn.x), "+f"(r.ncn.y), "+f"(r.ncn.z));
+    asm volatile("" : "+r"(r.oct), "+r"(r.noff));
 #endif
     return r;
 }
@@ -155,9 +157,16 @@ B2_DEV uint32_t spread3x(uint32_t x)
 B2_DEV void node_test(const float4* __restrict__ np, const RaySetup& r, float tbest, uint32_t& child_base, uint32_t& tri_base, uint32_t& inner, uint32_t& tris, uint32_t& trimask)
 {
     // near planes: the "lo" arrays for positive directions, the "hi" arrays otherwise; far planes: the other one (offset 6 quads apart)
-    const float4 nxa = ldg(np + r.onx), nxb = ldg(np + r.onx + 1), fxa = ldg(np + (6u - r.onx)), fxb = ldg(np + (7u - r.onx));
-    const float4 nya = ldg(np + r.ony), nyb = ldg(np + r.ony + 1), fya = ldg(np + (10u - r.ony)), fyb = ldg(np + (11u - r.ony));
-    const float4 nza = ldg(np + r.onz), nzb = ldg(np + r.onz + 1), fza = ldg(np + (14u - r.onz)), fzb = ldg(np + (15u - r.onz));
+    // derived HERE, per visit (three bit-field extracts), not hoisted out of the traversal loop into three more live registers (or spill slots)
+    uint32_t onx, ony, onz;
+#if B2_ON_DEVICE
+    asm volatile("bfe.u32 %0, %3, 0, 8;\n\tbfe.u32 %1, %3, 8, 8;\n\tbfe.u32 %2, %3, 16, 8;" : "=r"(onx), "=r"(ony), "=r"(onz) : "r"(r.noff));
+#else
+    onx = r.noff & 0xffu; ony = (r.noff >> 8) & 0xffu; onz = r.noff >> 16;
+#endif
+    const float4 nxa = ldg(np + onx), nxb = ldg(np + onx + 1), fxa = ldg(np + (6u - onx)), fxb = ldg(np + (7u - onx));
+    const float4 nya = ldg(np + ony), nyb = ldg(np + ony + 1), fya = ldg(np + (10u - ony)), fyb = ldg(np + (11u - ony));
+    const float4 nza = ldg(np + onz), nzb = ldg(np + onz + 1), fza = ldg(np + (14u - onz)), fzb = ldg(np + (15u - onz));
     const float4 h = ldg(np + 12);
     child_base = f2u(h.x); tri_base = f2u(h.y);
     const uint32_t masks = f2u(h.z), imask = masks & 0xffu;
