@@ -635,6 +635,27 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     ms = maxr(tot) / steps
     out["v1_batch"] = {"workload": "v1 correct(): 1000 poses x vlp16_900 (14400 rays) per GPU, fused trace+P2L+Umeyama", "rays_per_s": n_poses * world * mv.size / (ms * 1e-3),
                        "ms_per_step": ms, "reference_numbers": "Embree 0.201 s, OptiX 0.0169 s per correct() on a 1M-face sphere (BASELINE.md)"}
+    # ---- closest-point correspondences on the C2 scan: CPCEmbree::find + the same inner iterations ----
+    ds = h.datasetView()
+    hc = rmcl_b200.CPCB200(gmap)
+    hc.setStream(stream.cuda_stream)
+    hc.setTsb(Tsb); hc.setParams(MAX_DIST, ADAPTIVE_MIN); hc.setDataset(ds["points"], ds["mask"])
+    Tomc = synth.compose(Tgt, synth.scenario_pose_offset())
+    Ic = synth.make_transform()
+    cpc = {}
+    for name, skip in (("reference_behaviour", False), ("skip_masked", True)):
+        hc.setOptions(skip_masked=skip)
+        tt = []
+        for i in range(13):
+            flush.fill_(8)
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); hc.find(Tomc); bb.record(stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                tt.append(a.elapsed_time(bb))
+        cpc[name] = {"find_ms": maxr(float(np.mean(tt))), "queries_per_s": m.size * world / (maxr(float(np.mean(tt))) * 1e-3)}
+    out["cpc_c2"] = {"workload": "closest-point correspondences (CPCB200::find) for the 131072 dataset points of the C2 scan, 1M-triangle building", **cpc,
+                     "note": "reference_behaviour queries every dataset point like CPCEmbree.cpp:30-43; skip_masked leaves out the 2 % masked-out points (dropped beams far outside the map) whose results no statistic uses"}
     # ---- C4 (BASELINE.json configs[3]): PinholeCorrector, 640 x 480 depth camera on the 500k-triangle indoor mesh ----
     if rank == 0 or world > 1:
         V4, F4 = synth.indoor(500_000)

@@ -155,6 +155,10 @@ B2_API int b2_rcc_set_sim_options(b2_rcc* h, int tfar_mode, int min_mode, int mi
  * No sensor model is needed; the model buffers get n_dataset entries (ranges = cp.d), so b2_rcc_cross_statistics and
  * b2_rcc_correct_once work unchanged.  b2_rcc_correct_once_ranges is refused in this mode. */
 B2_API int b2_rcc_set_correspondence_type(b2_rcc* h, int type);
+/* closest-point mode only.  skip_masked != 0: dataset points whose mask is 0 are not queried (their model entry reads hits = 0, NaN).  The reference
+ * queries every point and never uses those entries (statistics_p2l tests dataset.mask); a dropped beam unpacked to range.max + 1 lies far outside the
+ * map and its query is the most expensive of the scan.  Default 0 = the reference's literal behaviour. */
+B2_API int b2_rcc_set_cpc_options(b2_rcc* h, int skip_masked);
 /* Correspondences{CPU,CUDA}::computeCrossStatistics, rmcl/src/rmcl/registration/CorrespondencesCPU.cpp:10-39 (CUDA twin CorrespondencesCUDA.cpp:9-30) */
 B2_API int b2_rcc_cross_statistics(b2_rcc* h, const b2_transform* T_snew_sold, double convergence_progress, b2_cross_stats* out_host);
 /* Scan-vs-map segmentation: the classification of ScanMapSegmentationEmbreeNode::scanCB (rmcl_ros/src/nodes/filter/

@@ -404,6 +404,7 @@ struct b2_rcc {
     float* mpts() const { return b_mpts ? b_mpts : d_mpts.p; }
     float* mnrm() const { return b_mpts ? b_mnrm : d_mnrm.p; }
     uint8_t* mhits() const { return b_mpts ? b_mhits : d_mhits.p; }
+    bool cpc_skip_masked = false;       // b2_rcc_set_cpc_options
     uint32_t sim_opts = 0;              // b2_rcc_set_sim_options
     int corr_type = B2_CORR_RCC;        // B2_CORR_CPC: find() is a closest-point query per dataset point (CPCEmbree), no sensor model needed
     uint32_t work_n() const { return corr_type == B2_CORR_CPC ? n_dataset : n; }   // correspondences per find
@@ -677,7 +678,7 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
         if (n == 0) { h->n_model = 0; h->found = true; return B2_OK; }
         RES(reserve_model(h, n));
         k_cpc_find<<<(n + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode_cp, icp_dev,
-                                                                                             Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, h->dpts(), n, h->max_dist, model_buffers(h));
+                                                                                             Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, h->dpts(), n, h->max_dist, model_buffers(h), h->cpc_skip_masked ? h->dmask() : nullptr);
         LAUNCHED();
         h->n_model = n; h->found = true;
         return B2_OK;
@@ -697,6 +698,12 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     return B2_OK;
 }
 
+extern "C" int b2_rcc_set_cpc_options(b2_rcc* h, int skip_masked)
+{
+    NOTNULL(h);
+    h->cpc_skip_masked = skip_masked != 0; h->found = false;
+    return B2_OK;
+}
 extern "C" int b2_rcc_bind_dataset(b2_rcc* h, const float* points_dev, const uint8_t* mask_dev, uint32_t n)
 {
     NOTNULL(h);

@@ -581,11 +581,21 @@ B2_DEV void cpc_find_one(const BvhView& bvh, Tf Tsm, Tf Tms, const float* __rest
 #ifdef __CUDACC__
 __global__ void __launch_bounds__(B2_FIND_BLOCK) k_cpc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const IcpState* __restrict__ icp,
                                                             b2_transform Tbm_val, b2_transform Tsb_val, const float* __restrict__ dpts, uint32_t n, float max_dist,
-                                                            ModelBuffers out)
+                                                            ModelBuffers out, const uint8_t* __restrict__ skip_mask)
 {
     prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (skip_mask && !(skip_mask[i] > 0)) {
+        // b2_rcc_set_cpc_options(skip_masked): a masked-out dataset point (e.g. a dropped beam unpacked to range.max + 1, far outside the map) never
+        // enters the statistics; its query is the most expensive of the scan (2 % of the points cost a third of the kernel: one such lane keeps
+        // its whole warp) and is skipped -- the entry reads hits = 0, NaN, like a miss.  Off by default: the reference queries every point.
+        const float qnan = u2f(0x7fc00000u);
+        out.pts[3 * i] = qnan; out.pts[3 * i + 1] = qnan; out.pts[3 * i + 2] = qnan;
+        out.nrm[3 * i] = qnan; out.nrm[3 * i + 1] = qnan; out.nrm[3 * i + 2] = qnan;
+        out.hits[i] = 0; out.faces[i] = B2_NOFACE; out.ranges[i] = u2f(0x7f800000u);
+        return;
+    }
     const Tf Tbm = icp ? tf_mul(tf_load(&icp->Tom), tf_load(&icp->Tbo)) : tf_from_pod(Tbm_val);
     const Tf Tsm = tf_mul(Tbm, tf_from_pod(Tsb_val));
     cpc_find_one(bvh, Tsm, tf_inv(Tsm), dpts, max_dist, i, out);

@@ -445,6 +445,16 @@ def test_cpc_correct_once(po, synth):
         assert abs(int(Cm["n_meas"]) - int(ref[2]["n_meas"])) <= 2
         assert np.abs(Tn["t"] - ref[0]["t"]).max() <= TOL_DT and quat_close(Tn["R"], ref[0]["R"], TOL_DT)
         assert np.abs(Td["t"] - ref[1]["t"]).max() <= TOL_DT and quat_close(Td["R"], ref[1]["R"], TOL_DT)
+    # skip_masked: the masked-out points (dropped beams, far outside the map) are not queried; nothing the statistics use changes
+    base = h.correctOnce(Tom, Tbo, 5, 0.0)
+    mv_all = h.modelView()
+    h.setOptions(skip_masked=True)
+    skip = h.correctOnce(Tom, Tbo, 5, 0.0)
+    mv_skip = h.modelView()
+    assert skip[0].tobytes() == base[0].tobytes() and skip[2].tobytes() == base[2].tobytes()
+    keep = dm > 0
+    assert np.array_equal(mv_skip["points"][keep], mv_all["points"][keep]) and (mv_skip["hits"][~keep] == 0).all() and np.isnan(mv_skip["points"][~keep]).all()
+    h.setOptions(skip_masked=False)
     # a scan already on the map: every point has distance ~0 -> (near-)identity update
     clean = osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"]
     dp2, dm2, _ = po.dataset_from_ranges(o, d, clean, m.range_min, m.range_max)
