@@ -357,6 +357,7 @@ struct HostPin {            // pinned (mapped) staging for small results
     uint4 chunks[B2_RING][B2_ICP_RESULT_CHUNKS + 1];   // results of k_icp_loop: 16-byte chunks {3 payload words, sequence number} written by the kernel
     IcpResult res[B2_RING];                         // D2H staging of the non-spin path
     unsigned long long dbg[8];
+    unsigned int flag_src[B2_RING];                 // source words of the "scan copy complete" flag copies
 };
 
 // What is still to be collected from an enqueued correctOnce (b2_rcc_correct_once_async .. _wait)
@@ -386,7 +387,8 @@ struct b2_rcc {
     int smem_u_cap = 0;                 // pairs per thread k_icp_loop can keep in shared memory (beyond the two in registers)
     int exec_mode = 2;                  // b2_rcc_set_exec_mode: 2 software grid barrier + programmatic launch (default), 1 cooperative launch, 0 one launch per reduction
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
-    DevBuf<unsigned int> d_bar; unsigned int bar_base = 0;      // arrival counter + abort word of the software grid barrier; counter value at the next launch
+    DevBuf<unsigned int> d_bar; unsigned int zc_seq = 0;        // [0] = "scan copy complete" flag (value: zc_seq of the call), [1] = abort word of the ICP loop
+    DevBuf<unsigned long long> d_slots; unsigned int tag_base = 0; // exchange buffers of the ICP loop (icp_loop.cuh: accumulators, base, FP64 slots); round number of the next launch
     unsigned int seq = 0;               // sequence number of the last k_icp_loop launch (carried by every result chunk)
     std::deque<PendingCall> pending;    // enqueued, not yet collected (oldest first), at most B2_RING
     unsigned int slot_counter = 0;
@@ -445,10 +447,11 @@ static int rcc_init(b2_rcc* h)
     }
     { const char* e = getenv("B2_FUSED"); h->exec_mode = e ? atoi(e) : 2; if (h->exec_mode < 0 || h->exec_mode > 2) h->exec_mode = 2; }
     RES(h->d_partials.reserve((size_t)(B2_NACC + 1) * std::max(h->red_grid, 2 * B2_ICP_MAX_GRID))); RES(h->d_ticket.reserve(1)); RES(h->d_stats.reserve(1)); RES(h->d_icp.reserve(1));
-    RES(h->d_bar.reserve(2)); RES(h->d_res.reserve(1)); RES(h->d_dbg.reserve(8));
+    RES(h->d_bar.reserve(2)); RES(h->d_res.reserve(1)); RES(h->d_dbg.reserve(16 + 4 * B2_ICP_MAX_GRID)); RES(h->d_slots.reserve((size_t)B2_ICP_ACC_WORDS + B2_ICP_BASE_WORDS + B2_ICP_SLOT_WORDS));
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
     CU(cudaMemset(h->d_bar.p, 0, 2 * sizeof(unsigned int)));
-    CU(cudaMemset(h->d_dbg.p, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(h->d_slots.p, 0, ((size_t)B2_ICP_ACC_WORDS + B2_ICP_BASE_WORDS + B2_ICP_SLOT_WORDS) * sizeof(unsigned long long)));      // accumulators and base agree (0); slot tag 0 is never used
+    CU(cudaMemset(h->d_dbg.p, 0, (16 + 4 * B2_ICP_MAX_GRID) * sizeof(unsigned long long)));
     CU(cudaHostAlloc((void**)&h->pin, sizeof(HostPin), cudaHostAllocMapped));
     memset((void*)h->pin, 0, sizeof(HostPin));
     CU(cudaHostGetDevicePointer((void**)&h->pin_chunks_dev, (void*)&h->pin->chunks[0][0], 0));
@@ -481,7 +484,7 @@ extern "C" int b2_rcc_destroy(b2_rcc* h)
     cudaStreamSynchronize(h->stream);
     h->d_dirs.release(); h->d_origs.release(); h->d_dpts.release(); h->d_dmask.release(); h->d_ranges_in.release();
     h->d_mpts.release(); h->d_mnrm.release(); h->d_mranges.release(); h->d_mhits.release(); h->d_mfaces.release();
-    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release(); h->d_res.release(); h->d_dbg.release();
+    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release(); h->d_res.release(); h->d_dbg.release(); h->d_slots.release();
     { DeviceCtx& dc = g_dev[h->map->device & 63]; std::lock_guard<std::mutex> lk(dc.m); dc.n_handles--; if (dc.last == h) { dc.last = nullptr; dc.recorded = false; } }
     h->d_poses.release(); h->d_tdelta.release(); h->d_ncorr.release(); h->d_bstats.release();
     if (h->pin) cudaFreeHost(h->pin);
@@ -518,12 +521,21 @@ extern "C" int b2_rcc_last_timing(b2_rcc* h, float* find_ms, float* reduce_ms)
 }
 
 // profiling aid (not part of the public header): SM-clock durations of the last reduction's phases
-extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc* h, unsigned long long* out8)
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc* h, unsigned long long* out16)
 {
-    NOTNULL(h); NOTNULL(out8);
+    NOTNULL(h); NOTNULL(out16);
     CU(cudaSetDevice(h->map->device));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(out8, h->d_dbg.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out16, h->d_dbg.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// make PROFILE=1 only: per block {ns at publish, ns at collect, cycles since the block reduce at publish, at collect} of iteration 1
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_blocks(b2_rcc* h, unsigned long long* out /* 4 * B2_ICP_MAX_GRID */)
+{
+    NOTNULL(h); NOTNULL(out);
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out, h->d_dbg.p + 16, 4 * B2_ICP_MAX_GRID * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 
@@ -862,11 +874,13 @@ static void fill_sensor_frames(IcpSensor& S, const b2_transform& Tbo, const b2_t
 
 static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem, int mode, bool pdl, int slot)
 {
-    double* parts = H->d_partials.p; IcpResult* res_dev = H->d_res.p; uint4* host_out = H->pin_chunks_dev + (size_t)slot * (B2_ICP_RESULT_CHUNKS + 1);
-    unsigned int* bar = H->d_bar.p; unsigned int bar_base = H->bar_base; unsigned int* bar_abort = H->d_bar.p + 1; unsigned long long* dbg = H->d_dbg.p;
+    unsigned long long* parts = H->d_slots.p; IcpResult* res_dev = H->d_res.p; uint4* host_out = H->pin_chunks_dev + (size_t)slot * (B2_ICP_RESULT_CHUNKS + 1);
+    unsigned int tag_base = H->tag_base; unsigned int* bar_abort = H->d_bar.p + 1; unsigned long long* dbg = H->d_dbg.p;
+    H->tag_base += L.iterations;                                  // tags tag_base + 1 .. tag_base + iterations belong to this launch
+    if (H->tag_base > 0xfffffff0u - 64u) H->tag_base = 0;          // wrap far away from anything a live slot can still hold
     if (mode == 1) {
         IcpLaunch Lc = L;
-        void* args[] = {&Lc, &parts, &res_dev, &host_out, &bar, &bar_base, &bar_abort, &dbg};
+        void* args[] = {&Lc, &parts, &res_dev, &host_out, &tag_base, &bar_abort, &dbg};
         CU(cudaLaunchCooperativeKernel((const void*)k_icp_loop<true>, dim3((unsigned)grid), dim3(B2_ICP_BLOCK), args, smem, H->stream));
     } else {
         // One software-barrier loop at a time per device: launches of different handles / streams are chained through the device's event
@@ -886,8 +900,7 @@ static int launch_icp_loop(b2_rcc* H, const IcpLaunch& L, int grid, size_t smem,
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, L, parts, res_dev, host_out, bar, bar_base, bar_abort, dbg));
-        H->bar_base += L.iterations * (unsigned int)grid;
+        CU(cudaLaunchKernelEx(&cfg, k_icp_loop<false>, L, parts, res_dev, host_out, tag_base, bar_abort, dbg));
         dc.recorded = false;
         if (dc.multi) { CU(cudaEventRecord(dc.loop_done, H->stream)); dc.recorded = true; }     // the marker the next foreign launch waits on
         dc.last = H; dc.last_stream = H->stream;
@@ -983,18 +996,26 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
         S.max_dist = (float)(h->max_dist * (1.0 - cp) + h->adaptive_max_dist_min * cp);       // CorrespondencesCPU.cpp:21-23
         S.merge_weight = sc[k].weight; S.range_min = h->range_min; S.range_max = h->range_max;
         fill_sensor_frames(S, sc[k].Tbo, h->Tsb);
-        // Zero-copy scan: when the caller's buffer is pinned host memory the loop kernel reads it directly (and unpacks it) instead of
-        // memcpy + unpack kernel + cross-stream event.  Needs every pair of the sensor resident in registers / shared memory.
-        const float* zc = nullptr;
+        // Pinned scan (B2_ZEROCOPY, default 1): a copy engine moves it into the handle's buffer on the side stream WHILE find runs, a second small
+        // copy behind it raises a flag, and the loop kernel -- launched programmatically behind find, no event in between -- checks the flag
+        // before it unpacks the scan.  2: the loop kernel reads the caller's buffer itself over PCIe (latency-sensitive: 10-20 us slower on some
+        // hosts).  Needs every pair of the sensor resident in registers / shared memory.  Pageable buffers take the staged upload below.
+        const float* zc = nullptr; bool zc_dma = false;
         if (sc[k].ranges_host && nw > 0 && use_zc && per_thread <= B2_ICP_REG_PAIRS + S.smem_u) {
             cudaPointerAttributes pa;      // asked on every call (about a microsecond): an address can change from pinned to pageable between calls
-            if (cudaPointerGetAttributes(&pa, sc[k].ranges_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) zc = (const float*)pa.devicePointer;
+            if (cudaPointerGetAttributes(&pa, sc[k].ranges_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+                if (use_zc == 2) zc = (const float*)pa.devicePointer; else { zc = h->d_ranges_in.p; zc_dma = true; }
+            }
             (void)cudaGetLastError();
         }
         const bool need_upload = sc[k].ranges_host && nw > 0 && !zc;
-        if (need_upload) {      // the side stream starts after whatever this sensor's stream had in flight BEFORE this call
-            CU(cudaEventRecord(h->ev_aux, h == H ? H->stream : h->stream));
-            CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+        if (need_upload || zc_dma) {      // the side stream starts after whatever this sensor's stream had in flight BEFORE this call
+            const cudaError_t idle = cudaStreamQuery(h->stream);        // (nothing in flight, the usual case of the synchronous calls: no event needed)
+            if (idle != cudaSuccess) {
+                (void)cudaGetLastError();
+                CU(cudaEventRecord(h->ev_aux, h->stream));
+                CU(cudaStreamWaitEvent(h->aux, h->ev_aux, 0));
+            }
         }
         if (h != H) {           // order the lead stream behind this sensor's own stream (pending set_ranges / set_dataset copies)
             CU(cudaEventRecord(h->ev_join, h->stream));
@@ -1018,6 +1039,14 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
             CU(cudaEventRecord(h->ev_aux, h->aux));
             CU(cudaStreamWaitEvent(H->stream, h->ev_aux, 0));
             aux_any = true;
+        }
+        if (zc_dma) {
+            // after the find launch, so that the GPU is busy while the host issues the two copies
+            const int fs = (int)(H->slot_counter % B2_RING);
+            h->pin->flag_src[fs] = ++h->zc_seq;
+            CU(cudaMemcpyAsync(h->d_ranges_in.p, sc[k].ranges_host, sizeof(float) * h->n, cudaMemcpyHostToDevice, h->aux));
+            CU(cudaMemcpyAsync(h->d_bar.p, &h->pin->flag_src[fs], sizeof(unsigned int), cudaMemcpyHostToDevice, h->aux));
+            S.zc_flag = h->d_bar.p; S.zc_seq = h->zc_seq;
         }
         S.dpts = h->dpts(); S.dmask = h->dmask(); S.mpts = h->mpts(); S.mnrm = h->mnrm(); S.mmask = h->mhits();
         S.zc_ranges = zc; S.zc_dirs = h->d_dirs.p; S.zc_origs = h->d_origs.p; S.zc_n_origs = h->n_origs;
@@ -1095,10 +1124,12 @@ static int micp_collect(b2_rcc* H, b2_transform* Tom_new, b2_transform* T_onew_o
                 unsigned int bar_state[2] = {0u, 0u};
                 CU(cudaMemcpy(bar_state, H->d_bar.p, sizeof(bar_state), cudaMemcpyDeviceToHost));
                 if (bar_state[1] != 0u) {
-                    // The software grid barrier gave up (its blocks were not co-resident: SMs held by something that itself waits).  That is a
-                    // scheduling condition, not an error: reset the barrier; this call and every later call already in flight (their kernels
+                    // The loop's grid-wide exchange gave up (its blocks were not co-resident: SMs held by something that itself waits).  That is a
+                    // scheduling condition, not an error: reset the abort word; this call and every later call already in flight (their kernels
                     // saw the abort word and left) run again through the cooperative launch, whose co-residency the driver guarantees.
-                    CU(cudaMemset(H->d_bar.p, 0, 2 * sizeof(unsigned int))); H->bar_base = 0;
+                    // (code 2: a block's partial sum left the fixed-point range of the atomic exchange; the cooperative variant exchanges FP64)
+                    CU(cudaMemset(H->d_bar.p + 1, 0, sizeof(unsigned int)));
+                    CU(cudaMemset(H->d_slots.p, 0, ((size_t)B2_ICP_ACC_WORDS + B2_ICP_BASE_WORDS) * sizeof(unsigned long long)));      // the aborted rounds left them inconsistent
                     pc.rerun = true;
                     for (PendingCall& q : H->pending) if (q.barrier_used) q.rerun = true;
                 }

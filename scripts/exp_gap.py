@@ -31,7 +31,7 @@ for k in range(8):
     t0 = time.perf_counter()
     h.correctOnce(Tom, I, 5, 0.0)
     wall = (time.perf_counter() - t0) * 1e6
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 16)()
     lib.b2_rcc_debug_clocks(h._h, out)
     t = buf.cpu().numpy().reshape(-1, 2)
     f0, f1 = int(t[:, 0].min()), int(t[:, 1].max())

@@ -15,7 +15,7 @@ Tom = synth.compose(Tgt, synth.scenario_pose_offset())
 lib = rmcl_b200.load_library()
 for k in range(3):
     h.correctOnce(Tom, I, 5, 0.0)
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 16)()
     lib.b2_rcc_debug_clocks(h._h, out)
     print("cycles (coop loop, iteration 1, block 0): pass+blockreduce %d | grid.sync %d | partial sum %d | tail %d || prologue (state + pair loads) %d | whole kernel in block 0: %d cycles = %d ns (globaltimer)" % (out[0], out[1], out[2], out[3], out[4], out[5], out[6]))
 h.enableTiming(True)
