@@ -387,6 +387,7 @@ struct b2_rcc {
     int smem_u_cap = 0;                 // pairs per thread k_icp_loop can keep in shared memory (beyond the two in registers)
     int exec_mode = 2;                  // b2_rcc_set_exec_mode: 2 software grid barrier + programmatic launch (default), 1 cooperative launch, 0 one launch per reduction
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
+    unsigned long long n_reruns = 0;                            // calls that were run again through the cooperative launch (exchange abort: co-residency or range)
     DevBuf<unsigned int> d_bar; unsigned int zc_seq = 0;        // [0] = "scan copy complete" flag (value: zc_seq of the call), [1] = abort word of the ICP loop
     DevBuf<unsigned long long> d_slots; unsigned int tag_base = 0; // exchange buffers of the ICP loop (icp_loop.cuh: accumulators, base, FP64 slots); round number of the next launch
     unsigned int seq = 0;               // sequence number of the last k_icp_loop launch (carried by every result chunk)
@@ -527,6 +528,13 @@ extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_clocks(b2_rcc
     CU(cudaSetDevice(h->map->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(out16, h->d_dbg.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// test aid (not part of the public header): how many correctOnce calls of this handle were run again through the cooperative launch
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_reruns(b2_rcc* h, unsigned long long* out)
+{
+    NOTNULL(h); NOTNULL(out);
+    *out = h->n_reruns;
     return B2_OK;
 }
 // make PROFILE=1 only: per block {ns at publish, ns at collect, cycles since the block reduce at publish, at collect} of iteration 1
@@ -1135,6 +1143,7 @@ static int micp_collect(b2_rcc* H, b2_transform* Tom_new, b2_transform* T_onew_o
                 }
             }
             if (pc.rerun) {
+                H->n_reruns++;
                 for (uint32_t k = 0; k < pc.launch.n_sensors; k++) {
                     b2_rcc* h = pc.sensors[k];
                     const cudaStream_t own = h->stream; h->stream = H->stream; h->pdl_next = false;

@@ -758,7 +758,7 @@ def test_large_scan_correct_once(po, synth, rows, cols):
 def test_exec_modes_agree(po, synth):
     """b2_rcc_set_exec_mode: 2 = software grid barrier + programmatic launch (default), 1 = cooperative launch of the same kernel, 0 = one
     k_p2l_reduce launch per inner iteration with the reference's own frame-algebra order (icp_step).  All against the oracle; 1 and 2 run the
-    same code and must agree bit for bit."""
+    same iteration code and differ only in how the block sums cross the grid (FP64 slots behind a grid sync vs 64-bit fixed-point atomics)."""
     name, m = "building:200000", synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 63, 64, -np.pi, 2 * np.pi / 512, 512, 0.5, 120.0)
     osc, o, d, Tsb, ranges, dp, dm, Tbo, Tom = _micp_case(po, synth, name, m, synth.building_gt_pose(), seed=9)
     ref64 = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 1.0, 0.15, 0.3, f64_accum=True)
@@ -771,7 +771,7 @@ def test_exec_modes_agree(po, synth):
         _assert_micp(outs[mode], ref64)
         outr = h.correctOnce(Tom, Tbo, 5, 0.3, ranges=ranges)
         _assert_micp(outr, ref64)
-    assert outs[1][0].tobytes() == outs[2][0].tobytes() and outs[1][2].tobytes() == outs[2][2].tobytes()
+    assert np.abs(outs[1][0]["t"] - outs[2][0]["t"]).max() <= 1e-6 and outs[1][2]["n_meas"] == outs[2][2]["n_meas"]
     # mode 0 reproduces the oracle's chain more closely still: the frame algebra is the reference's, only the sums differ in order
     assert np.abs(outs[0][0]["t"] - ref64[0]["t"]).max() <= 2e-6
     with pytest.raises(Exception):
@@ -780,6 +780,39 @@ def test_exec_modes_agree(po, synth):
     h.setExecMode(2)
     Tn, Td, Cm = h.correctOnce(Tom, Tbo, 0, 0.0)
     assert Tn["t"].tobytes() == Tom["t"].tobytes() and Cm["n_meas"] == 0 and quat_close(Td["R"], [0, 0, 0, 1], 0)
+
+
+def test_exchange_range_fallback(po, synth):
+    """The loop's default exchange carries the block sums as 64-bit fixed point (|block partial| < 2^46); sums beyond that must not fail or
+    wrap: the call runs again through the cooperative variant (FP64 exchange).  Scene: the cube scaled to 10 000 km, ranges of 5e6 m."""
+    import ctypes as C
+    import rmcl_b200
+    from oracle import pyoracle
+    V, F = synth.cube(29)
+    V = (V * np.float32(5e5)).astype(np.float32)
+    osc, gm = pyoracle.Scene(V, F), rmcl_b200.Map(V, F, device=0)
+    m = synth.SphericalModel(np.radians(-60.0), np.radians(120.0) / 31, 32, -np.pi, 2 * np.pi / 64, 64, 1.0, 1e8)
+    o, d = po.model_rays(m)
+    Tsb = synth.make_transform((0, 0, 0), (0, 0, 0))
+    Tgt = synth.make_transform((1e3, -2e3, 5e2), (0, 0, 0.2))
+    ranges = osc.simulate(Tgt, Tsb, o, d, m.range_max)["ranges"]
+    dp, dm, _ = po.dataset_from_ranges(o, d, ranges, m.range_min, m.range_max)
+    Tbo = synth.make_transform((0, 0, 0), (0, 0, 0))
+    Tom = synth.compose(Tgt, synth.make_transform((30.0, -20.0, 10.0), (0, 0, 1e-5)))
+    ref = osc.micp_correct_once(o, d, m.range_max, dp, dm, Tom, Tbo, Tsb, 5, 200.0, 200.0, 0.0, f64_accum=True)
+    assert ref[2]["n_meas"] > 1500
+    h = rmcl_b200.RCCB200Spherical(gm)
+    h.setTsb(Tsb); h.setModel(m); h.setParams(200.0, 200.0); h.setRanges(ranges)
+    lib, cnt = rmcl_b200.load_library(), C.c_ulonglong(0)
+    out1 = h.correctOnce(Tom, Tbo, 5, 0.0)
+    lib.b2_rcc_debug_reruns(h._h, C.byref(cnt))
+    assert cnt.value == 1                                                # the fixed-point exchange declined, the cooperative variant answered
+    out2 = h.correctOnce(Tom, Tbo, 5, 0.0)
+    lib.b2_rcc_debug_reruns(h._h, C.byref(cnt))
+    assert cnt.value == 2 and out1[0].tobytes() == out2[0].tobytes()      # and the handle is consistent afterwards
+    for out in (out1, out2):
+        assert abs(int(out[2]["n_meas"]) - int(ref[2]["n_meas"])) <= 8
+        assert np.abs(out[0]["t"] - ref[0]["t"]).max() <= 5.0 and quat_close(out[0]["R"], ref[0]["R"], 1e-5)      # FP32 coordinates of 5e6 m: ulp 0.5 m
 
 
 @pytest.mark.parametrize("case", ["pinhole", "o1dn", "ondn"])
