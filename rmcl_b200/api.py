@@ -12,7 +12,7 @@ import numpy as np
 from .synth import CROSS_STATS_DTYPE, PARTICLE_ATTR_DTYPE, RANGE_MEAS_DTYPE, TRANSFORM_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "librmcl_b200.so")
+_LIB_PATH = os.environ.get("B2_LIB_PATH") or os.path.join(_HERE, "lib", "librmcl_b200.so")     # B2_LIB_PATH: experiment builds (scripts/)
 _lib = None
 
 B2_BUILD_HOST_SAH = 0
