@@ -180,7 +180,9 @@ B2_API int b2_rcc_download_dataset(b2_rcc* h, float* points, uint8_t* mask);
  * find(Tom*Tbo), then `iterations` x { P2L cross statistics -> frame changes -> Umeyama -> compose }.  Outputs to HOST (may be NULL). */
 B2_API int b2_rcc_correct_once(b2_rcc* h, const b2_transform* Tom, const b2_transform* Tbo, uint32_t iterations,
                                double convergence_progress, b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
-/* same, but the scan arrives as HOST ranges and is uploaded inside the call (end-to-end entry point used by bench.py "e2e") */
+/* same, but the scan arrives as HOST ranges and is uploaded inside the call (end-to-end entry point used by bench.py "e2e").  A pinned buffer
+ * (cudaHostAlloc / cudaHostRegister) is moved by a copy engine while find runs and unpacked by the loop kernel; a pageable one is staged and
+ * uploaded on a side stream.  The buffer must stay unchanged until the call returns. */
 B2_API int b2_rcc_correct_once_ranges(b2_rcc* h, const float* ranges_host, uint32_t n, const b2_transform* Tom, const b2_transform* Tbo,
                                       uint32_t iterations, double convergence_progress, b2_transform* Tom_new, b2_transform* T_onew_oold,
                                       b2_cross_stats* Cmerged_o);
@@ -200,10 +202,12 @@ B2_API int b2_rcc_correct_once_wait(b2_rcc* h, b2_transform* Tom_new, b2_transfo
 B2_API int b2_micp_correct_once(b2_rcc* const* sensors, const b2_transform* Tbo, const double* merge_weights, const float* const* ranges_host, uint32_t n_sensors,
                                 const b2_transform* Tom, uint32_t iterations, double convergence_progress,
                                 b2_transform* Tom_new, b2_transform* T_onew_oold, b2_cross_stats* Cmerged_o);
-/* How b2_rcc_correct_once* runs the inner iterations: 2 (default) one kernel with a software grid barrier, launched programmatically behind
- * find; 1 the same kernel through a cooperative launch; 0 one reduction launch per inner iteration in the reference's own frame-algebra order
- * (MICPSensor.hpp:178-182).  Results agree within float rounding.  The environment variable B2_FUSED sets the default of new handles.  A
- * software barrier that cannot get its blocks co-resident falls back to the cooperative launch by itself. */
+/* How b2_rcc_correct_once* runs the inner iterations: 2 (default) one kernel for all of them, launched programmatically behind find; the block
+ * sums cross the grid as 64-bit fixed-point atomics (every block must be co-resident: one block per SM).  1 the same kernel through a cooperative
+ * launch, the sums as FP64 slots behind a grid sync.  0 one reduction launch per inner iteration in the reference's own frame-algebra order
+ * (MICPSensor.hpp:178-182).  Results agree within float rounding.  The environment variable B2_FUSED sets the default of new handles.  A mode-2
+ * call whose blocks cannot become co-resident, or whose sums leave the fixed-point range (|block partial| >= 2^46), is run again through mode 1
+ * by the library itself. */
 B2_API int b2_rcc_set_exec_mode(b2_rcc* h, int mode);
 
 /* v1 {Sphere,Pinhole,O1Dn}Corrector{Embree,Optix}::correct(Tbm[N]) -> {Tdelta[N], Ncorr[N]}

@@ -419,7 +419,7 @@ class RCCB200:
         _chk(load_library().b2_rcc_set_sim_options(self._h, C.c_int(tfar_mode), C.c_int(min_mode), C.c_int(miss_fill)))
 
     def setExecMode(self, mode):
-        """2 (default): one kernel, software grid barrier, programmatic launch; 1: cooperative launch; 0: one reduction launch per inner iteration."""
+        """2 (default): one kernel, block sums exchanged by 64-bit atomics, programmatic launch; 1: cooperative launch, FP64 exchange behind a grid sync; 0: one reduction launch per inner iteration."""
         _chk(load_library().b2_rcc_set_exec_mode(self._h, C.c_int(int(mode))))
 
     def correctOnceAsync(self, Tom, Tbo, iterations=5, convergence_progress=0.0):

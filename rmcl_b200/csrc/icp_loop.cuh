@@ -10,11 +10,12 @@
 //
 // Shape on the B200: one 512-thread block per SM; the blocks are split among the sensors in proportion to their pair counts.  Every thread
 // owns a fixed set of (dataset, model) pairs for the whole kernel -- two in registers, the next ones in shared memory, anything beyond
-// streamed from L2 -- so that after the first pass an iteration touches no global memory except 128 bytes of partial sums per block.
-// Per iteration:  P2L pass (FP32 per-pair math identical to the oracle, FP64 sums) -> reduce-scatter warp reduction -> block partial ->
-// software grid barrier (or cooperative grid sync) -> EVERY block re-sums the partials in the same fixed order and runs the serial tail
-// redundantly (no broadcast hop).  The result leaves through mapped pinned host memory in 16-byte chunks that each carry the sequence
-// number of the call, so the host needs no separate completion flag and the kernel no system-wide fence.
+// streamed from L2 -- so that after the first pass an iteration touches no global memory except the exchange of the block sums.
+// Per iteration:  P2L pass (FP32 per-pair math identical to the oracle, FP64 sums) -> reduce-scatter warp reduction -> block sums ->
+// grid-wide exchange (64-bit fixed-point atomics, see below; FP64 slots behind a grid sync in the cooperative variant) -> warp 0 of EVERY
+// block turns the sums into the per-sensor statistics (15 elements on 15 lanes) and runs the rest of the serial tail redundantly (no
+// broadcast hop).  The result leaves through mapped pinned host memory in 16-byte chunks that each carry the sequence number of the call,
+// so the host needs no separate completion flag and the kernel no system-wide fence.
 #pragma once
 
 #define B2_MAX_SENSORS 4
