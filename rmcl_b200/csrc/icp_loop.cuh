@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant
             const bool prof = it == 1 && blockIdx.x == 0 && dbg && lane == 0;
             const bool mine = lane < L.n_sensors;                                                    // lane k prepares sensor k's next pre-transform
             if (ok) icp_tail_rest(L, s_odo, s_n, T, s_Tpre, mine ? lane : 0u, mine ? lane + 1u : 0u, it + 1 == L.iterations, lane == 0 ? &s_res : nullptr, prof ? st : nullptr);
+            __syncwarp();                                           // every lane has read s_T (and the statistics) before lane 0 replaces it
             if (lane == 0) s_T = T;
             if (prof) {
                 const long long c4 = clock64();
