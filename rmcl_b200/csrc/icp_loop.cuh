@@ -300,6 +300,7 @@ __device__ __forceinline__ void block_reduce_to_smem(P2LAcc& a, double* smem)
 // the final words in `base` for the next launch.  Doubles with |x| >= 4096 convert without loss, smaller ones to 2^-40; a block partial
 // beyond +-2^46 (or non-finite) raises abort code 2 and the call runs again through the cooperative FP64 variant below.
 // ---------------------------------------------------------------------------------------------------------------------
+static_assert(B2_ICP_MAX_GRID < 256, "the arrival count of an accumulator word has 8 bits");
 #define B2_ICP_ACC_STRIDE 16                   // u64 words per accumulator (one 128-byte line each)
 #define B2_ICP_ACC_WORDS (2 * B2_MAX_SENSORS * 32 * B2_ICP_ACC_STRIDE)      // [parity][sensor][32 limbs] accumulators ...
 #define B2_ICP_BASE_WORDS (2 * B2_MAX_SENSORS * 32)                          // ... followed by the dense `base` copy

@@ -4,7 +4,7 @@ fractions together with the LIVE kernel durations it measures itself (a number t
     ncu --set full --clock-control none --import-source on -k regex:k_ -o gpurun_out/r02 python scripts/prof_workloads.py
     ncu -i gpurun_out/r02.ncu-rep --page raw --csv > gpurun_out/r02_raw.csv
     python scripts/ncu_counters.py gpurun_out/r02_raw.csv profiles/counters.json "note on the capture"
-For a kernel captured several times the LAST launch is kept (earlier ones include first-touch effects)."""
+For a kernel captured several times the LAST launch of each workload is kept (earlier ones include first-touch effects)."""
 import csv
 import json
 import re
@@ -67,7 +67,10 @@ def main():
             d["l1_bytes"] = d["l1_sectors"] * 32
         if "dram_read_bytes" in d:
             d["dram_bytes"] = d["dram_read_bytes"] + d.get("dram_write_bytes", 0.0)
-        k = f"{k}#{int(d.get('grid', 0))}"            # one entry per (kernel, grid size): the same kernel serves several workloads
+        k = f"{k}#{int(d.get('grid', 0))}"            # one entry per (kernel, grid size): the same kernel serves several workloads ...
+        base, v = k, 1
+        while k in out and abs(out[k].get("warp_instructions", 0.0) - d.get("warp_instructions", 0.0)) > 0.1 * max(out[k].get("warp_instructions", 1.0), 1.0):
+            v += 1; k = f"{base}~{v}"                 # ... and one per workload when the grid is the same (k_icp_loop: C2, then C4 as `~2`), in order of appearance
         d["launches_captured"] = out.get(k, {}).get("launches_captured", 0) + 1
         out[k] = d
     meta = {"source": sys.argv[1], "note": sys.argv[3] if len(sys.argv) > 3 else "", "per": "launch (last captured launch of each kernel)"}
