@@ -425,8 +425,8 @@ def main():
                                            algorithmic_bytes=c4["bytes_per_ray"] * 640 * 480)
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample ----
-    cpu = None
-    if world == 1 or rank == 0:
+    cpu = None                                   # N = 1 only: at N > 1 the other ranks' processes share the host cores with it
+    if world == 1:
         try:
             val, dt, cores, _, sample = cpu_reference_leg(args, 10, 1, budget_s=30.0)
             cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
