@@ -387,6 +387,7 @@ struct b2_rcc {
     int smem_u_cap = 0;                 // pairs per thread k_icp_loop can keep in shared memory (beyond the two in registers)
     int exec_mode = 2;                  // b2_rcc_set_exec_mode: 2 software grid barrier + programmatic launch (default), 1 cooperative launch, 0 one launch per reduction
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
+    DevBuf<uint32_t> d_tile_cost; DevBuf<uint16_t> d_tile_perm; uint32_t perm_tiles = 0, cost_tiles = 0;    // tile schedule of k_rcc_find: durations of the last launch, order for the next (valid for perm_tiles tiles)
     unsigned long long n_reruns = 0;                            // calls that were run again through the cooperative launch (exchange abort: co-residency or range)
     DevBuf<unsigned int> d_bar; unsigned int zc_seq = 0;        // [0] = "scan copy complete" flag (value: zc_seq of the call), [1] = abort word of the ICP loop
     DevBuf<unsigned long long> d_slots; unsigned int tag_base = 0; // exchange buffers of the ICP loop (icp_loop.cuh: accumulators, base, FP64 slots); round number of the next launch
@@ -485,7 +486,7 @@ extern "C" int b2_rcc_destroy(b2_rcc* h)
     cudaStreamSynchronize(h->stream);
     h->d_dirs.release(); h->d_origs.release(); h->d_dpts.release(); h->d_dmask.release(); h->d_ranges_in.release();
     h->d_mpts.release(); h->d_mnrm.release(); h->d_mranges.release(); h->d_mhits.release(); h->d_mfaces.release();
-    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release(); h->d_res.release(); h->d_dbg.release(); h->d_slots.release();
+    h->d_partials.release(); h->d_ticket.release(); h->d_stats.release(); h->d_icp.release(); h->d_bar.release(); h->d_res.release(); h->d_dbg.release(); h->d_slots.release(); h->d_tile_cost.release(); h->d_tile_perm.release();
     { DeviceCtx& dc = g_dev[h->map->device & 63]; std::lock_guard<std::mutex> lk(dc.m); dc.n_handles--; if (dc.last == h) { dc.last = nullptr; dc.recorded = false; } }
     h->d_poses.release(); h->d_tdelta.release(); h->d_ncorr.release(); h->d_bstats.release();
     if (h->pin) cudaFreeHost(h->pin);
@@ -576,6 +577,7 @@ static int set_model_tables(b2_rcc* h, uint32_t w, uint32_t hgt, const float* or
     CU(cudaMemcpy(h->d_dirs.p, dirs, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_origs.p, origs, sizeof(float) * 3 * (size_t)n_origs, cudaMemcpyHostToDevice));
     h->has_model = true; h->n = (uint32_t)n; h->width = w; h->height = hgt; h->n_origs = n_origs; h->range_min = rmin; h->range_max = rmax;
+    h->perm_tiles = 0;                                             // the tile schedule belongs to the previous model
     return B2_OK;
 }
 
@@ -712,7 +714,19 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     // dependent block can never take an SM slot a find block is still waiting for
     const int early = (h->pdl_next && grid <= 14u * (uint32_t)h->red_grid) ? 1 : 0;
     h->pdl_armed = early != 0;
-    k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h), early);
+    // tile schedule (kernels.cuh): whole tiles only, scans whose blocks are all resident in one wave (the order matters little otherwise, and
+    // the ICP loop's idle warps sort up to 8192 durations in the time they have)
+    static const int use_sched = [] { const char* e = getenv("B2_FIND_SCHED"); return e ? atoi(e) : 1; }();
+    const uint32_t n_tiles = h->n / 32u;
+    const bool sched = use_sched && (h->n % 32u) == 0u && n_tiles >= 2u && n_tiles <= 8192u && grid * (B2_FIND_BLOCK / 32u) == n_tiles && grid <= 14u * (uint32_t)h->red_grid;
+    uint32_t* cost = nullptr; const uint16_t* perm = nullptr;
+    if (sched) {
+        RES(h->d_tile_cost.reserve(n_tiles)); RES(h->d_tile_perm.reserve(n_tiles));
+        cost = h->d_tile_cost.p; h->cost_tiles = n_tiles;
+        if (h->perm_tiles == n_tiles) perm = h->d_tile_perm.p;
+    } else h->cost_tiles = 0;
+    k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h), early,
+                                                      perm, cost);
     LAUNCHED();
     h->n_model = h->n; h->found = true;
     return B2_OK;
@@ -1056,6 +1070,9 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
             CU(cudaMemcpyAsync(h->d_bar.p, &h->pin->flag_src[fs], sizeof(unsigned int), cudaMemcpyHostToDevice, h->aux));
             S.zc_flag = h->d_bar.p; S.zc_seq = h->zc_seq;
         }
+        if (h->corr_type == B2_CORR_RCC && h->cost_tiles) {
+            S.tile_cost = h->d_tile_cost.p; S.tile_perm = h->d_tile_perm.p; S.n_tiles = h->cost_tiles;
+        }
         S.dpts = h->dpts(); S.dmask = h->dmask(); S.mpts = h->mpts(); S.mnrm = h->mnrm(); S.mmask = h->mhits();
         S.zc_ranges = zc; S.zc_dirs = h->d_dirs.p; S.zc_origs = h->d_origs.p; S.zc_n_origs = h->n_origs;
         S.dpts_out = h->d_dpts.p; S.dmask_out = h->d_dmask.p; S.ranges_out = h->d_ranges_in.p;
@@ -1070,6 +1087,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
     pc.slot = (int)(H->slot_counter++ % B2_RING);
     RES(launch_icp_loop(H, L, grid, smem, mode, pdl, pc.slot));
     if (H->timing) { CU(cudaEventRecord(H->ev[2], H->stream)); H->timing_valid = true; }
+    for (uint32_t k = 0; k < ns; k++) if (L.s[k].tile_perm) { sc[k].h->perm_tiles = sc[k].h->cost_tiles; sc[k].h->cost_tiles = 0; }       // the loop kernel writes the next find's order
     for (uint32_t k = 1; k < ns; k++) {        // later work on the other sensors' own streams sees the model buffers this call wrote
         CU(cudaEventRecord(sc[k].h->ev_join, H->stream));
         CU(cudaStreamWaitEvent(sc[k].h->stream, sc[k].h->ev_join, 0));
@@ -1301,7 +1319,7 @@ extern "C" int b2_rcc_benchmark_batch(b2_rcc* h, const b2_transform* Tbm_host, u
     for (uint32_t r = 0; r < n_runs && e == cudaSuccess; r++) {
         cudaEventRecord(ev[0], h->stream);
         k_rcc_find<<<(uint32_t)((total + B2_FIND_BLOCK - 1) / B2_FIND_BLOCK), B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, 0, h->d_poses.p, nullptr,
-                                                                                                        tf_identity_pod(), h->Tsb, ray_model(h), n_poses, out, 0);
+                                                                                                        tf_identity_pod(), h->Tsb, ray_model(h), n_poses, out, 0, nullptr, nullptr);
         cudaEventRecord(ev[1], h->stream);
         k_p2l_batch<<<bpp * n_poses, B2_FUSED_BLOCK, 0, h->stream>>>(pts.p, nrm.p, hits.p, h->n, h->dpts(), h->dmask(), h->max_dist, bpp, rays_per_block, h->d_partials.p);
         cudaEventRecord(ev[2], h->stream);

@@ -38,6 +38,8 @@ struct IcpSensor {
     float max_dist, range_min, range_max;
     uint32_t n, blk0, nblk, zc_n_origs, smem_u;                 // pairs; blocks [blk0, blk0+nblk); pairs per thread kept in shared memory
     uint32_t zc_seq;
+    const uint32_t* tile_cost; uint16_t* tile_perm;             // != nullptr: the idle warps of this sensor's first block turn the warp durations of the find
+    uint32_t n_tiles, pad_;                                     //   kernel into the tile order of the NEXT find (kernels.cuh: tile schedule)
 };
 struct IcpLaunch {
     IcpSensor s[B2_MAX_SENSORS];
@@ -311,6 +313,69 @@ __device__ __forceinline__ unsigned long long acc_ld(const unsigned long long* p
     unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
 
+// The tile order of the next find (kernels.cuh: tile schedule) computed by warps 1..15 of one block while warp 0 is busy with the exchange and
+// the serial tail of the first iteration: tiles grouped into 16 duration classes relative to the slowest one, slowest class first, raster
+// order inside a class (only the slow tail of the distribution has to start early; the bulk may stay where it is).  Ballots and prefix sums,
+// no atomics on hot counters (most tiles share two or three classes).  `t` = 0..479; the group synchronises on named barrier 1, so the
+// block's own barrier 0 is untouched.
+#define B2_PERM_GROUP (B2_ICP_BLOCK - 32)
+#define B2_PERM_WARPS (B2_PERM_GROUP / 32)
+__device__ __forceinline__ void perm_group_sync() { asm volatile("bar.sync 1, %0;" ::"n"(B2_PERM_GROUP) : "memory"); }
+#define B2_PERM_MAX_TILES 8192
+__device__ __forceinline__ void tile_perm_group(const uint32_t* __restrict__ cost, uint32_t n_tiles, uint16_t* __restrict__ perm, uint32_t* s_bin /* 1 + 16 * 15 */, uint32_t t)
+{
+    constexpr int PT = (B2_PERM_MAX_TILES + B2_PERM_GROUP - 1) / B2_PERM_GROUP;      // tiles per thread, kept in registers: one round trip to L2 in all
+    const uint32_t lane = t & 31u, w = t >> 5;
+    if (t == 0) s_bin[0] = 1u;
+    uint32_t c[PT];
+    #pragma unroll
+    for (int k = 0; k < PT; k++) { const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP; c[k] = i < n_tiles ? __ldcg(cost + i) : 0u; }
+    perm_group_sync();
+    uint32_t m = 0;
+    #pragma unroll
+    for (int k = 0; k < PT; k++) m = max(m, c[k]);
+    #pragma unroll
+    for (int off = 16; off; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) atomicMax(&s_bin[0], m);
+    uint32_t* s_off = s_bin + 1;                                   // [(15 - class) * 15 + warp]: slowest class first, then by warp
+    if (lane < 16u) s_off[(15u - lane) * B2_PERM_WARPS + w] = 0u;
+    perm_group_sync();
+    const float scale = 16.0f / ((float)s_bin[0] + 1.0f);
+    #pragma unroll
+    for (int k = 0; k < PT; k++) {                                 // counts per (class, warp): the lowest lane of every class present adds its group
+        const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP;
+        if (i - lane >= n_tiles) break;                            // warp-uniform
+        const uint32_t cls = i < n_tiles ? min(15u, (uint32_t)((float)c[k] * scale)) : 16u;
+        c[k] = cls;
+        const uint32_t grp = __match_any_sync(0xffffffffu, cls);
+        if (cls < 16u && lane == (uint32_t)__ffs((int)grp) - 1u) s_off[(15u - cls) * B2_PERM_WARPS + w] += (uint32_t)__popc(grp);
+        __syncwarp();
+    }
+    perm_group_sync();
+    if (w == 0) {                                                  // exclusive prefix over the 240 counts: 8 per lane, then across the lanes
+        constexpr uint32_t PER = (16u * B2_PERM_WARPS + 31u) / 32u;
+        uint32_t sum = 0;
+        for (uint32_t j = 0; j < PER; j++) { const uint32_t e = lane * PER + j; if (e < 16u * B2_PERM_WARPS) sum += s_off[e]; }
+        uint32_t incl = sum;
+        for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        uint32_t run = incl - sum;
+        for (uint32_t j = 0; j < PER; j++) { const uint32_t e = lane * PER + j; if (e < 16u * B2_PERM_WARPS) { const uint32_t cc = s_off[e]; s_off[e] = run; run += cc; } }
+    }
+    perm_group_sync();
+    #pragma unroll
+    for (int k = 0; k < PT; k++) {                                 // s_off[class, warp] = next free position of the class for this warp
+        const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP;
+        if (i - lane >= n_tiles) break;
+        const uint32_t cls = c[k];
+        const uint32_t grp = __match_any_sync(0xffffffffu, cls);
+        uint32_t base = 0;
+        if (cls < 16u) { base = s_off[(15u - cls) * B2_PERM_WARPS + w]; perm[base + (uint32_t)__popc(grp & ((1u << lane) - 1u))] = (uint16_t)i; }
+        __syncwarp();
+        if (cls < 16u && lane == (uint32_t)__ffs((int)grp) - 1u) s_off[(15u - cls) * B2_PERM_WARPS + w] = base + (uint32_t)__popc(grp);
+        __syncwarp();
+    }
+}
+
 // The kernel.  COOP: cooperative launch + cg grid sync in front of the slot reads (fallback when co-residency cannot be guaranteed);
 // otherwise an ordinary launch, normally with programmatic stream serialization behind the last find kernel.
 template <bool COOP>
@@ -325,6 +390,7 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant
     __shared__ float s_Rt[B2_MAX_SENSORS][12];                     // Ros (9) + translation of Tos (3): lane-indexed reads in the tail
     __shared__ uint32_t s_n[B2_MAX_SENSORS];
     __shared__ unsigned long long s_prev[2][B2_MAX_SENSORS][32];   // accumulator words before the current round, per parity
+    __shared__ uint32_t s_bin[1 + 16 * 15];                        // tile schedule of the next find (first block of each sensor)
     __shared__ Tf s_Tpre[B2_MAX_SENSORS];
     __shared__ Tf s_T;                                             // T_onew_oold
     __shared__ IcpResult s_res;
@@ -434,6 +500,12 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant
         }
         block_reduce_to_smem<B2_ICP_BLOCK>(acc, smem);
         const long long c1 = clock64();
+        if (it == 0 && S.tile_perm && blockIdx.x == S.blk0 && warp >= 1u) {
+            tile_perm_group(S.tile_cost, S.n_tiles, S.tile_perm, s_bin, tid - 32u);
+#if defined(B2_ICP_PROFILE)
+            if (dbg && lane == 0 && blockIdx.x == 0) atomicMax(dbg + 640, (unsigned long long)(clock64() - c1));
+#endif
+        }
         constexpr int NW = B2_ICP_BLOCK / 32;
         const uint32_t par = (tag_base + it) & 1u;
         bool ok = true;
@@ -537,6 +609,9 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant
 #endif
             }
         }
+#if defined(B2_ICP_PROFILE)
+        if (dbg && blockIdx.x == 0 && it == 0 && lane == 0) { if (warp == 0) dbg[641] = (unsigned long long)(clock64() - c1); else atomicMax(dbg + 642, (unsigned long long)(clock64() - c1)); }
+#endif
         if (__syncthreads_or(!ok)) return;                         // gave up: the host finds the abort word set and re-runs the step cooperatively
     }
     if (!COOP && blockIdx.x == 0 && tid < 2u * B2_MAX_SENSORS * 32u) base_w[tid] = (&s_prev[0][0][0])[tid];      // the accumulators' state for the next launch

@@ -528,15 +528,22 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 // 14 blocks per SM (72 registers): the 2048 blocks of the C2 scan are resident in ONE wave on 148 SMs (13.84 per SM); with the 76
 // registers ptxas picks on its own only 13 fit and the last blocks wait for a slot (measured 54.0 -> 51.7 us).  A variant with 16 rays
 // per warp (half-empty warps, shorter max-over-lanes trip count) was measured slower (71 us: the idle lanes still own registers).
+// Tile schedule (single-pose launches): the block scheduler hands out blocks in index order over a few microseconds, and the kernel ends
+// with its slowest warp -- so the tiles that took longest in the PREVIOUS launch of this handle (same model, nearly the same pose: MICP-L
+// corrects continuously) go first.  Each warp leaves its duration in `tile_cost`; the ICP loop that follows the find turns the durations
+// into the order `tile_perm` of the next launch (icp_loop.cuh: tile_perm_group, idle warps of one block).  Purely a schedule: every tile is traced exactly once, results do not depend on it.
 __global__ void __launch_bounds__(B2_FIND_BLOCK, 14) k_rcc_find(BvhView bvh, uint32_t n_nodes, uint32_t n_tris, int prefetch_mode, const b2_transform* __restrict__ Tbm_dev,
                                                                 const IcpState* __restrict__ icp, b2_transform Tbm_val, b2_transform Tsb_val, RayModel model, uint32_t n_poses,
-                                                                ModelBuffers out, int early_dependents)
+                                                                ModelBuffers out, int early_dependents, const uint16_t* __restrict__ tile_perm, uint32_t* __restrict__ tile_cost)
 {
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_t0[B2_FIND_BLOCK / 32];
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile_perm) gid = ((uint64_t)tile_perm[gid >> 5] << 5) | (gid & 31u);                      // n_poses == 1; a permutation of the tiles
+    if (tile_cost && (threadIdx.x & 31u) == 0u) { uint32_t c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); s_t0[threadIdx.x >> 5] = c; }
     // let a dependent kernel launched with programmatic stream serialization (k_icp_loop) become resident as SMs drain; it still waits
     // (griddepcontrol.wait) for this grid to complete and flush before it reads the model buffers
     if (early_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (g_find_warp_times && (threadIdx.x & 31u) == 0u) g_find_warp_times[2 * (gid >> 5)] = globaltimer_ns();      // nothing stays live across the trace
+    if (g_find_warp_times && (threadIdx.x & 31u) == 0u) g_find_warp_times[2 * (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)] = globaltimer_ns();      // nothing stays live across the trace
     prefetch_map_l2(bvh, n_nodes, n_tris, prefetch_mode);
     const uint64_t total = (uint64_t)model.n * n_poses;
     if (gid < total) {
@@ -546,6 +553,10 @@ __global__ void __launch_bounds__(B2_FIND_BLOCK, 14) k_rcc_find(BvhView bvh, uin
         else if (Tbm_dev) Tbm = tf_load(Tbm_dev + pose);
         else Tbm = tf_from_pod(Tbm_val);
         find_one(bvh, tf_mul(Tbm, tf_from_pod(Tsb_val)), model, i, (uint64_t)pose * model.n + i, out);
+    }
+    if (tile_cost) {
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0u) { uint32_t c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); tile_cost[gid >> 5] = c - s_t0[threadIdx.x >> 5]; }
     }
     if (g_find_warp_times) {
         __syncwarp();

@@ -57,6 +57,11 @@ for name, src in (("resident", None), ("pageable", ranges), ("pinned", pinned)):
             print("%-9s find: last warp end %.1f us | loop block 0: start %.1f, end %.1f us (after find's end: %.1f) | host wall clock %.1f us"
                   % (name, (f1 - f0) / 1e3, (int(out[6]) - f0) / 1e3, (int(out[7]) - f0) / 1e3, (int(out[7]) - f1) / 1e3, wall))
     print("   %-9s cycles: pass %d | collect %d | statistics %d | rest of tail %d || prologue %d | whole kernel %d" % ((name,) + tuple(out[i] for i in range(6))))
+    if hasattr(lib, "b2_rcc_debug_blocks"):
+        blk = (C.c_ulonglong * 640)()
+        lib.b2_rcc_debug_blocks(h._h, blk)
+        print("   block 0, iteration 0, cycles after the block reduce: tile order of the next find done (slowest of warps 1..15, max over calls) %d | end barrier reached by warp 0 %d, by the slowest other warp (max over calls) %d"
+              % (blk[624], blk[625], blk[626]))
 lib.b2_rcc_debug_find_warp_times(h._h, None)
 for mode in (2, 1, 0):
     h.setExecMode(mode)
