@@ -387,7 +387,7 @@ struct b2_rcc {
     int smem_u_cap = 0;                 // pairs per thread k_icp_loop can keep in shared memory (beyond the two in registers)
     int exec_mode = 2;                  // b2_rcc_set_exec_mode: 2 software grid barrier + programmatic launch (default), 1 cooperative launch, 0 one launch per reduction
     bool pdl_next = false, pdl_armed = false;   // the next find is followed by k_icp_loop launched with programmatic stream serialization / the find let it start early
-    DevBuf<uint32_t> d_tile_cost; DevBuf<uint16_t> d_tile_perm; uint32_t perm_tiles = 0, cost_tiles = 0;    // tile schedule of k_rcc_find: durations of the last launch, order for the next (valid for perm_tiles tiles)
+    DevBuf<uint32_t> d_tile_cost; DevBuf<uint16_t> d_tile_perm; uint32_t perm_tiles = 0, cost_tiles = 0;    // tile schedule of k_rcc_find: warp durations of the last launch (cost_tiles of them if it recorded any), order for the next (always a permutation of perm_tiles tiles)
     unsigned long long n_reruns = 0;                            // calls that were run again through the cooperative launch (exchange abort: co-residency or range)
     DevBuf<unsigned int> d_bar; unsigned int zc_seq = 0;        // [0] = "scan copy complete" flag (value: zc_seq of the call), [1] = abort word of the ICP loop
     DevBuf<unsigned long long> d_slots; unsigned int tag_base = 0; // exchange buffers of the ICP loop (icp_loop.cuh: accumulators, base, FP64 slots); round number of the next launch
@@ -536,6 +536,16 @@ extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_reruns(b2_rcc
 {
     NOTNULL(h); NOTNULL(out);
     *out = h->n_reruns;
+    return B2_OK;
+}
+// test aid (not part of the public header): the tile order the next find of this handle will use (host copy; *n_tiles = 0 when the schedule is off)
+extern "C" __attribute__((visibility("default"))) int b2_rcc_debug_tile_perm(b2_rcc* h, uint16_t* out, uint32_t capacity, uint32_t* n_tiles)
+{
+    NOTNULL(h); NOTNULL(n_tiles);
+    CU(cudaSetDevice(h->map->device));
+    CU(cudaStreamSynchronize(h->stream));
+    *n_tiles = h->perm_tiles;
+    if (out && h->perm_tiles && capacity >= h->perm_tiles) CU(cudaMemcpy(out, h->d_tile_perm.p, h->perm_tiles * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 // make PROFILE=1 only: per block {ns at publish, ns at collect, cycles since the block reduce at publish, at collect} of iteration 1
@@ -721,9 +731,13 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     const bool sched = use_sched && (h->n % 32u) == 0u && n_tiles >= 2u && n_tiles <= 8192u && grid * (B2_FIND_BLOCK / 32u) == n_tiles && grid <= 14u * (uint32_t)h->red_grid;
     uint32_t* cost = nullptr; const uint16_t* perm = nullptr;
     if (sched) {
-        RES(h->d_tile_cost.reserve(n_tiles)); RES(h->d_tile_perm.reserve(n_tiles));
-        cost = h->d_tile_cost.p; h->cost_tiles = n_tiles;
-        if (h->perm_tiles == n_tiles) perm = h->d_tile_perm.p;
+        if (h->perm_tiles != n_tiles) {      // first launch with this model: identity order; from then on d_tile_perm always holds a permutation of the tiles
+            RES(h->d_tile_cost.reserve(n_tiles)); RES(h->d_tile_perm.reserve(n_tiles));
+            k_perm_identity<<<(n_tiles + 255u) / 256u, 256, 0, h->stream>>>(h->d_tile_perm.p, n_tiles);
+            LAUNCHED();
+            h->perm_tiles = n_tiles;
+        }
+        cost = h->d_tile_cost.p; perm = h->d_tile_perm.p; h->cost_tiles = n_tiles;
     } else h->cost_tiles = 0;
     k_rcc_find<<<grid, B2_FIND_BLOCK, 0, h->stream>>>(h->map->view(), h->map->n_nodes, h->map->n_tris, prefetch_mode, nullptr, icp_dev, Tbm_host ? *Tbm_host : tf_identity_pod(), h->Tsb, ray_model(h), 1u, model_buffers(h), early,
                                                       perm, cost);
@@ -1087,7 +1101,6 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
     pc.slot = (int)(H->slot_counter++ % B2_RING);
     RES(launch_icp_loop(H, L, grid, smem, mode, pdl, pc.slot));
     if (H->timing) { CU(cudaEventRecord(H->ev[2], H->stream)); H->timing_valid = true; }
-    for (uint32_t k = 0; k < ns; k++) if (L.s[k].tile_perm) { sc[k].h->perm_tiles = sc[k].h->cost_tiles; sc[k].h->cost_tiles = 0; }       // the loop kernel writes the next find's order
     for (uint32_t k = 1; k < ns; k++) {        // later work on the other sensors' own streams sees the model buffers this call wrote
         CU(cudaEventRecord(sc[k].h->ev_join, H->stream));
         CU(cudaStreamWaitEvent(sc[k].h->stream, sc[k].h->ev_join, 0));

@@ -564,6 +564,15 @@ __global__ void __launch_bounds__(B2_FIND_BLOCK, 14) k_rcc_find(BvhView bvh, uin
     }
 }
 
+#ifdef __CUDACC__
+// the tile order before any durations are known; also what a launch falls back to when the loop that should have sorted never ran
+__global__ void k_perm_identity(uint16_t* __restrict__ perm, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = (uint16_t)i;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // CPCEmbree::find (CPCEmbree.cpp:17-43): one thread per dataset point (the mask is NOT consulted, as in the reference);
 //   Pm = Tsm * d_i;  cp = closestPoint(Pm);  hits = cp.d <= max_dist;  points = Tms * cp.p;  normals = Tms.R * cp.n

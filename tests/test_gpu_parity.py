@@ -782,6 +782,46 @@ def test_exec_modes_agree(po, synth):
     assert Tn["t"].tobytes() == Tom["t"].tobytes() and Cm["n_meas"] == 0 and quat_close(Td["R"], [0, 0, 0, 1], 0)
 
 
+def test_tile_schedule_invisible(po, synth):
+    """k_rcc_find traces the tiles that were slowest in the previous launch first (order computed inside the ICP loop kernel).  The order must
+    always be a permutation of the tiles, and the results must not depend on it."""
+    import ctypes as C
+    import rmcl_b200
+    name, m = "building:200000", synth.SphericalModel(np.radians(-25.0), np.radians(40.0) / 63, 64, -np.pi, 2 * np.pi / 512, 512, 0.5, 120.0)
+    osc, o, d, Tsb, ranges, dp, dm, Tbo, Tom = _micp_case(po, synth, name, m, synth.building_gt_pose(), seed=3)
+    h = _rcc(synth, name, m)
+    h.setRanges(ranges)
+    lib = rmcl_b200.load_library()
+    n_tiles = m.size // 32
+
+    def order():
+        out, n = np.zeros(n_tiles, np.uint16), C.c_uint32(0)
+        assert lib.b2_rcc_debug_tile_perm(h._h, C.c_void_p(out.ctypes.data), C.c_uint32(n_tiles), C.byref(n)) == 0
+        return out, n.value
+
+    Tbm = synth.compose(Tom, Tbo)
+    h.find(Tbm)
+    first = {k: v.copy() for k, v in h.modelView().items()}
+    p0, n0 = order()
+    assert n0 == n_tiles and np.array_equal(p0, np.arange(n_tiles))           # no durations yet: identity
+    ref = h.correctOnce(Tom, Tbo, 5, 0.3)                                        # the loop kernel sorts the durations of this call's find
+    p1, _ = order()
+    assert np.array_equal(np.sort(p1), np.arange(n_tiles)) and not np.array_equal(p1, p0)
+    for mode in (2, 1):
+        h.setExecMode(mode)
+        for _ in range(3):
+            out = h.correctOnce(Tom, Tbo, 5, 0.3)
+            assert out[0].tobytes() == ref[0].tobytes() or mode == 1             # same exec mode: bit-identical whatever the order
+            assert np.abs(out[0]["t"] - ref[0]["t"]).max() <= 1e-6 and out[2]["n_meas"] == ref[2]["n_meas"]
+            pk, _ = order()
+            assert np.array_equal(np.sort(pk), np.arange(n_tiles))
+    h.setExecMode(2)
+    h.find(Tbm)
+    again = h.modelView()
+    for k in first:
+        assert first[k].tobytes() == again[k].tobytes(), k                     # find's outputs bit-identical under a different tile order
+
+
 def test_exchange_range_fallback(po, synth):
     """The loop's default exchange carries the block sums as 64-bit fixed point (|block partial| < 2^46); sums beyond that must not fail or
     wrap: the call runs again through the cooperative variant (FP64 exchange).  Scene: the cube scaled to 10 000 km, ranges of 5e6 m."""
