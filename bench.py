@@ -200,7 +200,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": "C2: MICP-L correctOnce, 1 pose x 128x1024 spherical scan, building mesh", "n_faces": args.faces, "rays_per_step_per_gpu": 131072,
               "inner_iterations": ITERATIONS, "poses_per_gpu": 1, "parallelism": f"pose-shard x{world} (map replicated, no collective)",
-              "l2": "flushed between timed steps (256 MiB write)", "map_build": "device LBVH (B2_BUILD_MODE=0 selects the host SAH build)"}
+              "l2": "flushed between timed steps (256 MiB write)", "map_build": "device LBVH (B2_BUILD_MODE=0 selects the host SAH build)",
+              "pose": "every step corrects a different pose estimate: the scenario pose with a fresh offset N(1 cm) / N(0.1 deg yaw) per step, like consecutive "
+                      "corrections of a tracking filter (B2_BENCH_JITTER=0: the same pose every step); the find kernel orders its tiles by the previous step's warp durations"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -264,19 +266,28 @@ def main():
     # sampler sharing one host, a single descheduled rank thread used to add milliseconds to one of 20 steps).  Every step is still a complete
     # correctOnce whose result lands in host memory; the synchronous call is what `e2e` times below.
     QUEUE = 4
-    for _ in range(args.warmup):
+    # one pose estimate per step (see config["pose"])
+    jit = np.random.default_rng(1234 + rank)
+    n_pose = args.steps + args.warmup + 8
+    Toms = synth.transforms(n_pose)
+    for k in range(n_pose):
+        if os.environ.get("B2_BENCH_JITTER", "1") != "0":
+            Toms[k] = synth.compose(Tom, synth.make_transform(tuple(jit.normal(0.0, 0.01, 3)), (0.0, 0.0, float(jit.normal(0.0, np.radians(0.1))))))
+        else:
+            Toms[k] = Tom
+    for k in range(args.warmup):
         flush.fill_(1)
-        h.correctOnce(Tom, I, ITERATIONS, 0.0)
+        h.correctOnce(Toms[k], I, ITERATIONS, 0.0)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     if sampler:
         sampler.mark()
     launches0 = rmcl_b200.kernel_launch_count()
     inflight = 0
-    for a, b in ev:
+    for k, (a, b) in enumerate(ev):
         flush.fill_(2)                      # untimed L2 flush
         a.record(stream)
-        h.correctOnceAsync(Tom, I, ITERATIONS, 0.0)              # the production kernels: no instrumentation inside the call
+        h.correctOnceAsync(Toms[args.warmup + k], I, ITERATIONS, 0.0)      # the production kernels: no instrumentation inside the call
         b.record(stream)
         inflight += 1
         if inflight == QUEUE:
@@ -294,9 +305,9 @@ def main():
     #      kernels cost ~3 us per step and keep the second kernel from launching early, hence not inside the timed region above) ----
     h.enableTiming(True)
     find_ms, red_ms = [], []
-    for _ in range(min(args.steps, 50)):
+    for k in range(min(args.steps, 50)):
         flush.fill_(2)
-        h.correctOnce(Tom, I, ITERATIONS, 0.0)
+        h.correctOnce(Toms[args.warmup + k], I, ITERATIONS, 0.0)
         f_ms, r_ms = h.lastTiming()
         find_ms.append(f_ms)
         red_ms.append(r_ms)
@@ -317,15 +328,15 @@ def main():
             find_alone.append(a.elapsed_time(b))
 
     # ---- end-to-end steps: host ranges in, host result out ----
-    for _ in range(max(3, args.warmup // 4)):
-        h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
+    for k in range(max(3, args.warmup // 4)):
+        h.correctOnce(Toms[k], I, ITERATIONS, 0.0, ranges=ranges_pinned)
     barrier()
     e2e_ms = np.zeros(args.steps)
     for k in range(args.steps):
         flush.fill_(3)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        Tn2, Td2, Cm2 = h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges_pinned)
+        Tn2, Td2, Cm2 = h.correctOnce(Toms[args.warmup + k], I, ITERATIONS, 0.0, ranges=ranges_pinned)
         e2e_ms[k] = (time.perf_counter() - t0) * 1e3
     e2e_s = float(e2e_ms.sum()) * 1e-3
     barrier()
@@ -335,7 +346,7 @@ def main():
         flush.fill_(3)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        h.correctOnce(Tom, I, ITERATIONS, 0.0, ranges=ranges)
+        h.correctOnce(Toms[k], I, ITERATIONS, 0.0, ranges=ranges)
         if k >= 3:
             pg_ms[k - 3] = (time.perf_counter() - t0) * 1e3
     barrier()
