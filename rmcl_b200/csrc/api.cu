@@ -435,9 +435,9 @@ static int rcc_init(b2_rcc* h)
         int coop = 0, per_sm = 0, optin = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, map->device);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, map->device);
-        cudaFuncAttributes fa{};
-        if (cudaFuncGetAttributes(&fa, k_icp_loop<false>) == cudaSuccess) {
-            const int room = optin - (int)fa.sharedSizeBytes - 1024;
+        cudaFuncAttributes fa{}, fb{};
+        if (cudaFuncGetAttributes(&fa, k_icp_loop<false>) == cudaSuccess && cudaFuncGetAttributes(&fb, k_icp_loop<true>) == cudaSuccess) {
+            const int room = optin - (int)std::max(fa.sharedSizeBytes, fb.sharedSizeBytes) - 1024;       // both variants must accept the same launch
             h->smem_u_cap = std::max(0, room / (9 * B2_ICP_BLOCK * 4));
             const int dyn = h->smem_u_cap * 9 * B2_ICP_BLOCK * 4;
             if (dyn > 0 && (cudaFuncSetAttribute(k_icp_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess ||
