@@ -724,11 +724,10 @@ static int launch_find(b2_rcc* h, const b2_transform* Tbm_host, const IcpState* 
     // dependent block can never take an SM slot a find block is still waiting for
     const int early = (h->pdl_next && grid <= 14u * (uint32_t)h->red_grid) ? 1 : 0;
     h->pdl_armed = early != 0;
-    // tile schedule (kernels.cuh): whole tiles only, scans whose blocks are all resident in one wave (the order matters little otherwise, and
-    // the ICP loop's idle warps sort up to 8192 durations in the time they have)
+    // tile schedule (kernels.cuh): whole tiles only, as many as the ICP loop's idle warps sort in the time they have (icp_loop.cuh)
     static const int use_sched = [] { const char* e = getenv("B2_FIND_SCHED"); return e ? atoi(e) : 1; }();
     const uint32_t n_tiles = h->n / 32u;
-    const bool sched = use_sched && (h->n % 32u) == 0u && n_tiles >= 2u && n_tiles <= 8192u && grid * (B2_FIND_BLOCK / 32u) == n_tiles && grid <= 14u * (uint32_t)h->red_grid;
+    const bool sched = use_sched && (h->n % 32u) == 0u && n_tiles >= 2u && n_tiles <= (uint32_t)B2_PERM_MAX_TILES && grid * (B2_FIND_BLOCK / 32u) == n_tiles;
     uint32_t* cost = nullptr; const uint16_t* perm = nullptr;
     if (sched) {
         if (h->perm_tiles != n_tiles) {      // first launch with this model: identity order; from then on d_tile_perm always holds a permutation of the tiles
@@ -1018,7 +1017,7 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
     while (assigned > grid) { uint32_t big = 0; for (uint32_t k = 1; k < ns; k++) if (nblk[k] > nblk[big]) big = k; nblk[big]--; assigned--; }
     while (assigned < grid) { uint32_t best = 0; double load = -1.0; for (uint32_t k = 0; k < ns; k++) { const double l = (double)sc[k].h->work_n() / nblk[k]; if (l > load) { load = l; best = k; } } nblk[best]++; assigned++; }
     bool aux_any = false;
-    uint32_t blk0 = 0, smem_u_max = 0;
+    uint32_t blk0 = 0, smem_u_max = 0, sort_tiles_max = 0;
     if (H->timing) CU(cudaEventRecord(H->ev[0], H->stream));
     for (uint32_t k = 0; k < ns; k++) {
         b2_rcc* h = sc[k].h;
@@ -1084,8 +1083,9 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
             CU(cudaMemcpyAsync(h->d_bar.p, &h->pin->flag_src[fs], sizeof(unsigned int), cudaMemcpyHostToDevice, h->aux));
             S.zc_flag = h->d_bar.p; S.zc_seq = h->zc_seq;
         }
-        if (h->corr_type == B2_CORR_RCC && h->cost_tiles) {
+        if (h->corr_type == B2_CORR_RCC && h->cost_tiles && iterations >= 3u) {
             S.tile_cost = h->d_tile_cost.p; S.tile_perm = h->d_tile_perm.p; S.n_tiles = h->cost_tiles;
+            sort_tiles_max = std::max(sort_tiles_max, h->cost_tiles);
         }
         S.dpts = h->dpts(); S.dmask = h->dmask(); S.mpts = h->mpts(); S.mnrm = h->mnrm(); S.mmask = h->mhits();
         S.zc_ranges = zc; S.zc_dirs = h->d_dirs.p; S.zc_origs = h->d_origs.p; S.zc_n_origs = h->n_origs;
@@ -1095,7 +1095,13 @@ static int micp_enqueue(SensorCall* sc, uint32_t ns, const b2_transform* Tom, ui
     L.smem_u_max = smem_u_max;
     unsigned int seq = ++H->seq; if (seq == 0) seq = ++H->seq;
     L.seq = seq;
-    const size_t smem = (size_t)smem_u_max * 9 * B2_ICP_BLOCK * sizeof(float);
+    size_t smem = (size_t)smem_u_max * 9 * B2_ICP_BLOCK * sizeof(float);
+    if (sort_tiles_max) {
+        // the tile sort stages the durations behind the pair cache (2 bytes per tile); no room (very large scans): no sort, the order stays as it is
+        const size_t want = smem + 2 * (size_t)sort_tiles_max;
+        if (want <= (size_t)H->smem_u_cap * 9 * B2_ICP_BLOCK * sizeof(float)) smem = want;
+        else for (uint32_t k = 0; k < ns; k++) { L.s[k].tile_cost = nullptr; L.s[k].tile_perm = nullptr; L.s[k].n_tiles = 0; }
+    }
     const bool pdl = mode == 2 && sc[ns - 1].h->pdl_armed && !aux_any;
     sc[ns - 1].h->pdl_armed = false;
     pc.slot = (int)(H->slot_counter++ % B2_RING);

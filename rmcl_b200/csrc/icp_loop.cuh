@@ -314,42 +314,46 @@ __device__ __forceinline__ unsigned long long acc_ld(const unsigned long long* p
 }
 
 // The tile order of the next find (kernels.cuh: tile schedule) computed by warps 1..15 of one block while warp 0 is busy with the exchange and
-// the serial tail of the first iteration: tiles grouped into 16 duration classes relative to the slowest one, slowest class first, raster
-// order inside a class (only the slow tail of the distribution has to start early; the bulk may stay where it is).  Ballots and prefix sums,
-// no atomics on hot counters (most tiles share two or three classes).  `t` = 0..479; the group synchronises on named barrier 1, so the
-// block's own barrier 0 is untouched.
+// the serial tail: tiles grouped into 16 duration classes relative to the slowest one, slowest class first, raster order inside a class
+// (only the slow tail of the distribution has to start early; the bulk may stay where it is: scripts/exp_find_sched*.py).  The work is
+// split over the idle windows of the first THREE iterations so that none outlasts its window: (0) durations -> shared memory, maximum;
+// (1) per-(class, warp) counts, prefix sums; (2) scatter.  No atomics on hot counters (most tiles share two or three classes): the lanes of a
+// warp that hold the same class are found with match.any and their lowest lane updates the warp's counter.  `t` = 0..479; the group
+// synchronises on named barrier 1, so the block's own barrier 0 is untouched.
 #define B2_PERM_GROUP (B2_ICP_BLOCK - 32)
 #define B2_PERM_WARPS (B2_PERM_GROUP / 32)
+#define B2_PERM_PT 24                                               // tiles per thread
+#define B2_PERM_MAX_TILES (B2_PERM_PT * B2_PERM_GROUP)              // 11 520 tiles = 368 640 rays; s_cost takes 2 bytes per tile of dynamic shared memory
 __device__ __forceinline__ void perm_group_sync() { asm volatile("bar.sync 1, %0;" ::"n"(B2_PERM_GROUP) : "memory"); }
-#define B2_PERM_MAX_TILES 8192
-__device__ __forceinline__ void tile_perm_group(const uint32_t* __restrict__ cost, uint32_t n_tiles, uint16_t* __restrict__ perm, uint32_t* s_bin /* 1 + 16 * 15 */, uint32_t t)
+__device__ __forceinline__ uint32_t perm_class(uint32_t v16, float scale) { return min(15u, (uint32_t)((float)v16 * scale)); }
+__device__ __forceinline__ void tile_perm_load(const uint32_t* __restrict__ cost, uint32_t n_tiles, uint16_t* s_cost, uint32_t* s_bin /* 1 + 16 * 15 */, uint32_t t)
 {
-    constexpr int PT = (B2_PERM_MAX_TILES + B2_PERM_GROUP - 1) / B2_PERM_GROUP;      // tiles per thread, kept in registers: one round trip to L2 in all
-    const uint32_t lane = t & 31u, w = t >> 5;
-    if (t == 0) s_bin[0] = 1u;
-    uint32_t c[PT];
-    #pragma unroll
-    for (int k = 0; k < PT; k++) { const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP; c[k] = i < n_tiles ? __ldcg(cost + i) : 0u; }
+    const uint32_t lane = t & 31u, w = t >> 5, iters = (n_tiles + B2_PERM_GROUP - 1) / B2_PERM_GROUP;
+    uint32_t* s_off = s_bin + 1;                                   // [(15 - class) * 15 + warp]: slowest class first, then by warp
+    if (t == 0) s_bin[0] = 0u;
+    if (lane < 16u) s_off[(15u - lane) * B2_PERM_WARPS + w] = 0u;
     perm_group_sync();
     uint32_t m = 0;
-    #pragma unroll
-    for (int k = 0; k < PT; k++) m = max(m, c[k]);
+    #pragma unroll 8
+    for (uint32_t k = 0; k < iters; k++) {                         // one coalesced pass over the durations (SM cycles / 64, 16 bits)
+        const uint32_t i = t + k * B2_PERM_GROUP;
+        if (i < n_tiles) { const uint32_t v = min(65535u, __ldcg(cost + i) >> 6); s_cost[i] = (uint16_t)v; m = max(m, v); }
+    }
     #pragma unroll
     for (int off = 16; off; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (lane == 0) atomicMax(&s_bin[0], m);
-    uint32_t* s_off = s_bin + 1;                                   // [(15 - class) * 15 + warp]: slowest class first, then by warp
-    if (lane < 16u) s_off[(15u - lane) * B2_PERM_WARPS + w] = 0u;
-    perm_group_sync();
+}
+__device__ __forceinline__ void tile_perm_count(uint32_t n_tiles, const uint16_t* s_cost, uint32_t* s_bin, uint32_t t)
+{
+    const uint32_t lane = t & 31u, w = t >> 5, iters = (n_tiles + B2_PERM_GROUP - 1) / B2_PERM_GROUP;
+    uint32_t* s_off = s_bin + 1;
     const float scale = 16.0f / ((float)s_bin[0] + 1.0f);
-    #pragma unroll
-    for (int k = 0; k < PT; k++) {                                 // counts per (class, warp): the lowest lane of every class present adds its group
-        const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP;
-        if (i - lane >= n_tiles) break;                            // warp-uniform
-        const uint32_t cls = i < n_tiles ? min(15u, (uint32_t)((float)c[k] * scale)) : 16u;
-        c[k] = cls;
+    #pragma unroll 4
+    for (uint32_t k = 0; k < iters; k++) {                         // counts per (class, warp): one shared-memory add per class present in the warp
+        const uint32_t i = t + k * B2_PERM_GROUP;
+        const uint32_t cls = i < n_tiles ? perm_class(s_cost[i], scale) : 16u;
         const uint32_t grp = __match_any_sync(0xffffffffu, cls);
-        if (cls < 16u && lane == (uint32_t)__ffs((int)grp) - 1u) s_off[(15u - cls) * B2_PERM_WARPS + w] += (uint32_t)__popc(grp);
-        __syncwarp();
+        if (cls < 16u && lane == (uint32_t)__ffs((int)grp) - 1u) atomicAdd(&s_off[(15u - cls) * B2_PERM_WARPS + w], (uint32_t)__popc(grp));
     }
     perm_group_sync();
     if (w == 0) {                                                  // exclusive prefix over the 240 counts: 8 per lane, then across the lanes
@@ -361,18 +365,22 @@ __device__ __forceinline__ void tile_perm_group(const uint32_t* __restrict__ cos
         uint32_t run = incl - sum;
         for (uint32_t j = 0; j < PER; j++) { const uint32_t e = lane * PER + j; if (e < 16u * B2_PERM_WARPS) { const uint32_t cc = s_off[e]; s_off[e] = run; run += cc; } }
     }
-    perm_group_sync();
-    #pragma unroll
-    for (int k = 0; k < PT; k++) {                                 // s_off[class, warp] = next free position of the class for this warp
-        const uint32_t i = t + (uint32_t)k * B2_PERM_GROUP;
-        if (i - lane >= n_tiles) break;
-        const uint32_t cls = c[k];
+}
+__device__ __forceinline__ void tile_perm_scatter(uint32_t n_tiles, const uint16_t* s_cost, uint32_t* s_bin, uint16_t* __restrict__ perm, uint32_t t)
+{
+    const uint32_t lane = t & 31u, w = t >> 5, iters = (n_tiles + B2_PERM_GROUP - 1) / B2_PERM_GROUP;
+    uint32_t* s_off = s_bin + 1;                                   // [class, warp] = next free position of the class for this warp
+    const float scale = 16.0f / ((float)s_bin[0] + 1.0f);
+    #pragma unroll 4
+    for (uint32_t k = 0; k < iters; k++) {
+        const uint32_t i = t + k * B2_PERM_GROUP;
+        const uint32_t cls = i < n_tiles ? perm_class(s_cost[i], scale) : 16u;
         const uint32_t grp = __match_any_sync(0xffffffffu, cls);
+        const uint32_t lead = (uint32_t)__ffs((int)grp) - 1u;
         uint32_t base = 0;
-        if (cls < 16u) { base = s_off[(15u - cls) * B2_PERM_WARPS + w]; perm[base + (uint32_t)__popc(grp & ((1u << lane) - 1u))] = (uint16_t)i; }
-        __syncwarp();
-        if (cls < 16u && lane == (uint32_t)__ffs((int)grp) - 1u) s_off[(15u - cls) * B2_PERM_WARPS + w] = base + (uint32_t)__popc(grp);
-        __syncwarp();
+        if (cls < 16u && lane == lead) base = atomicAdd(&s_off[(15u - cls) * B2_PERM_WARPS + w], (uint32_t)__popc(grp));      // the group's block of positions
+        base = __shfl_sync(0xffffffffu, base, lead);
+        if (cls < 16u) perm[base + (uint32_t)__popc(grp & ((1u << lane) - 1u))] = (uint16_t)i;
     }
 }
 
@@ -500,11 +508,11 @@ __global__ void __launch_bounds__(B2_ICP_BLOCK) k_icp_loop(const __grid_constant
         }
         block_reduce_to_smem<B2_ICP_BLOCK>(acc, smem);
         const long long c1 = clock64();
-        if (it == 0 && S.tile_perm && blockIdx.x == S.blk0 && warp >= 1u) {
-            tile_perm_group(S.tile_cost, S.n_tiles, S.tile_perm, s_bin, tid - 32u);
-#if defined(B2_ICP_PROFILE)
-            if (dbg && lane == 0 && blockIdx.x == 0) atomicMax(dbg + 640, (unsigned long long)(clock64() - c1));
-#endif
+        if (it < 3u && S.tile_perm && blockIdx.x == S.blk0 && warp >= 1u && L.iterations >= 3u) {
+            uint16_t* s_cost = reinterpret_cast<uint16_t*>(s_pairs + (size_t)L.smem_u_max * 9 * B2_ICP_BLOCK);      // behind the pair cache
+            if (it == 0) tile_perm_load(S.tile_cost, S.n_tiles, s_cost, s_bin, tid - 32u);          // the block barrier at the end of every iteration separates the phases
+            else if (it == 1) tile_perm_count(S.n_tiles, s_cost, s_bin, tid - 32u);
+            else tile_perm_scatter(S.n_tiles, s_cost, s_bin, S.tile_perm, tid - 32u);
         }
         constexpr int NW = B2_ICP_BLOCK / 32;
         const uint32_t par = (tag_base + it) & 1u;

@@ -734,6 +734,12 @@ def test_c4_pinhole_correct_once(po, synth):
     h.setRanges(osc.simulate(synth.indoor_gt_pose(), Tsb, o, d, m.range_max)["ranges"])
     Tn, Td, Cm = h.correctOnce(synth.indoor_gt_pose(), synth.make_transform(), 5, 0.0)
     assert np.abs(Td["t"]).max() < 1e-5 and quat_close(Td["R"], [0, 0, 0, 1], 1e-6) and Cm["n_meas"] > 250000
+    # the tile schedule covers this scan too (9600 tiles, 2.3 waves of the find kernel): the order stays a permutation
+    import ctypes as C
+    n_tiles = m.size // 32
+    perm, nt = np.zeros(n_tiles, np.uint16), C.c_uint32(0)
+    assert rmcl_b200.load_library().b2_rcc_debug_tile_perm(h._h, C.c_void_p(perm.ctypes.data), C.c_uint32(n_tiles), C.byref(nt)) == 0
+    assert nt.value == n_tiles and np.array_equal(np.sort(perm), np.arange(n_tiles)) and not np.array_equal(perm, np.arange(n_tiles))
 
 
 @pytest.mark.parametrize("rows,cols", [(256, 1024), (1024, 1024)])
