@@ -60,8 +60,8 @@ for name, src in (("resident", None), ("pageable", ranges), ("pinned", pinned)):
     if hasattr(lib, "b2_rcc_debug_blocks"):
         blk = (C.c_ulonglong * 640)()
         lib.b2_rcc_debug_blocks(h._h, blk)
-        print("   block 0, iteration 0, cycles after the block reduce: tile order of the next find done (slowest of warps 1..15, max over calls) %d | end barrier reached by warp 0 %d, by the slowest other warp (max over calls) %d"
-              % (blk[624], blk[625], blk[626]))
+        print("   block 0, iteration 0 (first phase of the tile sort on warps 1..15), cycles from the block reduce to the end barrier: warp 0 %d, slowest other warp (max over calls) %d"
+              % (blk[625], blk[626]))
 lib.b2_rcc_debug_find_warp_times(h._h, None)
 for mode in (2, 1, 0):
     h.setExecMode(mode)
