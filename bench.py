@@ -539,11 +539,16 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     # pinned host staging (like the scan of the headline step)
     Ph = torch.from_numpy(P[b:e].view(np.uint8).copy()).pin_memory().numpy().view(P.dtype).reshape(-1)
     Ah = torch.from_numpy(A[b:e].view(np.uint8).copy()).pin_memory().numpy().view(A.dtype).reshape(-1)
-    up.update(Ph, Ah, Tsb, beams, prm)               # untimed: first call sizes the staging buffers
-    t0 = time.perf_counter()
-    for _ in range(3):
-        up.update(Ph, Ah, Tsb, beams, prm)
-    e2e = maxr((time.perf_counter() - t0) / 3)
+    A_init = Ah.copy()
+    up.update(Ph, Ah, Tsb, beams, prm, inplace=True)               # untimed: first call sizes the staging buffers
+    e2e_t = 0.0
+    for _ in range(5):
+        Ah[:] = A_init                                   # every timed update starts from the same particle attributes
+        flush.fill_(4); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        up.update(Ph, Ah, Tsb, beams, prm, inplace=True)  # pinned host particles in, updated attributes back in the same (pinned) array
+        e2e_t += time.perf_counter() - t0
+    e2e = maxr(e2e_t / 5)
     out["c3_pf"] = {"workload": f"C3: particle-filter sensor update, {n_part} particles x 180 beams per GPU, 1M-triangle mesh", "rays_per_s": n_part * world * 180 / (ms * 1e-3),
                     "ms_per_step": ms, "e2e_rays_per_s": n_part * world * 180 / e2e, "e2e_ms_per_step": e2e * 1e3,
                     "h2d_bytes_per_step": n_part * (32 + 36) + 180 * 32, "d2h_bytes_per_step": n_part * 36}

@@ -567,8 +567,10 @@ class PCDSensorUpdaterB200:
     def setStream(self, cuda_stream):
         _chk(load_library().b2_pf_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
-    def update(self, particle_poses, particle_attrs, Tsb, beams, params: PFParams | None = None):
-        """RAM variant: numpy arrays in, updated attrs array out.  VRAM variant: torch CUDA tensors, attrs updated in place."""
+    def update(self, particle_poses, particle_attrs, Tsb, beams, params: PFParams | None = None, inplace=False):
+        """RAM variant: numpy arrays in, updated attrs array out (inplace=True: the caller's attrs array is updated itself, as the reference's
+        update(MemoryView) does -- no staging copy; pin the arrays and the transfers overlap the kernel).  VRAM variant: torch CUDA tensors, attrs
+        updated in place."""
         prm = params or self.config
         beams = np.ascontiguousarray(beams)
         assert beams.dtype.itemsize == 64
@@ -580,7 +582,11 @@ class PCDSensorUpdaterB200:
                                          C.c_uint32(len(beams)), C.byref(prm)))
             return particle_attrs
         poses = _tf(particle_poses).reshape(-1)
-        attrs = np.ascontiguousarray(particle_attrs).copy()
+        if inplace:
+            attrs = particle_attrs
+            assert isinstance(attrs, np.ndarray) and attrs.flags.c_contiguous and attrs.flags.writeable
+        else:
+            attrs = np.ascontiguousarray(particle_attrs).copy()
         assert attrs.dtype.itemsize == 36
         _chk(lib.b2_pf_sensor_update_host(self._h, _p(poses), _p(attrs), C.c_uint32(len(poses)), _p(Tsb), _p(beams), C.c_uint32(len(beams)), C.byref(prm)))
         return attrs

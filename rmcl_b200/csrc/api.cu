@@ -1437,6 +1437,7 @@ struct b2_pf {
     DevBuf<b2_transform> d_poses; DevBuf<b2_particle_attr> d_attrs;
     DevBuf<double> d_part; DevBuf<unsigned int> d_ticket; DevBuf<float> d_out; float* h_out = nullptr; int n_sm = 0;
     int smem_optin = 0;
+    cudaStream_t side = nullptr; cudaEvent_t ev_beams = nullptr, ev_side = nullptr;      // second stream of the chunked host variant (b2_pf_sensor_update_host)
     // sharded resampling over NVLink peer memory (b2_pf_p2p_*): own exchange buffers (cudaMalloc: exportable through CUDA IPC) + the peers' mappings
     b2_transform* x_poses = nullptr; b2_particle_attr* x_attrs = nullptr; uint32_t x_cap = 0;
     PfPeers peers{}; bool peers_open = false; DevBuf<unsigned long long> d_traffic;
@@ -1480,6 +1481,9 @@ extern "C" int b2_pf_destroy(b2_pf* h)
     h->d_beams.release(); h->d_poses.release(); h->d_attrs.release(); h->d_part.release(); h->d_ticket.release(); h->d_out.release();
     if (h->h_beams) cudaFreeHost(h->h_beams);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->ev_beams) cudaEventDestroy(h->ev_beams);
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->peers_open) for (uint32_t r = 0; r < h->peers.world; r++) if (r != h->peers.rank) {
         if (h->peers.poses[r]) cudaIpcCloseMemHandle((void*)h->peers.poses[r]);
         if (h->peers.attrs[r]) cudaIpcCloseMemHandle((void*)h->peers.attrs[r]);
@@ -1503,11 +1507,9 @@ static uint32_t dir_sort_key(const b2_range_meas& m)
     return spread(q(m.dir.x)) | (spread(q(m.dir.y)) << 1) | (spread(q(m.dir.z)) << 2);
 }
 
-static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,
-                          const b2_range_meas* beams, uint32_t n_beams, const b2_pf_params* prm)
+// beams: host -> compact, direction-sorted device table (merge order preserved through PfBeam::slot), on h->stream; particles per block
+static int pf_prepare_beams(b2_pf* h, const b2_range_meas* beams, uint32_t n_beams, uint32_t* ppb_out)
 {
-    if (n == 0 || n_beams == 0) return B2_OK;
-    // beams: host -> compact, direction-sorted device table (merge order preserved through PfBeam::slot)
     if (h->h_beams_cap < n_beams) {
         if (h->h_beams) cudaFreeHost(h->h_beams);
         h->h_beams = nullptr; h->h_beams_cap = 0;
@@ -1532,12 +1534,26 @@ static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_a
     uint32_t ppb = (uint32_t)std::min<size_t>((size_t)h->smem_optin / bytes_per_particle, 64);
     const uint32_t want = std::max(1u, (B2_PF_BLOCK * 8 + n_beams - 1) / n_beams);       // ~8 rays per thread
     ppb = std::max(1u, std::min(ppb, want));
-    ppb = std::min(ppb, (uint32_t)B2_PF_BLOCK);
+    *ppb_out = std::min(ppb, (uint32_t)B2_PF_BLOCK);
+    return B2_OK;
+}
+static int pf_launch(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb, uint32_t n_beams, const b2_pf_params* prm,
+                      uint32_t ppb, cudaStream_t stream)
+{
+    const size_t bytes_per_particle = sizeof(float) * (size_t)n_beams;
     const uint32_t grid = (n + ppb - 1) / ppb;
-    if (prm->correspondence_type == 1) k_pf_update<1><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
-    else                               k_pf_update<0><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, h->stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    if (prm->correspondence_type == 1) k_pf_update<1><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    else                               k_pf_update<0><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
     LAUNCHED();
     return B2_OK;
+}
+static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,
+                          const b2_range_meas* beams, uint32_t n_beams, const b2_pf_params* prm)
+{
+    if (n == 0 || n_beams == 0) return B2_OK;
+    uint32_t ppb = 1;
+    RES(pf_prepare_beams(h, beams, n_beams, &ppb));
+    return pf_launch(h, poses_dev, attrs_dev, n, Tsb, n_beams, prm, ppb, h->stream);
 }
 
 extern "C" int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,
@@ -1559,10 +1575,29 @@ extern "C" int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses, b2_
     if (n_beams) NOTNULL(beams);
     CU(cudaSetDevice(h->map->device));
     RES(h->d_poses.reserve(n)); RES(h->d_attrs.reserve(n));
-    CU(cudaMemcpyAsync(h->d_poses.p, poses, sizeof(b2_transform) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_attrs.p, attrs, sizeof(b2_particle_attr) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    RES(pf_update_impl(h, h->d_poses.p, h->d_attrs.p, n, Tsb, beams, n_beams, prm));
-    CU(cudaMemcpyAsync(attrs, h->d_attrs.p, sizeof(b2_particle_attr) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (n_beams == 0) return B2_OK;
+    uint32_t ppb = 1;
+    RES(pf_prepare_beams(h, beams, n_beams, &ppb));
+    // Particles are independent: the set is cut into chunks that alternate between two streams, so that the upload of chunk i+1 and the
+    // download of chunk i-1 (two copy engines) run under the kernel of chunk i.  With pinned host arrays the call then costs the kernel time
+    // plus one chunk's transfers instead of kernel + all transfers.
+    const uint32_t n_chunks = n >= 32768u ? 8u : 1u;
+    const uint32_t per = ((n + n_chunks - 1) / n_chunks + ppb - 1) / ppb * ppb;          // whole blocks per chunk
+    if (n_chunks > 1) {
+        if (!h->side) { CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&h->ev_beams, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming)); }
+        CU(cudaEventRecord(h->ev_beams, h->stream));                  // beam table (and whatever the caller had queued on the stream before)
+        CU(cudaStreamWaitEvent(h->side, h->ev_beams, 0));
+    }
+    uint32_t c = 0;
+    for (uint32_t first = 0; first < n; first += per, c++) {
+        const uint32_t m = std::min(per, n - first);
+        cudaStream_t st = (c & 1u) ? h->side : h->stream;
+        CU(cudaMemcpyAsync(h->d_poses.p + first, poses + first, sizeof(b2_transform) * (size_t)m, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_attrs.p + first, attrs + first, sizeof(b2_particle_attr) * (size_t)m, cudaMemcpyHostToDevice, st));
+        RES(pf_launch(h, h->d_poses.p + first, h->d_attrs.p + first, m, Tsb, n_beams, prm, ppb, st));
+        CU(cudaMemcpyAsync(attrs + first, h->d_attrs.p + first, sizeof(b2_particle_attr) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    }
+    if (n_chunks > 1) { CU(cudaEventRecord(h->ev_side, h->side)); CU(cudaStreamWaitEvent(h->stream, h->ev_side, 0)); }
     CU(cudaStreamSynchronize(h->stream));
     return B2_OK;
 }

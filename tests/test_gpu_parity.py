@@ -323,6 +323,15 @@ def test_full_size_properties_c3(po, synth):
     assert np.abs(out["likelihood"]["mean"][idx] - ref["likelihood"]["mean"]).max() <= TOL_LIK
     parts = [up.update(P[a:b], A[a:b], Tsb, beams, prm) for a, b in ((0, 12500), (12500, 50000), (50000, 100000))]
     assert np.concatenate(parts).tobytes() == out.tobytes()
+    # host arrays of this size go through the chunked two-stream path; it must equal the device-resident single launch, pinned or not, in place or not
+    import torch
+    Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+    up.update(Pd, Ad, Tsb, beams, prm)
+    assert Ad.cpu().numpy().tobytes() == out.tobytes()
+    Ph = torch.from_numpy(P.view(np.uint8).copy()).pin_memory().numpy().view(P.dtype).reshape(-1)
+    Ah = torch.from_numpy(A.view(np.uint8).copy()).pin_memory().numpy().view(A.dtype).reshape(-1)
+    assert up.update(Ph, Ah, Tsb, beams, prm, inplace=True) is Ah and Ah.tobytes() == out.tobytes()
     # second update accumulates: n_meas 360, and equals updating with the beams concatenated twice
     out2 = up.update(P[:2000], out[:2000], Tsb, beams, prm)
     both = up.update(P[:2000], A[:2000], Tsb, np.concatenate([beams, beams]), prm)
