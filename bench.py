@@ -212,7 +212,7 @@ def main():
         line = {"impl": "reference", "metric": "ray-correspondences/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "micp_iters_per_s": 1.0 / dt,
-                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "label": "oracle_port_baseline: the repo's own CPU restatement (oracle/), not Embree / rmagine",
                                  "sample": sample + " on the CPU oracle port, OpenMP over rays and over reduction chunks, threads = min(CPU affinity, cgroup CPU quota); Embree/rmagine not buildable here",
                                  "host_logical_cpus": os.cpu_count()},
                 "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -440,7 +440,7 @@ def main():
     if world == 1:
         try:
             val, dt, cores, _, sample = cpu_reference_leg(args, 10, 1, budget_s=30.0)
-            cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+            cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "label": "oracle_port_baseline: the repo's own CPU restatement (oracle/), not Embree / rmagine",
                    "sample": sample + " on the CPU oracle port (FP32 merges, OpenMP over rays and reduction chunks); Embree/rmagine unavailable",
                    "ms_per_step": dt * 1e3}
         except Exception as e:
