@@ -552,6 +552,36 @@ def extra_workloads(torch, rmcl_b200, synth, gmap, h, m, Tsb, Tgt, stream, flush
     out["c3_pf"] = {"workload": f"C3: particle-filter sensor update, {n_part} particles x 180 beams per GPU, 1M-triangle mesh", "rays_per_s": n_part * world * 180 / (ms * 1e-3),
                     "ms_per_step": ms, "e2e_rays_per_s": n_part * world * 180 / e2e, "e2e_ms_per_step": e2e * 1e3,
                     "h2d_bytes_per_step": n_part * (32 + 36) + 180 * 32, "d2h_bytes_per_step": n_part * 36}
+    # ---- the same update for a CONVERGED particle cloud (tracking): the updater times its two ray mappings and keeps the faster one ----
+    try:
+        rngc = np.random.default_rng(7 + rank)
+        Pc = P[b:e].copy()
+        gt = synth.building_gt_pose()
+        Pc["t"][:, 0] = gt["t"][0] + rngc.normal(0, 0.3, len(Pc)); Pc["t"][:, 1] = gt["t"][1] + rngc.normal(0, 0.3, len(Pc)); Pc["t"][:, 2] = gt["t"][2]
+        yawc = rngc.normal(0.0, np.radians(5.0), len(Pc))
+        Pc["R"][:, 0] = 0; Pc["R"][:, 1] = 0; Pc["R"][:, 2] = np.sin(yawc / 2); Pc["R"][:, 3] = np.cos(yawc / 2)
+        Pcd = torch.from_numpy(Pc.view(np.float32).reshape(-1, 8).copy()).cuda()
+        res = {}
+        for mode in (0, 3):
+            up.setMapping(mode)
+            tot = 0.0
+            for i in range(4 + 6):
+                Ad = A0.clone()
+                flush.fill_(4)
+                a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                up.update(Pcd, Ad, Tsb, beams, prm)
+                bb.record(stream)
+                torch.cuda.synchronize()
+                if i >= 4:
+                    tot += a.elapsed_time(bb)
+            res[mode] = maxr(tot) / 6
+        out["c3_pf_tracking"] = {"workload": f"C3 for a converged cloud: {n_part} particles per GPU within sigma 0.3 m / 5 deg of one pose, 180 beams",
+                                 "ms_per_step_lanes_are_beams": res[0], "ms_per_step": res[3], "rays_per_s": n_part * world * 180 / (res[3] * 1e-3),
+                                 "mapping_chosen": up.mapping()[1], "note": "mapping 2 = lanes are particles sorted by (heading, cell) on the device; the sort is inside the timed step"}
+        up.setMapping(3)
+    except Exception as ex:
+        out["c3_pf_tracking"] = {"error": repr(ex)}
     # ---- C5 (BASELINE.json configs[4]): 1M particles x 360 beams sharded 8 ways = 125 000 x 360 per GPU; runs when 8 ranks are present
     #      (B2_BENCH_C5=1 forces the per-GPU share on fewer GPUs)
     if world == 8 or os.environ.get("B2_BENCH_C5") == "1":

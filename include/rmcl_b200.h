@@ -226,6 +226,13 @@ B2_API int b2_umeyama_batch(const b2_cross_stats* stats, uint32_t n, b2_transfor
 B2_API int b2_pf_create(b2_mesh* map, b2_pf** out);
 B2_API int b2_pf_destroy(b2_pf* h);
 B2_API int b2_pf_set_stream(b2_pf* h, void* cuda_stream);
+/* How b2_pf_sensor_update maps rays to lanes (a schedule: results are bit-identical).  0: the 32 lanes of a warp trace 32 beams of ONE particle --
+ * the reference's loop order seen from a particle (PCDSensorUpdaterEmbree.cpp:290-342) and the better choice for particle sets spread over the map.
+ * 1: the lanes trace the SAME beam for 32 particles; 2: the same after sorting the particles by (heading, map cell) on the device, coherent and up to
+ * 1.7x faster once the cloud has converged.  3 (default): 0 or 2, whichever was faster when last timed (both on the first two updates, the slower one
+ * again every 64 updates).  The environment variable B2_PF_MAP sets the default of new handles. */
+B2_API int b2_pf_set_mapping(b2_pf* h, int mode);
+B2_API int b2_pf_get_mapping(b2_pf* h, int* mode, int* current);
 /* ParticleUpdater<VRAM_CUDA>::update (rmcl_ros/include/rmcl_ros/rmcl/ParticleUpdater.hpp:39-43) with the hot loop of
  * PCDSensorUpdaterEmbree::update (rmcl_ros/src/rmcl/PCDSensorUpdaterEmbree.cpp:290-342): all beams x all particles in ONE launch,
  * per-particle likelihood merged in beam order, attrs read-modified-written once.  poses/attrs: DEVICE pointers; beams: HOST. */

@@ -74,7 +74,7 @@ EXPORTS = [
     "b2_rcc_correct_once", "b2_rcc_correct_once_ranges", "b2_rcc_correct_batch", "b2_umeyama_batch", "b2_pf_create", "b2_pf_destroy",
     "b2_pf_set_stream", "b2_pf_sensor_update", "b2_pf_sensor_update_host", "b2_kernel_launch_count", "b2_rcc_enable_timing", "b2_rcc_last_timing", "b2_pf_motion_update", "b2_pf_likelihood_stats",
     "b2_rcc_set_correspondence_type", "b2_pf_resample_gladiator", "b2_pf_gladiator_randoms", "b2_rcc_segment", "b2_mesh_create_from_file", "b2_mesh_file_load", "b2_mesh_file_free", "b2_peek_cuda_error", "b2_mesh_blob_size", "b2_mesh_export_blob", "b2_mesh_create_from_blob", "b2_mesh_refit",
-    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers", "b2_rcc_benchmark_batch", "b2_pf_p2p_init", "b2_pf_p2p_connect", "b2_pf_p2p_publish", "b2_pf_resample_gladiator_p2p", "b2_pf_p2p_connect_local", "b2_rcc_set_cpc_options",
+    "b2_rcc_correct_once_async", "b2_rcc_correct_once_wait", "b2_micp_correct_once", "b2_rcc_set_exec_mode", "b2_debug_read_bandwidth", "b2_rcc_set_sim_options", "b2_rcc_bind_dataset", "b2_rcc_bind_model_buffers", "b2_rcc_benchmark_batch", "b2_pf_p2p_init", "b2_pf_p2p_connect", "b2_pf_p2p_publish", "b2_pf_resample_gladiator_p2p", "b2_pf_p2p_connect_local", "b2_rcc_set_cpc_options", "b2_pf_set_mapping", "b2_pf_get_mapping",
 ]
 
 
@@ -566,6 +566,15 @@ class PCDSensorUpdaterB200:
 
     def setStream(self, cuda_stream):
         _chk(load_library().b2_pf_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def setMapping(self, mode):
+        """0 lanes = beams of one particle, 1 lanes = particles, 2 lanes = particles sorted by pose, 3 (default) auto by timing; results identical."""
+        _chk(load_library().b2_pf_set_mapping(self._h, C.c_int(mode)))
+
+    def mapping(self):
+        mode, cur = C.c_int(0), C.c_int(0)
+        _chk(load_library().b2_pf_get_mapping(self._h, C.byref(mode), C.byref(cur)))
+        return mode.value, cur.value
 
     def update(self, particle_poses, particle_attrs, Tsb, beams, params: PFParams | None = None, inplace=False):
         """RAM variant: numpy arrays in, updated attrs array out (inplace=True: the caller's attrs array is updated itself, as the reference's

@@ -1438,6 +1438,11 @@ struct b2_pf {
     DevBuf<double> d_part; DevBuf<unsigned int> d_ticket; DevBuf<float> d_out; float* h_out = nullptr; int n_sm = 0;
     int smem_optin = 0;
     cudaStream_t side = nullptr; cudaEvent_t ev_beams = nullptr, ev_side = nullptr;      // second stream of the chunked host variant (b2_pf_sensor_update_host)
+    // ray mapping of k_pf_update (kernels.cuh): 0 lanes = beams, 1 lanes = particles, 2 lanes = particles sorted by pose, 3 (default) whichever of 0 / 2
+    // was faster when last timed -- both are timed on the first updates and the loser again every 64 updates (particle sets converge and spread out)
+    int map_mode = 3, map_cur = 0, map_best = 0; unsigned int map_updates = 0; float map_ms[2] = {0.f, 0.f}; bool map_timed = false;
+    cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
+    DevBuf<uint32_t> d_keys, d_keys2, d_idx, d_idx2; DevBuf<unsigned char> d_sort_tmp;
     // sharded resampling over NVLink peer memory (b2_pf_p2p_*): own exchange buffers (cudaMalloc: exportable through CUDA IPC) + the peers' mappings
     b2_transform* x_poses = nullptr; b2_particle_attr* x_attrs = nullptr; uint32_t x_cap = 0;
     PfPeers peers{}; bool peers_open = false; DevBuf<unsigned long long> d_traffic;
@@ -1454,8 +1459,12 @@ static int pf_init(b2_pf* h)
     RES(h->d_part.reserve(2 * (size_t)h->n_sm * 4)); RES(h->d_ticket.reserve(1)); RES(h->d_out.reserve(2));
     CU(cudaMemset(h->d_ticket.p, 0, sizeof(unsigned int)));
     CU(cudaMallocHost((void**)&h->h_out, 2 * sizeof(float)));
-    CU(cudaFuncSetAttribute(k_pf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-    CU(cudaFuncSetAttribute(k_pf_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaFuncSetAttribute(k_pf_update<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CU(cudaEventCreate(&h->ev_m0)); CU(cudaEventCreate(&h->ev_m1));
+    { const char* e = getenv("B2_PF_MAP"); if (e) h->map_mode = std::min(3, std::max(0, atoi(e))); }
     return B2_OK;
 }
 
@@ -1484,6 +1493,9 @@ extern "C" int b2_pf_destroy(b2_pf* h)
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
     if (h->ev_beams) cudaEventDestroy(h->ev_beams);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
+    if (h->ev_m0) cudaEventDestroy(h->ev_m0);
+    if (h->ev_m1) cudaEventDestroy(h->ev_m1);
+    h->d_keys.release(); h->d_keys2.release(); h->d_idx.release(); h->d_idx2.release(); h->d_sort_tmp.release();
     if (h->peers_open) for (uint32_t r = 0; r < h->peers.world; r++) if (r != h->peers.rank) {
         if (h->peers.poses[r]) cudaIpcCloseMemHandle((void*)h->peers.poses[r]);
         if (h->peers.attrs[r]) cudaIpcCloseMemHandle((void*)h->peers.attrs[r]);
@@ -1538,12 +1550,34 @@ static int pf_prepare_beams(b2_pf* h, const b2_range_meas* beams, uint32_t n_bea
     return B2_OK;
 }
 static int pf_launch(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb, uint32_t n_beams, const b2_pf_params* prm,
-                      uint32_t ppb, cudaStream_t stream)
+                     uint32_t ppb, cudaStream_t stream, int map = 0, const uint32_t* order = nullptr)
 {
     const size_t bytes_per_particle = sizeof(float) * (size_t)n_beams;
+    if (map) { ppb = 32; if (bytes_per_particle * ppb > (size_t)h->smem_optin) { map = 0; order = nullptr; ppb = std::max(1u, (uint32_t)((size_t)h->smem_optin / bytes_per_particle)); } }
     const uint32_t grid = (n + ppb - 1) / ppb;
-    if (prm->correspondence_type == 1) k_pf_update<1><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
-    else                               k_pf_update<0><<<grid, B2_PF_BLOCK, bytes_per_particle * ppb, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb);
+    const size_t smem = bytes_per_particle * ppb;
+    const bool cp = prm->correspondence_type == 1;
+    if (map) {
+        if (cp) k_pf_update<1, 1><<<grid, B2_PF_BLOCK, smem, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb, order);
+        else    k_pf_update<0, 1><<<grid, B2_PF_BLOCK, smem, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb, order);
+    } else {
+        if (cp) k_pf_update<1, 0><<<grid, B2_PF_BLOCK, smem, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb, nullptr);
+        else    k_pf_update<0, 0><<<grid, B2_PF_BLOCK, smem, stream>>>(h->map->view(), poses_dev, attrs_dev, n, *Tsb, h->d_beams.p, n_beams, *prm, ppb, nullptr);
+    }
+    LAUNCHED();
+    return B2_OK;
+}
+// particles sorted by (heading bin, Morton cell) for the lanes = particles mapping: h->d_idx2 = particle at position p
+static int pf_sort_particles(b2_pf* h, const b2_transform* poses_dev, uint32_t n, cudaStream_t stream)
+{
+    RES(h->d_keys.reserve(n)); RES(h->d_keys2.reserve(n)); RES(h->d_idx.reserve(n)); RES(h->d_idx2.reserve(n));
+    const BvhView v = h->map->view();
+    k_pf_sort_keys<<<(n + 255) / 256, 256, 0, stream>>>(poses_dev, n, v.bx, v.by, h->d_keys.p, h->d_idx.p);
+    LAUNCHED();
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->d_keys.p, h->d_keys2.p, h->d_idx.p, h->d_idx2.p, (int)n, 0, 24, stream));
+    RES(h->d_sort_tmp.reserve(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, h->d_keys.p, h->d_keys2.p, h->d_idx.p, h->d_idx2.p, (int)n, 0, 24, stream));
     LAUNCHED();
     return B2_OK;
 }
@@ -1553,7 +1587,45 @@ static int pf_update_impl(b2_pf* h, const b2_transform* poses_dev, b2_particle_a
     if (n == 0 || n_beams == 0) return B2_OK;
     uint32_t ppb = 1;
     RES(pf_prepare_beams(h, beams, n_beams, &ppb));
-    return pf_launch(h, poses_dev, attrs_dev, n, Tsb, n_beams, prm, ppb, h->stream);
+    int map = h->map_mode;
+    if (map == 3) {
+        // timing of the previous update (pf_prepare_beams synchronised the stream: its events are complete)
+        if (h->map_timed) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->ev_m0, h->ev_m1) == cudaSuccess) h->map_ms[h->map_cur ? 1 : 0] = ms; else (void)cudaGetLastError();
+            h->map_timed = false;
+        }
+        const unsigned int k = h->map_updates++;
+        if (n < 4096u) map = 0;                                        // too few particles for the sort to pay
+        else if (k == 0) map = 0;
+        else if (k == 1) map = 2;
+        else {
+            h->map_best = h->map_ms[1] > 0.f && h->map_ms[1] < h->map_ms[0] ? 2 : 0;
+            map = (k % 64u) == 0u ? (h->map_best ? 0 : 2) : h->map_best;      // the other one gets another chance now and then
+        }
+        h->map_cur = map;
+        CU(cudaEventRecord(h->ev_m0, h->stream));
+    }
+    const uint32_t* order = nullptr;
+    if (map == 2) { RES(pf_sort_particles(h, poses_dev, n, h->stream)); order = h->d_idx2.p; }
+    RES(pf_launch(h, poses_dev, attrs_dev, n, Tsb, n_beams, prm, ppb, h->stream, map != 0, order));
+    if (h->map_mode == 3) { CU(cudaEventRecord(h->ev_m1, h->stream)); h->map_timed = true; }
+    return B2_OK;
+}
+
+extern "C" int b2_pf_set_mapping(b2_pf* h, int mode)
+{
+    NOTNULL(h);
+    if (mode < 0 || mode > 3) return fail(B2_ERR_INVALID, "unknown ray mapping %d", mode);
+    h->map_mode = mode; h->map_updates = 0; h->map_timed = false; h->map_ms[0] = h->map_ms[1] = 0.f;
+    return B2_OK;
+}
+extern "C" int b2_pf_get_mapping(b2_pf* h, int* mode, int* current)
+{
+    NOTNULL(h);
+    if (mode) *mode = h->map_mode;
+    if (current) *current = h->map_mode == 3 ? h->map_cur : h->map_mode;
+    return B2_OK;
 }
 
 extern "C" int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n, const b2_transform* Tsb,

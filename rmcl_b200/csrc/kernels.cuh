@@ -974,9 +974,15 @@ B2_DEV void pf_merge(b2_gaussian1d& lk, const float* e, uint32_t n_beams)
 #define B2_PF_BLOCK 128
 // 72 registers (7 blocks/SM) measured 8 % faster than the uncapped 84 (6 blocks/SM); a persistent-lane variant with dynamic ray fetch
 // (idle lanes claim new rays) was measured SLOWER (2.3 vs 3.3 G rays/s: the extra live state and warp votes cost more than the refill gains)
-template <int CORR>
+// MAP 0: consecutive lanes = consecutive beams of one particle (rays of a warp share their origin: the mapping for particle sets spread over
+// the map, where no two particles are close).  MAP 1: consecutive lanes = the particles of the block, same beam -- coherent when neighbouring
+// particles have nearly the same pose, i.e. for a converged cloud after `order` sorted it by (heading, cell): 1.7x faster there, slower on
+// spread-out sets (scripts/exp_pf_mapping.py); the host picks by timing both (api.cu).  `order` (may be nullptr) = particle processed at
+// position p.  The per-particle merge runs over the beams in their original order either way: results are bit-identical.
+template <int CORR, int MAP>
 __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const b2_transform* __restrict__ poses, b2_particle_attr* __restrict__ attrs, uint32_t n_particles,
-                                                           b2_transform Tsb_val, const PfBeam* __restrict__ beams, uint32_t n_beams, b2_pf_params prm, uint32_t ppb)
+                                                           b2_transform Tsb_val, const PfBeam* __restrict__ beams, uint32_t n_beams, b2_pf_params prm, uint32_t ppb,
+                                                           const uint32_t* __restrict__ order)
 {
     extern __shared__ float s_eval[];            // [ppb][n_beams]
     const uint32_t p0 = blockIdx.x * ppb;
@@ -985,19 +991,36 @@ __global__ void __launch_bounds__(B2_PF_BLOCK, 7) k_pf_update(BvhView bvh, const
     const Tf Tsb = tf_from_pod(Tsb_val);
     const uint32_t total = np * n_beams;
     for (uint32_t w = threadIdx.x; w < total; w += blockDim.x) {
-        const uint32_t pl = w / n_beams, bi = w % n_beams;
-        const Tf Tsm = tf_mul(tf_load(poses + p0 + pl), Tsb);                              // :337-338
+        const uint32_t pl = MAP ? w % np : w / n_beams, bi = MAP ? w / np : w % n_beams;
+        const uint32_t pi = order ? order[p0 + pl] : p0 + pl;
+        const Tf Tsm = tf_mul(tf_load(poses + pi), Tsb);                                   // :337-338
         const PfBeam b = beams[bi];
         s_eval[pl * n_beams + b.slot] = pf_eval_one<CORR>(bvh, Tsm, b, prm, sigma_quad, denom);
     }
     __syncthreads();
     if (threadIdx.x < np) {
-        b2_particle_attr* ap = attrs + p0 + threadIdx.x;
+        b2_particle_attr* ap = attrs + (order ? order[p0 + threadIdx.x] : p0 + threadIdx.x);
         b2_gaussian1d lk = ap->likelihood;
         pf_merge(lk, s_eval + threadIdx.x * n_beams, n_beams);
         ap->likelihood = lk;
     }
 }
+
+#ifdef __CUDACC__
+// sort key of a particle for MAP 1: 16 heading bins (yaw), then the Morton code of its (x, y) cell on a 1024 x 1024 lattice over the map
+__global__ void k_pf_sort_keys(const b2_transform* __restrict__ poses, uint32_t n, float bx, float by, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Tf T = tf_load(poses + i);
+    const float yaw = atan2f(2.0f * (T.R.w * T.R.z + T.R.x * T.R.y), 1.0f - 2.0f * (T.R.y * T.R.y + T.R.z * T.R.z));
+    const uint32_t yb = min(15u, (uint32_t)((yaw + 3.14159265f) * (16.0f / 6.2831853f)));
+    auto cell = [](float v, float b) { const float u = (v / (b + 1e-6f)) * 0.5f + 0.5f; return (uint32_t)min(1023.0f, max(0.0f, u * 1023.0f)); };
+    auto spread = [](uint32_t x) { x &= 0x3ffu; x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u; return x; };
+    keys[i] = (yb << 20) | spread(cell(T.t.x, bx)) | (spread(cell(T.t.y, by)) << 1);
+    idx[i] = i;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // rest of the PF cycle

@@ -323,8 +323,17 @@ def test_full_size_properties_c3(po, synth):
     assert np.abs(out["likelihood"]["mean"][idx] - ref["likelihood"]["mean"]).max() <= TOL_LIK
     parts = [up.update(P[a:b], A[a:b], Tsb, beams, prm) for a, b in ((0, 12500), (12500, 50000), (50000, 100000))]
     assert np.concatenate(parts).tobytes() == out.tobytes()
-    # host arrays of this size go through the chunked two-stream path; it must equal the device-resident single launch, pinned or not, in place or not
+    # ray mappings (lanes = beams / particles / particles sorted by pose / chosen by timing): a schedule, bit-identical results
     import torch
+    Pd0 = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
+    for mode, reps in ((0, 1), (1, 1), (2, 1), (3, 4)):
+        up.setMapping(mode)
+        for _ in range(reps):
+            Am = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
+            up.update(Pd0, Am, Tsb, beams, prm)
+            assert Am.cpu().numpy().tobytes() == out.tobytes(), mode
+    assert up.mapping()[0] == 3 and up.mapping()[1] in (0, 2)
+    # host arrays of this size go through the chunked two-stream path; it must equal the device-resident single launch, pinned or not, in place or not
     Pd = torch.from_numpy(P.view(np.float32).reshape(-1, 8).copy()).cuda()
     Ad = torch.from_numpy(A.view(np.float32).reshape(-1, 9).copy()).cuda()
     up.update(Pd, Ad, Tsb, beams, prm)
