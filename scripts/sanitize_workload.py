@@ -41,6 +41,11 @@ for mode in (1, 0):
     up.motionUpdate(Pd, Ad, synth.make_transform((0.02, 0, 0), (0, 0, 0.01)), 0.01)
     up.motionUpdate(Pd, Ad, synth.make_transform((0.5, 0, 0), (0, 0, 0.01)), 0.01, check_collision=True)
     up.update(Pd, Ad, Tsb, beams)
+    for mode in (1, 2, 0, 3):                                  # both ray mappings of the PF kernel, with and without the device-side particle sort
+        up.setMapping(mode)
+        up.update(Pd, Ad, Tsb, beams)
+    P2, A2 = synth.pf_particles(40000)                        # the chunked two-stream host path
+    up.update(P2, A2, Tsb, beams)
     up.likelihoodStats(Ad)
     Pn, An = torch.empty_like(Pd), torch.empty_like(Ad)
     up.resample(Pd, Ad, Pn, An)
