@@ -238,7 +238,9 @@ B2_API int b2_pf_get_mapping(b2_pf* h, int* mode, int* current);
  * per-particle likelihood merged in beam order, attrs read-modified-written once.  poses/attrs: DEVICE pointers; beams: HOST. */
 B2_API int b2_pf_sensor_update(b2_pf* h, const b2_transform* poses_dev, b2_particle_attr* attrs_dev, uint32_t n_particles,
                                const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
-/* ParticleUpdater<RAM>::update: HOST poses/attrs; copies in, updates, copies attrs back (end-to-end entry point) */
+/* ParticleUpdater<RAM>::update: HOST poses/attrs; copies in, updates, copies attrs back (end-to-end entry point).  Sets of 32 768 particles and more
+ * are processed in 8 chunks alternating between two streams: with pinned host arrays the transfers run under the kernel (C3: 5.2 ms for 5.13 ms of
+ * kernel).  attrs_host is updated in place. */
 B2_API int b2_pf_sensor_update_host(b2_pf* h, const b2_transform* poses_host, b2_particle_attr* attrs_host, uint32_t n_particles,
                                     const b2_transform* Tsb, const b2_range_meas* beams_host, uint32_t n_beams, const b2_pf_params* params);
 

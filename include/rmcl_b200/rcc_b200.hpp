@@ -317,6 +317,8 @@ public:
     void setTsb(const rm::Transform& Tsb) { Tsb_ = Tsb; }
     // beams replace the random_device sampling of :276-327 (quirk D5): the caller samples the cloud and passes RangeMeasurements
     void setBeams(const std::vector<RangeMeasurement>& beams) { beams_ = beams; }
+    // how rays are mapped to lanes (a schedule, results identical): 0 beams of one particle, 1 particles, 2 particles sorted by pose, 3 (default) by timing
+    void setMapping(int mode) { b2_check(b2_pf_set_mapping(h_, mode), "setMapping"); }
     // ParticleUpdater<RAM>::update
     ParticleUpdateResults update(rm::MemoryView<rm::Transform, rm::RAM> poses, rm::MemoryView<ParticleAttributes, rm::RAM> attrs, const ParticleUpdateConfig& = {})
     {
